@@ -1,0 +1,212 @@
+/* veles_b200.h -- C ABI of the B200-native VelesDB vector-search hot path.
+ *
+ * This is the drop-in boundary.  Each entry point names the
+ * reference interface it replaces; paths are relative to
+ * /root/reference/crates/velesdb-core/src.  The Rust side (`HnswIndex`,
+ * `Bm25Index`, `Collection::hybrid_search`) keeps its signatures and binds these
+ * through `extern "C"` (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - every function returns int32 status: 0 = ok, < 0 = error (veles_status);
+ *     veles_last_error() returns a thread-local message.  Nothing throws.
+ *   - pointers are HOST pointers unless the parameter name ends in `_d`
+ *     (device pointers, for callers that already hold data in HBM).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Host-pointer calls copy H2D, launch, copy D2H and synchronise `stream`
+ *     before returning.  `_d` calls only enqueue work on `stream`.
+ *   - node ids are internal insertion indices (u32); external u64 ids, the
+ *     tombstone filter and transform_score stay with the caller exactly as
+ *     index/hnsw/index/search.rs:86-91 does today.
+ *   - there is no CPU fallback: without a CUDA device every call fails with
+ *     VELES_ERR_CUDA.
+ */
+#ifndef VELES_B200_H
+#define VELES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum veles_status {
+    VELES_OK = 0,
+    VELES_ERR_INVALID = -1,   /* bad argument (null pointer, k == 0, dim mismatch ...) */
+    VELES_ERR_CUDA = -2,      /* CUDA runtime error; message in veles_last_error()   */
+    VELES_ERR_IO = -3,        /* file missing / truncated / wrong version            */
+    VELES_ERR_OOM = -4,       /* device or host allocation failed                    */
+    VELES_ERR_OVERFLOW = -5,  /* an internal bounded structure overflowed            */
+    VELES_ERR_UNSUPPORTED = -6
+} veles_status;
+
+/* = DistanceMetric as u8 (core/distance.rs:16-39, index/hnsw/index/constructors.rs:204-217) */
+typedef enum veles_metric {
+    VELES_COSINE = 0,
+    VELES_EUCLIDEAN = 1,
+    VELES_DOT = 2,
+    VELES_HAMMING = 3,
+    VELES_JACCARD = 4
+} veles_metric;
+
+/* storage type of the vectors in HBM */
+typedef enum veles_dtype {
+    VELES_F32 = 0,  /* reference layout: Vec<Vec<f32>> (native/graph.rs:22)                        */
+    VELES_F16 = 1,  /* half::f16 round-to-nearest-even (core/half_precision.rs:97), f32 accumulate  */
+    VELES_BIN1 = 2  /* packed bits, LSB-first in u64 words (simd_explicit.rs:308-360); Hamming only */
+} veles_dtype;
+
+/* SearchQuality (index/hnsw/params.rs:283-320) */
+typedef enum veles_quality {
+    VELES_FAST = 0,
+    VELES_BALANCED = 1,
+    VELES_ACCURATE = 2,
+    VELES_PERFECT = 3,
+    VELES_CUSTOM = 4
+} veles_quality;
+
+#define VELES_INVALID_ID 0xFFFFFFFFu
+
+typedef struct veles_index veles_index_t; /* immutable device snapshot of one NativeHnsw */
+typedef struct veles_bm25 veles_bm25_t;   /* immutable device snapshot of one Bm25Index  */
+
+/* ---- runtime ------------------------------------------------------------------------- */
+int32_t veles_init(int32_t device);
+int32_t veles_shutdown(void);
+const char* veles_last_error(void);
+const char* veles_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t veles_launch_count(void);
+
+/* SearchQuality::ef_search (params.rs:309-319) */
+uint64_t veles_ef_search(int32_t quality, uint64_t k, uint64_t custom_ef);
+/* NativeHnsw::transform_score (native/backend_adapter.rs:160-168) */
+float veles_transform_score(int32_t metric, float raw_distance);
+
+/* ---- snapshot construction ------------------------------------------------------------ */
+/* NativeHnsw::file_load (native/backend_adapter.rs:274-380): parses `{dir}/{basename}.vectors`
+ * and `.graph` (format v1, little endian) and uploads them.  `store_dtype` selects the HBM
+ * storage type (F32 keeps the file's bits; F16 rounds once at load). */
+int32_t veles_index_from_reference_files(const char* dir, const char* basename, int32_t metric, int32_t store_dtype,
+                                         veles_index_t** out);
+
+/* The same snapshot from in-memory arrays -- what a Rust `HnswIndex` hands over after
+ * `insert`/`load` (native/graph.rs:18-44 fields).  `vectors`: n*dim f32 (dtype F32/F16) or
+ * n*(dim/64) u64 words (dtype BIN1, `dim` = number of bits).  Layer `l` is CSR:
+ * row_ptr[l][0..layer_nodes[l]] and cols[l]; rows of nodes >= layer_nodes[l] are empty
+ * (Layer::get_neighbors, native/layer.rs:33-39).  n == 0 gives an empty index. */
+int32_t veles_index_from_arrays(const void* vectors, uint64_t n, uint32_t dim, int32_t src_dtype, int32_t store_dtype,
+                                int32_t metric, uint32_t num_layers, const uint64_t* const* row_ptr,
+                                const uint32_t* const* cols, const uint64_t* layer_nodes, uint32_t M, uint32_t M0,
+                                uint64_t entry_point, uint32_t max_layer, veles_index_t** out);
+
+/* A snapshot with vectors only (no graph): enough for veles_bruteforce_batch, and the input
+ * of veles_index_build_graph. */
+int32_t veles_index_from_vectors(const void* vectors, uint64_t n, uint32_t dim, int32_t src_dtype, int32_t store_dtype,
+                                 int32_t metric, veles_index_t** out);
+int32_t veles_index_free(veles_index_t* idx);
+
+uint64_t veles_index_len(const veles_index_t* idx);       /* NativeHnsw::len  graph.rs:130 */
+uint32_t veles_index_dim(const veles_index_t* idx);       /* HnswIndex::dimension          */
+int32_t veles_index_metric(const veles_index_t* idx);     /* HnswIndex::metric             */
+uint32_t veles_index_max_layer(const veles_index_t* idx);
+uint64_t veles_index_entry_point(const veles_index_t* idx);
+uint64_t veles_index_device_bytes(const veles_index_t* idx);
+
+/* NativeHnsw::file_dump (native/backend_adapter.rs:184-261): writes the snapshot back in
+ * format v1 (vectors are written as f32). */
+int32_t veles_index_dump(const veles_index_t* idx, const char* dir, const char* basename);
+/* copies the layer-`l` adjacency out as CSR (row_ptr may be NULL to query sizes only) */
+int32_t veles_index_export_layer(const veles_index_t* idx, uint32_t layer, uint64_t* out_nodes, uint64_t* out_edges,
+                                 uint64_t* row_ptr, uint32_t* cols);
+
+/* ---- HNSW search ------------------------------------------------------------------------ */
+/* NativeHnsw::search (native/graph.rs:251-270) for a batch of queries, i.e. the body of
+ * HnswIndex::search_batch_parallel (index/hnsw/index/batch.rs:159-197) before id mapping:
+ * greedy descent (search_layer_single, graph.rs:405-428) then the ef-bounded beam on layer 0
+ * (search_layer, graph.rs:438-520), first k of the result.
+ *   queries       nq*dim f32
+ *   out_node_ids  nq*k, padded with VELES_INVALID_ID
+ *   out_raw_dist  nq*k in-graph distance (native/distance.rs:75-85), padded with NaN
+ *   out_counts    nq   number of valid results (<= k)
+ *   out_stats     nq*4 u32, optional (NULL): {layer-0 distance evaluations, layer-0 expansions,
+ *                 upper-layer distance evaluations, upper-layer adjacency scans}
+ * Order: ascending by (distance in IEEE total order, node id).  ef is used as given; apply
+ * veles_ef_search first to follow a SearchQuality. */
+int32_t veles_search_batch(const veles_index_t* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
+                           uint32_t* out_node_ids, float* out_raw_dist, uint32_t* out_counts, uint32_t* out_stats,
+                           void* stream);
+int32_t veles_search_batch_d(const veles_index_t* idx, const float* queries_d, uint32_t nq, uint32_t k, uint32_t ef,
+                             uint32_t* out_node_ids_d, float* out_raw_dist_d, uint32_t* out_counts_d,
+                             uint32_t* out_stats_d, void* stream);
+
+/* ---- brute force -------------------------------------------------------------------------- */
+/* HnswIndex::search_brute_force / brute_force_search_parallel (index/hnsw/index/search.rs:176-219,
+ * batch.rs:223-244) for a batch: metric value (compute_distance, search.rs:30-38) against every
+ * stored vector, ordered by DistanceMetric::sort_results (core/distance.rs:95-103) with ties by
+ * ascending node id, first k.  out_ids nq*k (VELES_INVALID_ID pad), out_score nq*k (NaN pad). */
+int32_t veles_bruteforce_batch(const veles_index_t* idx, const float* queries, uint32_t nq, uint32_t k,
+                               uint32_t* out_ids, float* out_score, void* stream);
+int32_t veles_bruteforce_batch_d(const veles_index_t* idx, const float* queries_d, uint32_t nq, uint32_t k,
+                                 uint32_t* out_ids_d, float* out_score_d, void* stream);
+/* exact metric value of explicit (query, node) pairs: the re-rank step of
+ * HnswIndex::search_with_rerank (index/hnsw/index/search.rs:118-160).  cand is nq*m node ids
+ * (VELES_INVALID_ID entries give NaN). */
+int32_t veles_rerank_batch(const veles_index_t* idx, const float* queries, uint32_t nq, const uint32_t* cand,
+                           uint32_t m, float* out_score, void* stream);
+/* DistanceEngine::batch_distance (native/distance.rs:22-24, 88-103): in-graph distance of one
+ * query to explicit host vectors; used by the parity tests of the distance kernels. */
+int32_t veles_distance_pairs(int32_t metric, const float* a, const float* b, uint32_t n_pairs, uint32_t dim,
+                             int32_t as_metric_value, float* out, void* stream);
+
+/* ---- BM25 ------------------------------------------------------------------------------------ */
+/* Device snapshot of a Bm25Index (index/bm25.rs:78-90).  Tokenisation (bm25.rs:114-120) and the
+ * string->term-id dictionary stay on the host.  Postings are CSR by term, doc ids ascending
+ * within a term, with the term frequency beside each doc (the reference keeps tf in per-document
+ * maps, bm25.rs:62-67).  doc_len is indexed by doc id (0 = absent).  df[t] is the posting-list
+ * length the reference would report (PostingList::len), which can exceed the live postings after
+ * a document was replaced (bm25.rs:188-196 keeps stale postings). */
+int32_t veles_bm25_from_csr(uint32_t n_terms, const uint64_t* term_ptr, const uint32_t* post_doc,
+                            const uint32_t* post_tf, const uint32_t* df, uint32_t n_doc_slots, const uint32_t* doc_len,
+                            uint64_t doc_count, uint64_t total_len, float k1, float b, veles_bm25_t** out);
+int32_t veles_bm25_free(veles_bm25_t* ix);
+/* Bm25Index::search (bm25.rs:269-341) for a batch.  q_term_ptr: nq+1 offsets into q_terms (term
+ * ids in query-token order, duplicates allowed, VELES_INVALID_ID = term not in the dictionary).
+ * Order: score descending (total order), ties by ascending doc id.  out_doc nq*k
+ * (VELES_INVALID_ID pad), out_score nq*k (NaN pad), out_counts nq. */
+int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_ptr, const uint32_t* q_terms,
+                                uint32_t nq, uint32_t k, uint32_t* out_doc, float* out_score, uint32_t* out_counts,
+                                void* stream);
+
+/* ---- fusion ----------------------------------------------------------------------------------- */
+/* The RRF of Collection::hybrid_search (collection/search/text.rs:133-180) for a batch: per query
+ * two ranked id lists (vector first, then text), score += w/(rank0+60) and (1-w)/(rank0+60), top-k
+ * by (score, id) keeping the largest, written score-descending (equal scores: larger id first).
+ * vec_ids / txt_ids are nq*in_k with per-query valid counts. */
+int32_t veles_rrf_hybrid(const uint32_t* vec_ids, const uint32_t* vec_cnt, const uint32_t* txt_ids,
+                         const uint32_t* txt_cnt, uint32_t nq, uint32_t in_k, float vector_weight, uint32_t k,
+                         uint32_t* out_ids, float* out_score, uint32_t* out_counts, void* stream);
+/* FusionStrategy::fuse (fusion/strategy.rs:138-300) for one multi-query request: n_lists ranked
+ * (id, score) lists.  strategy 0 Average, 1 Maximum, 2 RRF{k}, 3 Weighted{avg,max,hit}.  Output
+ * sorted score-descending, ties by ascending id; at most `cap` entries. */
+int32_t veles_fuse(int32_t strategy, const uint32_t* list_ptr, uint32_t n_lists, const uint32_t* ids,
+                   const float* scores, uint32_t rrf_k, float avg_w, float max_w, float hit_w, uint32_t cap,
+                   uint32_t* out_ids, float* out_score, uint32_t* out_count, void* stream);
+
+/* ---- graph construction (the path's producer) ---------------------------- */
+/* Bulk construction of the HNSW graph on the GPU for the vectors of `idx` -- the role of
+ * HnswIndex::insert_batch_parallel (index/hnsw/index/batch.rs:82-108), whose result the reference
+ * itself leaves order-dependent (rayon).  Levels follow the reference PRNG (graph.rs:368-403) in
+ * node-id order, so level assignment and entry point equal the reference's; neighbour lists follow
+ * select_neighbors (graph.rs:526-581) over the exact `cand_k` nearest nodes of each layer, plus
+ * reverse links pruned closest-first (graph.rs:592-639).  Replaces any graph held by `idx`. */
+int32_t veles_index_build_graph(veles_index_t* idx, uint32_t M, uint32_t cand_k, void* stream);
+
+/* ---- multi-GPU --------------------------------------------------------------------------------- */
+/* Queries shard by contiguous slices across ranks; the snapshot is replicated.  The only exchange
+ * is the final gather of [nq_local, k] ids + distances, done by the host runtime with NCCL
+ * all-gather (velesdb_b200/dist.py) on the buffers the `_d` calls fill. */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VELES_B200_H */

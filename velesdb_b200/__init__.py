@@ -1,0 +1,14 @@
+"""velesdb_b200 -- B200-native (sm_100a) implementation of VelesDB's vector-search hot path.
+
+The product is ``csrc/libveles_b200.so`` (hand-written CUDA behind the C ABI of
+``include/veles_b200.h``).  The Python modules mirror the reference's host-side wrapper types
+(``HnswIndex``, ``Bm25Index``, fusion) so the path can be driven and tested without Rust.
+There is no CPU fallback anywhere in this package.
+"""
+from . import _native
+from ._native import VelesError
+from .index import (DeviceSnapshot, DimensionMismatch, DistanceMetric, HnswIndex, HnswParams, SearchQuality,
+                    distance_pairs)
+
+__all__ = ["DeviceSnapshot", "DimensionMismatch", "DistanceMetric", "HnswIndex", "HnswParams", "SearchQuality",
+           "VelesError", "distance_pairs", "_native"]

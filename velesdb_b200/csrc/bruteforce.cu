@@ -1,0 +1,428 @@
+// bruteforce.cu -- exact scan: HnswIndex::search_brute_force / brute_force_search_parallel
+// (index/hnsw/index/search.rs:176-219, batch.rs:223-244), the re-rank step of search_with_rerank
+// (search.rs:118-160) and DistanceEngine::batch_distance (native/distance.rs:22-24).
+//
+// Kernel 1 (bf_tile_kernel) computes the metric value of every (query, row) pair with the
+// reference's accumulation tree, register-tiled: a warp owns RT rows x QT queries, lane l owns the
+// elements i = l (mod 32) of every row and query, so each global row element is loaded once per
+// QT queries and each shared-memory query element once per RT rows.  The 32 partial sums of a
+// pair are combined with the xor-8/16/4/2/1 butterfly (common.cuh) -> same bits as the CPU.
+// Kernel 2 (topk_kernel) selects, per query, the k best by DistanceMetric::sort_results order
+// (core/distance.rs:95-103; ties by ascending node id) with a threshold filter over the score row.
+#include <algorithm>
+
+#include "index.hpp"
+
+namespace veles {
+
+constexpr int kRT = 4;   // rows per warp tile
+constexpr int kQT = 8;   // queries per warp tile
+constexpr int kWarps = 8;
+
+// scores[q * n + r] = metric value (as_value) or in-graph distance of query q vs row r.
+// Fast path: F32/F16 rows, COSINE / EUCLIDEAN / DOT, dim >= 16.
+template <typename TB>
+__global__ void __launch_bounds__(kWarps * 32) bf_tile_kernel(IndexView ix, const float* __restrict__ queries,
+                                                              uint32_t nq, uint32_t q0, float* __restrict__ scores,
+                                                              bool as_value) {
+    extern __shared__ __align__(16) float qs[];  // kQT x dim, then kQT norms
+    const uint32_t dim = ix.dim;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t qbase = q0 + blockIdx.y * kQT;
+    const uint32_t nqt = min((uint32_t)kQT, q0 + nq - qbase);
+    float* qnorm = qs + (size_t)kQT * dim;
+    for (uint32_t i = threadIdx.x; i < kQT * dim; i += blockDim.x) {
+        uint32_t t = i / dim;
+        qs[i] = t < nqt ? queries[(size_t)(qbase - q0 + t) * dim + (i - t * dim)] : 0.0f;
+    }
+    __syncthreads();
+    if (ix.metric == VELES_COSINE) {
+        for (uint32_t t = warp; t < kQT; t += kWarps) {
+            const float* q = qs + (size_t)t * dim;
+            float s = warp_tree_reduce<0>(q, q, dim, lane);
+            if (lane == 0) qnorm[t] = __fsqrt_rn(s);
+        }
+    }
+    __syncthreads();
+    const uint32_t main_len = dim & ~31u;
+    const bool l2 = ix.metric == VELES_EUCLIDEAN;
+    const uint64_t n = ix.n;
+    const uint64_t tiles = (n + kRT - 1) / kRT;
+    for (uint64_t tile = blockIdx.x * (uint64_t)kWarps + warp; tile < tiles; tile += (uint64_t)gridDim.x * kWarps) {
+        const uint64_t r0 = tile * kRT;
+        const TB* rows[kRT];
+#pragma unroll
+        for (int r = 0; r < kRT; ++r) {
+            uint64_t rr = r0 + r < n ? r0 + r : n - 1;
+            rows[r] = reinterpret_cast<const TB*>(ix.vecs + rr * ix.row_bytes);
+        }
+        float acc[kRT][kQT];
+#pragma unroll
+        for (int r = 0; r < kRT; ++r)
+#pragma unroll
+            for (int t = 0; t < kQT; ++t) acc[r][t] = 0.0f;
+        for (uint32_t i = lane; i < main_len; i += 32) {
+            float x[kRT], q[kQT];
+#pragma unroll
+            for (int r = 0; r < kRT; ++r) x[r] = load_elem(rows[r], i);
+#pragma unroll
+            for (int t = 0; t < kQT; ++t) q[t] = qs[(size_t)t * dim + i];
+            if (l2) {
+#pragma unroll
+                for (int r = 0; r < kRT; ++r)
+#pragma unroll
+                    for (int t = 0; t < kQT; ++t) {
+                        float d = __fsub_rn(q[t], x[r]);
+                        acc[r][t] = __fmaf_rn(d, d, acc[r][t]);
+                    }
+            } else {
+#pragma unroll
+                for (int r = 0; r < kRT; ++r)
+#pragma unroll
+                    for (int t = 0; t < kQT; ++t) acc[r][t] = __fmaf_rn(q[t], x[r], acc[r][t]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kRT; ++r) {
+            if (r0 + r >= n) continue;
+            float nb = 0.0f;
+            if (ix.metric == VELES_COSINE)
+                nb = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(rows[r]) + ix.norm_off);
+#pragma unroll
+            for (int t = 0; t < kQT; ++t) {
+                float s = warp_tree_sum32(acc[r][t]);
+                if (t >= (int)nqt) continue;
+                const float* q = qs + (size_t)t * dim;
+                float v;
+                if (l2) {
+                    s = warp_tree_tail<1>(s, q, rows[r], dim, lane);
+                    v = __fsqrt_rn(s);
+                } else {
+                    s = warp_tree_tail<0>(s, q, rows[r], dim, lane);
+                    if (ix.metric == VELES_COSINE) {
+                        float sim = cosine_from_parts(s, qnorm[t], nb);
+                        v = as_value ? sim : __fsub_rn(1.0f, sim);
+                    } else {
+                        v = as_value ? s : -s;
+                    }
+                }
+                if (lane == 0) scores[(size_t)(qbase - q0 + t) * n + (r0 + r)] = v;
+            }
+        }
+    }
+}
+
+// generic path: any metric, any dim >= 1, F32/F16 rows: one warp per (query, row) pair
+template <typename TB>
+__global__ void bf_generic_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq,
+                                  float* __restrict__ scores, bool as_value) {
+    extern __shared__ __align__(16) float qs[];  // one query
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t q = blockIdx.y;
+    const uint32_t dim = ix.dim;
+    for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) qs[i] = queries[(size_t)q * dim + i];
+    __syncthreads();
+    float na = 0.0f;
+    if (ix.metric == VELES_COSINE) na = __fsqrt_rn(warp_tree_reduce<0>(qs, qs, dim, lane));
+    for (uint64_t r = blockIdx.x * (uint64_t)nw + warp; r < ix.n; r += (uint64_t)gridDim.x * nw) {
+        const uint8_t* row = ix.vecs + r * ix.row_bytes;
+        float nb = ix.metric == VELES_COSINE ? *reinterpret_cast<const float*>(row + ix.norm_off) : 0.0f;
+        float v = warp_metric(ix.metric, as_value, qs, reinterpret_cast<const TB*>(row), dim, na, nb, lane);
+        if (lane == 0) scores[(size_t)q * ix.n + r] = v;
+    }
+}
+
+// packed-bit rows: Hamming count of (query > 0.5) bits vs row bits; one thread per row chunk
+__global__ void bf_bin_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq, float* __restrict__ scores) {
+    extern __shared__ __align__(16) uint32_t qw[];  // dim/32 words
+    const uint32_t q = blockIdx.y, words = ix.dim >> 5;
+    for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) {
+        uint32_t bits = 0;
+        for (uint32_t b = 0; b < 32; ++b) bits |= (queries[(size_t)q * ix.dim + w * 32 + b] > 0.5f ? 1u : 0u) << b;
+        qw[w] = bits;
+    }
+    __syncthreads();
+    // 8 lanes per row, 16 bytes per lane per step: a warp reads 4 rows x 128 contiguous bytes
+    const uint32_t lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+    const uint64_t gw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r0 = gw * 4; r0 < ix.n; r0 += nwarps * 4) {
+        const uint64_t r = r0 + grp;
+        uint32_t d = 0;
+        if (r < ix.n) {
+            const uint4* row = reinterpret_cast<const uint4*>(ix.vecs + r * ix.row_bytes);
+            for (uint32_t w4 = sub; w4 * 4 < words; w4 += 8) {
+                uint4 x = row[w4];
+                const uint32_t* qq = qw + w4 * 4;
+                d += __popc(x.x ^ qq[0]);
+                if (w4 * 4 + 1 < words) d += __popc(x.y ^ qq[1]);
+                if (w4 * 4 + 2 < words) d += __popc(x.z ^ qq[2]);
+                if (w4 * 4 + 3 < words) d += __popc(x.w ^ qq[3]);
+            }
+        }
+        d += __shfl_xor_sync(FULL_MASK, d, 4);
+        d += __shfl_xor_sync(FULL_MASK, d, 2);
+        d += __shfl_xor_sync(FULL_MASK, d, 1);
+        if (sub == 0 && r < ix.n) scores[(size_t)q * ix.n + r] = (float)d;
+    }
+}
+
+// per query: k smallest keys of (order(score) << 32 | row); one warp per query
+__global__ void __launch_bounds__(32) topk_kernel(const float* __restrict__ scores, uint64_t n, uint32_t k,
+                                                  bool descending, uint32_t* __restrict__ out_ids,
+                                                  float* __restrict__ out_score) {
+    extern __shared__ __align__(16) uint64_t res[];
+    const uint32_t lane = threadIdx.x, q = blockIdx.x;
+    const float* row = scores + (size_t)q * n;
+    uint32_t len = 0;
+    uint64_t worst = ~0ull;
+    for (uint64_t base = 0; base < n; base += 32) {
+        const uint64_t i = base + lane;
+        uint64_t key = ~0ull;
+        bool cand = false;
+        if (i < n) {
+            uint32_t o = ord_key(row[i]);
+            if (descending) o = ~o;
+            key = ((uint64_t)o << 32) | (uint32_t)i;
+            cand = len < k || key < worst;
+        }
+        uint32_t msk = __ballot_sync(FULL_MASK, cand);
+        while (msk) {
+            const uint32_t src = __ffs(msk) - 1;
+            msk &= msk - 1;
+            const uint64_t kk = __shfl_sync(FULL_MASK, key, src);
+            if (len < k) {
+                const uint32_t pos = lower_bound_warp(res, len, kk, lane);
+                insert_at(res, pos, len + 1, kk, lane);
+                ++len;
+            } else if (kk < worst) {
+                const uint32_t pos = lower_bound_warp(res, len, kk, lane);
+                insert_at(res, pos, len, kk, lane);
+            }
+            if (len == k) worst = res[k - 1];
+        }
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < k; i += 32) {
+        uint32_t id = VELES_INVALID_ID;
+        float s = __uint_as_float(0x7fc00000u);
+        if (i < len) {
+            uint64_t key = res[i];
+            id = (uint32_t)key;
+            s = row[id];
+        }
+        out_ids[(size_t)q * k + i] = id;
+        out_score[(size_t)q * k + i] = s;
+    }
+}
+
+// metric value of explicit (query, candidate) pairs; one warp per pair
+template <typename TB>
+__global__ void rerank_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq, const uint32_t* __restrict__ cand,
+                              uint32_t m, float* __restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t gw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t pi = gw; pi < (uint64_t)nq * m; pi += nwarps) {
+        const uint32_t q = (uint32_t)(pi / m);
+        const uint32_t id = cand[pi];
+        float v = __uint_as_float(0x7fc00000u);
+        if (id != VELES_INVALID_ID && id < ix.n) {
+            const float* qv = queries + (size_t)q * ix.dim;
+            const uint8_t* row = ix.vecs + (size_t)id * ix.row_bytes;
+            if (ix.dtype == VELES_BIN1) {
+                uint32_t d = 0;
+                const uint32_t* rw = reinterpret_cast<const uint32_t*>(row);
+                for (uint32_t w = lane; w < (ix.dim >> 5); w += 32) {
+                    uint32_t bits = 0;
+                    for (uint32_t b = 0; b < 32; ++b) bits |= (qv[w * 32 + b] > 0.5f ? 1u : 0u) << b;
+                    d += __popc(bits ^ rw[w]);
+                }
+                v = (float)__reduce_add_sync(FULL_MASK, d);
+            } else {
+                float na = 0.0f, nb = 0.0f;
+                if (ix.metric == VELES_COSINE) {
+                    na = __fsqrt_rn(warp_tree_reduce<0>(qv, qv, ix.dim, lane));
+                    nb = *reinterpret_cast<const float*>(row + ix.norm_off);
+                }
+                v = warp_metric(ix.metric, true, qv, reinterpret_cast<const TB*>(row), ix.dim, na, nb, lane);
+            }
+        }
+        if (lane == 0) out[pi] = v;
+    }
+}
+
+// distance of explicit host-provided pairs (a[i], b[i]); one warp per pair
+__global__ void pairs_kernel(int metric, const float* __restrict__ a, const float* __restrict__ b, uint32_t n_pairs,
+                             uint32_t dim, bool as_value, float* __restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t gw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t i = gw; i < n_pairs; i += nwarps) {
+        const float* x = a + i * dim;
+        const float* y = b + i * dim;
+        float na = 0.0f, nb = 0.0f;
+        if (metric == VELES_COSINE) {
+            na = __fsqrt_rn(warp_tree_reduce<0>(x, x, dim, lane));
+            nb = __fsqrt_rn(warp_tree_reduce<0>(y, y, dim, lane));
+        }
+        float v = warp_metric(metric, as_value, x, y, dim, na, nb, lane);
+        if (lane == 0) out[i] = v;
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+static int32_t launch_scores(const veles_index* ix, const float* q_d, uint32_t nq, float* scores_d, bool as_value,
+                             cudaStream_t st) {
+    IndexView v = ix->view();
+    const int sms = device_sm_count();
+    if (ix->dtype == VELES_BIN1) {
+        dim3 grid((unsigned)std::min<uint64_t>((ix->n + 31) / 32 + 1, (uint64_t)sms * 8), nq);
+        bf_bin_kernel<<<grid, 256, (ix->dim / 32) * 4, st>>>(v, q_d, nq, scores_d);
+        count_launch();
+    } else if (ix->dim >= 16 && (ix->metric == VELES_COSINE || ix->metric == VELES_EUCLIDEAN || ix->metric == VELES_DOT)) {
+        const size_t smem = ((size_t)kQT * ix->dim + kQT) * 4;
+        auto kern = ix->dtype == VELES_F32 ? bf_tile_kernel<float> : bf_tile_kernel<__half>;
+        VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const uint32_t qtiles = (nq + kQT - 1) / kQT;
+        const uint64_t row_tiles = (ix->n + kRT - 1) / kRT;
+        uint64_t gx = (row_tiles + kWarps - 1) / kWarps;
+        // enough CTAs to fill the machine a few times over; the row loop is grid-strided
+        const uint64_t want = std::max<uint64_t>(1, ((uint64_t)sms * 4 + qtiles - 1) / qtiles);
+        gx = std::max<uint64_t>(1, std::min(gx, want));
+        // gridDim.y is limited to 65535: chunk the query tiles
+        for (uint32_t t0 = 0; t0 < qtiles; t0 += 32768) {
+            const uint32_t nt = std::min(32768u, qtiles - t0);
+            const uint32_t qoff = t0 * kQT;
+            dim3 grid((unsigned)gx, nt);
+            kern<<<grid, kWarps * 32, smem, st>>>(v, q_d + (size_t)qoff * ix->dim, nq - qoff, 0,
+                                                 scores_d + (size_t)qoff * ix->n, as_value);
+            count_launch();
+        }
+    } else {
+        auto kern = ix->dtype == VELES_F32 ? bf_generic_kernel<float> : bf_generic_kernel<__half>;
+        for (uint32_t q0 = 0; q0 < nq; q0 += 32768) {
+            const uint32_t nn = std::min(32768u, nq - q0);
+            dim3 grid((unsigned)std::min<uint64_t>((ix->n + 7) / 8 + 1, (uint64_t)sms * 4), nn);
+            kern<<<grid, 256, (size_t)ix->dim * 4, st>>>(v, q_d + (size_t)q0 * ix->dim, nn, scores_d + (size_t)q0 * ix->n,
+                                                         as_value);
+            count_launch();
+        }
+    }
+    VELES_CUDA(cudaGetLastError());
+    return VELES_OK;
+}
+
+static int32_t bruteforce_device(const veles_index* ix, const float* q_d, uint32_t nq, uint32_t k, uint32_t* ids_d,
+                                 float* score_d, cudaStream_t st) {
+    VELES_REQUIRE(k >= 1 && k <= 16384, "k must be in 1..16384, got %u", k);
+    if (nq == 0) return VELES_OK;
+    if (ix->n == 0) {
+        VELES_CUDA(cudaMemsetAsync(ids_d, 0xff, (size_t)nq * k * 4, st));
+        VELES_CUDA(cudaMemsetAsync(score_d, 0xff, (size_t)nq * k * 4, st));  // 0xffffffff is a NaN
+        return VELES_OK;
+    }
+    // bound the score matrix to ~1 GiB per pass
+    const uint64_t per_q = ix->n * 4;
+    const uint32_t chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(nq, (1ull << 30) / per_q));
+    VELES_TRY(ix->scores_d.ensure((size_t)chunk * per_q));
+    const bool desc = ix->metric == VELES_COSINE || ix->metric == VELES_DOT || ix->metric == VELES_JACCARD;
+    VELES_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(k * 8)));
+    for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
+        const uint32_t nn = std::min(chunk, nq - q0);
+        VELES_TRY(launch_scores(ix, q_d + (size_t)q0 * ix->dim, nn, ix->scores_d.as<float>(), true, st));
+        topk_kernel<<<nn, 32, (size_t)k * 8, st>>>(ix->scores_d.as<float>(), ix->n, k, desc, ids_d + (size_t)q0 * k,
+                                                   score_d + (size_t)q0 * k);
+        count_launch();
+        VELES_CUDA(cudaGetLastError());
+    }
+    return VELES_OK;
+}
+
+}  // namespace veles
+
+using namespace veles;
+
+extern "C" {
+
+int32_t veles_bruteforce_batch_d(const veles_index_t* idx, const float* queries_d, uint32_t nq, uint32_t k,
+                                 uint32_t* out_ids_d, float* out_score_d, void* stream) {
+    VELES_REQUIRE(idx != nullptr, "index is NULL");
+    VELES_REQUIRE(nq == 0 || (queries_d && out_ids_d && out_score_d), "NULL buffer");
+    std::lock_guard<std::mutex> g(idx->mu);
+    return bruteforce_device(idx, queries_d, nq, k, out_ids_d, out_score_d, (cudaStream_t)stream);
+}
+
+int32_t veles_bruteforce_batch(const veles_index_t* idx, const float* queries, uint32_t nq, uint32_t k,
+                               uint32_t* out_ids, float* out_score, void* stream) {
+    VELES_REQUIRE(idx != nullptr, "index is NULL");
+    VELES_REQUIRE(nq == 0 || (queries && out_ids && out_score), "NULL buffer");
+    if (nq == 0) return VELES_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> g(idx->mu);
+    const size_t qb = (size_t)nq * idx->dim * 4, ob = (size_t)nq * k * 4;
+    VELES_TRY(idx->q_d.ensure(qb));
+    VELES_TRY(idx->out_ids_d.ensure(ob));
+    VELES_TRY(idx->out_val_d.ensure(ob));
+    VELES_CUDA(cudaMemcpyAsync(idx->q_d.p, queries, qb, cudaMemcpyHostToDevice, st));
+    VELES_TRY(bruteforce_device(idx, idx->q_d.as<float>(), nq, k, idx->out_ids_d.as<uint32_t>(), idx->out_val_d.as<float>(), st));
+    VELES_CUDA(cudaMemcpyAsync(out_ids, idx->out_ids_d.p, ob, cudaMemcpyDeviceToHost, st));
+    VELES_CUDA(cudaMemcpyAsync(out_score, idx->out_val_d.p, ob, cudaMemcpyDeviceToHost, st));
+    VELES_CUDA(cudaStreamSynchronize(st));
+    return VELES_OK;
+}
+
+int32_t veles_rerank_batch(const veles_index_t* idx, const float* queries, uint32_t nq, const uint32_t* cand, uint32_t m,
+                           float* out_score, void* stream) {
+    VELES_REQUIRE(idx != nullptr, "index is NULL");
+    VELES_REQUIRE(nq == 0 || m == 0 || (queries && cand && out_score), "NULL buffer");
+    if (nq == 0 || m == 0) return VELES_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> g(idx->mu);
+    const size_t qb = (size_t)nq * idx->dim * 4, cb = (size_t)nq * m * 4;
+    VELES_TRY(idx->q_d.ensure(qb));
+    VELES_TRY(idx->out_ids_d.ensure(cb));
+    VELES_TRY(idx->out_val_d.ensure(cb));
+    VELES_CUDA(cudaMemcpyAsync(idx->q_d.p, queries, qb, cudaMemcpyHostToDevice, st));
+    VELES_CUDA(cudaMemcpyAsync(idx->out_ids_d.p, cand, cb, cudaMemcpyHostToDevice, st));
+    const int sms = device_sm_count();
+    const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)nq * m + 7) / 8, (uint64_t)sms * 8);
+    if (idx->dtype == VELES_F16)
+        rerank_kernel<__half><<<grid, 256, 0, st>>>(idx->view(), idx->q_d.as<float>(), nq, idx->out_ids_d.as<uint32_t>(), m,
+                                                    idx->out_val_d.as<float>());
+    else
+        rerank_kernel<float><<<grid, 256, 0, st>>>(idx->view(), idx->q_d.as<float>(), nq, idx->out_ids_d.as<uint32_t>(), m,
+                                                   idx->out_val_d.as<float>());
+    count_launch();
+    VELES_CUDA(cudaGetLastError());
+    VELES_CUDA(cudaMemcpyAsync(out_score, idx->out_val_d.p, cb, cudaMemcpyDeviceToHost, st));
+    VELES_CUDA(cudaStreamSynchronize(st));
+    return VELES_OK;
+}
+
+int32_t veles_distance_pairs(int32_t metric, const float* a, const float* b, uint32_t n_pairs, uint32_t dim,
+                             int32_t as_metric_value, float* out, void* stream) {
+    VELES_REQUIRE(metric >= VELES_COSINE && metric <= VELES_JACCARD, "unknown metric %d", metric);
+    VELES_REQUIRE(n_pairs == 0 || (a && b && out), "NULL buffer");
+    VELES_REQUIRE(dim >= 1, "dim must be >= 1");
+    if (n_pairs == 0) return VELES_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf da, db, dout;
+    const size_t bytes = (size_t)n_pairs * dim * 4;
+    VELES_TRY(da.alloc(bytes));
+    VELES_TRY(db.alloc(bytes));
+    VELES_TRY(dout.alloc((size_t)n_pairs * 4));
+    VELES_CUDA(cudaMemcpyAsync(da.p, a, bytes, cudaMemcpyHostToDevice, st));
+    VELES_CUDA(cudaMemcpyAsync(db.p, b, bytes, cudaMemcpyHostToDevice, st));
+    const int sms = device_sm_count();
+    const unsigned grid = (unsigned)std::min<uint64_t>(((uint64_t)n_pairs + 7) / 8, (uint64_t)sms * 8);
+    pairs_kernel<<<grid, 256, 0, st>>>(metric, da.as<float>(), db.as<float>(), n_pairs, dim, as_metric_value != 0,
+                                       dout.as<float>());
+    count_launch();
+    VELES_CUDA(cudaGetLastError());
+    VELES_CUDA(cudaMemcpyAsync(out, dout.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, st));
+    VELES_CUDA(cudaStreamSynchronize(st));
+    return VELES_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,509 @@
+// hnsw_search.cu -- batched HNSW search: NativeHnsw::search (native/graph.rs:251-270) for a batch
+// of queries, one warp per query, persistent grid.
+//
+// Reference semantics kept bit for bit:
+//   * search_layer_single (graph.rs:405-428): scan all neighbours of `best` in stored order,
+//     move on strict improvement, repeat until a scan brings none.
+//   * search_layer (graph.rs:438-520): candidates = min-heap on (dist, id), results = max-heap on
+//     (dist, id) capped at ef; pop the closest candidate, stop when it is farther than the worst
+//     result and the result set is full; every not-yet-visited neighbour is evaluated in stored
+//     order and accepted when `d < worst || len < ef`.
+//
+// How the two heaps are represented here.  Every accepted node enters both heaps, so
+//   candidates = {unexpanded members of results}  U  {evicted, not yet popped}.
+// `res` is one array sorted by (dist, id) with an "expanded" bit per entry; the next candidate is
+// its first unexpanded entry.  An evicted node can only ever be popped *without* ending the loop
+// when its distance equals the current worst distance (it was the maximum when evicted, and the
+// worst distance never grows), so only those are kept, in the per-query tie list `tie`; everything
+// else evicted could only trigger the break and is dropped.  Pop order between the two sets is
+// fixed: members of `res` always sort before anything evicted.  This reproduces the reference's
+// expansion order exactly, including on integer-valued metrics where ties are the rule.
+//
+// Data movement: a popped node's adjacency row (stride0 x u32) is read with coalesced 128-byte
+// loads, filtered through a per-query visited bitmap in HBM/L2 (atomicOr = test-and-set), and the
+// surviving neighbours' rows are fetched by 1-D bulk async copies (TMA engine, mbarrier
+// complete_tx) into a ring of shared-memory slots; the warp computes each distance from shared
+// memory with the reference's accumulation tree (common.cuh) while later rows are in flight.
+#include "index.hpp"
+
+namespace veles {
+
+constexpr uint32_t kMaxSlots = 16;      // ring slots per warp (upper bound)
+constexpr uint32_t kTieCap = 4096;      // per-query tie-list capacity (keys), lives in global scratch
+constexpr uint32_t kLogCap = 16384;     // visited-log entries per query slot before falling back to a full clear
+
+struct SearchParams {
+    IndexView ix;
+    const float* queries;
+    uint32_t nq, k, ef;
+    uint32_t* out_ids;
+    float* out_dist;
+    uint32_t* out_counts;
+    uint32_t* out_stats;  // may be null
+    uint32_t* visited;    // slots x vis_words
+    uint32_t* vlog;       // slots x kLogCap
+    uint64_t* tie;        // slots x kTieCap
+    uint32_t vis_words;
+    uint32_t* counters;   // [0] work counter, [1] error flag
+    uint32_t nslot;
+    // shared-memory carve (bytes from base)
+    uint32_t off_res, off_todo, off_q, off_ring;
+};
+
+struct WarpCtx {
+    uint64_t* bar;
+    uint64_t* res;
+    uint32_t* todo;
+    uint8_t* q;
+    uint8_t* ring;
+    uint32_t phases;
+    float norm_a;
+    uint32_t lane;
+};
+
+__device__ __forceinline__ uint64_t make_key(float d, uint32_t id) {
+    return ((uint64_t)ord_key(d) << 32) | ((uint64_t)id << 1);
+}
+__device__ __forceinline__ float key_dist(uint64_t key) { return ord_unkey((uint32_t)(key >> 32)); }
+__device__ __forceinline__ uint32_t key_id(uint64_t key) { return ((uint32_t)key) >> 1; }
+
+template <int DT>
+__device__ __forceinline__ float row_distance(const SearchParams& p, const WarpCtx& c, const uint8_t* row) {
+    if (DT == VELES_BIN1) {
+        const uint32_t words = p.ix.dim >> 5;
+        const uint32_t* qw = reinterpret_cast<const uint32_t*>(c.q);
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(row);
+        uint32_t d = 0;
+        for (uint32_t i = c.lane; i < words; i += 32) d += __popc(qw[i] ^ rw[i]);
+        return (float)__reduce_add_sync(FULL_MASK, d);
+    } else {
+        float norm_b = 0.0f;
+        if (p.ix.metric == VELES_COSINE) norm_b = *reinterpret_cast<const float*>(row + p.ix.norm_off);
+        if (DT == VELES_F32)
+            return warp_metric(p.ix.metric, false, reinterpret_cast<const float*>(c.q), reinterpret_cast<const float*>(row),
+                               p.ix.dim, c.norm_a, norm_b, c.lane);
+        else
+            return warp_metric(p.ix.metric, false, reinterpret_cast<const float*>(c.q), reinterpret_cast<const __half*>(row),
+                               p.ix.dim, c.norm_a, norm_b, c.lane);
+    }
+}
+
+__device__ __forceinline__ void issue_row(const SearchParams& p, const WarpCtx& c, uint32_t slot, uint32_t id) {
+    mbar_expect_tx(&c.bar[slot], p.ix.row_bytes);
+    bulk_g2s(c.ring + (size_t)slot * p.ix.row_bytes, p.ix.vecs + (size_t)id * p.ix.row_bytes, p.ix.row_bytes, &c.bar[slot]);
+}
+
+// Evaluates the distances of c.todo[0..m) in order, with up to nslot row fetches in flight.
+template <int DT, typename F>
+__device__ __forceinline__ void eval_list(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
+    const uint32_t nslot = p.nslot;
+    if (c.lane == 0) {
+        uint32_t pre = m < nslot ? m : nslot;
+        for (uint32_t i = 0; i < pre; ++i) issue_row(p, c, i, c.todo[i]);
+    }
+    uint32_t slot = 0;
+    for (uint32_t i = 0; i < m; ++i) {
+        mbar_wait(&c.bar[slot], (c.phases >> slot) & 1u);
+        c.phases ^= 1u << slot;
+        const uint32_t id = c.todo[i];
+        const float d = row_distance<DT>(p, c, c.ring + (size_t)slot * p.ix.row_bytes);
+        __syncwarp();  // every lane is done reading the slot before it is refilled
+        if (c.lane == 0 && i + nslot < m) issue_row(p, c, slot, c.todo[i + nslot]);
+        on_dist(id, d);
+        slot = (slot + 1 == nslot) ? 0 : slot + 1;
+    }
+}
+
+// Reads an adjacency row (padded with INVALID) into c.todo, optionally filtering through the
+// visited bitmap.  Returns the number of ids kept; `read` gets the number of valid ids in the row.
+template <bool FILTER>
+__device__ __forceinline__ uint32_t gather_row(const SearchParams& p, WarpCtx& c, const uint32_t* __restrict__ row,
+                                               uint32_t stride, uint32_t* vis, uint32_t* vlog, uint32_t& logn,
+                                               uint32_t& read) {
+    uint32_t m = 0;
+    read = 0;
+    for (uint32_t base = 0; base < stride; base += 32) {
+        const uint32_t nid = row[base + c.lane];
+        const bool valid = nid != VELES_INVALID_ID;
+        bool keep = valid;
+        if (FILTER && valid) {
+            const uint32_t bit = 1u << (nid & 31);
+            keep = (atomicOr(&vis[nid >> 5], bit) & bit) == 0;
+        }
+        const uint32_t vmask = __ballot_sync(FULL_MASK, valid);
+        const uint32_t kmask = __ballot_sync(FULL_MASK, keep);
+        if (keep) {
+            const uint32_t pos = m + __popc(kmask & ((1u << c.lane) - 1u));
+            c.todo[pos] = nid;
+            if (FILTER && logn + pos < kLogCap) vlog[logn + pos] = nid;
+        }
+        m += __popc(kmask);
+        read += __popc(vmask);
+        if (vmask != FULL_MASK) break;  // padding reached
+    }
+    if (FILTER) logn += m;
+    __syncwarp();
+    return m;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    WarpCtx c;
+    c.lane = threadIdx.x;
+    c.bar = reinterpret_cast<uint64_t*>(smem);
+    c.res = reinterpret_cast<uint64_t*>(smem + p.off_res);
+    c.todo = reinterpret_cast<uint32_t*>(smem + p.off_todo);
+    c.q = smem + p.off_q;
+    c.ring = smem + p.off_ring;
+    c.phases = 0;
+    c.norm_a = 0.0f;
+    const uint32_t lane = c.lane;
+    if (lane == 0) {
+        for (uint32_t i = 0; i < kMaxSlots; ++i) mbar_init(&c.bar[i], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+
+    uint32_t* vis = p.visited + (size_t)blockIdx.x * p.vis_words;
+    uint32_t* vlog = p.vlog + (size_t)blockIdx.x * kLogCap;
+    uint64_t* tie = p.tie + (size_t)blockIdx.x * kTieCap;
+    const uint32_t dim = p.ix.dim;
+    const uint32_t ef = p.ef;
+
+    for (;;) {
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(&p.counters[0], 1u);
+        qi = __shfl_sync(FULL_MASK, qi, 0);
+        if (qi >= p.nq) break;
+
+        // ---- stage the query ----
+        const float* qg = p.queries + (size_t)qi * dim;
+        if (DT == VELES_BIN1) {
+            uint32_t* qw = reinterpret_cast<uint32_t*>(c.q);
+            for (uint32_t w = lane; w < (dim >> 5); w += 32) {
+                uint32_t bits = 0;
+                for (uint32_t b = 0; b < 32; ++b) bits |= (qg[w * 32 + b] > 0.5f ? 1u : 0u) << b;
+                qw[w] = bits;
+            }
+        } else {
+            float* qs = reinterpret_cast<float*>(c.q);
+            for (uint32_t i = lane; i < dim; i += 32) qs[i] = qg[i];
+        }
+        __syncwarp();
+        if (DT != VELES_BIN1 && p.ix.metric == VELES_COSINE) {
+            const float* qs = reinterpret_cast<const float*>(c.q);
+            c.norm_a = __fsqrt_rn(warp_tree_reduce<0>(qs, qs, dim, lane));
+        }
+
+        uint32_t ndc0 = 0, hops0 = 0, ndc_up = 0, hops_up = 0;
+        uint32_t len = 0;
+
+        if (p.ix.has_entry) {
+            // ---- greedy descent, layers max_layer..1 (graph.rs:259-263, 405-428) ----
+            uint32_t cur = p.ix.entry;
+            uint32_t dummy_logn = 0, nread = 0;
+            for (uint32_t layer = p.ix.max_layer; layer >= 1; --layer) {
+                uint32_t best = cur;
+                float best_dist = 0.0f;
+                if (lane == 0) c.todo[0] = best;
+                __syncwarp();
+                eval_list<DT>(p, c, 1, [&](uint32_t, float d) { best_dist = d; });
+                ++ndc_up;
+                for (;;) {
+                    const uint32_t ref = p.ix.upper_ref[best];
+                    uint32_t m = 0;
+                    if (ref != VELES_INVALID_ID && layer <= (ref & 15u)) {
+                        const uint32_t* row = p.ix.upper_adj + ((size_t)(ref >> 4) + layer - 1) * p.ix.strideU;
+                        m = gather_row<false>(p, c, row, p.ix.strideU, nullptr, nullptr, dummy_logn, nread);
+                    }
+                    ++hops_up;
+                    ndc_up += m;
+                    bool improved = false;
+                    eval_list<DT>(p, c, m, [&](uint32_t id, float d) {
+                        if (d < best_dist) {
+                            best = id;
+                            best_dist = d;
+                            improved = true;
+                        }
+                    });
+                    __syncwarp();
+                    if (!improved) break;
+                }
+                cur = best;
+            }
+
+            // ---- layer 0 beam (graph.rs:266, 438-520) ----
+            uint32_t logn = 0, tlen = 0, scan_from = 0;
+            {
+                const uint32_t bit = 1u << (cur & 31);
+                if (lane == 0) {
+                    atomicOr(&vis[cur >> 5], bit);
+                    vlog[0] = cur;
+                    c.todo[0] = cur;
+                }
+                logn = 1;
+                __syncwarp();
+                float d0 = 0.0f;
+                eval_list<DT>(p, c, 1, [&](uint32_t, float d) { d0 = d; });
+                ++ndc0;
+                if (lane == 0) c.res[0] = make_key(d0, cur);
+                len = 1;
+                __syncwarp();
+            }
+            for (;;) {
+                // pop the closest candidate: first unexpanded entry of res, else the smallest tie
+                uint32_t cnode = VELES_INVALID_ID;
+                {
+                    uint32_t found = VELES_INVALID_ID;
+                    for (uint32_t base = scan_from & ~31u; base < len; base += 32) {
+                        const uint32_t i = base + lane;
+                        const bool un = i < len && i >= scan_from && (c.res[i] & 1ull) == 0;
+                        const uint32_t msk = __ballot_sync(FULL_MASK, un);
+                        if (msk) {
+                            found = base + __ffs(msk) - 1;
+                            break;
+                        }
+                    }
+                    if (found != VELES_INVALID_ID) {
+                        const uint64_t key = c.res[found];
+                        cnode = key_id(key);
+                        __syncwarp();
+                        if (lane == 0) c.res[found] = key | 1ull;
+                        scan_from = found + 1;
+                        __syncwarp();
+                    } else if (tlen > 0) {
+                        // every tie has dist == worst result dist: popped without the break (graph.rs:474)
+                        uint64_t best = ~0ull;
+                        for (uint32_t i = lane; i < tlen; i += 32) {
+                            const uint64_t v = tie[i];
+                            best = v < best ? v : best;
+                        }
+                        best = warp_min_u64(best);
+                        cnode = key_id(best);
+                        // remove it: move the last entry into its place
+                        const uint64_t lastv = tie[tlen - 1];
+                        __syncwarp();
+                        for (uint32_t i = lane; i < tlen; i += 32)
+                            if (tie[i] == best) tie[i] = lastv;
+                        --tlen;
+                        __syncwarp();
+                    } else {
+                        break;  // candidates exhausted, or everything left is farther than the worst result
+                    }
+                }
+                // expand cnode
+                uint32_t nread = 0;
+                const uint32_t m =
+                    gather_row<true>(p, c, p.ix.adj0 + (size_t)cnode * p.ix.stride0, p.ix.stride0, vis, vlog, logn, nread);
+                ++hops0;
+                ndc0 += m;
+                eval_list<DT>(p, c, m, [&](uint32_t id, float d) {
+                    const float worst = key_dist(c.res[len - 1]);
+                    if (d < worst || len < ef) {
+                        const uint64_t key = make_key(d, id);
+                        const uint32_t pos = lower_bound_warp(c.res, len, key, lane);
+                        if (len < ef) {
+                            insert_at(c.res, pos, len + 1, key, lane);
+                            ++len;
+                        } else {
+                            const uint64_t ev = c.res[len - 1];
+                            __syncwarp();
+                            insert_at(c.res, pos, len, key, lane);
+                            const float nworst = key_dist(c.res[len - 1]);
+                            // ties that are now farther than the worst result can only end the loop: drop them
+                            if (tlen > 0) {
+                                uint32_t w = 0;
+                                for (uint32_t base = 0; base < tlen; base += 32) {
+                                    const uint32_t i = base + lane;
+                                    uint64_t v = 0;
+                                    bool keep = false;
+                                    if (i < tlen) {
+                                        v = tie[i];
+                                        keep = !(key_dist(v) > nworst);
+                                    }
+                                    const uint32_t msk = __ballot_sync(FULL_MASK, keep);
+                                    __syncwarp();
+                                    if (keep) tie[w + __popc(msk & ((1u << lane) - 1u))] = v;
+                                    w += __popc(msk);
+                                    __syncwarp();
+                                }
+                                tlen = w;
+                            }
+                            if ((ev & 1ull) == 0 && !(key_dist(ev) > nworst)) {
+                                if (tlen < kTieCap) {
+                                    if (lane == 0) tie[tlen] = ev;
+                                    ++tlen;
+                                } else if (lane == 0) {
+                                    atomicExch(&p.counters[1], 1u);
+                                }
+                                __syncwarp();
+                            }
+                        }
+                        if (pos < scan_from) scan_from = pos;
+                    }
+                });
+                __syncwarp();
+            }
+
+            // ---- clear the visited bitmap for the next query of this slot ----
+            if (logn <= kLogCap) {
+                for (uint32_t i = lane; i < logn; i += 32) vis[vlog[i] >> 5] = 0u;
+            } else {
+                for (uint32_t i = lane; i < p.vis_words; i += 32) vis[i] = 0u;
+            }
+            __syncwarp();
+        }
+
+        // ---- write the first k results (graph.rs:269) ----
+        const uint32_t cnt = len < p.k ? len : p.k;
+        for (uint32_t i = lane; i < p.k; i += 32) {
+            uint32_t id = VELES_INVALID_ID;
+            float d = __uint_as_float(0x7fc00000u);
+            if (i < cnt) {
+                const uint64_t key = c.res[i];
+                id = key_id(key);
+                d = key_dist(key);
+            }
+            p.out_ids[(size_t)qi * p.k + i] = id;
+            p.out_dist[(size_t)qi * p.k + i] = d;
+        }
+        if (lane == 0) {
+            p.out_counts[qi] = cnt;
+            if (p.out_stats) {
+                p.out_stats[(size_t)qi * 4 + 0] = ndc0;
+                p.out_stats[(size_t)qi * 4 + 1] = hops0;
+                p.out_stats[(size_t)qi * 4 + 2] = ndc_up;
+                p.out_stats[(size_t)qi * 4 + 3] = hops_up;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+static int32_t launch_search(const veles_index* ix, const float* q_d, uint32_t nq, uint32_t k, uint32_t ef,
+                             uint32_t* ids_d, float* dist_d, uint32_t* cnt_d, uint32_t* stats_d, cudaStream_t st) {
+    VELES_REQUIRE(ix->has_graph, "snapshot has no graph; build or load one first");
+    VELES_REQUIRE(k >= 1 && k <= 65536, "k must be in 1..65536, got %u", k);
+    VELES_REQUIRE(ef >= 1 && ef <= 16384, "ef must be in 1..16384, got %u", ef);
+    if (nq == 0) return VELES_OK;
+    SearchParams p;
+    p.ix = ix->view();
+    p.queries = q_d;
+    p.nq = nq;
+    p.k = k;
+    p.ef = ef;
+    p.out_ids = ids_d;
+    p.out_dist = dist_d;
+    p.out_counts = cnt_d;
+    p.out_stats = stats_d;
+
+    // shared-memory carve
+    const uint32_t bar_bytes = kMaxSlots * 8;
+    p.off_res = bar_bytes;
+    const uint32_t res_bytes = round_up(ef * 8, 16);
+    p.off_todo = p.off_res + res_bytes;
+    const uint32_t todo_bytes = round_up(std::max(ix->stride0, ix->strideU) * 4, 16);
+    p.off_q = p.off_todo + todo_bytes;
+    const uint32_t q_bytes = round_up(ix->dtype == VELES_BIN1 ? ix->dim / 8 : ix->dim * 4, 16);
+    p.off_ring = round_up(p.off_q + q_bytes, 128);
+    int dev = 0, max_smem = 0, sms = 0;
+    VELES_CUDA(cudaGetDevice(&dev));
+    VELES_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    VELES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int sm_smem = 0;
+    VELES_CUDA(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    // aim for 8 resident warps (queries) per SM, at least 2 ring slots
+    const uint32_t per_cta_target = (uint32_t)sm_smem / 8 - 1024;
+    uint32_t nslot = 2;
+    if (per_cta_target > p.off_ring + 2 * ix->row_bytes) nslot = (per_cta_target - p.off_ring) / ix->row_bytes;
+    nslot = std::min(std::max(nslot, 2u), kMaxSlots);
+    p.nslot = nslot;
+    const uint32_t smem_bytes = p.off_ring + nslot * ix->row_bytes;
+    VELES_REQUIRE((int)smem_bytes <= max_smem, "search needs %u bytes of shared memory per query (dim %u, ef %u); limit %d",
+                  smem_bytes, ix->dim, ef, max_smem);
+
+    auto kern = ix->dtype == VELES_F32 ? hnsw_search_kernel<VELES_F32>
+                : ix->dtype == VELES_F16 ? hnsw_search_kernel<VELES_F16>
+                                         : hnsw_search_kernel<VELES_BIN1>;
+    VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    int ctas_per_sm = 0;
+    VELES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 32, smem_bytes));
+    VELES_REQUIRE(ctas_per_sm >= 1, "search kernel does not fit on an SM");
+    const uint32_t max_slots = (uint32_t)(ctas_per_sm * sms);
+    const uint32_t grid = std::min(nq, max_slots);
+
+    // scratch: visited bitmaps, logs, tie lists for `max_slots` resident queries
+    p.vis_words = (uint32_t)((ix->n + 31) / 32);
+    if (ix->scratch_slots < max_slots || !ix->visited.p) {
+        VELES_TRY(ix->visited.alloc((size_t)max_slots * std::max(p.vis_words, 1u) * 4));
+        VELES_CUDA(cudaMemsetAsync(ix->visited.p, 0, ix->visited.bytes, st));
+        VELES_TRY(ix->vlog.alloc((size_t)max_slots * kLogCap * 4));
+        VELES_TRY(ix->aux_d.alloc((size_t)max_slots * kTieCap * 8));
+        VELES_TRY(ix->counters.alloc(64));
+        ix->scratch_slots = max_slots;
+    }
+    p.visited = ix->visited.as<uint32_t>();
+    p.vlog = ix->vlog.as<uint32_t>();
+    p.tie = ix->aux_d.as<uint64_t>();
+    p.counters = ix->counters.as<uint32_t>();
+    VELES_CUDA(cudaMemsetAsync(p.counters, 0, 8, st));
+    kern<<<grid, 32, smem_bytes, st>>>(p);
+    count_launch();
+    VELES_CUDA(cudaGetLastError());
+    return VELES_OK;
+}
+
+static int32_t check_error_flag(const veles_index* ix, cudaStream_t st) {
+    uint32_t h[2] = {0, 0};
+    VELES_CUDA(cudaMemcpyAsync(h, ix->counters.p, 8, cudaMemcpyDeviceToHost, st));
+    VELES_CUDA(cudaStreamSynchronize(st));
+    if (h[1] != 0) {
+        set_error("tie list overflow (> %u equal-distance evicted candidates in one query)", kTieCap);
+        return VELES_ERR_OVERFLOW;
+    }
+    return VELES_OK;
+}
+
+}  // namespace veles
+
+using namespace veles;
+
+extern "C" {
+
+int32_t veles_search_batch_d(const veles_index_t* idx, const float* queries_d, uint32_t nq, uint32_t k, uint32_t ef,
+                             uint32_t* out_node_ids_d, float* out_raw_dist_d, uint32_t* out_counts_d,
+                             uint32_t* out_stats_d, void* stream) {
+    VELES_REQUIRE(idx != nullptr, "index is NULL");
+    VELES_REQUIRE(nq == 0 || (queries_d && out_node_ids_d && out_raw_dist_d && out_counts_d), "NULL buffer");
+    std::lock_guard<std::mutex> g(idx->mu);
+    return launch_search(idx, queries_d, nq, k, ef, out_node_ids_d, out_raw_dist_d, out_counts_d, out_stats_d,
+                         (cudaStream_t)stream);
+}
+
+int32_t veles_search_batch(const veles_index_t* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
+                           uint32_t* out_node_ids, float* out_raw_dist, uint32_t* out_counts, uint32_t* out_stats,
+                           void* stream) {
+    VELES_REQUIRE(idx != nullptr, "index is NULL");
+    VELES_REQUIRE(nq == 0 || (queries && out_node_ids && out_raw_dist && out_counts), "NULL buffer");
+    if (nq == 0) return VELES_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> g(idx->mu);
+    const size_t qb = (size_t)nq * idx->dim * 4, ob = (size_t)nq * k * 4;
+    VELES_TRY(idx->q_d.ensure(qb));
+    VELES_TRY(idx->out_ids_d.ensure(ob));
+    VELES_TRY(idx->out_val_d.ensure(ob));
+    VELES_TRY(idx->out_cnt_d.ensure((size_t)nq * 4));
+    if (out_stats) VELES_TRY(idx->out_stats_d.ensure((size_t)nq * 16));
+    VELES_CUDA(cudaMemcpyAsync(idx->q_d.p, queries, qb, cudaMemcpyHostToDevice, st));
+    VELES_TRY(launch_search(idx, idx->q_d.as<float>(), nq, k, ef, idx->out_ids_d.as<uint32_t>(), idx->out_val_d.as<float>(),
+                            idx->out_cnt_d.as<uint32_t>(), out_stats ? idx->out_stats_d.as<uint32_t>() : nullptr, st));
+    VELES_CUDA(cudaMemcpyAsync(out_node_ids, idx->out_ids_d.p, ob, cudaMemcpyDeviceToHost, st));
+    VELES_CUDA(cudaMemcpyAsync(out_raw_dist, idx->out_val_d.p, ob, cudaMemcpyDeviceToHost, st));
+    VELES_CUDA(cudaMemcpyAsync(out_counts, idx->out_cnt_d.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    if (out_stats) VELES_CUDA(cudaMemcpyAsync(out_stats, idx->out_stats_d.p, (size_t)nq * 16, cudaMemcpyDeviceToHost, st));
+    return check_error_flag(idx, st);
+}
+
+}  // extern "C"

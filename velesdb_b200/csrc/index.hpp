@@ -1,0 +1,69 @@
+// index.hpp -- host-side handle of a device snapshot (one NativeHnsw, native/graph.rs:18-44).
+#pragma once
+
+#include <mutex>
+
+#include "common.cuh"
+
+struct veles_index {
+    int device = 0;
+    int32_t metric = VELES_COSINE;
+    int32_t dtype = VELES_F32;
+    uint32_t dim = 0;
+    uint64_t n = 0;
+    uint32_t row_bytes = 0;
+    uint32_t norm_off = 0;
+    uint32_t M = 0, M0 = 0, ef_construction = 0;
+    uint32_t stride0 = 0, strideU = 0;
+    uint64_t upper_rows = 0;
+    uint64_t entry = 0;
+    uint32_t max_layer = 0;
+    uint32_t num_layers = 1;
+    bool has_entry = false;
+    bool has_graph = false;
+
+    veles::DevBuf vecs, adj0, upper_ref, upper_adj;
+
+    // search scratch, sized lazily and reused; guarded by `mu`
+    mutable std::mutex mu;
+    mutable veles::DevBuf visited, vlog, counters;
+    mutable uint32_t scratch_slots = 0;
+    mutable veles::DevBuf q_d, out_ids_d, out_val_d, out_cnt_d, out_stats_d, scores_d, aux_d;
+
+    veles::IndexView view() const {
+        veles::IndexView v;
+        v.vecs = vecs.as<uint8_t>();
+        v.adj0 = adj0.as<uint32_t>();
+        v.upper_ref = upper_ref.as<uint32_t>();
+        v.upper_adj = upper_adj.as<uint32_t>();
+        v.n = n;
+        v.dim = dim;
+        v.row_bytes = row_bytes;
+        v.norm_off = norm_off;
+        v.stride0 = stride0;
+        v.strideU = strideU;
+        v.entry = (uint32_t)entry;
+        v.max_layer = max_layer;
+        v.metric = metric;
+        v.dtype = dtype;
+        v.has_entry = (has_entry && has_graph) ? 1 : 0;
+        return v;
+    }
+    uint64_t device_bytes() const {
+        return vecs.bytes + adj0.bytes + upper_ref.bytes + upper_adj.bytes + visited.bytes + vlog.bytes;
+    }
+};
+
+namespace veles {
+inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
+inline uint32_t elt_bytes(int32_t dtype) { return dtype == VELES_F32 ? 4 : 2; }
+// sets row_bytes / norm_off from dim, dtype, metric
+void compute_row_layout(veles_index* ix);
+// uploads vectors into the row layout and fills the cosine norm trailer
+int32_t upload_vectors(veles_index* ix, const void* vectors, int32_t src_dtype, cudaStream_t st);
+// installs a padded fixed-stride adjacency built on the host
+int32_t install_graph_host(veles_index* ix, uint32_t num_layers, const uint64_t* const* row_ptr,
+                           const uint32_t* const* cols, const uint64_t* layer_nodes, uint32_t M, uint32_t M0,
+                           uint64_t entry_point, uint32_t max_layer);
+int device_sm_count();
+}  // namespace veles

@@ -1,0 +1,473 @@
+"""Host-side mirror of velesdb-core's ``HnswIndex`` over the C ABI (include/veles_b200.h).
+
+Same method names, argument meaning and error behaviour as the Rust type
+(crates/velesdb-core/src/index/hnsw/index/{mod,search,batch,trait_impl,constructors,vacuum}.rs and
+the ``VectorIndex`` trait, index/mod.rs:30-83), so the parity tests read like the reference's.
+Everything numeric happens in libveles_b200.so on the GPU; this file only does what the Rust
+wrapper does on the host: id <-> node mapping, tombstones, quality -> ef, score transform.
+
+A Rust panic (``assert_eq!`` on dimensions) is raised here as ``DimensionMismatch`` (a ValueError).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+import pickle
+
+import numpy as np
+
+from . import _native as nv
+
+
+class DistanceMetric(enum.IntEnum):
+    """core/distance.rs:16-39"""
+    Cosine = 0
+    Euclidean = 1
+    DotProduct = 2
+    Hamming = 3
+    Jaccard = 4
+
+    def higher_is_better(self) -> bool:  # core/distance.rs:76-81
+        return self in (DistanceMetric.Cosine, DistanceMetric.DotProduct, DistanceMetric.Jaccard)
+
+
+class SearchQuality:
+    """index/hnsw/params.rs:283-320"""
+
+    def __init__(self, kind, ef=0):
+        self.kind, self.ef = kind, ef
+
+    def ef_search(self, k: int) -> int:
+        return int(nv.lib().veles_ef_search(self.kind, k, self.ef))
+
+    @staticmethod
+    def Custom(ef: int) -> "SearchQuality":
+        return SearchQuality(nv.CUSTOM, ef)
+
+    def __repr__(self):
+        return f"SearchQuality({['Fast', 'Balanced', 'Accurate', 'Perfect', 'Custom'][self.kind]}, {self.ef})"
+
+
+SearchQuality.Fast = SearchQuality(nv.FAST)
+SearchQuality.Balanced = SearchQuality(nv.BALANCED)
+SearchQuality.Accurate = SearchQuality(nv.ACCURATE)
+SearchQuality.Perfect = SearchQuality(nv.PERFECT)
+
+
+class HnswParams:
+    """index/hnsw/params.rs:14-57 (auto)"""
+
+    def __init__(self, max_connections=32, ef_construction=400, max_elements=100_000):
+        self.max_connections, self.ef_construction, self.max_elements = max_connections, ef_construction, max_elements
+
+    @staticmethod
+    def auto(dimension: int) -> "HnswParams":
+        return HnswParams(24, 300) if dimension <= 256 else HnswParams(32, 400)
+
+
+class DimensionMismatch(ValueError):
+    pass
+
+
+_DT = {"f32": nv.F32, "f16": nv.F16, "bin1": nv.BIN1}
+
+
+def _as_f32_2d(a, dim, what):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim == 1:
+        a = a.reshape(1, -1)
+    if a.shape[1] != dim:
+        raise DimensionMismatch(f"{what} dimension mismatch: expected {dim}, got {a.shape[1]}")
+    return a
+
+
+class DeviceSnapshot:
+    """Owns one ``veles_index_t*``."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            try:
+                nv.lib().veles_index_free(self.h)
+            except Exception:  # interpreter shutdown
+                pass
+            self.h = None
+
+    @staticmethod
+    def from_vectors(vectors, metric, store_dtype="f32", src_dtype="f32", dim=None):
+        nv.init()
+        vectors = np.ascontiguousarray(vectors)
+        n = vectors.shape[0]
+        d = dim if dim is not None else vectors.shape[1]
+        h = C.c_void_p()
+        nv.check(nv.lib().veles_index_from_vectors(nv.ptr(vectors), n, d, _DT[src_dtype], _DT[store_dtype], int(metric),
+                                                   C.byref(h)))
+        return DeviceSnapshot(h)
+
+    @staticmethod
+    def from_arrays(vectors, metric, layers, M, M0, entry_point, max_layer, store_dtype="f32", src_dtype="f32",
+                    dim=None):
+        """layers: [(row_ptr u64[nodes+1], cols u32[edges])] per layer (CSR)."""
+        nv.init()
+        vectors = np.ascontiguousarray(vectors)
+        n = vectors.shape[0]
+        d = dim if dim is not None else vectors.shape[1]
+        rps = [np.ascontiguousarray(rp, dtype=np.uint64) for rp, _ in layers]
+        cls = [np.ascontiguousarray(c if len(c) else np.zeros(1, np.uint32), dtype=np.uint32) for _, c in layers]
+        nodes = np.array([rp.size - 1 for rp in rps], dtype=np.uint64)
+        rp_arr = (C.c_void_p * len(layers))(*[rp.ctypes.data for rp in rps])
+        c_arr = (C.c_void_p * len(layers))(*[c.ctypes.data for c in cls])
+        h = C.c_void_p()
+        nv.check(nv.lib().veles_index_from_arrays(nv.ptr(vectors), n, d, _DT[src_dtype], _DT[store_dtype], int(metric),
+                                                  len(layers), rp_arr, c_arr, nv.ptr(nodes), M, M0,
+                                                  entry_point or 0, max_layer, C.byref(h)))
+        return DeviceSnapshot(h)
+
+    @staticmethod
+    def from_reference_files(directory, metric, basename="native_hnsw", store_dtype="f32"):
+        nv.init()
+        h = C.c_void_p()
+        nv.check(nv.lib().veles_index_from_reference_files(os.fsencode(directory), basename.encode(), int(metric),
+                                                           _DT[store_dtype], C.byref(h)))
+        return DeviceSnapshot(h)
+
+    # -- properties
+    def __len__(self):
+        return int(nv.lib().veles_index_len(self.h))
+
+    @property
+    def dim(self):
+        return int(nv.lib().veles_index_dim(self.h))
+
+    @property
+    def metric(self):
+        return DistanceMetric(nv.lib().veles_index_metric(self.h))
+
+    @property
+    def max_layer(self):
+        return int(nv.lib().veles_index_max_layer(self.h))
+
+    @property
+    def entry_point(self):
+        return int(nv.lib().veles_index_entry_point(self.h))
+
+    @property
+    def device_bytes(self):
+        return int(nv.lib().veles_index_device_bytes(self.h))
+
+    # -- calls
+    def search_batch(self, queries, k, ef, with_stats=False, stream=None):
+        q = _as_f32_2d(queries, self.dim, "Query")
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.uint32)
+        dist = np.empty((nq, k), dtype=np.float32)
+        cnt = np.zeros(nq, dtype=np.uint32)
+        st = np.zeros((nq, 4), dtype=np.uint32) if with_stats else None
+        nv.check(nv.lib().veles_search_batch(self.h, nv.ptr(q), nq, k, ef, nv.ptr(ids), nv.ptr(dist), nv.ptr(cnt),
+                                             nv.ptr(st), stream))
+        return (ids, dist, cnt, st) if with_stats else (ids, dist, cnt)
+
+    def search_batch_device(self, q_t, k, ef, ids_t, dist_t, cnt_t, stats_t=None, stream=None):
+        """torch CUDA tensors in, results written to torch CUDA tensors; only enqueues on `stream`."""
+        nv.check(nv.lib().veles_search_batch_d(self.h, nv.ptr(q_t), q_t.shape[0], k, ef, nv.ptr(ids_t), nv.ptr(dist_t),
+                                               nv.ptr(cnt_t), nv.ptr(stats_t), stream))
+
+    def bruteforce_batch(self, queries, k, stream=None):
+        q = _as_f32_2d(queries, self.dim, "Query")
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.uint32)
+        sc = np.empty((nq, k), dtype=np.float32)
+        nv.check(nv.lib().veles_bruteforce_batch(self.h, nv.ptr(q), nq, k, nv.ptr(ids), nv.ptr(sc), stream))
+        return ids, sc
+
+    def bruteforce_batch_device(self, q_t, k, ids_t, score_t, stream=None):
+        nv.check(nv.lib().veles_bruteforce_batch_d(self.h, nv.ptr(q_t), q_t.shape[0], k, nv.ptr(ids_t), nv.ptr(score_t),
+                                                   stream))
+
+    def rerank_batch(self, queries, cand, stream=None):
+        q = _as_f32_2d(queries, self.dim, "Query")
+        cand = np.ascontiguousarray(cand, dtype=np.uint32).reshape(q.shape[0], -1)
+        out = np.empty(cand.shape, dtype=np.float32)
+        nv.check(nv.lib().veles_rerank_batch(self.h, nv.ptr(q), q.shape[0], nv.ptr(cand), cand.shape[1], nv.ptr(out),
+                                             stream))
+        return out
+
+    def build_graph(self, M, cand_k=0, stream=None):
+        nv.check(nv.lib().veles_index_build_graph(self.h, M, cand_k, stream))
+
+    def export_layer(self, layer):
+        nodes, edges = C.c_uint64(), C.c_uint64()
+        nv.check(nv.lib().veles_index_export_layer(self.h, layer, C.byref(nodes), C.byref(edges), None, None))
+        rp = np.zeros(nodes.value + 1, dtype=np.uint64)
+        cols = np.zeros(max(edges.value, 1), dtype=np.uint32)
+        nv.check(nv.lib().veles_index_export_layer(self.h, layer, C.byref(nodes), C.byref(edges), nv.ptr(rp),
+                                                   nv.ptr(cols)))
+        return rp, cols[:edges.value]
+
+    def export_graph(self):
+        return [self.export_layer(l) for l in range(self.max_layer + 1)]
+
+    def dump(self, directory, basename="native_hnsw"):
+        nv.check(nv.lib().veles_index_dump(self.h, os.fsencode(directory), basename.encode()))
+
+
+def distance_pairs(metric, a, b, as_metric_value=False):
+    """DistanceEngine::batch_distance on explicit pairs (native/distance.rs:22-24)."""
+    nv.init()
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    if a.ndim == 1:
+        a, b = a.reshape(1, -1), b.reshape(1, -1)
+    assert a.shape == b.shape, "Vector dimensions must match"
+    out = np.empty(a.shape[0], dtype=np.float32)
+    nv.check(nv.lib().veles_distance_pairs(int(metric), nv.ptr(a), nv.ptr(b), a.shape[0], a.shape[1],
+                                           1 if as_metric_value else 0, nv.ptr(out), None))
+    return out
+
+
+class HnswIndex:
+    """``HnswIndex`` (index/hnsw/index/mod.rs:93-131) over a GPU snapshot.
+
+    The reference mutates its graph in place under a RwLock.  Here inserts are staged on the host
+    and the immutable device snapshot is (re)built on the next search -- the bulk path the reference
+    calls ``insert_batch_parallel`` (index/hnsw/index/batch.rs:82-108), whose graph is order
+    dependent in the reference too.  Indexes loaded from the reference's files keep the file's graph.
+    """
+
+    def __init__(self, dimension, metric, params=None, enable_vector_storage=True, store_dtype="f32"):
+        self._dimension = int(dimension)
+        self._metric = DistanceMetric(metric)
+        self._params = params or HnswParams.auto(self._dimension)
+        self.enable_vector_storage = enable_vector_storage
+        self._store_dtype = store_dtype
+        self._id_to_idx = {}
+        self._idx_to_id = {}
+        self._next_idx = 0
+        self._staged = []          # vectors by node index
+        self._snapshot = None
+        self._dirty = False
+        self._vectors_present = True  # False after load(): ShardedVectors is left empty (constructors.rs:240)
+
+    # ---- constructors (index/hnsw/index/constructors.rs:29-177)
+    @classmethod
+    def new(cls, dimension, metric):
+        return cls(dimension, metric)
+
+    @classmethod
+    def with_params(cls, dimension, metric, params):
+        return cls(dimension, metric, params)
+
+    @classmethod
+    def with_params_full(cls, dimension, metric, params, enable_vector_storage):
+        return cls(dimension, metric, params, enable_vector_storage)
+
+    @classmethod
+    def from_snapshot(cls, snapshot: DeviceSnapshot, ids=None, vectors_present=False):
+        ix = cls(snapshot.dim, snapshot.metric)
+        n = len(snapshot)
+        ids = list(range(n)) if ids is None else list(ids)
+        ix._id_to_idx = {int(e): i for i, e in enumerate(ids)}
+        ix._idx_to_id = {i: int(e) for i, e in enumerate(ids)}
+        ix._next_idx = n
+        ix._snapshot = snapshot
+        ix._vectors_present = vectors_present
+        return ix
+
+    # ---- VectorIndex (index/mod.rs:30-83; trait_impl.rs)
+    def insert(self, id, vector):
+        v = np.asarray(vector, dtype=np.float32).reshape(-1)
+        if v.size != self._dimension:
+            raise DimensionMismatch(f"Vector dimension mismatch: expected {self._dimension}, got {v.size}")
+        if id in self._id_to_idx:  # duplicate ids are skipped silently (trait_impl.rs:12-25)
+            return
+        self._materialise_staged()
+        idx = self._next_idx
+        self._next_idx += 1
+        self._id_to_idx[id] = idx
+        self._idx_to_id[idx] = id
+        self._staged.append(v.copy())
+        self._dirty = True
+
+    def insert_batch_parallel(self, vectors) -> int:
+        """index/hnsw/index/batch.rs:82-108: (id, vector) pairs; returns how many were new."""
+        count = 0
+        for id, v in vectors:
+            before = len(self._id_to_idx)
+            self.insert(id, v)
+            count += len(self._id_to_idx) - before
+        return count
+
+    def remove(self, id) -> bool:
+        """Soft delete (trait_impl.rs:54-58): the mapping goes, the node stays in the graph."""
+        idx = self._id_to_idx.pop(id, None)
+        if idx is None:
+            return False
+        del self._idx_to_id[idx]
+        return True
+
+    def len(self) -> int:
+        return len(self._id_to_idx)
+
+    __len__ = len
+
+    def is_empty(self) -> bool:
+        return self.len() == 0
+
+    def dimension(self) -> int:
+        return self._dimension
+
+    def metric(self) -> DistanceMetric:
+        return self._metric
+
+    def search(self, query, k):
+        return self.search_with_quality(query, k, SearchQuality.Balanced)
+
+    # ---- inherent search API (index/hnsw/index/search.rs, batch.rs)
+    def search_with_quality(self, query, k, quality):
+        q = _as_f32_2d(query, self._dimension, "Query")
+        if quality.kind == nv.PERFECT:
+            return self.search_brute_force(q[0], k)
+        if self.len() <= 100 and self.enable_vector_storage and self._vectors_present and self._next_idx > 0:
+            return self.search_brute_force(q[0], k)
+        return self._graph_search(q, k, quality.ef_search(k))[0]
+
+    def search_batch_parallel(self, queries, k, quality):
+        """batch.rs:159-197 -- no brute-force short-circuits on this path."""
+        qs = np.ascontiguousarray(queries, dtype=np.float32)
+        if qs.ndim != 2:
+            qs = np.stack([np.asarray(x, dtype=np.float32) for x in queries]) if len(queries) else np.zeros(
+                (0, self._dimension), np.float32)
+        for i in range(qs.shape[0]):
+            if qs.shape[1] != self._dimension:
+                raise DimensionMismatch(f"Query {i} dimension mismatch: expected {self._dimension}, got {qs.shape[1]}")
+        if qs.shape[0] == 0:
+            return []
+        return self._graph_search(qs, k, quality.ef_search(k))
+
+    def search_brute_force(self, query, k):
+        q = _as_f32_2d(query, self._dimension, "Query")
+        if not self.enable_vector_storage or not self._vectors_present or self._next_idx == 0:
+            if self._next_idx == 0:
+                return []
+            return self._graph_search(q, k, SearchQuality.Accurate.ef_search(k))[0]  # search.rs:180-194
+        return self._brute(q, k)[0]
+
+    search_brute_force_buffered = search_brute_force
+    brute_force_search_parallel = search_brute_force
+
+    def search_brute_force_gpu(self, query, k):
+        """search.rs:229-279 (cosine only in the reference's wgpu path); always available here."""
+        return self.search_brute_force(query, k)
+
+    def search_with_rerank(self, query, k, rerank_k):
+        return self.search_with_rerank_quality(query, k, rerank_k, SearchQuality.Accurate)
+
+    def search_with_rerank_quality(self, query, k, rerank_k, initial_quality):
+        q = _as_f32_2d(query, self._dimension, "Query")
+        if initial_quality.kind == nv.PERFECT:
+            initial_quality = SearchQuality.Accurate
+        cands = self.search_with_quality(q[0], rerank_k, initial_quality)
+        if not cands:
+            return []
+        if not self._vectors_present:  # rerank finds no vectors after load() (search.rs:130-137)
+            return []
+        snap = self._ensure_snapshot()
+        pairs = [(id, self._id_to_idx[id]) for id, _ in cands if id in self._id_to_idx]
+        if not pairs:
+            return []
+        scores = snap.rerank_batch(q, np.array([[p[1] for p in pairs]], dtype=np.uint32))[0]
+        out = [(p[0], float(s)) for p, s in zip(pairs, scores)]
+        out = _sort_results(self._metric, out)
+        return out[:k]
+
+    def set_searching_mode(self):
+        self._ensure_snapshot()
+
+    # ---- persistence (constructors.rs:190-287)
+    def save(self, path):
+        os.makedirs(path, exist_ok=True)
+        snap = self._ensure_snapshot()
+        snap.dump(path, "native_hnsw")
+        with open(os.path.join(path, "native_mappings.bin"), "wb") as f:
+            pickle.dump((self._id_to_idx, self._idx_to_id, self._next_idx), f)
+        with open(os.path.join(path, "native_meta.bin"), "wb") as f:
+            pickle.dump((self._dimension, int(self._metric), self.enable_vector_storage), f)
+
+    @classmethod
+    def load(cls, path, dimension, metric):
+        for name in ("native_hnsw.vectors", "native_hnsw.graph", "native_mappings.bin"):
+            if not os.path.exists(os.path.join(path, name)):
+                raise FileNotFoundError(f"{name} not found in {path}")
+        snap = DeviceSnapshot.from_reference_files(path, metric)
+        ix = cls(dimension, metric)
+        with open(os.path.join(path, "native_mappings.bin"), "rb") as f:
+            ix._id_to_idx, ix._idx_to_id, ix._next_idx = pickle.load(f)
+        ix._snapshot = snap
+        ix._vectors_present = False  # ShardedVectors stays empty after load (constructors.rs:240)
+        return ix
+
+    # ---- vacuum.rs
+    def tombstone_count(self) -> int:
+        return self._next_idx - len(self._id_to_idx)
+
+    def tombstone_ratio(self) -> float:
+        return 0.0 if self._next_idx == 0 else self.tombstone_count() / self._next_idx
+
+    def needs_vacuum(self) -> bool:
+        return self.tombstone_ratio() > 0.2
+
+    # ---- internals
+    def _materialise_staged(self):
+        """Bring host copies of a loaded snapshot's vectors back before more inserts (not supported yet)."""
+        if self._snapshot is not None and not self._staged and self._next_idx > 0:
+            raise NotImplementedError("inserting into an index restored from files needs vacuum/rebuild support")
+
+    def _ensure_snapshot(self) -> DeviceSnapshot:
+        if self._snapshot is None or self._dirty:
+            vecs = np.stack(self._staged) if self._staged else np.zeros((0, self._dimension), np.float32)
+            snap = DeviceSnapshot.from_vectors(vecs, self._metric, self._store_dtype)
+            snap.build_graph(self._params.max_connections)
+            self._snapshot, self._dirty = snap, False
+        return self._snapshot
+
+    def _map(self, ids, vals, cnt, transform):
+        lib = nv.lib()
+        out = []
+        for r in range(ids.shape[0]):
+            row = []
+            for j in range(int(cnt[r])):
+                ext = self._idx_to_id.get(int(ids[r, j]))
+                if ext is None:  # tombstoned: dropped silently (search.rs:86-91)
+                    continue
+                v = float(vals[r, j])
+                row.append((ext, float(lib.veles_transform_score(int(self._metric), v)) if transform else v))
+            out.append(row)
+        return out
+
+    def _graph_search(self, q, k, ef):
+        if self._next_idx == 0:
+            return [[] for _ in range(q.shape[0])]
+        ids, dist, cnt = self._ensure_snapshot().search_batch(q, k, ef)
+        return self._map(ids, dist, cnt, True)
+
+    def _brute(self, q, k):
+        snap = self._ensure_snapshot()
+        # tombstoned nodes are filtered before the sort in the reference (search.rs:205-208): over-fetch
+        kk = min(len(snap), k + self.tombstone_count())
+        if kk == 0:
+            return [[] for _ in range(q.shape[0])]
+        ids, sc = snap.bruteforce_batch(q, kk)
+        cnt = (ids != nv.INVALID_ID).sum(axis=1)
+        return [row[:k] for row in self._map(ids, sc, cnt, False)]
+
+
+def _sort_results(metric, results):
+    """DistanceMetric::sort_results (core/distance.rs:95-103): stable, total order on the score."""
+    def key(x):
+        b = np.float32(x[1]).view(np.int32).item()
+        b ^= ((b >> 31) & 0x7FFFFFFF)
+        return b
+    return sorted(results, key=key, reverse=DistanceMetric(metric).higher_is_better())
