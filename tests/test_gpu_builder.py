@@ -1,0 +1,66 @@
+"""GPU bulk graph builder (veles_index_build_graph): structural invariants that equal the
+reference (levels, entry point, degree bounds), search parity *given the built graph*, and
+recall against exact brute force."""
+import numpy as np
+import pytest
+
+from oracle import oracle as vo
+from tests.gpu_util import bits_equal, latent_data, queries_near
+from velesdb_b200 import DeviceSnapshot, DistanceMetric
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("metric,dim,n,M", [(vo.COSINE, 64, 6000, 16), (vo.EUCLIDEAN, 100, 3000, 8),
+                                           (vo.DOT, 64, 3000, 16)])
+def test_built_graph_invariants_and_parity(metric, dim, n, M):
+    x = latent_data(n, dim, latent=8, noise=0.3, seed=3, normalize=(metric != vo.EUCLIDEAN))
+    snap = DeviceSnapshot.from_vectors(x, metric)
+    snap.build_graph(M)
+    # levels / entry point follow the reference PRNG in node-id order (graph.rs:368-403, 230-233)
+    lv = vo.levels(M, n)
+    assert snap.max_layer == int(lv.max())
+    assert snap.entry_point == int(np.argmax(lv == lv.max()))
+    layers = snap.export_graph()
+    assert len(layers) == snap.max_layer + 1
+    for l, (rp, cols) in enumerate(layers):
+        deg = np.diff(rp.astype(np.int64))
+        maxc = 2 * M if l == 0 else M
+        assert deg.max() <= maxc
+        members = np.nonzero(lv >= l)[0]
+        assert (deg[lv < l] == 0).all()                     # only nodes of level >= l have links on layer l
+        if len(members) > 1:
+            assert (deg[members] >= 1).all()
+        assert np.isin(cols, members).all()                  # links stay inside the layer
+        owner = np.repeat(np.arange(n), deg)
+        assert (cols != owner).all()                         # no self loops
+        pairs = owner.astype(np.int64) * n + cols
+        assert len(np.unique(pairs)) == len(pairs)           # no duplicate links
+    # search parity given this graph: the oracle on the exported graph must agree bit for bit
+    g = vo.Hnsw.from_arrays(metric, x, layers, M, 2 * M, snap.entry_point, snap.max_layer)
+    q = queries_near(x, 200, jitter=0.05, seed=4)
+    ids, dist, cnt, st = snap.search_batch(q, 10, 64, with_stats=True)
+    oi, od, oc, ost = g.search_batch(q, 10, 64, order="canonical", threads=8)
+    keep = ost[:, 4] == 0
+    assert np.array_equal(ids[keep], oi[keep].astype(np.uint32)) and bits_equal(dist, od)
+    assert np.array_equal(st[:, 0], ost[:, 0].astype(np.uint32))
+    # quality: recall@10 against exact brute force (cosine/L2; MIPS graphs are not metric)
+    if metric != vo.DOT:
+        bi, _ = snap.bruteforce_batch(q, 10)
+        rec = np.mean([len(set(ids[i].tolist()) & set(bi[i].tolist())) / 10 for i in range(len(q))])
+        assert rec >= 0.95, rec
+
+
+def test_build_edge_cases():
+    e = DeviceSnapshot.from_vectors(np.zeros((0, 16), np.float32), DistanceMetric.Cosine)
+    e.build_graph(16)
+    ids, dist, cnt = e.search_batch(np.ones((2, 16), np.float32), 5, 32)
+    assert (cnt == 0).all()
+    one = DeviceSnapshot.from_vectors(np.ones((1, 16), np.float32), DistanceMetric.Cosine)
+    one.build_graph(16)
+    ids, dist, cnt = one.search_batch(np.ones((2, 16), np.float32), 5, 32)
+    assert (cnt == 1).all() and (ids[:, 0] == 0).all()
+    few = DeviceSnapshot.from_vectors(latent_data(5, 16, seed=1), DistanceMetric.Euclidean)
+    few.build_graph(16)
+    ids, dist, cnt = few.search_batch(latent_data(5, 16, seed=1), 5, 32)
+    assert (cnt == 5).all() and (ids[:, 0] == np.arange(5)).all()

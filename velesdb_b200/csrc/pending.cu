@@ -25,8 +25,4 @@ int32_t veles_fuse(int32_t, const uint32_t*, uint32_t, const uint32_t*, const fl
     set_error("veles_fuse: not implemented yet");
     return VELES_ERR_UNSUPPORTED;
 }
-int32_t veles_index_build_graph(veles_index_t*, uint32_t, uint32_t, void*) {
-    set_error("veles_index_build_graph: not implemented yet");
-    return VELES_ERR_UNSUPPORTED;
-}
 }
