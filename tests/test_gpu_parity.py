@@ -212,3 +212,23 @@ def test_persistent_grid_more_queries_than_slots():
     x, g, snap = graph_case(vo.COSINE, 20)
     q = queries_near(x, 5000, seed=17)
     check_search(g, snap, q, 10, 32)
+
+
+@pytest.mark.parametrize("dim", [128, 256])
+def test_packed_binary_wide_rows(dim):
+    # dim % 128 == 0 takes the four-rows-per-step path of the search kernel
+    x, g, _ = graph_case(vo.HAMMING, dim, n=1200, binary=True)
+    snap = DeviceSnapshot.from_arrays(x, vo.HAMMING, g.export_graph(), g.M, g.M0, g.entry_point, g.max_layer,
+                                      store_dtype="bin1")
+    q = (queries_near(x, 64, jitter=0.4, seed=9) > 0.5).astype(np.float32)
+    check_search(g, snap, q, 10, 64)
+
+
+@pytest.mark.parametrize("metric", [vo.COSINE, vo.EUCLIDEAN, vo.DOT])
+def test_hnsw_search_f16_quad_path(metric):
+    x, g, _ = graph_case(metric, 96)
+    xh = x.astype(np.float16).astype(np.float32)
+    gh = vo.Hnsw.from_arrays(metric, xh, g.export_graph(), g.M, g.M0, g.entry_point, g.max_layer)
+    snap = DeviceSnapshot.from_arrays(x, metric, g.export_graph(), g.M, g.M0, g.entry_point, g.max_layer,
+                                      store_dtype="f16")
+    check_search(gh, snap, queries_near(x, 48, seed=13), 10, 64)

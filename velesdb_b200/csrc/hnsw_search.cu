@@ -24,6 +24,8 @@
 // surviving neighbours' rows are fetched by 1-D bulk async copies (TMA engine, mbarrier
 // complete_tx) into a ring of shared-memory slots; the warp computes each distance from shared
 // memory with the reference's accumulation tree (common.cuh) while later rows are in flight.
+#include <cstdlib>
+
 #include "index.hpp"
 
 namespace veles {
@@ -45,7 +47,9 @@ struct SearchParams {
     uint64_t* tie;        // slots x kTieCap
     uint32_t vis_words;
     uint32_t* counters;   // [0] work counter, [1] error flag
-    uint32_t nslot;
+    uint32_t nslot;       // ring slots (multiple of 4 when quad != 0)
+    uint32_t quad;        // 1: evaluate four candidates per step (8 lanes each), needs dim % 32 == 0
+    uint32_t evict_first; // 1: vector rows are fetched with an L2 evict-first policy
     // shared-memory carve (bytes from base)
     uint32_t off_res, off_todo, off_q, off_ring;
 };
@@ -57,6 +61,7 @@ struct WarpCtx {
     uint8_t* q;
     uint8_t* ring;
     uint32_t phases;
+    uint64_t policy;
     float norm_a;
     uint32_t lane;
 };
@@ -88,14 +93,138 @@ __device__ __forceinline__ float row_distance(const SearchParams& p, const WarpC
     }
 }
 
+__device__ __forceinline__ void copy_row(const SearchParams& p, const WarpCtx& c, uint32_t slot, uint32_t id, uint64_t* bar) {
+    void* dst = c.ring + (size_t)slot * p.ix.row_bytes;
+    const void* src = p.ix.vecs + (size_t)id * p.ix.row_bytes;
+    if (p.evict_first)
+        bulk_g2s_hint(dst, src, p.ix.row_bytes, bar, c.policy);
+    else
+        bulk_g2s(dst, src, p.ix.row_bytes, bar);
+}
 __device__ __forceinline__ void issue_row(const SearchParams& p, const WarpCtx& c, uint32_t slot, uint32_t id) {
     mbar_expect_tx(&c.bar[slot], p.ix.row_bytes);
-    bulk_g2s(c.ring + (size_t)slot * p.ix.row_bytes, p.ix.vecs + (size_t)id * p.ix.row_bytes, p.ix.row_bytes, &c.bar[slot]);
+    copy_row(p, c, slot, id, &c.bar[slot]);
+}
+
+// ---- four candidates per step: lane = 8*g + t, group g owns one row, sub-lane t owns elements
+// 32*it + 4t .. 4t+3 of it, i.e. the reference accumulators P[4t+e] = P[a][j] with a = t/2,
+// j = 4*(t%2) + e.  Combination order of simd_avx512.rs:182-184 + wide::reduce_add:
+//   xor 2 (a^1), xor 4 (a^2)  ->  C[j] = (P0+P1)+(P2+P3)
+//   xor 1                     ->  q[e] = C[e] + C[e+4]
+//   in-thread                 ->  (q0+q2) + (q1+q3)
+// Each step adds a commutative pair, so the result has the CPU's bits.
+__device__ __forceinline__ float quad_tree_sum(float a0, float a1, float a2, float a3) {
+    a0 = __fadd_rn(a0, __shfl_xor_sync(FULL_MASK, a0, 2));
+    a1 = __fadd_rn(a1, __shfl_xor_sync(FULL_MASK, a1, 2));
+    a2 = __fadd_rn(a2, __shfl_xor_sync(FULL_MASK, a2, 2));
+    a3 = __fadd_rn(a3, __shfl_xor_sync(FULL_MASK, a3, 2));
+    a0 = __fadd_rn(a0, __shfl_xor_sync(FULL_MASK, a0, 4));
+    a1 = __fadd_rn(a1, __shfl_xor_sync(FULL_MASK, a1, 4));
+    a2 = __fadd_rn(a2, __shfl_xor_sync(FULL_MASK, a2, 4));
+    a3 = __fadd_rn(a3, __shfl_xor_sync(FULL_MASK, a3, 4));
+    a0 = __fadd_rn(a0, __shfl_xor_sync(FULL_MASK, a0, 1));
+    a1 = __fadd_rn(a1, __shfl_xor_sync(FULL_MASK, a1, 1));
+    a2 = __fadd_rn(a2, __shfl_xor_sync(FULL_MASK, a2, 1));
+    a3 = __fadd_rn(a3, __shfl_xor_sync(FULL_MASK, a3, 1));
+    return __fadd_rn(__fadd_rn(a0, a2), __fadd_rn(a1, a3));
+}
+
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __half* p) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(p);
+    const __half2 lo = *reinterpret_cast<const __half2*>(&raw.x), hi = *reinterpret_cast<const __half2*>(&raw.y);
+    const float2 a = __half22float2(lo), b = __half22float2(hi);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// distance of the row owned by this lane's group (dim % 32 == 0, dim >= 32)
+template <int DT>
+__device__ __forceinline__ float quad_distance(const SearchParams& p, const WarpCtx& c, const uint8_t* row) {
+    const uint32_t t = c.lane & 7;
+    if (DT == VELES_BIN1) {
+        const uint32_t words = p.ix.dim >> 5;
+        const uint32_t* qw = reinterpret_cast<const uint32_t*>(c.q);
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(row);
+        uint32_t d = 0;
+        for (uint32_t w = t * 4; w < words; w += 32) {
+            const uint4 x = *reinterpret_cast<const uint4*>(rw + w);
+            const uint4 y = *reinterpret_cast<const uint4*>(qw + w);
+            d += __popc(x.x ^ y.x) + __popc(x.y ^ y.y) + __popc(x.z ^ y.z) + __popc(x.w ^ y.w);
+        }
+        d += __shfl_xor_sync(FULL_MASK, d, 1);
+        d += __shfl_xor_sync(FULL_MASK, d, 2);
+        d += __shfl_xor_sync(FULL_MASK, d, 4);
+        return (float)d;
+    } else {
+        using TB = typename std::conditional<DT == VELES_F32, float, __half>::type;
+        const TB* r = reinterpret_cast<const TB*>(row);
+        const float* q = reinterpret_cast<const float*>(c.q);
+        const uint32_t dim = p.ix.dim;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (p.ix.metric == VELES_EUCLIDEAN) {
+#pragma unroll 4
+            for (uint32_t i = t * 4; i < dim; i += 32) {
+                const float4 x = load4(r + i), y = load4(q + i);
+                const float d0 = __fsub_rn(y.x, x.x), d1 = __fsub_rn(y.y, x.y), d2 = __fsub_rn(y.z, x.z), d3 = __fsub_rn(y.w, x.w);
+                a0 = __fmaf_rn(d0, d0, a0);
+                a1 = __fmaf_rn(d1, d1, a1);
+                a2 = __fmaf_rn(d2, d2, a2);
+                a3 = __fmaf_rn(d3, d3, a3);
+            }
+            return __fsqrt_rn(quad_tree_sum(a0, a1, a2, a3));
+        }
+#pragma unroll 4
+        for (uint32_t i = t * 4; i < dim; i += 32) {
+            const float4 x = load4(r + i), y = load4(q + i);
+            a0 = __fmaf_rn(y.x, x.x, a0);
+            a1 = __fmaf_rn(y.y, x.y, a1);
+            a2 = __fmaf_rn(y.z, x.z, a2);
+            a3 = __fmaf_rn(y.w, x.w, a3);
+        }
+        const float dot = quad_tree_sum(a0, a1, a2, a3);
+        if (p.ix.metric == VELES_COSINE) {
+            const float nb = *reinterpret_cast<const float*>(row + p.ix.norm_off);
+            return __fsub_rn(1.0f, cosine_from_parts(dot, c.norm_a, nb));
+        }
+        return -dot;
+    }
+}
+
+// Evaluates c.todo[0..m) in order, four rows per step; stage s uses slots 4s..4s+3 and barrier s.
+template <int DT, typename F>
+__device__ __forceinline__ void eval_list_quad(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
+    const uint32_t stages = p.nslot >> 2;
+    const uint32_t nquad = (m + 3) >> 2;
+    auto issue_quad = [&](uint32_t j, uint32_t s) {
+        const uint32_t cnt = min(4u, m - 4 * j);
+        mbar_expect_tx(&c.bar[s], cnt * p.ix.row_bytes);
+        for (uint32_t g = 0; g < cnt; ++g) copy_row(p, c, 4 * s + g, c.todo[4 * j + g], &c.bar[s]);
+    };
+    if (c.lane == 0) {
+        const uint32_t pre = nquad < stages ? nquad : stages;
+        for (uint32_t j = 0; j < pre; ++j) issue_quad(j, j);
+    }
+    const uint32_t g = c.lane >> 3;
+    uint32_t s = 0;
+    for (uint32_t j = 0; j < nquad; ++j) {
+        mbar_wait(&c.bar[s], (c.phases >> s) & 1u);
+        c.phases ^= 1u << s;
+        const uint32_t cnt = min(4u, m - 4 * j);
+        float d = 0.0f;
+        if (g < cnt) d = quad_distance<DT>(p, c, c.ring + (size_t)(4 * s + g) * p.ix.row_bytes);
+        __syncwarp();
+        if (c.lane == 0 && j + stages < nquad) issue_quad(j + stages, s);
+        for (uint32_t e = 0; e < cnt; ++e) {
+            const float de = __shfl_sync(FULL_MASK, d, e * 8);
+            on_dist(c.todo[4 * j + e], de);
+        }
+        s = (s + 1 == stages) ? 0 : s + 1;
+    }
 }
 
 // Evaluates the distances of c.todo[0..m) in order, with up to nslot row fetches in flight.
 template <int DT, typename F>
-__device__ __forceinline__ void eval_list(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
+__device__ __forceinline__ void eval_list_single(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
     const uint32_t nslot = p.nslot;
     if (c.lane == 0) {
         uint32_t pre = m < nslot ? m : nslot;
@@ -112,6 +241,14 @@ __device__ __forceinline__ void eval_list(const SearchParams& p, WarpCtx& c, uin
         on_dist(id, d);
         slot = (slot + 1 == nslot) ? 0 : slot + 1;
     }
+}
+
+template <int DT, typename F>
+__device__ __forceinline__ void eval_list(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
+    if (p.quad)
+        eval_list_quad<DT>(p, c, m, on_dist);
+    else
+        eval_list_single<DT>(p, c, m, on_dist);
 }
 
 // Reads an adjacency row (padded with INVALID) into c.todo, optionally filtering through the
@@ -158,6 +295,7 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
     c.ring = smem + p.off_ring;
     c.phases = 0;
     c.norm_a = 0.0f;
+    c.policy = make_evict_first_policy();
     const uint32_t lane = c.lane;
     if (lane == 0) {
         for (uint32_t i = 0; i < kMaxSlots; ++i) mbar_init(&c.bar[i], 1);
@@ -382,6 +520,11 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
 }
 
 // ---- host side ---------------------------------------------------------------------------------
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+    const char* v = std::getenv(name);
+    return v && *v ? (uint32_t)std::strtoul(v, nullptr, 10) : dflt;
+}
+
 static int32_t launch_search(const veles_index* ix, const float* q_d, uint32_t nq, uint32_t k, uint32_t ef,
                              uint32_t* ids_d, float* dist_d, uint32_t* cnt_d, uint32_t* stats_d, cudaStream_t st) {
     VELES_REQUIRE(ix->has_graph, "snapshot has no graph; build or load one first");
@@ -414,11 +557,26 @@ static int32_t launch_search(const veles_index* ix, const float* q_d, uint32_t n
     VELES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int sm_smem = 0;
     VELES_CUDA(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
-    // aim for 8 resident warps (queries) per SM, at least 2 ring slots
-    const uint32_t per_cta_target = (uint32_t)sm_smem / 8 - 1024;
+    // Quad path: four candidates per step (8 lanes each) when the row splits into 32-element blocks.
+    const bool can_quad = (ix->dtype == VELES_BIN1 && ix->dim % 128 == 0) ||
+                          (ix->dtype != VELES_BIN1 && ix->dim % 32 == 0 &&
+                           (ix->metric == VELES_COSINE || ix->metric == VELES_EUCLIDEAN || ix->metric == VELES_DOT));
+    p.quad = (can_quad && env_u32("VELES_SEARCH_QUAD", 1) != 0) ? 1 : 0;
+    p.evict_first = env_u32("VELES_SEARCH_EVICT_FIRST", 1) != 0 ? 1 : 0;
+    // resident warps (queries) per SM: fewer, fatter rings for the quad path (3 stages of 4 rows)
+    const uint32_t want_ctas = std::max(1u, env_u32("VELES_SEARCH_CTAS_PER_SM", p.quad ? 5 : 8));
+    const uint32_t per_cta_target = (uint32_t)sm_smem / want_ctas - 1024;
     uint32_t nslot = 2;
     if (per_cta_target > p.off_ring + 2 * ix->row_bytes) nslot = (per_cta_target - p.off_ring) / ix->row_bytes;
     nslot = std::min(std::max(nslot, 2u), kMaxSlots);
+    if (p.quad) {
+        nslot &= ~3u;
+        if (nslot < 8) nslot = 8;  // at least two stages
+        if (p.off_ring + nslot * ix->row_bytes > (uint32_t)max_smem) {
+            p.quad = 0;
+            nslot = 2;
+        }
+    }
     p.nslot = nslot;
     const uint32_t smem_bytes = p.off_ring + nslot * ix->row_bytes;
     VELES_REQUIRE((int)smem_bytes <= max_smem, "search needs %u bytes of shared memory per query (dim %u, ef %u); limit %d",
