@@ -210,8 +210,9 @@ __device__ __forceinline__ void eval_list_quad(const SearchParams& p, WarpCtx& c
         mbar_wait(&c.bar[s], (c.phases >> s) & 1u);
         c.phases ^= 1u << s;
         const uint32_t cnt = min(4u, m - 4 * j);
-        float d = 0.0f;
-        if (g < cnt) d = quad_distance<DT>(p, c, c.ring + (size_t)(4 * s + g) * p.ix.row_bytes);
+        // all 32 lanes run the shuffles; groups beyond a partial quad recompute row 0 and are ignored
+        const uint32_t gg = g < cnt ? g : 0;
+        const float d = quad_distance<DT>(p, c, c.ring + (size_t)(4 * s + gg) * p.ix.row_bytes);
         __syncwarp();
         if (c.lane == 0 && j + stages < nquad) issue_quad(j + stages, s);
         for (uint32_t e = 0; e < cnt; ++e) {
