@@ -1,0 +1,170 @@
+"""GPU parity for BM25 posting scan (index/bm25.rs:269-376), hybrid RRF (collection/search/text.rs:133-180)
+and FusionStrategy (fusion/strategy.rs:138-300) against the CPU oracle.  Scores are compared bit for bit
+(the bar in BASELINE.md is 1e-5 relative)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as vo
+from tests.gpu_util import bits_equal
+from velesdb_b200 import Bm25Index, Bm25Snapshot, FusionStrategy, hybrid_search, rrf_hybrid_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def zipf_corpus(n_docs, vocab, seed, s=1.07, lo=8, hi=120):
+    rng = np.random.default_rng(seed)
+    p = 1.0 / np.arange(1, vocab + 1) ** s
+    p /= p.sum()
+    lens = np.clip(np.exp(rng.normal(np.log(40), 0.5, n_docs)).astype(int), lo, hi)
+    return [rng.choice(vocab, size=l, p=p).astype(np.uint32) for l in lens], p
+
+
+def build_both(docs, k1=1.2, b=0.75):
+    o = vo.Bm25(k1, b)
+    tf_lists = {}
+    total = 0
+    for d, terms in enumerate(docs):
+        o.add_document_terms(d, terms)
+        total += len(terms)
+        u, c = np.unique(terms, return_counts=True)
+        for t, f in zip(u, c):
+            tf_lists.setdefault(int(t), []).append((d, int(f)))
+    n_terms = max(tf_lists) + 1
+    term_ptr = np.zeros(n_terms + 1, np.uint64)
+    pd, pt, df = [], [], np.zeros(n_terms, np.uint32)
+    for t in range(n_terms):
+        l = tf_lists.get(t, [])
+        df[t] = len(l)
+        pd += [x[0] for x in l]
+        pt += [x[1] for x in l]
+        term_ptr[t + 1] = len(pd)
+    doc_len = np.array([len(t) for t in docs], np.uint32)
+    snap = Bm25Snapshot(term_ptr, np.array(pd, np.uint32), np.array(pt, np.uint32), df, doc_len, len(docs), total, k1, b)
+    return o, snap
+
+
+@pytest.mark.parametrize("n_docs,vocab", [(300, 50), (20000, 2000)])
+def test_bm25_batch_bit_exact(n_docs, vocab):
+    docs, p = zipf_corpus(n_docs, vocab, seed=n_docs)
+    o, snap = build_both(docs)
+    rng = np.random.default_rng(1)
+    nq, k = 64, 20
+    q_ptr, q_terms = [0], []
+    for i in range(nq):
+        l = int(rng.integers(1, 7))
+        t = rng.choice(vocab, size=l, p=p).astype(np.uint32)
+        if i % 7 == 0:
+            t = np.concatenate([t, t[:1]])          # duplicate query term: scored again (bm25_tests.rs:270-281)
+        if i % 11 == 0:
+            t = np.concatenate([t, [0xFFFFFFFF]])   # term missing from the dictionary
+        q_terms += t.tolist()
+        q_ptr.append(len(q_terms))
+    docs_g, sc_g, cnt_g = snap.search_batch(q_ptr, q_terms, k)
+    oi, os_, oc = o.search_batch_terms(q_ptr, q_terms, k, threads=8)
+    assert np.array_equal(cnt_g, oc)
+    for i in range(nq):
+        c = int(cnt_g[i])
+        assert np.array_equal(docs_g[i, :c], oi[i, :c].astype(np.uint32)), i
+        assert bits_equal(sc_g[i, :c], os_[i, :c]), i
+        assert (docs_g[i, c:] == 0xFFFFFFFF).all()
+    assert cnt_g.max() == k
+
+
+def test_bm25_reference_known_answers_on_gpu():
+    # bm25_tests.rs:109-122, 160-179, 217-236, 270-281 through the host mirror
+    ix = Bm25Index()
+    ix.add_document(1, "rust programming language")
+    ix.add_document(2, "python programming language")
+    ix.add_document(3, "rust is fast")
+    r = ix.search("rust", 10)
+    assert sorted(x[0] for x in r) == [1, 3]
+    assert Bm25Index().search("rust", 10) == []
+    ix = Bm25Index()
+    for i in range(1, 101):
+        ix.add_document(i, f"document number {i} about rust")
+    assert len(ix.search("rust", 5)) == 5
+    ix = Bm25Index()
+    ix.add_document(1, "rust")
+    ix.add_document(2, "rust is a systems programming language that runs blazingly fast")
+    r = ix.search("rust", 10)
+    assert len(r) == 2 and r[0][0] == 1
+    ix = Bm25Index()
+    ix.add_document(1, "rust programming")
+    assert len(ix.search("rust rust rust", 10)) == 1
+    ix.add_document(1, "updated text")
+    assert len(ix) == 1 and ix.search("rust", 10) == []       # stale posting scores 0 and is filtered
+    assert ix.remove_document(1) and not ix.remove_document(1)
+    # same answers as the oracle, including the replaced-document df quirk
+    o, g = vo.Bm25(), Bm25Index()
+    for d, t in [(1, "alpha beta gamma"), (2, "beta beta delta"), (1, "gamma delta delta epsilon"), (3, "alpha")]:
+        o.add_document(d, t)
+        g.add_document(d, t)
+    for q in ("alpha", "beta delta", "gamma gamma epsilon", "zeta"):
+        oi, os_ = o.search(q, 5)
+        r = g.search(q, 5)
+        assert [x[0] for x in r] == oi.tolist() and bits_equal([x[1] for x in r], os_), q
+
+
+def test_rrf_hybrid_batch_bit_exact():
+    rng = np.random.default_rng(5)
+    nq, in_k, k = 200, 20, 10
+    vi = np.stack([rng.choice(60, in_k, replace=False) for _ in range(nq)]).astype(np.uint32)
+    ti = np.stack([rng.choice(60, in_k, replace=False) for _ in range(nq)]).astype(np.uint32)
+    vc = rng.integers(0, in_k + 1, nq).astype(np.uint32)
+    tc = rng.integers(0, in_k + 1, nq).astype(np.uint32)
+    for w in (0.5, 0.3, 1.0, 0.0, 7.0):
+        ids, sc, cnt = rrf_hybrid_batch(vi, vc, ti, tc, k, w)
+        for q in range(nq):
+            oi, os_ = vo.rrf_hybrid(vi[q, :vc[q]], ti[q, :tc[q]], k, w)
+            assert cnt[q] == len(oi)
+            assert np.array_equal(ids[q, :cnt[q]], oi.astype(np.uint32)), (w, q)
+            assert bits_equal(sc[q, :cnt[q]], os_)
+
+
+def sample_results():
+    return [[(1, 0.95), (2, 0.85), (3, 0.75), (4, 0.65)], [(2, 0.90), (1, 0.80), (5, 0.70), (3, 0.60)],
+            [(1, 0.92), (3, 0.82), (2, 0.72), (6, 0.62)]]
+
+
+def test_fusion_strategies_bit_exact():
+    # fusion/strategy_tests.rs:54-272 + random lists with in-list duplicates
+    rng = np.random.default_rng(2)
+    cases = [sample_results(), [[(1, 0.9), (2, 0.8)], [], [(1, 0.85), (3, 0.75)]], [[(1, 0.95), (2, 0.85), (3, 0.75)]]]
+    for _ in range(5):
+        cases.append([[(int(rng.integers(0, 40)), float(np.float32(rng.random()))) for _ in range(int(rng.integers(0, 50)))]
+                      for _ in range(int(rng.integers(1, 10)))])
+    strategies = [(FusionStrategy.Average(), (vo.AVERAGE, {})), (FusionStrategy.Maximum(), (vo.MAXIMUM, {})),
+                  (FusionStrategy.RRF(60), (vo.RRF, {"rrf_k": 60})), (FusionStrategy.RRF(1), (vo.RRF, {"rrf_k": 1})),
+                  (FusionStrategy.weighted(0.6, 0.3, 0.1), (vo.WEIGHTED, {"avg_w": 0.6, "max_w": 0.3, "hit_w": 0.1}))]
+    for lists in cases:
+        for st, (kind, kw) in strategies:
+            got = st.fuse(lists)
+            oi, os_ = vo.fuse(kind, lists, **kw)
+            assert [g[0] for g in got] == oi.tolist(), (kind, lists)
+            assert bits_equal([g[1] for g in got], os_)
+    assert FusionStrategy.RRF().fuse([]) == [] and FusionStrategy.Average().fuse([[], []]) == []
+    d1 = dict(FusionStrategy.RRF(60).fuse(sample_results()))[1]
+    assert d1 > 0.04
+
+
+def test_hybrid_search_end_to_end():
+    # Collection::hybrid_search (text.rs:113-203): vector top-2k + BM25 top-2k -> RRF -> top-k
+    from velesdb_b200 import DistanceMetric, HnswIndex
+    from tests.gpu_util import latent_data
+
+    n, dim, k = 400, 32, 5
+    x = latent_data(n, dim, seed=8)
+    words = ["alpha", "beta", "gamma", "delta", "epsilon", "zeta", "eta", "theta"]
+    rng = np.random.default_rng(3)
+    hx, tx, ob = HnswIndex(dim, DistanceMetric.Cosine), Bm25Index(), vo.Bm25()
+    for i in range(n):
+        hx.insert(i, x[i])
+        text = " ".join(rng.choice(words, size=int(rng.integers(2, 8))))
+        tx.add_document(i, text)
+        ob.add_document(i, text)
+    q = x[7] + 0.05
+    got = hybrid_search(hx, tx, q, "alpha gamma", k, 0.5)
+    vres = hx.search(q, 2 * k)
+    ti, _ = ob.search("alpha gamma", 2 * k)
+    oi, os_ = vo.rrf_hybrid([r[0] for r in vres], ti, k, 0.5)
+    assert [g[0] for g in got] == oi.tolist() and bits_equal([g[1] for g in got], os_)

@@ -1,0 +1,311 @@
+// bm25.cu -- batched BM25 posting scan: Bm25Index::search + score_document_fast
+// (index/bm25.rs:269-376) on an immutable device snapshot of the inverted index.
+//
+// Reference arithmetic kept exactly (all f32):
+//   avgdl    = total_len as f32 / doc_count as f32                              bm25.rs:281
+//   idf(t)   = ln((N - df + 0.5) / (df + 0.5) + 1.0), 0 when df == 0            bm25.rs:297-306 (host, logf)
+//   len_norm = 1.0 - b + b * doc_len / avgdl                                    bm25.rs:357-358
+//   score(d) = sum over query tokens IN QUERY ORDER (duplicates again) of
+//              idf * (tf * (k1 + 1.0)) / (tf + k1 * len_norm)                   bm25.rs:360-375
+//   keep score > 0; order by score descending (total order), ties by doc id ascending (the reference's
+//   tie order is hash/roaring iteration + select_nth_unstable, i.e. unspecified -- SURVEY 8a a19).
+//
+// Layout in HBM: postings CSR by term, doc ids ascending within a term, (doc u32, tf u32) in two
+// arrays; doc_len[doc]; idf[term]; and a skip table skip[term][r] = first posting of `term` whose doc
+// id is >= r * kRange, so a CTA that owns the doc-id range r of one query reads exactly its slice of
+// every posting list, coalesced, with no search.
+//
+// Kernel 1 (bm25_range_kernel): one CTA per (doc range, query).  A dense f32 accumulator for the
+// range lives in shared memory; the query's terms are applied one after another with a block
+// barrier in between, so every document receives its term contributions in query order (a document
+// occurs at most once per posting list: no intra-term conflicts, no atomics).  Warp 0 then extracts
+// the range's k best.  Kernel 2 merges the per-range lists of a query.
+#include <algorithm>
+#include <cmath>
+#include <memory>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace veles {
+constexpr uint32_t kRange = 8192;  // docs per CTA range: 32 KB of f32 accumulators
+}
+
+struct veles_bm25 {
+    uint32_t n_terms = 0, n_doc_slots = 0, n_ranges = 0;
+    uint64_t doc_count = 0, total_len = 0, n_postings = 0;
+    float k1 = 1.2f, b = 0.75f, avgdl = 0.0f;
+    veles::DevBuf term_ptr, post_doc, post_tf, doc_len, idf, skip;
+    mutable std::mutex mu;
+    mutable veles::DevBuf q_ptr_d, q_terms_d, partial_d, out_doc_d, out_score_d, out_cnt_d;
+};
+
+namespace veles {
+
+struct Bm25View {
+    const uint32_t* post_doc;
+    const uint32_t* post_tf;
+    const uint32_t* doc_len;
+    const float* idf;
+    const uint64_t* skip;  // n_terms x (n_ranges + 1)
+    uint32_t n_terms, n_ranges, n_doc_slots;
+    float k1, b, avgdl;
+};
+
+__global__ void __launch_bounds__(256) bm25_range_kernel(Bm25View v, const uint32_t* __restrict__ q_ptr,
+                                                         const uint32_t* __restrict__ q_terms, uint32_t k,
+                                                         uint64_t* __restrict__ partial) {
+    extern __shared__ __align__(16) uint8_t bm_smem[];
+    float* acc = reinterpret_cast<float*>(bm_smem);
+    uint64_t* res = reinterpret_cast<uint64_t*>(bm_smem + kRange * 4);
+    const uint32_t r = blockIdx.x, q = blockIdx.y;
+    const uint32_t base_doc = r * kRange;
+    for (uint32_t i = threadIdx.x; i < kRange; i += blockDim.x) acc[i] = 0.0f;
+    __syncthreads();
+    const uint32_t t0 = q_ptr[q], t1 = q_ptr[q + 1];
+    const float k1p1 = __fadd_rn(v.k1, 1.0f);
+    const float one_minus_b = __fsub_rn(1.0f, v.b);
+    bool touched = false;
+    for (uint32_t ti = t0; ti < t1; ++ti) {
+        const uint32_t term = q_terms[ti];
+        if (term >= v.n_terms) continue;  // unknown term: df = 0, contributes nothing
+        const float idf = v.idf[term];
+        const uint64_t lo = v.skip[(size_t)term * (v.n_ranges + 1) + r];
+        const uint64_t hi = v.skip[(size_t)term * (v.n_ranges + 1) + r + 1];
+        for (uint64_t p = lo + threadIdx.x; p < hi; p += blockDim.x) {
+            const uint32_t d = v.post_doc[p];
+            const float tf = (float)v.post_tf[p];
+            const float dl = (float)v.doc_len[d];
+            const float len_norm = __fadd_rn(one_minus_b, __fdiv_rn(__fmul_rn(v.b, dl), v.avgdl));
+            const float num = __fmul_rn(tf, k1p1);
+            const float den = __fadd_rn(tf, __fmul_rn(v.k1, len_norm));
+            const float contrib = __fdiv_rn(__fmul_rn(idf, num), den);
+            acc[d - base_doc] = __fadd_rn(acc[d - base_doc], contrib);
+        }
+        touched |= hi > lo;
+        __syncthreads();  // next term's contributions come after this term's, per document
+    }
+    // warp 0: the range's k best (score desc, doc asc) as ascending keys (~order(score) << 32 | doc)
+    if (threadIdx.x >= 32) return;
+    const uint32_t lane = threadIdx.x;
+    uint32_t len = 0;
+    uint64_t worst = ~0ull;
+    if (touched) {
+        const uint32_t lim = min(kRange, v.n_doc_slots - base_doc);
+        for (uint32_t i0 = 0; i0 < lim; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            uint64_t key = ~0ull;
+            if (i < lim) {
+                const float s = acc[i];
+                if (s > 0.0f) key = ((uint64_t)(~ord_key(s)) << 32) | (base_doc + i);
+            }
+            uint32_t msk = __ballot_sync(FULL_MASK, key < worst);
+            while (msk) {
+                const uint32_t src = __ffs(msk) - 1;
+                msk &= msk - 1;
+                const uint64_t kk = __shfl_sync(FULL_MASK, key, src);
+                if (kk >= worst) continue;
+                const uint32_t pos = lower_bound_warp(res, len, kk, lane);
+                if (len < k) {
+                    insert_at(res, pos, len + 1, kk, lane);
+                    ++len;
+                } else {
+                    insert_at(res, pos, len, kk, lane);
+                }
+                if (len == k) worst = res[k - 1];
+            }
+        }
+    }
+    __syncwarp();
+    uint64_t* out = partial + ((size_t)q * v.n_ranges + r) * k;
+    for (uint32_t j = lane; j < k; j += 32) out[j] = j < len ? res[j] : ~0ull;
+}
+
+// one warp per query: k smallest keys over its n_ranges x k partial keys
+__global__ void __launch_bounds__(32) bm25_merge_kernel(const uint64_t* __restrict__ partial, uint32_t n_ranges, uint32_t k,
+                                                        uint32_t* __restrict__ out_doc, float* __restrict__ out_score,
+                                                        uint32_t* __restrict__ out_cnt) {
+    extern __shared__ __align__(16) uint64_t mres[];
+    const uint32_t lane = threadIdx.x, q = blockIdx.x;
+    const uint64_t* src = partial + (size_t)q * n_ranges * k;
+    const uint32_t total = n_ranges * k;
+    uint32_t len = 0;
+    uint64_t worst = ~0ull;
+    for (uint32_t i0 = 0; i0 < total; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const uint64_t key = i < total ? src[i] : ~0ull;
+        uint32_t msk = __ballot_sync(FULL_MASK, key < worst);
+        while (msk) {
+            const uint32_t s = __ffs(msk) - 1;
+            msk &= msk - 1;
+            const uint64_t kk = __shfl_sync(FULL_MASK, key, s);
+            if (kk >= worst) continue;
+            const uint32_t pos = lower_bound_warp(mres, len, kk, lane);
+            if (len < k) {
+                insert_at(mres, pos, len + 1, kk, lane);
+                ++len;
+            } else {
+                insert_at(mres, pos, len, kk, lane);
+            }
+            if (len == k) worst = mres[k - 1];
+        }
+    }
+    __syncwarp();
+    for (uint32_t j = lane; j < k; j += 32) {
+        uint32_t doc = VELES_INVALID_ID;
+        float s = __uint_as_float(0x7fc00000u);
+        if (j < len) {
+            const uint64_t key = mres[j];
+            doc = (uint32_t)key;
+            s = ord_unkey(~(uint32_t)(key >> 32));
+        }
+        out_doc[(size_t)q * k + j] = doc;
+        out_score[(size_t)q * k + j] = s;
+    }
+    if (lane == 0) out_cnt[q] = len;
+}
+
+}  // namespace veles
+
+using namespace veles;
+
+extern "C" {
+
+int32_t veles_bm25_from_csr(uint32_t n_terms, const uint64_t* term_ptr, const uint32_t* post_doc,
+                            const uint32_t* post_tf, const uint32_t* df, uint32_t n_doc_slots, const uint32_t* doc_len,
+                            uint64_t doc_count, uint64_t total_len, float k1, float b, veles_bm25_t** out) {
+    VELES_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    VELES_REQUIRE(n_terms == 0 || (term_ptr && df), "term arrays are NULL");
+    VELES_REQUIRE(n_doc_slots == 0 || doc_len, "doc_len is NULL");
+    const uint64_t np = n_terms ? term_ptr[n_terms] : 0;
+    VELES_REQUIRE(np == 0 || (post_doc && post_tf), "posting arrays are NULL");
+    std::unique_ptr<veles_bm25> ix(new veles_bm25());
+    ix->n_terms = n_terms;
+    ix->n_doc_slots = n_doc_slots;
+    ix->n_ranges = std::max(1u, (n_doc_slots + kRange - 1) / kRange);
+    ix->doc_count = doc_count;
+    ix->total_len = total_len;
+    ix->n_postings = np;
+    ix->k1 = k1;
+    ix->b = b;
+    ix->avgdl = doc_count ? (float)total_len / (float)doc_count : 0.0f;  // bm25.rs:281
+    // idf on the host with logf, as f32::ln does (bm25.rs:297-306)
+    std::vector<float> idf(std::max(n_terms, 1u), 0.0f);
+    const float n = (float)doc_count;
+    for (uint32_t t = 0; t < n_terms; ++t) {
+        if (df[t] == 0) continue;
+        const float df_f = (float)df[t];
+        const float num = n - df_f + 0.5f;
+        const float den = df_f + 0.5f;
+        const float r = num / den + 1.0f;
+        idf[t] = std::log(r);
+    }
+    // skip table + validation (doc ids ascending within a term, < n_doc_slots, tf > 0)
+    const uint32_t nr = ix->n_ranges;
+    std::vector<uint64_t> skip((size_t)std::max(n_terms, 1u) * (nr + 1), 0);
+    for (uint32_t t = 0; t < n_terms; ++t) {
+        uint64_t p = term_ptr[t];
+        const uint64_t e = term_ptr[t + 1];
+        VELES_REQUIRE(e >= p, "term_ptr must be non-decreasing");
+        uint64_t* row = skip.data() + (size_t)t * (nr + 1);
+        uint32_t r = 0;
+        row[0] = p;
+        int64_t prev = -1;
+        for (; p < e; ++p) {
+            const uint32_t d = post_doc[p];
+            VELES_REQUIRE(d < n_doc_slots, "posting doc id %u out of range", d);
+            VELES_REQUIRE((int64_t)d > prev, "postings of term %u are not strictly ascending by doc id", t);
+            VELES_REQUIRE(post_tf[p] > 0, "posting with tf == 0 (term %u, doc %u)", t, d);
+            prev = d;
+            while (r < d / kRange) row[++r] = p;
+        }
+        while (r < nr) row[++r] = e;
+    }
+    VELES_TRY(ix->term_ptr.alloc(((size_t)n_terms + 1) * 8));
+    VELES_TRY(ix->post_doc.alloc(std::max<size_t>(np * 4, 16)));
+    VELES_TRY(ix->post_tf.alloc(std::max<size_t>(np * 4, 16)));
+    VELES_TRY(ix->doc_len.alloc(std::max<size_t>((size_t)n_doc_slots * 4, 16)));
+    VELES_TRY(ix->idf.alloc(idf.size() * 4));
+    VELES_TRY(ix->skip.alloc(skip.size() * 8));
+    if (np) {
+        VELES_CUDA(cudaMemcpy(ix->post_doc.p, post_doc, np * 4, cudaMemcpyHostToDevice));
+        VELES_CUDA(cudaMemcpy(ix->post_tf.p, post_tf, np * 4, cudaMemcpyHostToDevice));
+    }
+    if (n_doc_slots) VELES_CUDA(cudaMemcpy(ix->doc_len.p, doc_len, (size_t)n_doc_slots * 4, cudaMemcpyHostToDevice));
+    VELES_CUDA(cudaMemcpy(ix->idf.p, idf.data(), idf.size() * 4, cudaMemcpyHostToDevice));
+    VELES_CUDA(cudaMemcpy(ix->skip.p, skip.data(), skip.size() * 8, cudaMemcpyHostToDevice));
+    *out = ix.release();
+    return VELES_OK;
+}
+
+int32_t veles_bm25_free(veles_bm25_t* ix) {
+    delete ix;
+    return VELES_OK;
+}
+
+int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_ptr, const uint32_t* q_terms, uint32_t nq,
+                                uint32_t k, uint32_t* out_doc, float* out_score, uint32_t* out_counts, void* stream) {
+    VELES_REQUIRE(ix != nullptr, "index is NULL");
+    VELES_REQUIRE(nq == 0 || (q_term_ptr && out_doc && out_score && out_counts), "NULL buffer");
+    VELES_REQUIRE(k >= 1 && k <= 4096, "k must be in 1..4096, got %u", k);
+    if (nq == 0) return VELES_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> g(ix->mu);
+    const uint32_t n_qterms = q_term_ptr[nq];
+    VELES_REQUIRE(n_qterms == 0 || q_terms, "q_terms is NULL");
+    // Bm25Index::search returns nothing for an empty index (bm25.rs:275-278)
+    if (ix->doc_count == 0 || ix->n_postings == 0) {
+        for (uint32_t i = 0; i < nq; ++i) out_counts[i] = 0;
+        for (size_t i = 0; i < (size_t)nq * k; ++i) {
+            out_doc[i] = VELES_INVALID_ID;
+            out_score[i] = std::nanf("");
+        }
+        return VELES_OK;
+    }
+    VELES_TRY(ix->q_ptr_d.ensure(((size_t)nq + 1) * 4));
+    VELES_TRY(ix->q_terms_d.ensure(std::max<size_t>((size_t)n_qterms * 4, 16)));
+    VELES_TRY(ix->out_doc_d.ensure((size_t)nq * k * 4));
+    VELES_TRY(ix->out_score_d.ensure((size_t)nq * k * 4));
+    VELES_TRY(ix->out_cnt_d.ensure((size_t)nq * 4));
+    VELES_CUDA(cudaMemcpyAsync(ix->q_ptr_d.p, q_term_ptr, ((size_t)nq + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (n_qterms) VELES_CUDA(cudaMemcpyAsync(ix->q_terms_d.p, q_terms, (size_t)n_qterms * 4, cudaMemcpyHostToDevice, st));
+    Bm25View v;
+    v.post_doc = ix->post_doc.as<uint32_t>();
+    v.post_tf = ix->post_tf.as<uint32_t>();
+    v.doc_len = ix->doc_len.as<uint32_t>();
+    v.idf = ix->idf.as<float>();
+    v.skip = ix->skip.as<uint64_t>();
+    v.n_terms = ix->n_terms;
+    v.n_ranges = ix->n_ranges;
+    v.n_doc_slots = ix->n_doc_slots;
+    v.k1 = ix->k1;
+    v.b = ix->b;
+    v.avgdl = ix->avgdl;
+    const size_t smem1 = (size_t)kRange * 4 + (size_t)k * 8;
+    VELES_CUDA(cudaFuncSetAttribute(bm25_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    VELES_CUDA(cudaFuncSetAttribute(bm25_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(k * 8)));
+    // gridDim.y <= 65535: chunk the queries; the partial buffer is bounded to ~512 MiB per pass
+    const size_t per_q = (size_t)ix->n_ranges * k * 8;
+    const uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(nq, 32768), ((size_t)512 << 20) / per_q));
+    VELES_TRY(ix->partial_d.ensure((size_t)chunk * per_q));
+    for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
+        const uint32_t nn = std::min(chunk, nq - q0);
+        dim3 grid(ix->n_ranges, nn);
+        bm25_range_kernel<<<grid, 256, smem1, st>>>(v, ix->q_ptr_d.as<uint32_t>() + q0, ix->q_terms_d.as<uint32_t>(), k,
+                                                    ix->partial_d.as<uint64_t>());
+        bm25_merge_kernel<<<nn, 32, (size_t)k * 8, st>>>(ix->partial_d.as<uint64_t>(), ix->n_ranges, k,
+                                                         ix->out_doc_d.as<uint32_t>() + (size_t)q0 * k,
+                                                         ix->out_score_d.as<float>() + (size_t)q0 * k,
+                                                         ix->out_cnt_d.as<uint32_t>() + q0);
+        count_launch(2);
+        VELES_CUDA(cudaGetLastError());
+    }
+    VELES_CUDA(cudaMemcpyAsync(out_doc, ix->out_doc_d.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+    VELES_CUDA(cudaMemcpyAsync(out_score, ix->out_score_d.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+    VELES_CUDA(cudaMemcpyAsync(out_counts, ix->out_cnt_d.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    VELES_CUDA(cudaStreamSynchronize(st));
+    return VELES_OK;
+}
+
+}  // extern "C"

@@ -564,8 +564,10 @@ static int32_t launch_search(const veles_index* ix, const float* q_d, uint32_t n
                            (ix->metric == VELES_COSINE || ix->metric == VELES_EUCLIDEAN || ix->metric == VELES_DOT));
     p.quad = (can_quad && env_u32("VELES_SEARCH_QUAD", 1) != 0) ? 1 : 0;
     p.evict_first = env_u32("VELES_SEARCH_EVICT_FIRST", 1) != 0 ? 1 : 0;
-    // resident warps (queries) per SM: fewer, fatter rings for the quad path (3 stages of 4 rows)
-    const uint32_t want_ctas = std::max(1u, env_u32("VELES_SEARCH_CTAS_PER_SM", p.quad ? 5 : 8));
+    // resident warps (queries) per SM.  Measured on B200 (profiles/): every query of a 1024-batch must be
+    // resident at once (7 x 148 = 1036 slots) -- with fewer slots a second wave of queries starts late and
+    // the batch time nearly doubles; 7 CTAs leave room for 2 stages of 4 rows each.
+    const uint32_t want_ctas = std::max(1u, env_u32("VELES_SEARCH_CTAS_PER_SM", p.quad ? 7 : 8));
     const uint32_t per_cta_target = (uint32_t)sm_smem / want_ctas - 1024;
     uint32_t nslot = 2;
     if (per_cta_target > p.off_ring + 2 * ix->row_bytes) nslot = (per_cta_target - p.off_ring) / ix->row_bytes;

@@ -1,0 +1,102 @@
+"""Host-side mirror of ``FusionStrategy`` (crates/velesdb-core/src/fusion/strategy.rs) and of the RRF
+inside ``Collection::hybrid_search`` (collection/search/text.rs:113-203) over the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as nv
+
+
+class FusionError(ValueError):
+    pass
+
+
+class FusionStrategy:
+    AVERAGE, MAXIMUM, RRF_KIND, WEIGHTED = 0, 1, 2, 3
+
+    def __init__(self, kind, k=60, avg_weight=0.0, max_weight=0.0, hit_weight=0.0):
+        self.kind, self.k = kind, k
+        self.avg_weight, self.max_weight, self.hit_weight = avg_weight, max_weight, hit_weight
+
+    @staticmethod
+    def Average():
+        return FusionStrategy(FusionStrategy.AVERAGE)
+
+    @staticmethod
+    def Maximum():
+        return FusionStrategy(FusionStrategy.MAXIMUM)
+
+    @staticmethod
+    def RRF(k=60):
+        return FusionStrategy(FusionStrategy.RRF_KIND, k=k)
+
+    @staticmethod
+    def rrf_default():
+        return FusionStrategy.RRF(60)
+
+    @staticmethod
+    def weighted(avg_weight, max_weight, hit_weight):
+        """strategy.rs:88-122: weights must be non-negative and sum to 1 (+-0.001)."""
+        if min(avg_weight, max_weight, hit_weight) < 0:
+            raise FusionError("weights must be non-negative")
+        if abs(avg_weight + max_weight + hit_weight - 1.0) > 0.001:
+            raise FusionError("weights must sum to 1.0")
+        return FusionStrategy(FusionStrategy.WEIGHTED, avg_weight=avg_weight, max_weight=max_weight,
+                              hit_weight=hit_weight)
+
+    def fuse(self, results):
+        """results: [[(id, score), ...], ...] -> [(id, fused_score)] sorted score-descending."""
+        nv.init()
+        ptr = np.zeros(len(results) + 1, np.uint32)
+        ids, sc = [], []
+        for i, l in enumerate(results):
+            for d, s in l:
+                if not (0 <= d <= 0xFFFFFFFF):
+                    raise FusionError("device fusion handles 32-bit ids")
+                ids.append(d)
+                sc.append(s)
+            ptr[i + 1] = len(ids)
+        cap = max(len(ids), 1)
+        ia = np.array(ids or [0], np.uint32)
+        sa = np.array(sc or [0], np.float32)
+        oi = np.zeros(cap, np.uint32)
+        os_ = np.zeros(cap, np.float32)
+        cnt = C.c_uint32(0)
+        nv.check(nv.lib().veles_fuse(self.kind, nv.ptr(ptr), len(results), nv.ptr(ia), nv.ptr(sa), self.k,
+                                     self.avg_weight, self.max_weight, self.hit_weight, cap, nv.ptr(oi), nv.ptr(os_),
+                                     C.byref(cnt), None))
+        return [(int(oi[i]), float(os_[i])) for i in range(cnt.value)]
+
+
+def rrf_hybrid_batch(vec_ids, vec_cnt, txt_ids, txt_cnt, k, vector_weight=0.5):
+    """text.rs:133-180 for a batch: [nq, in_k] id lists with valid counts -> (ids, scores, counts)."""
+    nv.init()
+    vec_ids = np.ascontiguousarray(vec_ids, np.uint32)
+    txt_ids = np.ascontiguousarray(txt_ids, np.uint32)
+    nq, in_k = vec_ids.shape
+    assert txt_ids.shape == (nq, in_k)
+    vec_cnt = np.ascontiguousarray(vec_cnt, np.uint32)
+    txt_cnt = np.ascontiguousarray(txt_cnt, np.uint32)
+    oi = np.empty((nq, k), np.uint32)
+    os_ = np.empty((nq, k), np.float32)
+    oc = np.zeros(nq, np.uint32)
+    nv.check(nv.lib().veles_rrf_hybrid(nv.ptr(vec_ids), nv.ptr(vec_cnt), nv.ptr(txt_ids), nv.ptr(txt_cnt), nq, in_k,
+                                       float(vector_weight), k, nv.ptr(oi), nv.ptr(os_), nv.ptr(oc), None))
+    return oi, os_, oc
+
+
+def hybrid_search(index, text_index, vector_query, text_query, k, vector_weight=None):
+    """``Collection::hybrid_search`` (text.rs:113-203) minus the storage fetch: vector top-2k (Balanced) and
+    BM25 top-2k, fused by RRF on the device.  Ids are the external ids of ``index`` (must fit u32)."""
+    w = 0.5 if vector_weight is None else vector_weight
+    vres = index.search(vector_query, k * 2)
+    tres = text_index.search(text_query, k * 2)
+    in_k = max(2 * k, 1)
+    vi = np.full((1, in_k), nv.INVALID_ID, np.uint32)
+    ti = np.full((1, in_k), nv.INVALID_ID, np.uint32)
+    vi[0, :len(vres)] = [r[0] for r in vres]
+    ti[0, :len(tres)] = [r[0] for r in tres]
+    ids, sc, cnt = rrf_hybrid_batch(vi, [len(vres)], ti, [len(tres)], k, w)
+    return [(int(ids[0, j]), float(sc[0, j])) for j in range(int(cnt[0]))]
