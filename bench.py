@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--ef", type=int, default=64)
     ap.add_argument("--M", type=int, default=32)
-    ap.add_argument("--latent", type=int, default=32)
+    ap.add_argument("--latent", type=int, default=24)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
