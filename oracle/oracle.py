@@ -182,7 +182,7 @@ class Hnsw:
             raise RuntimeError("oracle: could not create index")
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:
             _lib.vo_hnsw_free(self._h)
             self._h = None
 
@@ -360,7 +360,7 @@ class Bm25:
         self.vocab = {}
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:
             _lib.vo_bm25_free(self._h)
             self._h = None
 
