@@ -198,6 +198,55 @@ static float wide32_avx(const float* a, const float* b, size_t len) {
 
 static bool g_force_scalar = false;  // tests flip this to cross-check AVX vs scalar emulation
 
+#if VO_HAVE_AVX2
+// simd_avx512.rs:271-352 in one pass: 12 accumulators (dot, |a|^2, |b|^2 x 4).  The three trees are
+// independent, so this has the same bits as three separate wide32<0> passes (the tests check it).
+static void cosine_parts_avx(const float* a, const float* b, size_t len, float& dot, float& na, float& nb) {
+    __m256 d0 = _mm256_setzero_ps(), d1 = d0, d2 = d0, d3 = d0;
+    __m256 x0 = d0, x1 = d0, x2 = d0, x3 = d0, y0 = d0, y1 = d0, y2 = d0, y3 = d0;
+    size_t simd_len = len / 32;
+    for (size_t it = 0; it < simd_len; ++it) {
+        const float* pa = a + it * 32;
+        const float* pb = b + it * 32;
+        __m256 a0 = _mm256_loadu_ps(pa), b0 = _mm256_loadu_ps(pb);
+        d0 = _mm256_fmadd_ps(a0, b0, d0);
+        x0 = _mm256_fmadd_ps(a0, a0, x0);
+        y0 = _mm256_fmadd_ps(b0, b0, y0);
+        __m256 a1 = _mm256_loadu_ps(pa + 8), b1 = _mm256_loadu_ps(pb + 8);
+        d1 = _mm256_fmadd_ps(a1, b1, d1);
+        x1 = _mm256_fmadd_ps(a1, a1, x1);
+        y1 = _mm256_fmadd_ps(b1, b1, y1);
+        __m256 a2 = _mm256_loadu_ps(pa + 16), b2 = _mm256_loadu_ps(pb + 16);
+        d2 = _mm256_fmadd_ps(a2, b2, d2);
+        x2 = _mm256_fmadd_ps(a2, a2, x2);
+        y2 = _mm256_fmadd_ps(b2, b2, y2);
+        __m256 a3 = _mm256_loadu_ps(pa + 24), b3 = _mm256_loadu_ps(pb + 24);
+        d3 = _mm256_fmadd_ps(a3, b3, d3);
+        x3 = _mm256_fmadd_ps(a3, a3, x3);
+        y3 = _mm256_fmadd_ps(b3, b3, y3);
+    }
+    dot = hsum8_avx(_mm256_add_ps(_mm256_add_ps(d0, d1), _mm256_add_ps(d2, d3)));
+    na = hsum8_avx(_mm256_add_ps(_mm256_add_ps(x0, x1), _mm256_add_ps(x2, x3)));
+    nb = hsum8_avx(_mm256_add_ps(_mm256_add_ps(y0, y1), _mm256_add_ps(y2, y3)));
+    size_t pos = simd_len * 32;
+    while (pos + 8 <= len) {
+        __m256 va = _mm256_loadu_ps(a + pos), vb = _mm256_loadu_ps(b + pos);
+        dot += hsum8_avx(_mm256_fmadd_ps(va, vb, _mm256_setzero_ps()));
+        na += hsum8_avx(_mm256_fmadd_ps(va, va, _mm256_setzero_ps()));
+        nb += hsum8_avx(_mm256_fmadd_ps(vb, vb, _mm256_setzero_ps()));
+        pos += 8;
+    }
+    while (pos < len) {
+        float ai = a[pos], bi = b[pos];
+        float p0 = ai * bi, p1 = ai * ai, p2 = bi * bi;
+        dot += p0;
+        na += p1;
+        nb += p2;
+        ++pos;
+    }
+}
+#endif
+
 template <int OP>
 static inline float wide32(const float* a, const float* b, size_t len, bool fma) {
 #if VO_HAVE_AVX2
@@ -256,6 +305,11 @@ static float euclidean_auto(const float* a, const float* b, size_t len, bool fma
 // exactly the dot-product tree applied to (a,b), (a,a), (b,b).
 static float cosine_similarity_auto(const float* a, const float* b, size_t len, bool fma) {
     float dot, na, nb;
+#if VO_HAVE_AVX2
+    if (len >= 16 && fma && !g_force_scalar) {
+        cosine_parts_avx(a, b, len, dot, na, nb);
+    } else
+#endif
     if (len >= 16) {
         dot = wide32<0>(a, b, len, fma);
         na = wide32<0>(a, a, len, fma);
@@ -427,6 +481,47 @@ struct DNGreater {
 // ---------------------------------------------------------------------------
 // NativeHnsw (graph.rs)
 // ---------------------------------------------------------------------------
+// FxHashSet<usize> stand-in (rustc-hash 2.1.1 is a multiply hash; only membership matters)
+struct FxSet {
+    std::vector<uint64_t> slots;
+    size_t mask, count = 0;
+    explicit FxSet(size_t cap_pow2 = 1024) : slots(cap_pow2, UINT64_MAX), mask(cap_pow2 - 1) {}
+    static inline size_t h(uint64_t k) { return (size_t)((k * 0xf1357aea2e62a9c5ull) >> 20); }
+    void grow() {
+        std::vector<uint64_t> old;
+        old.swap(slots);
+        slots.assign(old.size() * 2, UINT64_MAX);
+        mask = slots.size() - 1;
+        count = 0;
+        for (uint64_t k : old)
+            if (k != UINT64_MAX) insert(k);
+    }
+    bool insert(uint64_t k) {  // true if newly inserted
+        if ((count + 1) * 2 > slots.size()) grow();
+        size_t i = h(k) & mask;
+        while (slots[i] != UINT64_MAX) {
+            if (slots[i] == k) return false;
+            i = (i + 1) & mask;
+        }
+        slots[i] = k;
+        ++count;
+        return true;
+    }
+};
+
+// simd.rs:40-51 calculate_prefetch_distance, simd.rs:80-107 prefetch_vector (first cache line, T0)
+static inline size_t prefetch_distance(size_t dim) {
+    size_t raw = dim * 4 / 64;
+    return raw < 4 ? 4 : (raw > 16 ? 16 : raw);
+}
+static inline void prefetch_vector(const float* p) {
+#if VO_HAVE_AVX2
+    _mm_prefetch((const char*)p, _MM_HINT_T0);
+#else
+    (void)p;
+#endif
+}
+
 struct SearchStats {
     uint64_t ndc0 = 0;       // distance evaluations on layer 0 (incl. entry point)
     uint64_t hops0 = 0;      // layer-0 expansions (pops that were not the break)
@@ -508,8 +603,9 @@ struct Hnsw {
     // order of the max-heap, then a stable sort by distance.
     std::vector<DN> search_layer(const float* q, const std::vector<uint64_t>& entries, size_t ef, uint32_t layer,
                                  SearchStats* st) const {
-        std::unordered_set<uint64_t> visited;
+        FxSet visited;
         RustHeap<DN, DNGreater> cand;  // min-heap
+        const size_t pd = prefetch_distance(dim);
         RustHeap<DN, DNLess> res;      // max-heap
         for (uint64_t e : entries) {
             float d = dist(q, vec(e));
@@ -527,8 +623,14 @@ struct Hnsw {
                 st->hops0++;
                 st->adj0 += nb.size();
             }
-            for (uint32_t x : nb) {
-                if (visited.insert(x).second) {
+            // graph.rs:480-497: software prefetch of upcoming neighbour vectors for dim >= 384
+            if (dim >= 384 && nb.size() > pd)
+                for (size_t i = 0; i < pd; ++i)
+                    if (nb[i] < n) prefetch_vector(vec(nb[i]));
+            for (size_t i = 0; i < nb.size(); ++i) {
+                const uint32_t x = nb[i];
+                if (dim >= 384 && i + pd < nb.size() && nb[i + pd] < n) prefetch_vector(vec(nb[i + pd]));
+                if (visited.insert(x)) {
                     float d = dist(q, vec(x));
                     if (st) st->ndc0++;
                     float f = res.empty() ? std::numeric_limits<float>::max() : res.peek().d;
