@@ -91,7 +91,14 @@ def check(status):
 _initialised = {}
 
 
-def init(device=0):
+def init(device=None):
+    """Selects the CUDA device for this thread (veles_init).  ``init()`` with no argument only makes sure
+    *some* device has been initialised and never switches away from the one chosen earlier -- the
+    multi-GPU runtime calls ``init(local_rank)`` once and every later implicit ``init()`` must keep it."""
+    if device is None:
+        if _initialised:
+            return
+        device = 0
     if not _initialised.get(device):
         check(lib().veles_init(device))
         _initialised[device] = True
