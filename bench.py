@@ -319,7 +319,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "hnsw_search_kernel<f32>",
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "ndc_per_query": float(ndc.mean()), "expansions_per_query": float(hops0.mean())}}
+                         "ndc_per_query": float(ndc.mean()), "ndc_max": int(ndc.max()),
+                         "ndc_p99": float(np.percentile(ndc, 99)), "expansions_per_query": float(hops0.mean())}}
     if rank == 0 and not a.no_cpu_baseline:
         v, oi, passes = cpu_run(a.cpu_seconds, ncores)
         par = bool(np.array_equal(oi.astype(np.int32), got))
