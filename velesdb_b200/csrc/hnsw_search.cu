@@ -252,6 +252,29 @@ __device__ __forceinline__ void eval_list(const SearchParams& p, WarpCtx& c, uin
         eval_list_single<DT>(p, c, m, on_dist);
 }
 
+// One 32-id chunk of an adjacency row (lane holds `nid`): optional visited test-and-set, then ordered
+// compaction into c.todo.  Returns false once the row's INVALID padding was reached.
+template <bool FILTER>
+__device__ __forceinline__ bool gather_chunk(WarpCtx& c, uint32_t nid, uint32_t* vis, uint32_t* vlog, uint32_t logn,
+                                             uint32_t& m, uint32_t& read) {
+    const bool valid = nid != VELES_INVALID_ID;
+    bool keep = valid;
+    if (FILTER && valid) {
+        const uint32_t bit = 1u << (nid & 31);
+        keep = (atomicOr(&vis[nid >> 5], bit) & bit) == 0;
+    }
+    const uint32_t vmask = __ballot_sync(FULL_MASK, valid);
+    const uint32_t kmask = __ballot_sync(FULL_MASK, keep);
+    if (keep) {
+        const uint32_t pos = m + __popc(kmask & ((1u << c.lane) - 1u));
+        c.todo[pos] = nid;
+        if (FILTER && logn + pos < kLogCap) vlog[logn + pos] = nid;
+    }
+    m += __popc(kmask);
+    read += __popc(vmask);
+    return vmask == FULL_MASK;
+}
+
 // Reads an adjacency row (padded with INVALID) into c.todo, optionally filtering through the
 // visited bitmap.  Returns the number of ids kept; `read` gets the number of valid ids in the row.
 template <bool FILTER>
@@ -260,29 +283,14 @@ __device__ __forceinline__ uint32_t gather_row(const SearchParams& p, WarpCtx& c
                                                uint32_t& read) {
     uint32_t m = 0;
     read = 0;
-    for (uint32_t base = 0; base < stride; base += 32) {
-        const uint32_t nid = row[base + c.lane];
-        const bool valid = nid != VELES_INVALID_ID;
-        bool keep = valid;
-        if (FILTER && valid) {
-            const uint32_t bit = 1u << (nid & 31);
-            keep = (atomicOr(&vis[nid >> 5], bit) & bit) == 0;
-        }
-        const uint32_t vmask = __ballot_sync(FULL_MASK, valid);
-        const uint32_t kmask = __ballot_sync(FULL_MASK, keep);
-        if (keep) {
-            const uint32_t pos = m + __popc(kmask & ((1u << c.lane) - 1u));
-            c.todo[pos] = nid;
-            if (FILTER && logn + pos < kLogCap) vlog[logn + pos] = nid;
-        }
-        m += __popc(kmask);
-        read += __popc(vmask);
-        if (vmask != FULL_MASK) break;  // padding reached
-    }
+    for (uint32_t base = 0; base < stride; base += 32)
+        if (!gather_chunk<FILTER>(c, row[base + c.lane], vis, vlog, logn, m, read)) break;
     if (FILTER) logn += m;
     __syncwarp();
     return m;
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int DT>
 __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
@@ -373,7 +381,23 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
             }
 
             // ---- layer 0 beam (graph.rs:266, 438-520) ----
-            uint32_t logn = 0, tlen = 0, scan_from = 0;
+            uint32_t logn = 0, tlen = 0;
+            uint32_t nxt = 0;  // index of the first unexpanded entry of res (== len when there is none)
+            // Next-candidate prefetch (the GPU counterpart of graph.rs:480-497): as soon as a node becomes the
+            // first unexpanded entry its adjacency row is loaded into registers (two ids per lane) and, a few
+            // distance evaluations later, the visited-bitmap words of its neighbours are pulled into L2.  If
+            // that node is still the one popped next, its expansion starts without the two dependent DRAM
+            // round trips.  Purely read-only speculation: results do not change.
+            const bool can_pre = p.ix.stride0 <= 64;
+            uint32_t pre_node = VELES_INVALID_ID, pre_a = VELES_INVALID_ID, pre_b = VELES_INVALID_ID, pre_age = 0;
+            auto learn = [&](uint32_t x) {
+                if (!can_pre || x == pre_node) return;
+                pre_node = x;
+                const uint32_t* row = p.ix.adj0 + (size_t)x * p.ix.stride0;
+                pre_a = row[lane];
+                pre_b = p.ix.stride0 > 32 ? row[32 + lane] : VELES_INVALID_ID;
+                pre_age = 1;
+            };
             {
                 const uint32_t bit = 1u << (cur & 31);
                 if (lane == 0) {
@@ -393,51 +417,62 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
             for (;;) {
                 // pop the closest candidate: first unexpanded entry of res, else the smallest tie
                 uint32_t cnode = VELES_INVALID_ID;
-                {
-                    uint32_t found = VELES_INVALID_ID;
-                    for (uint32_t base = scan_from & ~31u; base < len; base += 32) {
+                if (nxt < len) {
+                    const uint64_t key = c.res[nxt];
+                    cnode = key_id(key);
+                    __syncwarp();
+                    if (lane == 0) c.res[nxt] = key | 1ull;
+                    __syncwarp();
+                    // advance to the following unexpanded entry
+                    uint32_t found = len;
+                    for (uint32_t base = (nxt + 1) & ~31u; base < len; base += 32) {
                         const uint32_t i = base + lane;
-                        const bool un = i < len && i >= scan_from && (c.res[i] & 1ull) == 0;
+                        const bool un = i < len && i > nxt && (c.res[i] & 1ull) == 0;
                         const uint32_t msk = __ballot_sync(FULL_MASK, un);
                         if (msk) {
                             found = base + __ffs(msk) - 1;
                             break;
                         }
                     }
-                    if (found != VELES_INVALID_ID) {
-                        const uint64_t key = c.res[found];
-                        cnode = key_id(key);
-                        __syncwarp();
-                        if (lane == 0) c.res[found] = key | 1ull;
-                        scan_from = found + 1;
-                        __syncwarp();
-                    } else if (tlen > 0) {
-                        // every tie has dist == worst result dist: popped without the break (graph.rs:474)
-                        uint64_t best = ~0ull;
-                        for (uint32_t i = lane; i < tlen; i += 32) {
-                            const uint64_t v = tie[i];
-                            best = v < best ? v : best;
-                        }
-                        best = warp_min_u64(best);
-                        cnode = key_id(best);
-                        // remove it: move the last entry into its place
-                        const uint64_t lastv = tie[tlen - 1];
-                        __syncwarp();
-                        for (uint32_t i = lane; i < tlen; i += 32)
-                            if (tie[i] == best) tie[i] = lastv;
-                        --tlen;
-                        __syncwarp();
-                    } else {
-                        break;  // candidates exhausted, or everything left is farther than the worst result
+                    nxt = found;
+                } else if (tlen > 0) {
+                    // every tie has dist == worst result dist: popped without the break (graph.rs:474)
+                    uint64_t best = ~0ull;
+                    for (uint32_t i = lane; i < tlen; i += 32) {
+                        const uint64_t v = tie[i];
+                        best = v < best ? v : best;
                     }
+                    best = warp_min_u64(best);
+                    cnode = key_id(best);
+                    // remove it: move the last entry into its place
+                    const uint64_t lastv = tie[tlen - 1];
+                    __syncwarp();
+                    for (uint32_t i = lane; i < tlen; i += 32)
+                        if (tie[i] == best) tie[i] = lastv;
+                    --tlen;
+                    __syncwarp();
+                } else {
+                    break;  // candidates exhausted, or everything left is farther than the worst result
                 }
-                // expand cnode
-                uint32_t nread = 0;
-                const uint32_t m =
-                    gather_row<true>(p, c, p.ix.adj0 + (size_t)cnode * p.ix.stride0, p.ix.stride0, vis, vlog, logn, nread);
+                // expand cnode: adjacency from the prefetch registers when the prediction held
+                uint32_t nread = 0, m = 0;
+                if (can_pre && cnode == pre_node) {
+                    if (gather_chunk<true>(c, pre_a, vis, vlog, logn, m, nread) && p.ix.stride0 > 32)
+                        gather_chunk<true>(c, pre_b, vis, vlog, logn, m, nread);
+                    logn += m;
+                    __syncwarp();
+                } else {
+                    m = gather_row<true>(p, c, p.ix.adj0 + (size_t)cnode * p.ix.stride0, p.ix.stride0, vis, vlog, logn, nread);
+                }
                 ++hops0;
                 ndc0 += m;
+                if (nxt < len) learn(key_id(c.res[nxt]));
                 eval_list<DT>(p, c, m, [&](uint32_t id, float d) {
+                    if (pre_age != 0 && ++pre_age == 10) {  // the row landed long ago: warm its bitmap words
+                        if (pre_a != VELES_INVALID_ID) prefetch_l2(&vis[pre_a >> 5]);
+                        if (pre_b != VELES_INVALID_ID) prefetch_l2(&vis[pre_b >> 5]);
+                        pre_age = 0;
+                    }
                     const float worst = key_dist(c.res[len - 1]);
                     if (d < worst || len < ef) {
                         const uint64_t key = make_key(d, id);
@@ -445,6 +480,14 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
                         if (len < ef) {
                             insert_at(c.res, pos, len + 1, key, lane);
                             ++len;
+                            if (pos <= nxt) {
+                                nxt = pos;
+                                learn(id);
+                            } else if (nxt == len - 1) {
+                                // there was no unexpanded entry: the new one (at pos) is now the first
+                                nxt = pos;
+                                learn(id);
+                            }
                         } else {
                             const uint64_t ev = c.res[len - 1];
                             __syncwarp();
@@ -478,8 +521,15 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
                                 }
                                 __syncwarp();
                             }
+                            // index of the first unexpanded entry after the shift (the last entry fell off)
+                            if (pos <= nxt) {
+                                nxt = pos;
+                                learn(id);
+                            } else if (nxt >= len) {
+                                nxt = pos;
+                                learn(id);
+                            }
                         }
-                        if (pos < scan_from) scan_from = pos;
                     }
                 });
                 __syncwarp();
