@@ -45,17 +45,15 @@ __global__ void __launch_bounds__(kWarps * 32) bf_tile_kernel(IndexView ix, cons
     }
     __syncthreads();
     const uint32_t main_len = dim & ~31u;
+    const bool has_tail = main_len != dim;
     const bool l2 = ix.metric == VELES_EUCLIDEAN;
     const uint64_t n = ix.n;
     const uint64_t tiles = (n + kRT - 1) / kRT;
     for (uint64_t tile = blockIdx.x * (uint64_t)kWarps + warp; tile < tiles; tile += (uint64_t)gridDim.x * kWarps) {
         const uint64_t r0 = tile * kRT;
-        const TB* rows[kRT];
-#pragma unroll
-        for (int r = 0; r < kRT; ++r) {
-            uint64_t rr = r0 + r < n ? r0 + r : n - 1;
-            rows[r] = reinterpret_cast<const TB*>(ix.vecs + rr * ix.row_bytes);
-        }
+        // rows past the end alias the last row; their results are simply not stored
+        const uint8_t* base = ix.vecs + r0 * ix.row_bytes;
+        const uint64_t last_off = (n - 1 - r0) * (uint64_t)ix.row_bytes;
         float acc[kRT][kQT];
 #pragma unroll
         for (int r = 0; r < kRT; ++r)
@@ -64,7 +62,10 @@ __global__ void __launch_bounds__(kWarps * 32) bf_tile_kernel(IndexView ix, cons
         for (uint32_t i = lane; i < main_len; i += 32) {
             float x[kRT], q[kQT];
 #pragma unroll
-            for (int r = 0; r < kRT; ++r) x[r] = load_elem(rows[r], i);
+            for (int r = 0; r < kRT; ++r) {
+                const uint64_t off = min((uint64_t)r * ix.row_bytes, last_off);
+                x[r] = load_elem(reinterpret_cast<const TB*>(base + off), i);
+            }
 #pragma unroll
             for (int t = 0; t < kQT; ++t) q[t] = qs[(size_t)t * dim + i];
             if (l2) {
@@ -84,21 +85,21 @@ __global__ void __launch_bounds__(kWarps * 32) bf_tile_kernel(IndexView ix, cons
         }
 #pragma unroll
         for (int r = 0; r < kRT; ++r) {
-            if (r0 + r >= n) continue;
+            const bool row_ok = r0 + r < n;
+            const uint64_t off = min((uint64_t)r * ix.row_bytes, last_off);
+            const TB* rowp = reinterpret_cast<const TB*>(base + off);
             float nb = 0.0f;
-            if (ix.metric == VELES_COSINE)
-                nb = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(rows[r]) + ix.norm_off);
+            if (ix.metric == VELES_COSINE) nb = *reinterpret_cast<const float*>(base + off + ix.norm_off);
 #pragma unroll
             for (int t = 0; t < kQT; ++t) {
                 float s = warp_tree_sum32(acc[r][t]);
-                if (t >= (int)nqt) continue;
                 const float* q = qs + (size_t)t * dim;
                 float v;
                 if (l2) {
-                    s = warp_tree_tail<1>(s, q, rows[r], dim, lane);
+                    if (has_tail) s = warp_tree_tail<1>(s, q, rowp, dim, lane);
                     v = __fsqrt_rn(s);
                 } else {
-                    s = warp_tree_tail<0>(s, q, rows[r], dim, lane);
+                    if (has_tail) s = warp_tree_tail<0>(s, q, rowp, dim, lane);
                     if (ix.metric == VELES_COSINE) {
                         float sim = cosine_from_parts(s, qnorm[t], nb);
                         v = as_value ? sim : __fsub_rn(1.0f, sim);
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(kWarps * 32) bf_tile_kernel(IndexView ix, cons
                         v = as_value ? s : -s;
                     }
                 }
-                if (lane == 0) scores[(size_t)(qbase - q0 + t) * n + (r0 + r)] = v;
+                if (lane == 0 && row_ok && t < (int)nqt) scores[(size_t)(qbase - q0 + t) * n + (r0 + r)] = v;
             }
         }
     }
