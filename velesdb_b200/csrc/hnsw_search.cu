@@ -50,6 +50,8 @@ struct SearchParams {
     uint32_t nslot;       // ring slots (multiple of 4 when quad != 0)
     uint32_t quad;        // 1: evaluate four candidates per step (8 lanes each), needs dim % 32 == 0
     uint32_t evict_first; // 1: vector rows are fetched with an L2 evict-first policy
+    uint32_t peek;        // 1: speculative read-only visited test of the predicted next candidate's neighbours
+    uint32_t row_prefetch; // rows of the predicted next expansion warmed into L2 (0 = off)
     // shared-memory carve (bytes from base)
     uint32_t off_res, off_todo, off_q, off_ring;
 };
@@ -290,6 +292,24 @@ __device__ __forceinline__ uint32_t gather_row(const SearchParams& p, WarpCtx& c
     return m;
 }
 
+// Same as gather_chunk<true> but with the visited word already known (`word`): no waiting on the atomic.
+__device__ __forceinline__ void gather_peeked(WarpCtx& c, uint32_t nid, uint32_t word, uint32_t* vis, uint32_t* vlog,
+                                              uint32_t logn, uint32_t& m, uint32_t& read) {
+    const bool valid = nid != VELES_INVALID_ID;
+    const uint32_t bit = 1u << (nid & 31);
+    const bool keep = valid && (word & bit) == 0;
+    if (keep) atomicOr(&vis[nid >> 5], bit);  // result unused: compiles to a fire-and-forget RED
+    const uint32_t vmask = __ballot_sync(FULL_MASK, valid);
+    const uint32_t kmask = __ballot_sync(FULL_MASK, keep);
+    if (keep) {
+        const uint32_t pos = m + __popc(kmask & ((1u << c.lane) - 1u));
+        c.todo[pos] = nid;
+        if (logn + pos < kLogCap) vlog[logn + pos] = nid;
+    }
+    m += __popc(kmask);
+    read += __popc(vmask);
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int DT>
@@ -390,6 +410,8 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
             // round trips.  Purely read-only speculation: results do not change.
             const bool can_pre = p.ix.stride0 <= 64;
             uint32_t pre_node = VELES_INVALID_ID, pre_a = VELES_INVALID_ID, pre_b = VELES_INVALID_ID, pre_age = 0;
+            uint32_t pre_va = 0, pre_vb = 0;  // visited words of pre_a / pre_b, peeked read-only
+            bool pre_peeked = false;          // true once pre_va / pre_vb are valid for the *next* expansion
             auto learn = [&](uint32_t x) {
                 if (!can_pre || x == pre_node) return;
                 pre_node = x;
@@ -397,6 +419,7 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
                 pre_a = row[lane];
                 pre_b = p.ix.stride0 > 32 ? row[32 + lane] : VELES_INVALID_ID;
                 pre_age = 1;
+                pre_peeked = false;
             };
             {
                 const uint32_t bit = 1u << (cur & 31);
@@ -456,7 +479,14 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
                 }
                 // expand cnode: adjacency from the prefetch registers when the prediction held
                 uint32_t nread = 0, m = 0;
-                if (can_pre && cnode == pre_node) {
+                if (can_pre && cnode == pre_node && pre_peeked) {
+                    // The visited words were read after the previous expansion's marking and nothing has been
+                    // marked since: the peek is exact.  Mark now without waiting for the atomics' results.
+                    gather_peeked(c, pre_a, pre_va, vis, vlog, logn, m, nread);
+                    if (p.ix.stride0 > 32) gather_peeked(c, pre_b, pre_vb, vis, vlog, logn, m, nread);
+                    logn += m;
+                    __syncwarp();
+                } else if (can_pre && cnode == pre_node) {
                     if (gather_chunk<true>(c, pre_a, vis, vlog, logn, m, nread) && p.ix.stride0 > 32)
                         gather_chunk<true>(c, pre_b, vis, vlog, logn, m, nread);
                     logn += m;
@@ -466,12 +496,43 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
                 }
                 ++hops0;
                 ndc0 += m;
+                pre_peeked = false;  // this expansion's marking invalidates any earlier peek
                 if (nxt < len) learn(key_id(c.res[nxt]));
                 eval_list<DT>(p, c, m, [&](uint32_t id, float d) {
-                    if (pre_age != 0 && ++pre_age == 10) {  // the row landed long ago: warm its bitmap words
-                        if (pre_a != VELES_INVALID_ID) prefetch_l2(&vis[pre_a >> 5]);
-                        if (pre_b != VELES_INVALID_ID) prefetch_l2(&vis[pre_b >> 5]);
-                        pre_age = 0;
+                    if (pre_age != 0) {
+                        ++pre_age;
+                        if (pre_age == 10) {  // the adjacency row landed long ago: fetch its visited words
+                            if (p.peek) {
+                                pre_va = pre_a != VELES_INVALID_ID ? __ldcg(&vis[pre_a >> 5]) : 0u;
+                                pre_vb = pre_b != VELES_INVALID_ID ? __ldcg(&vis[pre_b >> 5]) : 0u;
+                            } else {
+                                if (pre_a != VELES_INVALID_ID) prefetch_l2(&vis[pre_a >> 5]);
+                                if (pre_b != VELES_INVALID_ID) prefetch_l2(&vis[pre_b >> 5]);
+                                pre_age = 0;
+                            }
+                        } else if (pre_age == 16) {  // the words landed: the peek is usable; warm the first rows
+                            pre_peeked = true;
+                            pre_age = 0;
+                            if (p.row_prefetch) {
+                                const bool ka = pre_a != VELES_INVALID_ID && !((pre_va >> (pre_a & 31)) & 1u);
+                                const bool kb = pre_b != VELES_INVALID_ID && !((pre_vb >> (pre_b & 31)) & 1u);
+                                uint32_t ma = __ballot_sync(FULL_MASK, ka), mb = __ballot_sync(FULL_MASK, kb);
+                                for (uint32_t r = 0; r < p.row_prefetch && (ma | mb); ++r) {
+                                    uint32_t nid;
+                                    if (ma) {
+                                        const uint32_t src = __ffs(ma) - 1;
+                                        ma &= ma - 1;
+                                        nid = __shfl_sync(FULL_MASK, pre_a, src);
+                                    } else {
+                                        const uint32_t src = __ffs(mb) - 1;
+                                        mb &= mb - 1;
+                                        nid = __shfl_sync(FULL_MASK, pre_b, src);
+                                    }
+                                    if (lane * 128u < p.ix.row_bytes)
+                                        prefetch_l2(p.ix.vecs + (size_t)nid * p.ix.row_bytes + lane * 128u);
+                                }
+                            }
+                        }
                     }
                     const float worst = key_dist(c.res[len - 1]);
                     if (d < worst || len < ef) {
@@ -614,6 +675,8 @@ static int32_t launch_search(const veles_index* ix, const float* q_d, uint32_t n
                            (ix->metric == VELES_COSINE || ix->metric == VELES_EUCLIDEAN || ix->metric == VELES_DOT));
     p.quad = (can_quad && env_u32("VELES_SEARCH_QUAD", 1) != 0) ? 1 : 0;
     p.evict_first = env_u32("VELES_SEARCH_EVICT_FIRST", 1) != 0 ? 1 : 0;
+    p.peek = env_u32("VELES_SEARCH_PEEK", 1) != 0 ? 1 : 0;
+    p.row_prefetch = std::min(32u, env_u32("VELES_SEARCH_ROW_PREFETCH", 8));
     // resident warps (queries) per SM.  Measured on B200 (profiles/): every query of a 1024-batch must be
     // resident at once (7 x 148 = 1036 slots) -- with fewer slots a second wave of queries starts late and
     // the batch time nearly doubles; 7 CTAs leave room for 2 stages of 4 rows each.
