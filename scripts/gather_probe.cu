@@ -48,8 +48,8 @@ int main(int argc, char** argv) {
     uint8_t* d; float* sink;
     cudaMalloc(&d, n * row); cudaMemset(d, 1, n * row); cudaMalloc(&sink, 4);
     printf("ctas/SM stages x rows : GB/s\n");
-    for (int cfg = 0; cfg < 7; ++cfg) {
-        uint32_t ctas[] = {7, 7, 5, 4, 8, 14, 3}, stages[] = {2, 8, 3, 4, 7, 1, 5}, per[] = {4, 1, 4, 4, 1, 4, 4};
+    for (int cfg = 0; cfg < 12; ++cfg) {
+        uint32_t ctas[] = {7, 7, 5, 4, 8, 14, 3, 7, 4, 2, 1, 7}, stages[] = {2, 8, 3, 4, 7, 1, 5, 1, 1, 1, 1, 2}, per[] = {4, 1, 4, 4, 1, 4, 4, 4, 4, 4, 4, 2};
         uint32_t grid = ctas[cfg] * 148, rows = 3584;
         size_t smem = 128 + (size_t)stages[cfg] * per[cfg] * row;
         cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -192,67 +192,74 @@ __device__ __forceinline__ float quad_distance(const SearchParams& p, const Warp
     }
 }
 
-// Evaluates c.todo[0..m) in order, four rows per step; stage s uses slots 4s..4s+3 and barrier s.
-template <int DT, typename F>
-__device__ __forceinline__ void eval_list_quad(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
-    const uint32_t stages = p.nslot >> 2;
-    const uint32_t nquad = (m + 3) >> 2;
-    auto issue_quad = [&](uint32_t j, uint32_t s) {
-        const uint32_t cnt = min(4u, m - 4 * j);
-        mbar_expect_tx(&c.bar[s], cnt * p.ix.row_bytes);
-        for (uint32_t g = 0; g < cnt; ++g) copy_row(p, c, 4 * s + g, c.todo[4 * j + g], &c.bar[s]);
-    };
-    if (c.lane == 0) {
-        const uint32_t pre = nquad < stages ? nquad : stages;
-        for (uint32_t j = 0; j < pre; ++j) issue_quad(j, j);
+// Evaluates the distances of c.todo[0..m) in order.  Iterator style (no closures, so the caller's state
+// stays in registers):   ListEval<DT> ev; ev.begin(p, c, m);  while (ev.next(p, c, id, d)) { ... }
+//  * quad mode: four rows per step; stage s uses slots 4s..4s+3 and barrier s, the next stage is in flight
+//    while the current one is computed;
+//  * single mode: one row per step with up to nslot row fetches in flight.
+template <int DT>
+struct ListEval {
+    uint32_t m, j, e, cnt, s, steps;
+    float d;
+    __device__ __forceinline__ void issue_quad(const SearchParams& p, const WarpCtx& c, uint32_t jj, uint32_t ss) const {
+        const uint32_t n4 = min(4u, m - 4 * jj);
+        mbar_expect_tx(&c.bar[ss], n4 * p.ix.row_bytes);
+        for (uint32_t g = 0; g < n4; ++g) copy_row(p, c, 4 * ss + g, c.todo[4 * jj + g], &c.bar[ss]);
     }
-    const uint32_t g = c.lane >> 3;
-    uint32_t s = 0;
-    for (uint32_t j = 0; j < nquad; ++j) {
-        mbar_wait(&c.bar[s], (c.phases >> s) & 1u);
-        c.phases ^= 1u << s;
-        const uint32_t cnt = min(4u, m - 4 * j);
-        // all 32 lanes run the shuffles; groups beyond a partial quad recompute row 0 and are ignored
-        const uint32_t gg = g < cnt ? g : 0;
-        const float d = quad_distance<DT>(p, c, c.ring + (size_t)(4 * s + gg) * p.ix.row_bytes);
-        __syncwarp();
-        if (c.lane == 0 && j + stages < nquad) issue_quad(j + stages, s);
-        for (uint32_t e = 0; e < cnt; ++e) {
-            const float de = __shfl_sync(FULL_MASK, d, e * 8);
-            on_dist(c.todo[4 * j + e], de);
+    __device__ __forceinline__ void begin(const SearchParams& p, WarpCtx& c, uint32_t m_) {
+        m = m_;
+        j = 0;
+        e = 0;
+        cnt = 0;
+        s = 0;
+        d = 0.0f;
+        if (p.quad) {
+            steps = (m + 3) >> 2;
+            const uint32_t stages = p.nslot >> 2;
+            if (c.lane == 0) {
+                const uint32_t pre = steps < stages ? steps : stages;
+                for (uint32_t jj = 0; jj < pre; ++jj) issue_quad(p, c, jj, jj);
+            }
+        } else {
+            steps = m;
+            if (c.lane == 0) {
+                const uint32_t pre = m < p.nslot ? m : p.nslot;
+                for (uint32_t i = 0; i < pre; ++i) issue_row(p, c, i, c.todo[i]);
+            }
         }
-        s = (s + 1 == stages) ? 0 : s + 1;
     }
-}
-
-// Evaluates the distances of c.todo[0..m) in order, with up to nslot row fetches in flight.
-template <int DT, typename F>
-__device__ __forceinline__ void eval_list_single(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
-    const uint32_t nslot = p.nslot;
-    if (c.lane == 0) {
-        uint32_t pre = m < nslot ? m : nslot;
-        for (uint32_t i = 0; i < pre; ++i) issue_row(p, c, i, c.todo[i]);
+    // yields the next (id, distance) pair; false when the list is exhausted
+    __device__ __forceinline__ bool next(const SearchParams& p, WarpCtx& c, uint32_t& id, float& dist) {
+        if (e == cnt) {
+            if (j == steps) return false;
+            mbar_wait(&c.bar[s], (c.phases >> s) & 1u);
+            c.phases ^= 1u << s;
+            if (p.quad) {
+                const uint32_t stages = p.nslot >> 2;
+                cnt = min(4u, m - 4 * j);
+                // all 32 lanes run the shuffles; groups beyond a partial quad recompute row 0 and are ignored
+                const uint32_t g = c.lane >> 3, gg = g < cnt ? g : 0;
+                d = quad_distance<DT>(p, c, c.ring + (size_t)(4 * s + gg) * p.ix.row_bytes);
+                __syncwarp();  // every lane is done reading the stage before it is refilled
+                if (c.lane == 0 && j + stages < steps) issue_quad(p, c, j + stages, s);
+                s = (s + 1 == stages) ? 0 : s + 1;
+            } else {
+                cnt = 1;
+                d = row_distance<DT>(p, c, c.ring + (size_t)s * p.ix.row_bytes);
+                __syncwarp();
+                if (c.lane == 0 && j + p.nslot < steps) issue_row(p, c, s, c.todo[j + p.nslot]);
+                s = (s + 1 == p.nslot) ? 0 : s + 1;
+            }
+            e = 0;
+            ++j;
+        }
+        const uint32_t base = p.quad ? 4 * (j - 1) : (j - 1);
+        id = c.todo[base + e];
+        dist = p.quad ? __shfl_sync(FULL_MASK, d, e * 8) : d;
+        ++e;
+        return true;
     }
-    uint32_t slot = 0;
-    for (uint32_t i = 0; i < m; ++i) {
-        mbar_wait(&c.bar[slot], (c.phases >> slot) & 1u);
-        c.phases ^= 1u << slot;
-        const uint32_t id = c.todo[i];
-        const float d = row_distance<DT>(p, c, c.ring + (size_t)slot * p.ix.row_bytes);
-        __syncwarp();  // every lane is done reading the slot before it is refilled
-        if (c.lane == 0 && i + nslot < m) issue_row(p, c, slot, c.todo[i + nslot]);
-        on_dist(id, d);
-        slot = (slot + 1 == nslot) ? 0 : slot + 1;
-    }
-}
-
-template <int DT, typename F>
-__device__ __forceinline__ void eval_list(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
-    if (p.quad)
-        eval_list_quad<DT>(p, c, m, on_dist);
-    else
-        eval_list_single<DT>(p, c, m, on_dist);
-}
+};
 
 // One 32-id chunk of an adjacency row (lane holds `nid`): optional visited test-and-set, then ordered
 // compaction into c.todo.  Returns false once the row's INVALID padding was reached.
@@ -312,7 +319,95 @@ __device__ __forceinline__ void gather_peeked(WarpCtx& c, uint32_t nid, uint32_t
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-template <int DT>
+
+// The ef-bounded result set (graph.rs:450) as one array sorted by key.  R == 0: in shared memory (any
+// ef).  R > 0: in registers, R keys per lane (ef <= 32*R): position i lives in lane i % 32, slot i / 32;
+// an insert is a ballot (lower bound) plus one shuffle-up per slot instead of a shared-memory shift.
+template <int R>
+struct ResArr {
+    uint64_t k[R > 0 ? R : 1];
+    uint64_t* sm;
+    uint32_t lane;
+    __device__ __forceinline__ void init(uint64_t* smem_ptr, uint32_t lane_) {
+        sm = smem_ptr;
+        lane = lane_;
+        if (R > 0) {
+#pragma unroll
+            for (int s = 0; s < R; ++s) k[s] = ~0ull;
+        }
+    }
+    __device__ __forceinline__ uint64_t get(uint32_t i) const {
+        if (R == 0) return sm[i];
+        uint64_t v = 0;
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            const uint64_t t = __shfl_sync(FULL_MASK, k[s], i & 31);
+            v = ((int)(i >> 5) == s) ? t : v;  // select, never an indexed access: keeps k[] in registers
+        }
+        return v;
+    }
+    __device__ __forceinline__ void set(uint32_t i, uint64_t key) {
+        if (R == 0) {
+            __syncwarp();
+            if (lane == 0) sm[i] = key;
+            __syncwarp();
+            return;
+        }
+#pragma unroll
+        for (int s = 0; s < R; ++s) k[s] = ((int)(i >> 5) == s && lane == (i & 31)) ? key : k[s];
+    }
+    // first position in (after, len) whose expanded flag (bit 0) is clear, else len
+    __device__ __forceinline__ uint32_t next_unexpanded(uint32_t after_excl, bool from_start, uint32_t len) const {
+        const uint32_t lo = from_start ? 0 : after_excl + 1;
+        if (R == 0) {
+            for (uint32_t base = lo & ~31u; base < len; base += 32) {
+                const uint32_t i = base + lane;
+                const bool un = i < len && i >= lo && (sm[i] & 1ull) == 0;
+                const uint32_t msk = __ballot_sync(FULL_MASK, un);
+                if (msk) return base + __ffs(msk) - 1;
+            }
+            return len;
+        }
+        uint32_t found = len;
+#pragma unroll
+        for (int s = R - 1; s >= 0; --s) {
+            const uint32_t i = 32u * s + lane;
+            const bool un = i < len && i >= lo && (k[s] & 1ull) == 0;
+            const uint32_t msk = __ballot_sync(FULL_MASK, un);
+            if (msk) found = 32u * s + __ffs(msk) - 1;
+        }
+        return found;
+    }
+    __device__ __forceinline__ uint32_t lower_bound(uint32_t len, uint64_t key) const {
+        if (R == 0) return lower_bound_warp(sm, len, key, lane);
+        uint32_t p = 0;
+#pragma unroll
+        for (int s = 0; s < R; ++s) p += __popc(__ballot_sync(FULL_MASK, k[s] < key));  // empty slots hold ~0
+        return p;
+    }
+    // insert key at pos; positions >= cap fall off (cap = ef)
+    __device__ __forceinline__ void insert(uint32_t pos, uint32_t new_len, uint32_t cap, uint64_t key) {
+        if (R == 0) {
+            insert_at(sm, pos, new_len, key, lane);
+            return;
+        }
+#pragma unroll
+        for (int s = R - 1; s >= 0; --s) {
+            uint64_t up = __shfl_up_sync(FULL_MASK, k[s], 1);
+            if (s > 0) {
+                const uint64_t carry = __shfl_sync(FULL_MASK, k[s - 1], 31);
+                if (lane == 0) up = carry;
+            }
+            const uint32_t i = 32u * s + lane;
+            uint64_t nv = i > pos ? up : k[s];
+            nv = i == pos ? key : nv;
+            nv = i >= cap ? ~0ull : nv;
+            k[s] = nv;
+        }
+    }
+};
+
+template <int DT, int R>
 __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     WarpCtx c;
@@ -326,6 +421,7 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
     c.norm_a = 0.0f;
     c.policy = make_evict_first_policy();
     const uint32_t lane = c.lane;
+    ResArr<R> res;
     if (lane == 0) {
         for (uint32_t i = 0; i < kMaxSlots; ++i) mbar_init(&c.bar[i], 1);
         fence_barrier_init();
@@ -365,6 +461,7 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
 
         uint32_t ndc0 = 0, hops0 = 0, ndc_up = 0, hops_up = 0;
         uint32_t len = 0;
+        res.init(c.res, lane);
 
         if (p.ix.has_entry) {
             // ---- greedy descent, layers max_layer..1 (graph.rs:259-263, 405-428) ----
@@ -375,7 +472,13 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
                 float best_dist = 0.0f;
                 if (lane == 0) c.todo[0] = best;
                 __syncwarp();
-                eval_list<DT>(p, c, 1, [&](uint32_t, float d) { best_dist = d; });
+                {
+                    ListEval<DT> ev;
+                    ev.begin(p, c, 1);
+                    uint32_t id_;
+                    float d_;
+                    while (ev.next(p, c, id_, d_)) best_dist = d_;
+                }
                 ++ndc_up;
                 for (;;) {
                     const uint32_t ref = p.ix.upper_ref[best];
@@ -387,13 +490,19 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
                     ++hops_up;
                     ndc_up += m;
                     bool improved = false;
-                    eval_list<DT>(p, c, m, [&](uint32_t id, float d) {
-                        if (d < best_dist) {
-                            best = id;
-                            best_dist = d;
-                            improved = true;
+                    {
+                        ListEval<DT> ev;
+                        ev.begin(p, c, m);
+                        uint32_t id;
+                        float d;
+                        while (ev.next(p, c, id, d)) {
+                            if (d < best_dist) {
+                                best = id;
+                                best_dist = d;
+                                improved = true;
+                            }
                         }
-                    });
+                    }
                     __syncwarp();
                     if (!improved) break;
                 }
@@ -402,6 +511,7 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
 
             // ---- layer 0 beam (graph.rs:266, 438-520) ----
             uint32_t logn = 0, tlen = 0;
+            float worst = 0.0f;  // distance of res[len-1] (results.peek()), kept in a register
             uint32_t nxt = 0;  // index of the first unexpanded entry of res (== len when there is none)
             // Next-candidate prefetch (the GPU counterpart of graph.rs:480-497): as soon as a node becomes the
             // first unexpanded entry its adjacency row is loaded into registers (two ids per lane) and, a few
@@ -431,33 +541,27 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
                 logn = 1;
                 __syncwarp();
                 float d0 = 0.0f;
-                eval_list<DT>(p, c, 1, [&](uint32_t, float d) { d0 = d; });
+                {
+                    ListEval<DT> ev;
+                    ev.begin(p, c, 1);
+                    uint32_t id_;
+                    float d_;
+                    while (ev.next(p, c, id_, d_)) d0 = d_;
+                }
                 ++ndc0;
-                if (lane == 0) c.res[0] = make_key(d0, cur);
+                res.set(0, make_key(d0, cur));
                 len = 1;
+                worst = d0;
                 __syncwarp();
             }
             for (;;) {
                 // pop the closest candidate: first unexpanded entry of res, else the smallest tie
                 uint32_t cnode = VELES_INVALID_ID;
                 if (nxt < len) {
-                    const uint64_t key = c.res[nxt];
+                    const uint64_t key = res.get(nxt);
                     cnode = key_id(key);
-                    __syncwarp();
-                    if (lane == 0) c.res[nxt] = key | 1ull;
-                    __syncwarp();
-                    // advance to the following unexpanded entry
-                    uint32_t found = len;
-                    for (uint32_t base = (nxt + 1) & ~31u; base < len; base += 32) {
-                        const uint32_t i = base + lane;
-                        const bool un = i < len && i > nxt && (c.res[i] & 1ull) == 0;
-                        const uint32_t msk = __ballot_sync(FULL_MASK, un);
-                        if (msk) {
-                            found = base + __ffs(msk) - 1;
-                            break;
-                        }
-                    }
-                    nxt = found;
+                    res.set(nxt, key | 1ull);
+                    nxt = res.next_unexpanded(nxt, false, len);  // the following unexpanded entry
                 } else if (tlen > 0) {
                     // every tie has dist == worst result dist: popped without the break (graph.rs:474)
                     uint64_t best = ~0ull;
@@ -497,8 +601,12 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
                 ++hops0;
                 ndc0 += m;
                 pre_peeked = false;  // this expansion's marking invalidates any earlier peek
-                if (nxt < len) learn(key_id(c.res[nxt]));
-                eval_list<DT>(p, c, m, [&](uint32_t id, float d) {
+                if (nxt < len) learn(key_id(res.get(nxt)));
+                ListEval<DT> ev;
+                ev.begin(p, c, m);
+                uint32_t id;
+                float d;
+                while (ev.next(p, c, id, d)) {
                     if (pre_age != 0) {
                         ++pre_age;
                         if (pre_age == 10) {  // the adjacency row landed long ago: fetch its visited words
@@ -534,13 +642,13 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
                             }
                         }
                     }
-                    const float worst = key_dist(c.res[len - 1]);
                     if (d < worst || len < ef) {
                         const uint64_t key = make_key(d, id);
-                        const uint32_t pos = lower_bound_warp(c.res, len, key, lane);
+                        const uint32_t pos = res.lower_bound(len, key);
                         if (len < ef) {
-                            insert_at(c.res, pos, len + 1, key, lane);
+                            res.insert(pos, len + 1, ef, key);
                             ++len;
+                            worst = key_dist(res.get(len - 1));
                             if (pos <= nxt) {
                                 nxt = pos;
                                 learn(id);
@@ -550,10 +658,11 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
                                 learn(id);
                             }
                         } else {
-                            const uint64_t ev = c.res[len - 1];
+                            const uint64_t ev = res.get(len - 1);
                             __syncwarp();
-                            insert_at(c.res, pos, len, key, lane);
-                            const float nworst = key_dist(c.res[len - 1]);
+                            res.insert(pos, len, ef, key);
+                            const float nworst = key_dist(res.get(len - 1));
+                            worst = nworst;
                             // ties that are now farther than the worst result can only end the loop: drop them
                             if (tlen > 0) {
                                 uint32_t w = 0;
@@ -592,7 +701,7 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
                             }
                         }
                     }
-                });
+                }
                 __syncwarp();
             }
 
@@ -607,16 +716,20 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
 
         // ---- write the first k results (graph.rs:269) ----
         const uint32_t cnt = len < p.k ? len : p.k;
-        for (uint32_t i = lane; i < p.k; i += 32) {
-            uint32_t id = VELES_INVALID_ID;
-            float d = __uint_as_float(0x7fc00000u);
-            if (i < cnt) {
-                const uint64_t key = c.res[i];
-                id = key_id(key);
-                d = key_dist(key);
+        auto emit = [&](uint32_t i, uint64_t key) {
+            if (i < p.k) {
+                const bool ok = i < cnt;
+                p.out_ids[(size_t)qi * p.k + i] = ok ? key_id(key) : VELES_INVALID_ID;
+                p.out_dist[(size_t)qi * p.k + i] = ok ? key_dist(key) : __uint_as_float(0x7fc00000u);
             }
-            p.out_ids[(size_t)qi * p.k + i] = id;
-            p.out_dist[(size_t)qi * p.k + i] = d;
+        };
+        if (R == 0) {
+            for (uint32_t i = lane; i < p.k; i += 32) emit(i, i < cnt ? c.res[i] : 0ull);
+        } else {
+            // static slot indices only: position 32*s + lane lives in this lane's k[s]
+#pragma unroll
+            for (int s2 = 0; s2 < (R > 0 ? R : 1); ++s2) emit(32u * s2 + lane, res.k[s2]);
+            for (uint32_t i = 32u * R + lane; i < p.k; i += 32) emit(i, 0ull);
         }
         if (lane == 0) {
             p.out_counts[qi] = cnt;
@@ -676,7 +789,7 @@ static int32_t launch_search(const veles_index* ix, const float* q_d, uint32_t n
     p.quad = (can_quad && env_u32("VELES_SEARCH_QUAD", 1) != 0) ? 1 : 0;
     p.evict_first = env_u32("VELES_SEARCH_EVICT_FIRST", 1) != 0 ? 1 : 0;
     p.peek = env_u32("VELES_SEARCH_PEEK", 1) != 0 ? 1 : 0;
-    p.row_prefetch = std::min(32u, env_u32("VELES_SEARCH_ROW_PREFETCH", 8));
+    p.row_prefetch = std::min(32u, env_u32("VELES_SEARCH_ROW_PREFETCH", 0));
     // resident warps (queries) per SM.  Measured on B200 (profiles/): every query of a 1024-batch must be
     // resident at once (7 x 148 = 1036 slots) -- with fewer slots a second wave of queries starts late and
     // the batch time nearly doubles; 7 CTAs leave room for 2 stages of 4 rows each.
@@ -698,9 +811,16 @@ static int32_t launch_search(const veles_index* ix, const float* q_d, uint32_t n
     VELES_REQUIRE((int)smem_bytes <= max_smem, "search needs %u bytes of shared memory per query (dim %u, ef %u); limit %d",
                   smem_bytes, ix->dim, ef, max_smem);
 
-    auto kern = ix->dtype == VELES_F32 ? hnsw_search_kernel<VELES_F32>
-                : ix->dtype == VELES_F16 ? hnsw_search_kernel<VELES_F16>
-                                         : hnsw_search_kernel<VELES_BIN1>;
+    // result array in registers when ef allows (2 or 8 keys per lane), else in shared memory
+    const uint32_t reg_mode = env_u32("VELES_SEARCH_REG_RESULTS", 1) == 0 ? 0 : (ef <= 64 ? 2 : (ef <= 256 ? 8 : 0));
+    using KernT = void (*)(const SearchParams);
+    KernT kern;
+    if (ix->dtype == VELES_F32)
+        kern = reg_mode == 2 ? hnsw_search_kernel<VELES_F32, 2> : reg_mode == 8 ? hnsw_search_kernel<VELES_F32, 8> : hnsw_search_kernel<VELES_F32, 0>;
+    else if (ix->dtype == VELES_F16)
+        kern = reg_mode == 2 ? hnsw_search_kernel<VELES_F16, 2> : reg_mode == 8 ? hnsw_search_kernel<VELES_F16, 8> : hnsw_search_kernel<VELES_F16, 0>;
+    else
+        kern = reg_mode == 2 ? hnsw_search_kernel<VELES_BIN1, 2> : reg_mode == 8 ? hnsw_search_kernel<VELES_BIN1, 8> : hnsw_search_kernel<VELES_BIN1, 0>;
     VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     int ctas_per_sm = 0;
     VELES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 32, smem_bytes));
