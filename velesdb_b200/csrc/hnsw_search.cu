@@ -192,74 +192,67 @@ __device__ __forceinline__ float quad_distance(const SearchParams& p, const Warp
     }
 }
 
-// Evaluates the distances of c.todo[0..m) in order.  Iterator style (no closures, so the caller's state
-// stays in registers):   ListEval<DT> ev; ev.begin(p, c, m);  while (ev.next(p, c, id, d)) { ... }
-//  * quad mode: four rows per step; stage s uses slots 4s..4s+3 and barrier s, the next stage is in flight
-//    while the current one is computed;
-//  * single mode: one row per step with up to nslot row fetches in flight.
-template <int DT>
-struct ListEval {
-    uint32_t m, j, e, cnt, s, steps;
-    float d;
-    __device__ __forceinline__ void issue_quad(const SearchParams& p, const WarpCtx& c, uint32_t jj, uint32_t ss) const {
-        const uint32_t n4 = min(4u, m - 4 * jj);
-        mbar_expect_tx(&c.bar[ss], n4 * p.ix.row_bytes);
-        for (uint32_t g = 0; g < n4; ++g) copy_row(p, c, 4 * ss + g, c.todo[4 * jj + g], &c.bar[ss]);
+// Evaluates c.todo[0..m) in order, four rows per step; stage s uses slots 4s..4s+3 and barrier s.
+template <int DT, typename F>
+__device__ __forceinline__ void eval_list_quad(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
+    const uint32_t stages = p.nslot >> 2;
+    const uint32_t nquad = (m + 3) >> 2;
+    auto issue_quad = [&](uint32_t j, uint32_t s) {
+        const uint32_t cnt = min(4u, m - 4 * j);
+        mbar_expect_tx(&c.bar[s], cnt * p.ix.row_bytes);
+        for (uint32_t g = 0; g < cnt; ++g) copy_row(p, c, 4 * s + g, c.todo[4 * j + g], &c.bar[s]);
+    };
+    if (c.lane == 0) {
+        const uint32_t pre = nquad < stages ? nquad : stages;
+        for (uint32_t j = 0; j < pre; ++j) issue_quad(j, j);
     }
-    __device__ __forceinline__ void begin(const SearchParams& p, WarpCtx& c, uint32_t m_) {
-        m = m_;
-        j = 0;
-        e = 0;
-        cnt = 0;
-        s = 0;
-        d = 0.0f;
-        if (p.quad) {
-            steps = (m + 3) >> 2;
-            const uint32_t stages = p.nslot >> 2;
-            if (c.lane == 0) {
-                const uint32_t pre = steps < stages ? steps : stages;
-                for (uint32_t jj = 0; jj < pre; ++jj) issue_quad(p, c, jj, jj);
-            }
-        } else {
-            steps = m;
-            if (c.lane == 0) {
-                const uint32_t pre = m < p.nslot ? m : p.nslot;
-                for (uint32_t i = 0; i < pre; ++i) issue_row(p, c, i, c.todo[i]);
-            }
+    const uint32_t g = c.lane >> 3;
+    uint32_t s = 0;
+    for (uint32_t j = 0; j < nquad; ++j) {
+        mbar_wait(&c.bar[s], (c.phases >> s) & 1u);
+        c.phases ^= 1u << s;
+        const uint32_t cnt = min(4u, m - 4 * j);
+        // all 32 lanes run the shuffles; groups beyond a partial quad recompute row 0 and are ignored
+        const uint32_t gg = g < cnt ? g : 0;
+        const float d = quad_distance<DT>(p, c, c.ring + (size_t)(4 * s + gg) * p.ix.row_bytes);
+        __syncwarp();
+        if (c.lane == 0 && j + stages < nquad) issue_quad(j + stages, s);
+        for (uint32_t e = 0; e < cnt; ++e) {
+            const float de = __shfl_sync(FULL_MASK, d, e * 8);
+            on_dist(c.todo[4 * j + e], de);
         }
+        s = (s + 1 == stages) ? 0 : s + 1;
     }
-    // yields the next (id, distance) pair; false when the list is exhausted
-    __device__ __forceinline__ bool next(const SearchParams& p, WarpCtx& c, uint32_t& id, float& dist) {
-        if (e == cnt) {
-            if (j == steps) return false;
-            mbar_wait(&c.bar[s], (c.phases >> s) & 1u);
-            c.phases ^= 1u << s;
-            if (p.quad) {
-                const uint32_t stages = p.nslot >> 2;
-                cnt = min(4u, m - 4 * j);
-                // all 32 lanes run the shuffles; groups beyond a partial quad recompute row 0 and are ignored
-                const uint32_t g = c.lane >> 3, gg = g < cnt ? g : 0;
-                d = quad_distance<DT>(p, c, c.ring + (size_t)(4 * s + gg) * p.ix.row_bytes);
-                __syncwarp();  // every lane is done reading the stage before it is refilled
-                if (c.lane == 0 && j + stages < steps) issue_quad(p, c, j + stages, s);
-                s = (s + 1 == stages) ? 0 : s + 1;
-            } else {
-                cnt = 1;
-                d = row_distance<DT>(p, c, c.ring + (size_t)s * p.ix.row_bytes);
-                __syncwarp();
-                if (c.lane == 0 && j + p.nslot < steps) issue_row(p, c, s, c.todo[j + p.nslot]);
-                s = (s + 1 == p.nslot) ? 0 : s + 1;
-            }
-            e = 0;
-            ++j;
-        }
-        const uint32_t base = p.quad ? 4 * (j - 1) : (j - 1);
-        id = c.todo[base + e];
-        dist = p.quad ? __shfl_sync(FULL_MASK, d, e * 8) : d;
-        ++e;
-        return true;
+}
+
+// Evaluates the distances of c.todo[0..m) in order, with up to nslot row fetches in flight.
+template <int DT, typename F>
+__device__ __forceinline__ void eval_list_single(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
+    const uint32_t nslot = p.nslot;
+    if (c.lane == 0) {
+        uint32_t pre = m < nslot ? m : nslot;
+        for (uint32_t i = 0; i < pre; ++i) issue_row(p, c, i, c.todo[i]);
     }
-};
+    uint32_t slot = 0;
+    for (uint32_t i = 0; i < m; ++i) {
+        mbar_wait(&c.bar[slot], (c.phases >> slot) & 1u);
+        c.phases ^= 1u << slot;
+        const uint32_t id = c.todo[i];
+        const float d = row_distance<DT>(p, c, c.ring + (size_t)slot * p.ix.row_bytes);
+        __syncwarp();  // every lane is done reading the slot before it is refilled
+        if (c.lane == 0 && i + nslot < m) issue_row(p, c, slot, c.todo[i + nslot]);
+        on_dist(id, d);
+        slot = (slot + 1 == nslot) ? 0 : slot + 1;
+    }
+}
+
+template <int DT, typename F>
+__device__ __forceinline__ void eval_list(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
+    if (p.quad)
+        eval_list_quad<DT>(p, c, m, on_dist);
+    else
+        eval_list_single<DT>(p, c, m, on_dist);
+}
 
 // One 32-id chunk of an adjacency row (lane holds `nid`): optional visited test-and-set, then ordered
 // compaction into c.todo.  Returns false once the row's INVALID padding was reached.
@@ -472,13 +465,7 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
                 float best_dist = 0.0f;
                 if (lane == 0) c.todo[0] = best;
                 __syncwarp();
-                {
-                    ListEval<DT> ev;
-                    ev.begin(p, c, 1);
-                    uint32_t id_;
-                    float d_;
-                    while (ev.next(p, c, id_, d_)) best_dist = d_;
-                }
+                eval_list<DT>(p, c, 1, [&](uint32_t, float d) { best_dist = d; });
                 ++ndc_up;
                 for (;;) {
                     const uint32_t ref = p.ix.upper_ref[best];
@@ -490,19 +477,13 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
                     ++hops_up;
                     ndc_up += m;
                     bool improved = false;
-                    {
-                        ListEval<DT> ev;
-                        ev.begin(p, c, m);
-                        uint32_t id;
-                        float d;
-                        while (ev.next(p, c, id, d)) {
-                            if (d < best_dist) {
-                                best = id;
-                                best_dist = d;
-                                improved = true;
-                            }
+                    eval_list<DT>(p, c, m, [&](uint32_t id, float d) {
+                        if (d < best_dist) {
+                            best = id;
+                            best_dist = d;
+                            improved = true;
                         }
-                    }
+                    });
                     __syncwarp();
                     if (!improved) break;
                 }
@@ -541,13 +522,7 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
                 logn = 1;
                 __syncwarp();
                 float d0 = 0.0f;
-                {
-                    ListEval<DT> ev;
-                    ev.begin(p, c, 1);
-                    uint32_t id_;
-                    float d_;
-                    while (ev.next(p, c, id_, d_)) d0 = d_;
-                }
+                eval_list<DT>(p, c, 1, [&](uint32_t, float d) { d0 = d; });
                 ++ndc0;
                 res.set(0, make_key(d0, cur));
                 len = 1;
@@ -602,11 +577,7 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
                 ndc0 += m;
                 pre_peeked = false;  // this expansion's marking invalidates any earlier peek
                 if (nxt < len) learn(key_id(res.get(nxt)));
-                ListEval<DT> ev;
-                ev.begin(p, c, m);
-                uint32_t id;
-                float d;
-                while (ev.next(p, c, id, d)) {
+                eval_list<DT>(p, c, m, [&](uint32_t id, float d) {
                     if (pre_age != 0) {
                         ++pre_age;
                         if (pre_age == 10) {  // the adjacency row landed long ago: fetch its visited words
@@ -701,7 +672,7 @@ __global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
                             }
                         }
                     }
-                }
+                });
                 __syncwarp();
             }
 

@@ -10,6 +10,7 @@
 
 using namespace veles::host;
 
+#define STEP(msg) std::fprintf(stderr, "[host mirror] %s\n", msg)
 #define CHECK(cond)                                                        \
     do {                                                                   \
         if (!(cond)) {                                                     \
@@ -31,6 +32,7 @@ int main(int argc, char** argv) {
         CHECK(e.len() == 0 && e.is_empty());
         CHECK(e.search(std::vector<float>(dim, 1.0f), 5).empty());
     }
+    STEP("empty ok");
     HnswIndex index(dim, DistanceMetric::Cosine);
     std::vector<std::vector<float>> data(n, std::vector<float>(dim));
     for (size_t i = 0; i < n; ++i)
@@ -46,6 +48,7 @@ int main(int argc, char** argv) {
         threw = true;
     }
     CHECK(threw);
+    STEP("insert + mismatch ok");
     // recall >= 0.8 for Accurate vs brute force (index_tests.rs:1108-1159)
     std::vector<float> q(dim);
     for (size_t j = 0; j < dim; ++j) q[j] = std::sin((float)j * 0.001f);
@@ -59,6 +62,7 @@ int main(int argc, char** argv) {
     CHECK(hits >= 8);
     for (size_t i = 1; i < exact.size(); ++i) CHECK(exact[i - 1].second >= exact[i].second);  // cosine: descending
     for (auto& h : res) CHECK(h.second >= 0.0f && h.second <= 1.0f);                           // transform_score clamp
+    STEP("recall ok");
     // batch == single (index_tests.rs:1018-1053 checks lengths; ids must agree too)
     std::vector<std::vector<float>> qs(data.begin(), data.begin() + 16);
     auto batch = index.search_batch_parallel(qs, k, SearchQuality::Balanced());
@@ -72,15 +76,18 @@ int main(int argc, char** argv) {
         for (auto& h : batch[i]) self_found |= h.first == i;
         CHECK(self_found);
     }
+    STEP("batch ok");
     // soft delete: the node stays in the graph, the id is never returned (trait_impl.rs:54-58, search.rs:86-91)
     CHECK(index.remove(0) && !index.remove(0));
     CHECK(index.len() == n - 1 && index.tombstone_count() == 1);
     for (auto& h : index.search(data[0], k)) CHECK(h.first != 0);
     for (auto& h : index.search_brute_force(data[0], k)) CHECK(h.first != 0);
+    STEP("remove ok");
     // rerank returns metric values sorted by sort_results
     auto rr = index.search_with_rerank(q, 5, 50);
     CHECK(rr.size() == 5);
     for (size_t i = 1; i < rr.size(); ++i) CHECK(rr[i - 1].second >= rr[i].second);
+    STEP("rerank ok");
     // save / load round trip (constructors.rs:190-287): same first hit, vectors absent after load
     index.save(tmp);
     HnswIndex* loaded = HnswIndex::load(tmp, dim, DistanceMetric::Cosine);
@@ -91,6 +98,7 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < a.size(); ++i) CHECK(a[i] == b[i]);
     CHECK(loaded->search_with_rerank(q, 5, 50).empty());  // rerank finds no vectors after load (search.rs:130-137)
     delete loaded;
+    STEP("save/load ok");
     // <= 100 vectors: exact brute-force path; Euclidean top-1 at the origin (index_tests.rs:1691-1712)
     HnswIndex small(16, DistanceMetric::Euclidean);
     for (uint64_t i = 0; i < 50; ++i) {
