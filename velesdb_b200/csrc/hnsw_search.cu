@@ -139,6 +139,47 @@ __device__ __forceinline__ float4 load4(const __half* p) {
     return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// U steps of the quad accumulation with all 2*U shared-memory loads issued before the first FMA, so the
+// LDS latency is paid once per block instead of once per step (the FMA order per accumulator -- increasing
+// element index -- is unchanged, hence so are the bits).
+template <int U, bool L2, typename TB>
+__device__ __forceinline__ void quad_block(const TB* __restrict__ r, const float* __restrict__ q, uint32_t i, float& a0,
+                                           float& a1, float& a2, float& a3) {
+    float4 x[U], y[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        x[u] = load4(r + i + 32 * u);
+        y[u] = load4(q + i + 32 * u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (L2) {
+            const float d0 = __fsub_rn(y[u].x, x[u].x), d1 = __fsub_rn(y[u].y, x[u].y);
+            const float d2 = __fsub_rn(y[u].z, x[u].z), d3 = __fsub_rn(y[u].w, x[u].w);
+            a0 = __fmaf_rn(d0, d0, a0);
+            a1 = __fmaf_rn(d1, d1, a1);
+            a2 = __fmaf_rn(d2, d2, a2);
+            a3 = __fmaf_rn(d3, d3, a3);
+        } else {
+            a0 = __fmaf_rn(y[u].x, x[u].x, a0);
+            a1 = __fmaf_rn(y[u].y, x[u].y, a1);
+            a2 = __fmaf_rn(y[u].z, x[u].z, a2);
+            a3 = __fmaf_rn(y[u].w, x[u].w, a3);
+        }
+    }
+}
+
+template <bool L2, typename TB>
+__device__ __forceinline__ float quad_accumulate(const TB* __restrict__ r, const float* __restrict__ q, uint32_t dim,
+                                                 uint32_t t) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    uint32_t i = t * 4;
+    for (; i + 32 * 7 < dim; i += 32 * 8) quad_block<8, L2>(r, q, i, a0, a1, a2, a3);
+    for (; i + 32 * 3 < dim; i += 32 * 4) quad_block<4, L2>(r, q, i, a0, a1, a2, a3);
+    for (; i < dim; i += 32) quad_block<1, L2>(r, q, i, a0, a1, a2, a3);
+    return quad_tree_sum(a0, a1, a2, a3);
+}
+
 // distance of the row owned by this lane's group (dim % 32 == 0, dim >= 32)
 template <int DT>
 __device__ __forceinline__ float quad_distance(const SearchParams& p, const WarpCtx& c, const uint8_t* row) {
@@ -162,28 +203,8 @@ __device__ __forceinline__ float quad_distance(const SearchParams& p, const Warp
         const TB* r = reinterpret_cast<const TB*>(row);
         const float* q = reinterpret_cast<const float*>(c.q);
         const uint32_t dim = p.ix.dim;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        if (p.ix.metric == VELES_EUCLIDEAN) {
-#pragma unroll 4
-            for (uint32_t i = t * 4; i < dim; i += 32) {
-                const float4 x = load4(r + i), y = load4(q + i);
-                const float d0 = __fsub_rn(y.x, x.x), d1 = __fsub_rn(y.y, x.y), d2 = __fsub_rn(y.z, x.z), d3 = __fsub_rn(y.w, x.w);
-                a0 = __fmaf_rn(d0, d0, a0);
-                a1 = __fmaf_rn(d1, d1, a1);
-                a2 = __fmaf_rn(d2, d2, a2);
-                a3 = __fmaf_rn(d3, d3, a3);
-            }
-            return __fsqrt_rn(quad_tree_sum(a0, a1, a2, a3));
-        }
-#pragma unroll 4
-        for (uint32_t i = t * 4; i < dim; i += 32) {
-            const float4 x = load4(r + i), y = load4(q + i);
-            a0 = __fmaf_rn(y.x, x.x, a0);
-            a1 = __fmaf_rn(y.y, x.y, a1);
-            a2 = __fmaf_rn(y.z, x.z, a2);
-            a3 = __fmaf_rn(y.w, x.w, a3);
-        }
-        const float dot = quad_tree_sum(a0, a1, a2, a3);
+        if (p.ix.metric == VELES_EUCLIDEAN) return __fsqrt_rn(quad_accumulate<true>(r, q, dim, t));
+        const float dot = quad_accumulate<false>(r, q, dim, t);
         if (p.ix.metric == VELES_COSINE) {
             const float nb = *reinterpret_cast<const float*>(row + p.ix.norm_off);
             return __fsub_rn(1.0f, cosine_from_parts(dot, c.norm_a, nb));
