@@ -85,35 +85,54 @@ __global__ void __launch_bounds__(256) bm25_range_kernel(Bm25View v, const uint3
         touched |= hi > lo;
         __syncthreads();  // next term's contributions come after this term's, per document
     }
-    // warp 0: the range's k best (score desc, doc asc) as ascending keys (~order(score) << 32 | doc)
-    if (threadIdx.x >= 32) return;
-    const uint32_t lane = threadIdx.x;
-    uint32_t len = 0;
-    uint64_t worst = ~0ull;
+    // All warps compact the positive accumulators into a candidate list (ordered keys
+    // ~order(score) << 32 | doc: ascending = score desc, doc asc); warp 0 then keeps the k smallest.
+    uint32_t* cand = reinterpret_cast<uint32_t*>(res + k);  // indices of positive accumulators (<= kRange)
+    __shared__ uint32_t s_ncand;
+    if (threadIdx.x == 0) s_ncand = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
     if (touched) {
         const uint32_t lim = min(kRange, v.n_doc_slots - base_doc);
-        for (uint32_t i0 = 0; i0 < lim; i0 += 32) {
+        for (uint32_t i0 = (threadIdx.x & ~31u); i0 < lim; i0 += blockDim.x) {
             const uint32_t i = i0 + lane;
-            uint64_t key = ~0ull;
-            if (i < lim) {
-                const float s = acc[i];
-                if (s > 0.0f) key = ((uint64_t)(~ord_key(s)) << 32) | (base_doc + i);
+            const float s = i < lim ? acc[i] : 0.0f;
+            const bool pos = s > 0.0f;
+            const uint32_t msk = __ballot_sync(FULL_MASK, pos);
+            if (msk) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&s_ncand, __popc(msk));
+                base = __shfl_sync(FULL_MASK, base, 0);
+                if (pos) cand[base + __popc(msk & ((1u << lane) - 1u))] = i;
             }
-            uint32_t msk = __ballot_sync(FULL_MASK, key < worst);
-            while (msk) {
-                const uint32_t src = __ffs(msk) - 1;
-                msk &= msk - 1;
-                const uint64_t kk = __shfl_sync(FULL_MASK, key, src);
-                if (kk >= worst) continue;
-                const uint32_t pos = lower_bound_warp(res, len, kk, lane);
-                if (len < k) {
-                    insert_at(res, pos, len + 1, kk, lane);
-                    ++len;
-                } else {
-                    insert_at(res, pos, len, kk, lane);
-                }
-                if (len == k) worst = res[k - 1];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const uint32_t ncand = s_ncand;
+    uint32_t len = 0;
+    uint64_t worst = ~0ull;
+    for (uint32_t i0 = 0; i0 < ncand; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        uint64_t key = ~0ull;
+        if (i < ncand) {
+            const uint32_t ci = cand[i];
+            key = ((uint64_t)(~ord_key(acc[ci])) << 32) | (base_doc + ci);
+        }
+        uint32_t msk = __ballot_sync(FULL_MASK, key < worst);
+        while (msk) {
+            const uint32_t src = __ffs(msk) - 1;
+            msk &= msk - 1;
+            const uint64_t kk = __shfl_sync(FULL_MASK, key, src);
+            if (kk >= worst) continue;
+            const uint32_t pos = lower_bound_warp(res, len, kk, lane);
+            if (len < k) {
+                insert_at(res, pos, len + 1, kk, lane);
+                ++len;
+            } else {
+                insert_at(res, pos, len, kk, lane);
             }
+            if (len == k) worst = res[k - 1];
         }
     }
     __syncwarp();
@@ -282,7 +301,7 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
     v.k1 = ix->k1;
     v.b = ix->b;
     v.avgdl = ix->avgdl;
-    const size_t smem1 = (size_t)kRange * 4 + (size_t)k * 8;
+    const size_t smem1 = (size_t)kRange * 4 + (size_t)k * 8 + (size_t)kRange * 4;  // accumulators, top-k, candidate indices
     VELES_CUDA(cudaFuncSetAttribute(bm25_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     VELES_CUDA(cudaFuncSetAttribute(bm25_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(k * 8)));
     // gridDim.y <= 65535: chunk the queries; the partial buffer is bounded to ~512 MiB per pass

@@ -267,9 +267,50 @@ __device__ __forceinline__ void eval_list_single(const SearchParams& p, WarpCtx&
     }
 }
 
+// Packed-bit rows of at most 1024 bits (128 bytes): no staging ring.  8 lanes x 16 bytes read one row with
+// a single 128-bit load per lane, 16 rows (4 groups x 4) are requested back to back before the first
+// popcount, so a whole neighbour list is ~4 rounds of independent loads.  Integer sums: order free.
+template <typename F>
+__device__ __forceinline__ void eval_list_bits(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
+    const uint32_t g = c.lane >> 3, t = c.lane & 7;
+    const uint32_t words4 = p.ix.dim >> 7;  // uint4 per row, <= 8
+    const uint4* qw = reinterpret_cast<const uint4*>(c.q);
+    const uint4 y = t < words4 ? qw[t] : make_uint4(0, 0, 0, 0);
+    for (uint32_t base = 0; base < m; base += 16) {
+        uint4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t idx = base + 4 * u + g;
+            const uint32_t id = c.todo[idx < m ? idx : base];
+            x[u] = make_uint4(0, 0, 0, 0);
+            if (t < words4) x[u] = __ldg(reinterpret_cast<const uint4*>(p.ix.vecs + (size_t)id * p.ix.row_bytes) + t);
+        }
+        uint32_t d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            uint32_t v = __popc(x[u].x ^ y.x) + __popc(x[u].y ^ y.y) + __popc(x[u].z ^ y.z) + __popc(x[u].w ^ y.w);
+            v += __shfl_xor_sync(FULL_MASK, v, 1);
+            v += __shfl_xor_sync(FULL_MASK, v, 2);
+            v += __shfl_xor_sync(FULL_MASK, v, 4);
+            d[u] = v;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            for (uint32_t e = 0; e < 4; ++e) {
+                const uint32_t idx = base + 4 * u + e;
+                if (idx >= m) break;
+                const uint32_t de = __shfl_sync(FULL_MASK, d[u], e * 8);
+                on_dist(c.todo[idx], (float)de);
+            }
+        }
+    }
+}
+
 template <int DT, typename F>
 __device__ __forceinline__ void eval_list(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
-    if (p.quad)
+    if (DT == VELES_BIN1 && p.quad == 2)
+        eval_list_bits(p, c, m, on_dist);
+    else if (p.quad)
         eval_list_quad<DT>(p, c, m, on_dist);
     else
         eval_list_single<DT>(p, c, m, on_dist);
@@ -779,6 +820,8 @@ static int32_t launch_search(const veles_index* ix, const float* q_d, uint32_t n
                           (ix->dtype != VELES_BIN1 && ix->dim % 32 == 0 &&
                            (ix->metric == VELES_COSINE || ix->metric == VELES_EUCLIDEAN || ix->metric == VELES_DOT));
     p.quad = (can_quad && env_u32("VELES_SEARCH_QUAD", 1) != 0) ? 1 : 0;
+    // packed rows of <= 128 bytes are read directly (no ring), see eval_list_bits
+    if (p.quad && ix->dtype == VELES_BIN1 && ix->dim <= 1024 && env_u32("VELES_SEARCH_BITS_DIRECT", 1) != 0) p.quad = 2;
     p.evict_first = env_u32("VELES_SEARCH_EVICT_FIRST", 1) != 0 ? 1 : 0;
     p.peek = env_u32("VELES_SEARCH_PEEK", 1) != 0 ? 1 : 0;
     p.row_prefetch = std::min(32u, env_u32("VELES_SEARCH_ROW_PREFETCH", 0));
