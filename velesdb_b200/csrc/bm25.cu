@@ -29,6 +29,7 @@
 
 namespace veles {
 constexpr uint32_t kRange = 8192;  // docs per CTA range: 32 KB of f32 accumulators
+constexpr uint32_t kTermChunk = 32; // query tokens whose metadata is staged at once
 }
 
 struct veles_bm25 {
@@ -66,73 +67,74 @@ __global__ void __launch_bounds__(256) bm25_range_kernel(Bm25View v, const uint3
     const float k1p1 = __fadd_rn(v.k1, 1.0f);
     const float one_minus_b = __fsub_rn(1.0f, v.b);
     bool touched = false;
-    for (uint32_t ti = t0; ti < t1; ++ti) {
-        const uint32_t term = q_terms[ti];
-        if (term >= v.n_terms) continue;  // unknown term: df = 0, contributes nothing
-        const float idf = v.idf[term];
-        const uint64_t lo = v.skip[(size_t)term * (v.n_ranges + 1) + r];
-        const uint64_t hi = v.skip[(size_t)term * (v.n_ranges + 1) + r + 1];
-        for (uint64_t p = lo + threadIdx.x; p < hi; p += blockDim.x) {
-            const uint32_t d = v.post_doc[p];
-            const float tf = (float)v.post_tf[p];
-            const float dl = (float)v.doc_len[d];
-            const float len_norm = __fadd_rn(one_minus_b, __fdiv_rn(__fmul_rn(v.b, dl), v.avgdl));
-            const float num = __fmul_rn(tf, k1p1);
-            const float den = __fadd_rn(tf, __fmul_rn(v.k1, len_norm));
-            const float contrib = __fdiv_rn(__fmul_rn(idf, num), den);
-            acc[d - base_doc] = __fadd_rn(acc[d - base_doc], contrib);
-        }
-        touched |= hi > lo;
-        __syncthreads();  // next term's contributions come after this term's, per document
-    }
-    // All warps compact the positive accumulators into a candidate list (ordered keys
-    // ~order(score) << 32 | doc: ascending = score desc, doc asc); warp 0 then keeps the k smallest.
-    uint32_t* cand = reinterpret_cast<uint32_t*>(res + k);  // indices of positive accumulators (<= kRange)
-    __shared__ uint32_t s_ncand;
-    if (threadIdx.x == 0) s_ncand = 0;
-    __syncthreads();
-    const uint32_t lane = threadIdx.x & 31;
-    if (touched) {
-        const uint32_t lim = min(kRange, v.n_doc_slots - base_doc);
-        for (uint32_t i0 = (threadIdx.x & ~31u); i0 < lim; i0 += blockDim.x) {
-            const uint32_t i = i0 + lane;
-            const float s = i < lim ? acc[i] : 0.0f;
-            const bool pos = s > 0.0f;
-            const uint32_t msk = __ballot_sync(FULL_MASK, pos);
-            if (msk) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&s_ncand, __popc(msk));
-                base = __shfl_sync(FULL_MASK, base, 0);
-                if (pos) cand[base + __popc(msk & ((1u << lane) - 1u))] = i;
+    // term metadata for up to kTermChunk query tokens at a time, fetched by parallel threads so the
+    // dependent global loads (term id -> skip entries) are paid once per chunk, not once per term
+    __shared__ uint64_t s_lo[kTermChunk], s_hi[kTermChunk];
+    __shared__ float s_idf[kTermChunk];
+    for (uint32_t c0 = t0; c0 < t1; c0 += kTermChunk) {
+        const uint32_t nt = min(kTermChunk, t1 - c0);
+        if (threadIdx.x < nt) {
+            const uint32_t term = q_terms[c0 + threadIdx.x];
+            uint64_t lo = 0, hi = 0;
+            float idf = 0.0f;
+            if (term < v.n_terms) {  // unknown term: df = 0, contributes nothing
+                lo = v.skip[(size_t)term * (v.n_ranges + 1) + r];
+                hi = v.skip[(size_t)term * (v.n_ranges + 1) + r + 1];
+                idf = v.idf[term];
             }
+            s_lo[threadIdx.x] = lo;
+            s_hi[threadIdx.x] = hi;
+            s_idf[threadIdx.x] = idf;
         }
+        __syncthreads();
+        for (uint32_t ti = 0; ti < nt; ++ti) {
+            const uint64_t lo = s_lo[ti], hi = s_hi[ti];
+            if (hi == lo) continue;  // uniform: nothing of this term in the range
+            const float idf = s_idf[ti];
+            for (uint64_t p = lo + threadIdx.x; p < hi; p += blockDim.x) {
+                const uint32_t d = v.post_doc[p];
+                const float tf = (float)v.post_tf[p];
+                const float dl = (float)v.doc_len[d];
+                const float len_norm = __fadd_rn(one_minus_b, __fdiv_rn(__fmul_rn(v.b, dl), v.avgdl));
+                const float num = __fmul_rn(tf, k1p1);
+                const float den = __fadd_rn(tf, __fmul_rn(v.k1, len_norm));
+                const float contrib = __fdiv_rn(__fmul_rn(idf, num), den);
+                acc[d - base_doc] = __fadd_rn(acc[d - base_doc], contrib);
+            }
+            touched = true;
+            __syncthreads();  // next term's contributions come after this term's, per document
+        }
+        __syncthreads();
     }
-    __syncthreads();
+    // warp 0: the range's k best (score desc, doc asc) as ascending keys (~order(score) << 32 | doc)
     if (threadIdx.x >= 32) return;
-    const uint32_t ncand = s_ncand;
+    const uint32_t lane = threadIdx.x;
     uint32_t len = 0;
     uint64_t worst = ~0ull;
-    for (uint32_t i0 = 0; i0 < ncand; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        uint64_t key = ~0ull;
-        if (i < ncand) {
-            const uint32_t ci = cand[i];
-            key = ((uint64_t)(~ord_key(acc[ci])) << 32) | (base_doc + ci);
-        }
-        uint32_t msk = __ballot_sync(FULL_MASK, key < worst);
-        while (msk) {
-            const uint32_t src = __ffs(msk) - 1;
-            msk &= msk - 1;
-            const uint64_t kk = __shfl_sync(FULL_MASK, key, src);
-            if (kk >= worst) continue;
-            const uint32_t pos = lower_bound_warp(res, len, kk, lane);
-            if (len < k) {
-                insert_at(res, pos, len + 1, kk, lane);
-                ++len;
-            } else {
-                insert_at(res, pos, len, kk, lane);
+    if (touched) {
+        const uint32_t lim = min(kRange, v.n_doc_slots - base_doc);
+        for (uint32_t i0 = 0; i0 < lim; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            uint64_t key = ~0ull;
+            if (i < lim) {
+                const float s = acc[i];
+                if (s > 0.0f) key = ((uint64_t)(~ord_key(s)) << 32) | (base_doc + i);
             }
-            if (len == k) worst = res[k - 1];
+            uint32_t msk = __ballot_sync(FULL_MASK, key < worst);
+            while (msk) {
+                const uint32_t src = __ffs(msk) - 1;
+                msk &= msk - 1;
+                const uint64_t kk = __shfl_sync(FULL_MASK, key, src);
+                if (kk >= worst) continue;
+                const uint32_t pos = lower_bound_warp(res, len, kk, lane);
+                if (len < k) {
+                    insert_at(res, pos, len + 1, kk, lane);
+                    ++len;
+                } else {
+                    insert_at(res, pos, len, kk, lane);
+                }
+                if (len == k) worst = res[k - 1];
+            }
         }
     }
     __syncwarp();
@@ -301,7 +303,7 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
     v.k1 = ix->k1;
     v.b = ix->b;
     v.avgdl = ix->avgdl;
-    const size_t smem1 = (size_t)kRange * 4 + (size_t)k * 8 + (size_t)kRange * 4;  // accumulators, top-k, candidate indices
+    const size_t smem1 = (size_t)kRange * 4 + (size_t)k * 8;
     VELES_CUDA(cudaFuncSetAttribute(bm25_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     VELES_CUDA(cudaFuncSetAttribute(bm25_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(k * 8)));
     // gridDim.y <= 65535: chunk the queries; the partial buffer is bounded to ~512 MiB per pass
