@@ -112,28 +112,33 @@ __global__ void __launch_bounds__(256) bm25_range_kernel(Bm25View v, const uint3
     uint32_t len = 0;
     uint64_t worst = ~0ull;
     if (touched) {
-        const uint32_t lim = min(kRange, v.n_doc_slots - base_doc);
-        for (uint32_t i0 = 0; i0 < lim; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            uint64_t key = ~0ull;
-            if (i < lim) {
-                const float s = acc[i];
-                if (s > 0.0f) key = ((uint64_t)(~ord_key(s)) << 32) | (base_doc + i);
-            }
-            uint32_t msk = __ballot_sync(FULL_MASK, key < worst);
-            while (msk) {
-                const uint32_t src = __ffs(msk) - 1;
-                msk &= msk - 1;
-                const uint64_t kk = __shfl_sync(FULL_MASK, key, src);
-                if (kk >= worst) continue;
-                const uint32_t pos = lower_bound_warp(res, len, kk, lane);
-                if (len < k) {
-                    insert_at(res, pos, len + 1, kk, lane);
-                    ++len;
-                } else {
-                    insert_at(res, pos, len, kk, lane);
+        // 128 accumulators per step (one float4 per lane); most are zero, so whole steps are skipped on one
+        // ballot.  Padding docs past n_doc_slots never receive postings and stay 0.
+        const float4* acc4 = reinterpret_cast<const float4*>(acc);
+        for (uint32_t i0 = 0; i0 < kRange; i0 += 128) {
+            const float4 s4 = acc4[(i0 >> 2) + lane];
+            const bool any = s4.x > 0.0f || s4.y > 0.0f || s4.z > 0.0f || s4.w > 0.0f;
+            if (!__ballot_sync(FULL_MASK, any)) continue;
+            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint64_t key = ~0ull;
+                if (sv[e] > 0.0f) key = ((uint64_t)(~ord_key(sv[e])) << 32) | (base_doc + i0 + lane * 4 + e);
+                uint32_t msk = __ballot_sync(FULL_MASK, key < worst);
+                while (msk) {
+                    const uint32_t src = __ffs(msk) - 1;
+                    msk &= msk - 1;
+                    const uint64_t kk = __shfl_sync(FULL_MASK, key, src);
+                    if (kk >= worst) continue;
+                    const uint32_t pos = lower_bound_warp(res, len, kk, lane);
+                    if (len < k) {
+                        insert_at(res, pos, len + 1, kk, lane);
+                        ++len;
+                    } else {
+                        insert_at(res, pos, len, kk, lane);
+                    }
+                    if (len == k) worst = res[k - 1];
                 }
-                if (len == k) worst = res[k - 1];
             }
         }
     }
