@@ -274,9 +274,11 @@ def main():
     kernel_ms = float(np.mean(kt))
 
     # ---------------- timed: end to end through the host-pointer C ABI ----------------
-    out_ids = np.empty((a.nq, a.k), dtype=np.uint32)
-    out_dist = np.empty((a.nq, a.k), dtype=np.float32)
-    out_cnt = np.empty(a.nq, dtype=np.uint32)
+    # pinned host buffers, as a serving front-end would hold (pageable memory also works, slower D2H)
+    out_ids_t = torch.empty((a.nq, a.k), dtype=torch.int32).pin_memory()
+    out_dist_t = torch.empty((a.nq, a.k), dtype=torch.float32).pin_memory()
+    out_cnt_t = torch.empty(a.nq, dtype=torch.int32).pin_memory()
+    out_ids, out_dist, out_cnt = out_ids_t.numpy(), out_dist_t.numpy(), out_cnt_t.numpy()
     qn = q_h.numpy()
 
     def step_e2e():

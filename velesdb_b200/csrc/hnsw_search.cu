@@ -218,12 +218,15 @@ template <int DT, typename F>
 __device__ __forceinline__ void eval_list_quad(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
     const uint32_t stages = p.nslot >> 2;
     const uint32_t nquad = (m + 3) >> 2;
+    // lanes 0..3 each issue one row copy of the quad (address arithmetic in parallel); lane 0 arms the barrier.
+    // The barrier's pending-arrival count stays at 1 until lane 0 arrives, so complete_tx from a copy that
+    // lands before the expect_tx cannot complete the phase early.
     auto issue_quad = [&](uint32_t j, uint32_t s) {
         const uint32_t cnt = min(4u, m - 4 * j);
-        mbar_expect_tx(&c.bar[s], cnt * p.ix.row_bytes);
-        for (uint32_t g = 0; g < cnt; ++g) copy_row(p, c, 4 * s + g, c.todo[4 * j + g], &c.bar[s]);
+        if (c.lane == 0) mbar_expect_tx(&c.bar[s], cnt * p.ix.row_bytes);
+        if (c.lane < cnt) copy_row(p, c, 4 * s + c.lane, c.todo[4 * j + c.lane], &c.bar[s]);
     };
-    if (c.lane == 0) {
+    {
         const uint32_t pre = nquad < stages ? nquad : stages;
         for (uint32_t j = 0; j < pre; ++j) issue_quad(j, j);
     }
@@ -237,7 +240,7 @@ __device__ __forceinline__ void eval_list_quad(const SearchParams& p, WarpCtx& c
         const uint32_t gg = g < cnt ? g : 0;
         const float d = quad_distance<DT>(p, c, c.ring + (size_t)(4 * s + gg) * p.ix.row_bytes);
         __syncwarp();
-        if (c.lane == 0 && j + stages < nquad) issue_quad(j + stages, s);
+        if (j + stages < nquad) issue_quad(j + stages, s);
         for (uint32_t e = 0; e < cnt; ++e) {
             const float de = __shfl_sync(FULL_MASK, d, e * 8);
             on_dist(c.todo[4 * j + e], de);
