@@ -1,0 +1,120 @@
+"""CPU tests of the host mirror's own logic (velesdb_b200/index.py): id <-> node mapping, tombstones,
+quality -> ef routing, score transform, error behaviour.  The device snapshot is replaced by a stand-in
+that answers from the CPU oracle (test infrastructure), so no GPU is needed."""
+import numpy as np
+import pytest
+
+from oracle import oracle as vo
+from velesdb_b200 import DimensionMismatch, DistanceMetric, HnswIndex, SearchQuality
+from velesdb_b200 import _native as nv
+
+
+class OracleSnapshot:
+    """Duck-types DeviceSnapshot for HnswIndex: answers search / brute force from the oracle."""
+
+    def __init__(self, metric, vectors, M=16, ef_c=100):
+        self.metric_, self.x = metric, np.ascontiguousarray(vectors, np.float32)
+        self.g = vo.Hnsw(int(metric), self.x.shape[1], M=M, ef_construction=ef_c)
+        if len(self.x):
+            self.g.insert_many(self.x)
+        self.calls = []
+
+    def __len__(self):
+        return len(self.x)
+
+    def search_batch(self, q, k, ef):
+        self.calls.append(("search", k, ef))
+        ids, d, cnt, _ = self.g.search_batch(q, k, ef, order="canonical")
+        return ids.astype(np.uint32), d, cnt
+
+    def bruteforce_batch(self, q, k):
+        self.calls.append(("brute", k))
+        ids, sc = vo.bruteforce_batch(int(self.metric_), self.x, q, k)
+        return ids.astype(np.uint32), sc
+
+    def rerank_batch(self, q, cand):
+        return np.array([[vo.metric_value(int(self.metric_), q[0], self.x[c]) for c in cand[0]]], np.float32)
+
+
+def make_index(n=300, dim=16, metric=DistanceMetric.Cosine, seed=0):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(size=(n, dim)).astype(np.float32)
+    ix = HnswIndex(dim, metric)
+    ids = [1000 + 7 * i for i in range(n)]  # external ids differ from node indices
+    for e, v in zip(ids, x):
+        ix.insert(e, v)
+    ix.insert(ids[0], x[1])  # duplicate id: skipped
+    snap = OracleSnapshot(metric, x)
+    ix._snapshot, ix._dirty = snap, False
+    return ix, snap, x, ids
+
+
+def test_len_dimension_metric_and_duplicates():
+    ix, _, _, ids = make_index()
+    assert ix.len() == 300 and ix.dimension() == 16 and ix.metric() == DistanceMetric.Cosine and not ix.is_empty()
+    assert ix.tombstone_count() == 0
+
+
+def test_quality_routes_to_ef_and_transform_score():
+    ix, snap, x, ids = make_index()
+    res = ix.search(x[5], 10)                      # Balanced -> ef = max(128, 4k)
+    assert snap.calls[-1] == ("search", 10, 128)
+    assert res[0][0] == ids[5] and 0.0 <= res[0][1] <= 1.0   # cosine scores clamp into [0, 1]
+    ix.search_with_quality(x[5], 40, SearchQuality.Fast)
+    assert snap.calls[-1] == ("search", 40, 80)
+    ix.search_with_quality(x[5], 10, SearchQuality.Custom(77))
+    assert snap.calls[-1] == ("search", 10, 77)
+    ix.search_with_quality(x[5], 10, SearchQuality.Perfect)    # Perfect short-circuits to brute force
+    assert snap.calls[-1][0] == "brute"
+    ix.search_batch_parallel(x[:4], 10, SearchQuality.Accurate)
+    assert snap.calls[-1] == ("search", 10, 512)
+
+
+def test_small_index_uses_brute_force_only_on_the_single_query_path():
+    ix, snap, x, ids = make_index(n=50)
+    ix.search(x[0], 5)
+    assert snap.calls[-1][0] == "brute"            # len <= 100 (search.rs:75-77)
+    ix.search_batch_parallel(x[:2], 5, SearchQuality.Balanced)
+    assert snap.calls[-1][0] == "search"           # no short-circuit in batch (batch.rs:159-197)
+
+
+def test_soft_delete_filters_results_everywhere():
+    ix, snap, x, ids = make_index()
+    assert ix.remove(ids[5]) and not ix.remove(ids[5])
+    assert ix.len() == 299 and ix.tombstone_count() == 1
+    assert all(r[0] != ids[5] for r in ix.search(x[5], 10))
+    bf = ix.search_brute_force(x[5], 10)
+    assert len(bf) == 10 and all(r[0] != ids[5] for r in bf)   # over-fetch keeps k results after the filter
+    assert ix.tombstone_ratio() == pytest.approx(1 / 300)
+
+
+def test_dimension_mismatch_is_an_error_like_the_reference_panic():
+    ix, _, x, _ = make_index()
+    with pytest.raises(DimensionMismatch, match="Query dimension mismatch: expected 16, got 3"):
+        ix.search(np.zeros(3, np.float32), 5)
+    with pytest.raises(DimensionMismatch, match="Vector dimension mismatch"):
+        ix.insert(99999, np.zeros(5, np.float32))
+    with pytest.raises(DimensionMismatch):
+        ix.search_batch_parallel(np.zeros((2, 4), np.float32), 5, SearchQuality.Balanced)
+
+
+def test_euclidean_and_dot_score_transforms():
+    for metric, sign in ((DistanceMetric.Euclidean, 1), (DistanceMetric.DotProduct, -1)):
+        ix, snap, x, ids = make_index(metric=metric)
+        res = ix.search(x[3], 5)
+        raw = snap.g.search(x[3], 5, 128, order="canonical")[1]
+        assert [r[1] for r in res] == [sign * float(d) for d in raw]
+
+
+def test_rerank_sorts_by_metric_value():
+    ix, snap, x, ids = make_index()
+    rr = ix.search_with_rerank(x[9], 5, 30)
+    assert len(rr) == 5 and rr[0][0] == ids[9]
+    assert all(rr[i][1] >= rr[i + 1][1] for i in range(4))
+
+
+def test_empty_index_returns_nothing():
+    ix = HnswIndex(8, DistanceMetric.Cosine)
+    assert ix.search_brute_force(np.zeros(8, np.float32), 3) == []
+    assert ix.search_batch_parallel(np.zeros((0, 8), np.float32), 3, SearchQuality.Balanced) == []
+    assert nv.lib().veles_ef_search(nv.BALANCED, 10, 0) == 128
