@@ -201,6 +201,14 @@ int32_t veles_fuse(int32_t strategy, const uint32_t* list_ptr, uint32_t n_lists,
  * reverse links pruned closest-first (graph.rs:592-639).  Replaces any graph held by `idx`. */
 int32_t veles_index_build_graph(veles_index_t* idx, uint32_t M, uint32_t cand_k, void* stream);
 
+/* The reference's *sequential* construction, exactly: NativeHnsw::insert (native/graph.rs:158-237) for nodes
+ * 0..n-1 in id order -- what HnswIndex::insert (index/hnsw/index/trait_impl.rs:10-36) builds, the one path on
+ * which the reference graph is deterministic.  Same levels (graph.rs:368-403), search_layer with
+ * ef_construction, select_neighbors (graph.rs:526-581, alpha = 1), add_bidirectional_connection
+ * (graph.rs:592-639).  One warp, latency bound: meant for small/medium graphs and for build parity; f32
+ * storage only.  Equal distances are ordered by node id (the reference: heap-internal order). */
+int32_t veles_index_build_graph_exact(veles_index_t* idx, uint32_t M, uint32_t ef_construction, void* stream);
+
 /* ---- multi-GPU --------------------------------------------------------------------------------- */
 /* Queries shard by contiguous slices across ranks; the snapshot is replicated.  The only exchange
  * is the final gather of [nq_local, k] ids + distances, done by the host runtime with NCCL

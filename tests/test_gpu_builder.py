@@ -64,3 +64,43 @@ def test_build_edge_cases():
     few.build_graph(16)
     ids, dist, cnt = few.search_batch(latent_data(5, 16, seed=1), 5, 32)
     assert (cnt == 5).all() and (ids[:, 0] == np.arange(5)).all()
+
+
+@pytest.mark.parametrize("metric,dim,n,M,ef_c", [(vo.COSINE, 48, 1500, 8, 60), (vo.EUCLIDEAN, 32, 1200, 16, 100),
+                                                 (vo.DOT, 64, 800, 8, 40), (vo.COSINE, 768, 400, 16, 64)])
+def test_exact_sequential_build_equals_reference_graph(metric, dim, n, M, ef_c):
+    """Build parity: veles_index_build_graph_exact restates NativeHnsw::insert (graph.rs:158-237) for nodes in
+    id order; every adjacency list, on every layer, must equal the oracle's (= the reference's deterministic
+    sequential build), id for id and in the same order."""
+    x = latent_data(n, dim, latent=8, noise=0.4, seed=11 + dim)
+    g = vo.Hnsw(metric, dim, M=M, ef_construction=ef_c)
+    g.insert_many(x)
+    snap = DeviceSnapshot.from_vectors(x, metric)
+    snap.build_graph_exact(M, ef_c)
+    assert snap.max_layer == g.max_layer and snap.entry_point == g.entry_point
+    ref_layers = g.export_graph()
+    got_layers = snap.export_graph()
+    assert len(got_layers) == len(ref_layers)
+    for l, ((rp, cols), (orp, ocols)) in enumerate(zip(got_layers, ref_layers)):
+        assert np.array_equal(rp, orp), f"layer {l}: degrees differ"
+        assert np.array_equal(cols, ocols), f"layer {l}: neighbour lists differ"
+    # and the search on it agrees as well
+    q = queries_near(x, 64, seed=2)
+    ids, dist, cnt = snap.search_batch(q, 10, 64)
+    oi, od, oc, ost = g.search_batch(q, 10, 64, order="canonical", threads=8)
+    keep = ost[:, 4] == 0
+    assert np.array_equal(ids[keep], oi[keep].astype(np.uint32)) and bits_equal(dist, od)
+
+
+def test_exact_build_edge_cases():
+    for n in (0, 1, 2, 5):
+        x = latent_data(max(n, 1), 16, seed=n)[:n]
+        snap = DeviceSnapshot.from_vectors(x, DistanceMetric.Euclidean)
+        snap.build_graph_exact(8, 32)
+        g = vo.Hnsw(vo.EUCLIDEAN, 16, M=8, ef_construction=32)
+        if n:
+            g.insert_many(x)
+            for (rp, cols), (orp, ocols) in zip(snap.export_graph(), g.export_graph()):
+                assert np.array_equal(rp, orp) and np.array_equal(cols, ocols)
+        ids, dist, cnt = snap.search_batch(np.zeros((1, 16), np.float32), 3, 16)
+        assert cnt[0] == min(n, 3)

@@ -198,6 +198,10 @@ class DeviceSnapshot:
     def build_graph(self, M, cand_k=0, stream=None):
         nv.check(nv.lib().veles_index_build_graph(self.h, M, cand_k, stream))
 
+    def build_graph_exact(self, M, ef_construction, stream=None):
+        """NativeHnsw::insert for nodes 0..n-1 in order (graph.rs:158-237): the reference's deterministic graph."""
+        nv.check(nv.lib().veles_index_build_graph_exact(self.h, M, ef_construction, stream))
+
     def export_layer(self, layer):
         nodes, edges = C.c_uint64(), C.c_uint64()
         nv.check(nv.lib().veles_index_export_layer(self.h, layer, C.byref(nodes), C.byref(edges), None, None))
