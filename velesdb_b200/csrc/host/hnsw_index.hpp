@@ -18,6 +18,7 @@
 #include <cstdint>
 #include <cstring>
 #include <fstream>
+#include <iterator>
 #include <mutex>
 #include <shared_mutex>
 #include <stdexcept>
@@ -90,7 +91,8 @@ class HnswIndex {
         dirty_ = true;
     }
     template <typename It>
-    size_t insert_batch_parallel(It first, It last) {  // batch.rs:82-108
+    size_t insert_batch_parallel(It first, It last) {  // batch.rs:82-108; < 100 vectors go sequentially there too
+        if (std::distance(first, last) >= 100) bulk_ = true;
         size_t count = 0;
         for (; first != last; ++first) {
             const size_t before = len();
@@ -259,7 +261,10 @@ class HnswIndex {
             if (snap_) veles_index_free(snap_);
             snap_ = nullptr;
             check(veles_index_from_vectors(staged_.data(), next_idx_, (uint32_t)dimension_, VELES_F32, VELES_F32, (int32_t)metric_, &snap_));
-            check(veles_index_build_graph(snap_, params_.max_connections, 0, nullptr));
+            if (!bulk_ && next_idx_ <= 20000)  // sequential inserts: the reference's deterministic graph
+                check(veles_index_build_graph_exact(snap_, params_.max_connections, params_.ef_construction, nullptr));
+            else
+                check(veles_index_build_graph(snap_, params_.max_connections, 0, nullptr));
             dirty_ = false;
         }
         return snap_;
@@ -291,6 +296,7 @@ class HnswIndex {
     std::vector<float> staged_;
     veles_index_t* snap_ = nullptr;
     bool dirty_ = false;
+    bool bulk_ = false;
     bool vectors_present_ = true;
 };
 

@@ -241,6 +241,8 @@ class HnswIndex:
     dependent in the reference too.  Indexes loaded from the reference's files keep the file's graph.
     """
 
+    EXACT_BUILD_LIMIT = 20_000  # above this the one-warp sequential builder is too slow; use the bulk builder
+
     def __init__(self, dimension, metric, params=None, enable_vector_storage=True, store_dtype="f32"):
         self._dimension = int(dimension)
         self._metric = DistanceMetric(metric)
@@ -253,6 +255,7 @@ class HnswIndex:
         self._staged = []          # vectors by node index
         self._snapshot = None
         self._dirty = False
+        self._bulk = False            # True once a batch of >= 100 vectors went through insert_batch_parallel
         self._vectors_present = True  # False after load(): ShardedVectors is left empty (constructors.rs:240)
 
     # ---- constructors (index/hnsw/index/constructors.rs:29-177)
@@ -296,7 +299,11 @@ class HnswIndex:
         self._dirty = True
 
     def insert_batch_parallel(self, vectors) -> int:
-        """index/hnsw/index/batch.rs:82-108: (id, vector) pairs; returns how many were new."""
+        """index/hnsw/index/batch.rs:82-108: (id, vector) pairs; returns how many were new.  Batches of fewer
+        than 100 vectors are inserted sequentially by the reference too (backend_adapter.rs:110-118)."""
+        vectors = list(vectors)
+        if len(vectors) >= 100:
+            self._bulk = True
         count = 0
         for id, v in vectors:
             before = len(self._id_to_idx)
@@ -433,7 +440,11 @@ class HnswIndex:
         if self._snapshot is None or self._dirty:
             vecs = np.stack(self._staged) if self._staged else np.zeros((0, self._dimension), np.float32)
             snap = DeviceSnapshot.from_vectors(vecs, self._metric, self._store_dtype)
-            snap.build_graph(self._params.max_connections)
+            if not self._bulk and self._store_dtype == "f32" and len(vecs) <= self.EXACT_BUILD_LIMIT:
+                # sequential inserts: the reference's deterministic graph (graph.rs:158-237), id for id
+                snap.build_graph_exact(self._params.max_connections, self._params.ef_construction)
+            else:
+                snap.build_graph(self._params.max_connections)
             self._snapshot, self._dirty = snap, False
         return self._snapshot
 
