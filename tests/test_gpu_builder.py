@@ -104,3 +104,28 @@ def test_exact_build_edge_cases():
                 assert np.array_equal(rp, orp) and np.array_equal(cols, ocols)
         ids, dist, cnt = snap.search_batch(np.zeros((1, 16), np.float32), 3, 16)
         assert cnt[0] == min(n, 3)
+
+
+def test_host_mirror_sequential_inserts_reproduce_the_reference_index():
+    """index_tests.rs:1108-1159 through the host mirror: HnswIndex::insert one by one (HnswParams::auto(64) =
+    M 24 / ef_construction 300), then Accurate search.  The mirror builds with the exact sequential builder,
+    so ids and scores must equal the oracle's end to end (insert -> search -> id map -> transform_score)."""
+    import math
+
+    from velesdb_b200 import HnswIndex, SearchQuality
+
+    dim, n, k = 64, 500, 10
+    data = np.array([[math.sin(np.float32(i * dim + j) * np.float32(0.001)) for j in range(dim)] for i in range(n)], np.float32)
+    ix = HnswIndex(dim, DistanceMetric.Cosine)
+    g = vo.Hnsw(vo.COSINE, dim, M=24, ef_construction=300)
+    for i in range(n):
+        ix.insert(i, data[i])
+        g.insert(data[i])
+    q = np.array([math.sin(np.float32(j) * np.float32(0.001)) for j in range(dim)], np.float32)
+    res = ix.search_with_quality(q, k, SearchQuality.Accurate)
+    oi, od, st = g.search(q, k, vo.ef_search(vo.ACCURATE, k), order="canonical", with_stats=True)
+    if not st["tie_at_k"]:
+        assert [r[0] for r in res] == oi.tolist()
+    assert bits_equal([r[1] for r in res], [vo.transform_score(vo.COSINE, d) for d in od])
+    gt, _ = vo.bruteforce(vo.COSINE, data, q, k)
+    assert len(set(r[0] for r in res) & set(gt.tolist())) / k >= 0.8   # the reference's own assertion
