@@ -831,7 +831,13 @@ static int32_t launch_search(const veles_index* ix, const float* q_d, uint32_t n
     // resident warps (queries) per SM.  Measured on B200 (profiles/): every query of a 1024-batch must be
     // resident at once (7 x 148 = 1036 slots) -- with fewer slots a second wave of queries starts late and
     // the batch time nearly doubles; 7 CTAs leave room for 2 stages of 4 rows each.
-    const uint32_t want_ctas = std::max(1u, env_u32("VELES_SEARCH_CTAS_PER_SM", p.quad ? 7 : 8));
+    // Batches larger than 7 x SMs prefer more resident queries with the minimal ring (two stages) over
+    // deeper rings: measured on C3s (f16, 8192 queries) 7 -> 13 CTAs/SM = 173 K -> 222 K queries/s.
+    const uint32_t min_ring = (p.quad == 1 ? 8u : 2u) * ix->row_bytes;
+    const uint32_t cmax = std::max(1u, (uint32_t)sm_smem / (p.off_ring + min_ring + 1024u));
+    const uint32_t need = (nq + (uint32_t)sms - 1) / (uint32_t)sms;
+    const uint32_t auto_ctas = std::min(std::min(cmax, 16u), std::max(need, p.quad ? 7u : 8u));
+    const uint32_t want_ctas = std::max(1u, env_u32("VELES_SEARCH_CTAS_PER_SM", auto_ctas));
     const uint32_t per_cta_target = (uint32_t)sm_smem / want_ctas - 1024;
     uint32_t nslot = 2;
     if (per_cta_target > p.off_ring + 2 * ix->row_bytes) nslot = (per_cta_target - p.off_ring) / ix->row_bytes;
