@@ -113,6 +113,110 @@ __global__ void __launch_bounds__(kWarps * 32) bf_tile_kernel(IndexView ix, cons
     }
 }
 
+// ---- 8 rows x 8 queries per warp, dim % 32 == 0 ------------------------------------------------------
+// Same lane <-> element-class mapping as above, but the 64 accumulators of a warp are reduced with a
+// *transposing* butterfly: at the xor-8 step a lane keeps half of its accumulators and hands the other half
+// to its partner, and so on (xor 16, 4, 2, 1), so 32 accumulators cost 31 shuffles instead of 160 and end
+// up one per lane.  Every addition still combines the same commutative pair of partial sums as
+// warp_tree_sum32, so the bits are unchanged.  Lane l ends up owning accumulator
+// a(l) = b0 + 2*b1 + 4*b2 + 8*b4 + 16*b3 (b_i = bit i of l).
+template <int N>
+__device__ __forceinline__ void butterfly_halve(float* v, uint32_t lane, uint32_t bit_mask, uint32_t xor_mask) {
+    const bool hi = (lane & bit_mask) != 0;
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        const float mine = hi ? v[N / 2 + i] : v[i];
+        const float theirs = hi ? v[i] : v[N / 2 + i];
+        v[i] = __fadd_rn(mine, __shfl_xor_sync(FULL_MASK, theirs, xor_mask));
+    }
+}
+__device__ __forceinline__ float butterfly32(float* v, uint32_t lane) {
+    butterfly_halve<32>(v, lane, 8, 8);
+    butterfly_halve<16>(v, lane, 16, 16);
+    butterfly_halve<8>(v, lane, 4, 4);
+    butterfly_halve<4>(v, lane, 2, 2);
+    butterfly_halve<2>(v, lane, 1, 1);
+    return v[0];
+}
+
+constexpr int kRT8 = 8;
+template <typename TB>
+__global__ void __launch_bounds__(kWarps * 32) bf_tile8_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq,
+                                                               float* __restrict__ scores, bool as_value) {
+    extern __shared__ __align__(16) float qs[];  // kQT x dim, then kQT norms
+    const uint32_t dim = ix.dim;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t qbase = blockIdx.y * kQT;
+    const uint32_t nqt = min((uint32_t)kQT, nq - qbase);
+    float* qnorm = qs + (size_t)kQT * dim;
+    for (uint32_t i = threadIdx.x; i < kQT * dim; i += blockDim.x) {
+        const uint32_t t = i / dim;
+        qs[i] = t < nqt ? queries[(size_t)(qbase + t) * dim + (i - t * dim)] : 0.0f;
+    }
+    __syncthreads();
+    if (ix.metric == VELES_COSINE) {
+        for (uint32_t t = warp; t < kQT; t += kWarps) {
+            const float* q = qs + (size_t)t * dim;
+            const float s = warp_tree_reduce<0>(q, q, dim, lane);
+            if (lane == 0) qnorm[t] = __fsqrt_rn(s);
+        }
+    }
+    __syncthreads();
+    const bool l2 = ix.metric == VELES_EUCLIDEAN;
+    const uint64_t n = ix.n;
+    const uint64_t tiles = (n + kRT8 - 1) / kRT8;
+    // accumulator owned by this lane after the butterfly: row a/8 (within a half-tile of 4 rows), query a%8
+    const uint32_t a = (lane & 1) | (lane & 2) | (lane & 4) | ((lane & 16) >> 1) | ((lane & 8) << 1);
+    const uint32_t my_r = a >> 3, my_t = a & 7;
+    for (uint64_t tile = blockIdx.x * (uint64_t)kWarps + warp; tile < tiles; tile += (uint64_t)gridDim.x * kWarps) {
+        const uint64_t r0 = tile * kRT8;
+        const uint8_t* base = ix.vecs + r0 * ix.row_bytes;
+        const uint64_t last_off = (n - 1 - r0) * (uint64_t)ix.row_bytes;  // rows past the end alias the last row
+        float acc[kRT8 * kQT];
+#pragma unroll
+        for (int j = 0; j < kRT8 * kQT; ++j) acc[j] = 0.0f;
+        for (uint32_t i = lane; i < dim; i += 32) {
+            float x[kRT8], q[kQT];
+#pragma unroll
+            for (int r = 0; r < kRT8; ++r) {
+                const uint64_t off = min((uint64_t)r * ix.row_bytes, last_off);
+                x[r] = load_elem(reinterpret_cast<const TB*>(base + off), i);
+            }
+#pragma unroll
+            for (int t = 0; t < kQT; ++t) q[t] = qs[(size_t)t * dim + i];
+#pragma unroll
+            for (int r = 0; r < kRT8; ++r)
+#pragma unroll
+                for (int t = 0; t < kQT; ++t) {
+                    if (l2) {
+                        const float d = __fsub_rn(q[t], x[r]);
+                        acc[r * kQT + t] = __fmaf_rn(d, d, acc[r * kQT + t]);
+                    } else {
+                        acc[r * kQT + t] = __fmaf_rn(q[t], x[r], acc[r * kQT + t]);
+                    }
+                }
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const float s = butterfly32(acc + half * 32, lane);
+            const uint64_t row = r0 + half * 4 + my_r;
+            if (row < n && my_t < nqt) {
+                float v;
+                if (l2) {
+                    v = __fsqrt_rn(s);
+                } else if (ix.metric == VELES_COSINE) {
+                    const float nb = *reinterpret_cast<const float*>(ix.vecs + row * ix.row_bytes + ix.norm_off);
+                    const float sim = cosine_from_parts(s, qnorm[my_t], nb);
+                    v = as_value ? sim : __fsub_rn(1.0f, sim);
+                } else {
+                    v = as_value ? s : -s;
+                }
+                scores[(size_t)(qbase + my_t) * n + row] = v;
+            }
+        }
+    }
+}
+
 // generic path: any metric, any dim >= 1, F32/F16 rows: one warp per (query, row) pair
 template <typename TB>
 __global__ void bf_generic_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq,
@@ -217,6 +321,91 @@ __global__ void __launch_bounds__(32) topk_kernel(const float* __restrict__ scor
     }
 }
 
+// k <= 512: one CTA of kTopWarps warps per query, each warp streams a slice of the score row (float4 loads)
+// through a threshold filter into its own sorted list; warp 0 merges the lists.
+constexpr int kTopWarps = 8;
+__global__ void __launch_bounds__(kTopWarps * 32) topk_cta_kernel(const float* __restrict__ scores, uint64_t n, uint32_t k,
+                                                                 bool descending, uint32_t* __restrict__ out_ids,
+                                                                 float* __restrict__ out_score) {
+    extern __shared__ __align__(16) uint64_t tk_smem[];
+    __shared__ uint32_t s_len[kTopWarps];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = blockIdx.x;
+    const float* row = scores + (size_t)q * n;
+    uint64_t* res = tk_smem + (size_t)warp * k;
+    // slices start at multiples of 128 elements past the row's 16-byte alignment point
+    const uint64_t mis = (((uintptr_t)row) >> 2) & 3;       // elements until the next 16-byte boundary: (4 - mis) % 4
+    const uint64_t head = (4 - mis) & 3;
+    uint64_t seg = (n + kTopWarps - 1) / kTopWarps;
+    seg = (seg + 127) & ~(uint64_t)127;
+    const uint64_t c_begin = warp * seg, c_end = min(n, c_begin + seg);
+    uint32_t len = 0;
+    uint64_t worst = ~0ull;
+    auto offer = [&](uint64_t key) {
+        uint32_t msk = __ballot_sync(FULL_MASK, key < worst);
+        while (msk) {
+            const uint32_t src = __ffs(msk) - 1;
+            msk &= msk - 1;
+            const uint64_t kk = __shfl_sync(FULL_MASK, key, src);
+            if (kk >= worst) continue;
+            const uint32_t pos = lower_bound_warp(res, len, kk, lane);
+            if (len < k) {
+                insert_at(res, pos, len + 1, kk, lane);
+                ++len;
+            } else {
+                insert_at(res, pos, len, kk, lane);
+            }
+            if (len == k) worst = res[k - 1];
+        }
+    };
+    auto make_key = [&](float v, uint64_t i) {
+        uint32_t o = ord_key(v);
+        if (descending) o = ~o;
+        return ((uint64_t)o << 32) | (uint32_t)i;
+    };
+    (void)head;
+    for (uint64_t base = c_begin; base < c_end; base += 128) {
+        const uint64_t i0 = base + (uint64_t)lane * 4;
+        uint64_t key[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+        if (mis == 0 && i0 + 3 < c_end) {
+            const float4 v = *reinterpret_cast<const float4*>(row + i0);
+            key[0] = make_key(v.x, i0);
+            key[1] = make_key(v.y, i0 + 1);
+            key[2] = make_key(v.z, i0 + 2);
+            key[3] = make_key(v.w, i0 + 3);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (i0 + e < c_end) key[e] = make_key(row[i0 + e], i0 + e);
+        }
+        const bool any = key[0] < worst || key[1] < worst || key[2] < worst || key[3] < worst;
+        if (!__any_sync(FULL_MASK, any)) continue;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) offer(key[e]);
+    }
+    if (lane == 0) s_len[warp] = len;
+    __syncthreads();
+    if (warp != 0) return;
+    for (uint32_t w = 1; w < kTopWarps; ++w) {
+        const uint64_t* other = tk_smem + (size_t)w * k;
+        const uint32_t olen = s_len[w];
+        for (uint32_t j0 = 0; j0 < olen; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            offer(j < olen ? other[j] : ~0ull);
+        }
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < k; i += 32) {
+        uint32_t id = VELES_INVALID_ID;
+        float sc = __uint_as_float(0x7fc00000u);
+        if (i < len) {
+            id = (uint32_t)res[i];
+            sc = row[id];
+        }
+        out_ids[(size_t)q * k + i] = id;
+        out_score[(size_t)q * k + i] = sc;
+    }
+}
+
 // metric value of explicit (query, candidate) pairs; one warp per pair
 template <typename TB>
 __global__ void rerank_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq, const uint32_t* __restrict__ cand,
@@ -283,9 +472,27 @@ static int32_t launch_scores(const veles_index* ix, const float* q_d, uint32_t n
         count_launch();
     } else if (ix->dim >= 16 && (ix->metric == VELES_COSINE || ix->metric == VELES_EUCLIDEAN || ix->metric == VELES_DOT)) {
         const size_t smem = ((size_t)kQT * ix->dim + kQT) * 4;
+        const uint32_t qtiles = (nq + kQT - 1) / kQT;
+        if (ix->dim % 32 == 0) {
+            auto kern8 = ix->dtype == VELES_F32 ? bf_tile8_kernel<float> : bf_tile8_kernel<__half>;
+            VELES_CUDA(cudaFuncSetAttribute(kern8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const uint64_t row_tiles = (ix->n + kRT8 - 1) / kRT8;
+            uint64_t gx = (row_tiles + kWarps - 1) / kWarps;
+            const uint64_t want = std::max<uint64_t>(1, ((uint64_t)sms * 4 + qtiles - 1) / qtiles);
+            gx = std::max<uint64_t>(1, std::min(gx, want));
+            for (uint32_t t0 = 0; t0 < qtiles; t0 += 32768) {
+                const uint32_t nt = std::min(32768u, qtiles - t0);
+                const uint32_t qoff = t0 * kQT;
+                dim3 grid((unsigned)gx, nt);
+                kern8<<<grid, kWarps * 32, smem, st>>>(v, q_d + (size_t)qoff * ix->dim, nq - qoff, scores_d + (size_t)qoff * ix->n,
+                                                      as_value);
+                count_launch();
+            }
+            VELES_CUDA(cudaGetLastError());
+            return VELES_OK;
+        }
         auto kern = ix->dtype == VELES_F32 ? bf_tile_kernel<float> : bf_tile_kernel<__half>;
         VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const uint32_t qtiles = (nq + kQT - 1) / kQT;
         const uint64_t row_tiles = (ix->n + kRT - 1) / kRT;
         uint64_t gx = (row_tiles + kWarps - 1) / kWarps;
         // enough CTAs to fill the machine a few times over; the row loop is grid-strided
@@ -329,11 +536,18 @@ static int32_t bruteforce_device(const veles_index* ix, const float* q_d, uint32
     VELES_TRY(ix->scores_d.ensure((size_t)chunk * per_q));
     const bool desc = ix->metric == VELES_COSINE || ix->metric == VELES_DOT || ix->metric == VELES_JACCARD;
     VELES_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(k * 8)));
+    if (k <= 512)
+        VELES_CUDA(cudaFuncSetAttribute(topk_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTopWarps * k * 8)));
     for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
         const uint32_t nn = std::min(chunk, nq - q0);
         VELES_TRY(launch_scores(ix, q_d + (size_t)q0 * ix->dim, nn, ix->scores_d.as<float>(), true, st));
-        topk_kernel<<<nn, 32, (size_t)k * 8, st>>>(ix->scores_d.as<float>(), ix->n, k, desc, ids_d + (size_t)q0 * k,
-                                                   score_d + (size_t)q0 * k);
+        if (k <= 512) {
+            topk_cta_kernel<<<nn, kTopWarps * 32, (size_t)kTopWarps * k * 8, st>>>(ix->scores_d.as<float>(), ix->n, k, desc,
+                                                                                  ids_d + (size_t)q0 * k, score_d + (size_t)q0 * k);
+        } else {
+            topk_kernel<<<nn, 32, (size_t)k * 8, st>>>(ix->scores_d.as<float>(), ix->n, k, desc, ids_d + (size_t)q0 * k,
+                                                       score_d + (size_t)q0 * k);
+        }
         count_launch();
         VELES_CUDA(cudaGetLastError());
     }
