@@ -52,10 +52,8 @@ struct SearchParams {
     uint32_t evict_first; // 1: vector rows are fetched with an L2 evict-first policy
     uint32_t peek;        // 1: speculative read-only visited test of the predicted next candidate's neighbours
     uint32_t row_prefetch; // rows of the predicted next expansion warmed into L2 (0 = off)
-    uint32_t speculate;   // 1: idle stages at the end of a list fetch the first quads of the predicted next list
     // shared-memory carve (bytes from base)
     uint32_t off_res, off_todo, off_q, off_ring;
-    uint32_t todo_cap;    // entries of the todo list; spec_ids (16 entries) follow it
 };
 
 struct WarpCtx {
@@ -68,13 +66,6 @@ struct WarpCtx {
     uint64_t policy;
     float norm_a;
     uint32_t lane;
-    // quad pipeline state that survives across lists
-    uint32_t cur;         // stage the next list starts on (rotation continues from list to list)
-    uint32_t* spec_ids;   // first rows of the predicted next expansion (<= 4 * stages ids)
-    uint32_t spec_m;      // number of unvisited neighbours of the predicted next expansion
-    uint32_t spec_node;   // node that expansion belongs to
-    uint32_t spec_quads;  // how many of its quads are already in flight (stages cur, cur+1, ...)
-    bool spec_armed;      // spec_ids / spec_m are valid for spec_node and the prediction still holds
 };
 
 __device__ __forceinline__ uint64_t make_key(float d, uint32_t id) {
@@ -222,34 +213,25 @@ __device__ __forceinline__ float quad_distance(const SearchParams& p, const Warp
     }
 }
 
-// Evaluates c.todo[0..m) in order, four rows per step; stage s uses slots 4s..4s+3 and barrier s.  The stage
-// rotation continues from list to list (c.cur).  When a list has no more quads of its own to issue, the
-// freed stage fetches the next quad of the *predicted next list* (c.spec_ids) instead of idling, so that list
-// starts with its first stages already in flight (c.spec_quads tells it how many).  ALLOW_SPEC is off for the
-// upper-layer lists.
-template <int DT, bool ALLOW_SPEC, typename F>
+// Evaluates c.todo[0..m) in order, four rows per step; stage s uses slots 4s..4s+3 and barrier s.
+template <int DT, typename F>
 __device__ __forceinline__ void eval_list_quad(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
     const uint32_t stages = p.nslot >> 2;
     const uint32_t nquad = (m + 3) >> 2;
     // lanes 0..3 each issue one row copy of the quad (address arithmetic in parallel); lane 0 arms the barrier.
     // The barrier's pending-arrival count stays at 1 until lane 0 arrives, so complete_tx from a copy that
     // lands before the expect_tx cannot complete the phase early.
-    auto issue_rows = [&](const uint32_t* ids, uint32_t cnt, uint32_t s) {
+    auto issue_quad = [&](uint32_t j, uint32_t s) {
+        const uint32_t cnt = min(4u, m - 4 * j);
         if (c.lane == 0) mbar_expect_tx(&c.bar[s], cnt * p.ix.row_bytes);
-        if (c.lane < cnt) copy_row(p, c, 4 * s + c.lane, ids[c.lane], &c.bar[s]);
+        if (c.lane < cnt) copy_row(p, c, 4 * s + c.lane, c.todo[4 * j + c.lane], &c.bar[s]);
     };
-    const uint32_t pre_issued = c.spec_quads;  // quads of THIS list already in flight (0 unless speculated)
-    c.spec_quads = 0;
-    uint32_t s = c.cur;
     {
-        uint32_t ss = s;
         const uint32_t pre = nquad < stages ? nquad : stages;
-        for (uint32_t j = 0; j < pre; ++j) {
-            if (j >= pre_issued) issue_rows(c.todo + 4 * j, min(4u, m - 4 * j), ss);
-            ss = (ss + 1 == stages) ? 0 : ss + 1;
-        }
+        for (uint32_t j = 0; j < pre; ++j) issue_quad(j, j);
     }
     const uint32_t g = c.lane >> 3;
+    uint32_t s = 0;
     for (uint32_t j = 0; j < nquad; ++j) {
         mbar_wait(&c.bar[s], (c.phases >> s) & 1u);
         c.phases ^= 1u << s;
@@ -258,36 +240,13 @@ __device__ __forceinline__ void eval_list_quad(const SearchParams& p, WarpCtx& c
         const uint32_t gg = g < cnt ? g : 0;
         const float d = quad_distance<DT>(p, c, c.ring + (size_t)(4 * s + gg) * p.ix.row_bytes);
         __syncwarp();
-        if (j + stages < nquad) {
-            issue_rows(c.todo + 4 * (j + stages), min(4u, m - 4 * (j + stages)), s);
-        } else if (ALLOW_SPEC && nquad >= stages && c.spec_armed) {
-            const uint32_t t = j + stages - nquad;  // quad index within the predicted list
-            if (t == c.spec_quads && 4 * t < c.spec_m) {
-                issue_rows(c.spec_ids + 4 * t, min(4u, c.spec_m - 4 * t), s);
-                c.spec_quads = t + 1;
-            }
-        }
+        if (j + stages < nquad) issue_quad(j + stages, s);
         for (uint32_t e = 0; e < cnt; ++e) {
             const float de = __shfl_sync(FULL_MASK, d, e * 8);
             on_dist(c.todo[4 * j + e], de);
         }
         s = (s + 1 == stages) ? 0 : s + 1;
     }
-    c.cur = s;
-}
-
-// waits out speculative quads whose prediction did not hold, so their stages can be reused
-__device__ __forceinline__ void drain_spec(const SearchParams& p, WarpCtx& c) {
-    const uint32_t stages = p.nslot >> 2;
-    uint32_t s = c.cur;
-    for (uint32_t t = 0; t < c.spec_quads; ++t) {
-        mbar_wait(&c.bar[s], (c.phases >> s) & 1u);
-        c.phases ^= 1u << s;
-        s = (s + 1 == stages) ? 0 : s + 1;
-    }
-    // the stages are free again and the rotation restarts where it was: nothing of the next list is in flight
-    c.spec_quads = 0;
-    __syncwarp();
 }
 
 // Evaluates the distances of c.todo[0..m) in order, with up to nslot row fetches in flight.
@@ -350,12 +309,12 @@ __device__ __forceinline__ void eval_list_bits(const SearchParams& p, WarpCtx& c
     }
 }
 
-template <int DT, bool ALLOW_SPEC = false, typename F>
+template <int DT, typename F>
 __device__ __forceinline__ void eval_list(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
     if (DT == VELES_BIN1 && p.quad == 2)
         eval_list_bits(p, c, m, on_dist);
     else if (p.quad)
-        eval_list_quad<DT, ALLOW_SPEC>(p, c, m, on_dist);
+        eval_list_quad<DT>(p, c, m, on_dist);
     else
         eval_list_single<DT>(p, c, m, on_dist);
 }
@@ -507,7 +466,7 @@ struct ResArr {
 };
 
 template <int DT, int R>
-__global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p) {
+__global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     WarpCtx c;
     c.lane = threadIdx.x;
@@ -519,12 +478,6 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
     c.phases = 0;
     c.norm_a = 0.0f;
     c.policy = make_evict_first_policy();
-    c.cur = 0;
-    c.spec_ids = c.todo + p.todo_cap;
-    c.spec_m = 0;
-    c.spec_node = VELES_INVALID_ID;
-    c.spec_quads = 0;
-    c.spec_armed = false;
     const uint32_t lane = c.lane;
     ResArr<R> res;
     if (lane == 0) {
@@ -617,7 +570,6 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
             bool pre_peeked = false;          // true once pre_va / pre_vb are valid for the *next* expansion
             auto learn = [&](uint32_t x) {
                 if (!can_pre || x == pre_node) return;
-                c.spec_armed = false;  // the prediction changed: stop feeding the old one
                 pre_node = x;
                 const uint32_t* row = p.ix.adj0 + (size_t)x * p.ix.stride0;
                 pre_a = row[lane];
@@ -669,10 +621,6 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
                 } else {
                     break;  // candidates exhausted, or everything left is farther than the worst result
                 }
-                // speculative quads are only usable if they were fetched for exactly this expansion
-                const bool spec_hit = c.spec_quads > 0 && can_pre && cnode == pre_node && pre_peeked && cnode == c.spec_node;
-                if (c.spec_quads > 0 && !spec_hit) drain_spec(p, c);
-                c.spec_armed = false;
                 // expand cnode: adjacency from the prefetch registers when the prediction held
                 uint32_t nread = 0, m = 0;
                 if (can_pre && cnode == pre_node && pre_peeked) {
@@ -694,7 +642,7 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
                 ndc0 += m;
                 pre_peeked = false;  // this expansion's marking invalidates any earlier peek
                 if (nxt < len) learn(key_id(res.get(nxt)));
-                eval_list<DT, true>(p, c, m, [&](uint32_t id, float d) {
+                eval_list<DT>(p, c, m, [&](uint32_t id, float d) {
                     if (pre_age != 0) {
                         ++pre_age;
                         if (pre_age == 10) {  // the adjacency row landed long ago: fetch its visited words
@@ -709,21 +657,6 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
                         } else if (pre_age == 16) {  // the words landed: the peek is usable; warm the first rows
                             pre_peeked = true;
                             pre_age = 0;
-                            if (p.speculate && p.quad == 1) {
-                                // first rows of the predicted expansion, in the order gather_peeked will produce
-                                const bool ka = pre_a != VELES_INVALID_ID && !((pre_va >> (pre_a & 31)) & 1u);
-                                const bool kb = pre_b != VELES_INVALID_ID && !((pre_vb >> (pre_b & 31)) & 1u);
-                                const uint32_t ma = __ballot_sync(FULL_MASK, ka), mb = __ballot_sync(FULL_MASK, kb);
-                                const uint32_t cap = (p.nslot >> 2) * 4;
-                                const uint32_t lt = (1u << lane) - 1u;
-                                const uint32_t pa = __popc(ma & lt), pb = __popc(ma) + __popc(mb & lt);
-                                if (ka && pa < cap) c.spec_ids[pa] = pre_a;
-                                if (kb && pb < cap) c.spec_ids[pb] = pre_b;
-                                c.spec_m = __popc(ma) + __popc(mb);
-                                c.spec_node = pre_node;
-                                c.spec_armed = c.spec_m > 0 && c.spec_quads == 0;
-                                __syncwarp();
-                            }
                             if (p.row_prefetch) {
                                 const bool ka = pre_a != VELES_INVALID_ID && !((pre_va >> (pre_a & 31)) & 1u);
                                 const bool kb = pre_b != VELES_INVALID_ID && !((pre_vb >> (pre_b & 31)) & 1u);
@@ -808,9 +741,6 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
                 __syncwarp();
             }
 
-            if (c.spec_quads > 0) drain_spec(p, c);
-            c.spec_armed = false;
-
             // ---- clear the visited bitmap for the next query of this slot ----
             if (logn <= kLogCap) {
                 for (uint32_t i = lane; i < logn; i += 32) vis[vlog[i] >> 5] = 0u;
@@ -878,8 +808,7 @@ static int32_t launch_search(const veles_index* ix, const float* q_d, uint32_t n
     p.off_res = bar_bytes;
     const uint32_t res_bytes = round_up(ef * 8, 16);
     p.off_todo = p.off_res + res_bytes;
-    p.todo_cap = std::max(ix->stride0, ix->strideU);
-    const uint32_t todo_bytes = round_up(p.todo_cap * 4, 16) + 64;  // + spec_ids
+    const uint32_t todo_bytes = round_up(std::max(ix->stride0, ix->strideU) * 4, 16);
     p.off_q = p.off_todo + todo_bytes;
     const uint32_t q_bytes = round_up(ix->dtype == VELES_BIN1 ? ix->dim / 8 : ix->dim * 4, 16);
     p.off_ring = round_up(p.off_q + q_bytes, 128);
@@ -899,7 +828,6 @@ static int32_t launch_search(const veles_index* ix, const float* q_d, uint32_t n
     p.evict_first = env_u32("VELES_SEARCH_EVICT_FIRST", 1) != 0 ? 1 : 0;
     p.peek = env_u32("VELES_SEARCH_PEEK", 1) != 0 ? 1 : 0;
     p.row_prefetch = std::min(32u, env_u32("VELES_SEARCH_ROW_PREFETCH", 0));
-    p.speculate = env_u32("VELES_SEARCH_SPECULATE", 1) != 0 ? 1 : 0;
     // resident warps (queries) per SM.  Measured on B200 (profiles/): every query of a 1024-batch must be
     // resident at once (7 x 148 = 1036 slots) -- with fewer slots a second wave of queries starts late and
     // the batch time nearly doubles; 7 CTAs leave room for 2 stages of 4 rows each.
