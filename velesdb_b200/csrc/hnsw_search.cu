@@ -466,7 +466,7 @@ struct ResArr {
 };
 
 template <int DT, int R>
-__global__ void __launch_bounds__(32) hnsw_search_kernel(const SearchParams p) {
+__global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     WarpCtx c;
     c.lane = threadIdx.x;
