@@ -11,8 +11,8 @@
 //
 // How the two heaps are represented here.  Every accepted node enters both heaps, so
 //   candidates = {unexpanded members of results}  U  {evicted, not yet popped}.
-// `res` is one array sorted by (dist, id) with an "expanded" bit per entry; the next candidate is
-// its first unexpanded entry.  An evicted node can only ever be popped *without* ending the loop
+// `res` is one array sorted by (dist, id) with an "expanded" bit per entry (in registers for ef <= 256, else
+// in shared memory: ResArr); the next candidate is its first unexpanded entry.  An evicted node can only ever be popped *without* ending the loop
 // when its distance equals the current worst distance (it was the maximum when evicted, and the
 // worst distance never grows), so only those are kept, in the per-query tie list `tie`; everything
 // else evicted could only trigger the break and is dropped.  Pop order between the two sets is
