@@ -36,7 +36,7 @@ struct veles_bm25 {
     uint32_t n_terms = 0, n_doc_slots = 0, n_ranges = 0;
     uint64_t doc_count = 0, total_len = 0, n_postings = 0;
     float k1 = 1.2f, b = 0.75f, avgdl = 0.0f;
-    veles::DevBuf term_ptr, post_doc, post_tf, doc_len, idf, skip;
+    veles::DevBuf term_ptr, post_doc, post_tf, post_den, doc_len, idf, skip;
     mutable std::mutex mu;
     mutable veles::DevBuf q_ptr_d, q_terms_d, partial_d, out_doc_d, out_score_d, out_cnt_d;
 };
@@ -46,6 +46,7 @@ namespace veles {
 struct Bm25View {
     const uint32_t* post_doc;
     const uint32_t* post_tf;
+    const float* post_den;  // tf + k1 * (1 - b + b * doc_len / avgdl), the denominator of bm25.rs:371-372 per posting
     const uint32_t* doc_len;
     const float* idf;
     const uint64_t* skip;  // n_terms x (n_ranges + 1)
@@ -65,7 +66,6 @@ __global__ void __launch_bounds__(256) bm25_range_kernel(Bm25View v, const uint3
     __syncthreads();
     const uint32_t t0 = q_ptr[q], t1 = q_ptr[q + 1];
     const float k1p1 = __fadd_rn(v.k1, 1.0f);
-    const float one_minus_b = __fsub_rn(1.0f, v.b);
     bool touched = false;
     // term metadata for up to kTermChunk query tokens at a time, fetched by parallel threads so the
     // dependent global loads (term id -> skip entries) are paid once per chunk, not once per term
@@ -87,22 +87,47 @@ __global__ void __launch_bounds__(256) bm25_range_kernel(Bm25View v, const uint3
             s_idf[threadIdx.x] = idf;
         }
         __syncthreads();
-        for (uint32_t ti = 0; ti < nt; ++ti) {
-            const uint64_t lo = s_lo[ti], hi = s_hi[ti];
-            if (hi == lo) continue;  // uniform: nothing of this term in the range
-            const float idf = s_idf[ti];
-            for (uint64_t p = lo + threadIdx.x; p < hi; p += blockDim.x) {
-                const uint32_t d = v.post_doc[p];
-                const float tf = (float)v.post_tf[p];
-                const float dl = (float)v.doc_len[d];
-                const float len_norm = __fadd_rn(one_minus_b, __fdiv_rn(__fmul_rn(v.b, dl), v.avgdl));
-                const float num = __fmul_rn(tf, k1p1);
-                const float den = __fadd_rn(tf, __fmul_rn(v.k1, len_norm));
-                const float contrib = __fdiv_rn(__fmul_rn(idf, num), den);
-                acc[d - base_doc] = __fadd_rn(acc[d - base_doc], contrib);
+        // Walk the (term, 256-posting chunk) sequence in query order.  Chunks of one term touch distinct
+        // documents, so a block barrier is only needed when the term changes; the next chunk's postings are
+        // requested before the current chunk is applied.
+        uint32_t g = 0;
+        while (g < nt && s_hi[g] == s_lo[g]) ++g;
+        uint64_t base = g < nt ? s_lo[g] : 0;
+        uint32_t d_cur = VELES_INVALID_ID, tf_cur = 0;
+        float den_cur = 1.0f;
+        if (g < nt && base + threadIdx.x < s_hi[g]) {
+            d_cur = v.post_doc[base + threadIdx.x];
+            tf_cur = v.post_tf[base + threadIdx.x];
+            den_cur = v.post_den[base + threadIdx.x];
+        }
+        while (g < nt) {
+            // next chunk (uniform across the block)
+            uint32_t g2 = g;
+            uint64_t base2 = base + blockDim.x;
+            if (base2 >= s_hi[g2]) {
+                ++g2;
+                while (g2 < nt && s_hi[g2] == s_lo[g2]) ++g2;
+                base2 = g2 < nt ? s_lo[g2] : 0;
+            }
+            uint32_t d_nxt = VELES_INVALID_ID, tf_nxt = 0;
+            float den_nxt = 1.0f;
+            if (g2 < nt && base2 + threadIdx.x < s_hi[g2]) {
+                d_nxt = v.post_doc[base2 + threadIdx.x];
+                tf_nxt = v.post_tf[base2 + threadIdx.x];
+                den_nxt = v.post_den[base2 + threadIdx.x];
+            }
+            if (d_cur != VELES_INVALID_ID) {
+                const float num = __fmul_rn((float)tf_cur, k1p1);
+                const float contrib = __fdiv_rn(__fmul_rn(s_idf[g], num), den_cur);
+                acc[d_cur - base_doc] = __fadd_rn(acc[d_cur - base_doc], contrib);
             }
             touched = true;
-            __syncthreads();  // next term's contributions come after this term's, per document
+            if (g2 != g) __syncthreads();  // next term's contributions come after this term's, per document
+            g = g2;
+            base = base2;
+            d_cur = d_nxt;
+            tf_cur = tf_nxt;
+            den_cur = den_nxt;
         }
         __syncthreads();
     }
@@ -248,15 +273,31 @@ int32_t veles_bm25_from_csr(uint32_t n_terms, const uint64_t* term_ptr, const ui
         }
         while (r < nr) row[++r] = e;
     }
+    // per-posting denominator, with the reference's f32 operation order (bm25.rs:357-358, 371-372); the host
+    // compiler targets baseline x86-64, so nothing here is contracted into an FMA
+    std::vector<float> den(std::max<uint64_t>(np, 1));
+    {
+        const volatile float one_minus_b = 1.0f - b;
+        for (uint64_t p = 0; p < np; ++p) {
+            const float dl = (float)doc_len[post_doc[p]];
+            const volatile float bl = b * dl;
+            const volatile float q = bl / ix->avgdl;
+            const volatile float len_norm = one_minus_b + q;
+            const volatile float kl = k1 * len_norm;
+            den[p] = (float)post_tf[p] + kl;
+        }
+    }
     VELES_TRY(ix->term_ptr.alloc(((size_t)n_terms + 1) * 8));
     VELES_TRY(ix->post_doc.alloc(std::max<size_t>(np * 4, 16)));
     VELES_TRY(ix->post_tf.alloc(std::max<size_t>(np * 4, 16)));
+    VELES_TRY(ix->post_den.alloc(std::max<size_t>(np * 4, 16)));
     VELES_TRY(ix->doc_len.alloc(std::max<size_t>((size_t)n_doc_slots * 4, 16)));
     VELES_TRY(ix->idf.alloc(idf.size() * 4));
     VELES_TRY(ix->skip.alloc(skip.size() * 8));
     if (np) {
         VELES_CUDA(cudaMemcpy(ix->post_doc.p, post_doc, np * 4, cudaMemcpyHostToDevice));
         VELES_CUDA(cudaMemcpy(ix->post_tf.p, post_tf, np * 4, cudaMemcpyHostToDevice));
+        VELES_CUDA(cudaMemcpy(ix->post_den.p, den.data(), np * 4, cudaMemcpyHostToDevice));
     }
     if (n_doc_slots) VELES_CUDA(cudaMemcpy(ix->doc_len.p, doc_len, (size_t)n_doc_slots * 4, cudaMemcpyHostToDevice));
     VELES_CUDA(cudaMemcpy(ix->idf.p, idf.data(), idf.size() * 4, cudaMemcpyHostToDevice));
@@ -299,6 +340,7 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
     Bm25View v;
     v.post_doc = ix->post_doc.as<uint32_t>();
     v.post_tf = ix->post_tf.as<uint32_t>();
+    v.post_den = ix->post_den.as<float>();
     v.doc_len = ix->doc_len.as<uint32_t>();
     v.idf = ix->idf.as<float>();
     v.skip = ix->skip.as<uint64_t>();
