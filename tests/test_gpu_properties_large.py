@@ -30,8 +30,9 @@ def test_results_sorted_padded_and_deterministic(big):
     x, q, snap = big
     ids, dist, cnt, st = snap.search_batch(q, 10, 64, with_stats=True)
     assert (cnt == 10).all()
-    key = dist.astype(np.float64) * 2**32 + ids          # (dist, id) lexicographic for non-negative distances
-    assert (np.diff(key, axis=1) > 0).all()
+    dd = np.diff(dist, axis=1)
+    assert (dd >= 0).all()                                # ascending by distance ...
+    assert (np.diff(ids.astype(np.int64), axis=1)[dd == 0] > 0).all()   # ... ties by ascending node id
     ids2, dist2, cnt2, st2 = snap.search_batch(q, 10, 64, with_stats=True)
     assert np.array_equal(ids, ids2) and bits_equal(dist, dist2) and np.array_equal(st, st2)
     # a batch is the concatenation of its single-query searches

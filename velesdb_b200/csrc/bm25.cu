@@ -30,6 +30,7 @@
 namespace veles {
 constexpr uint32_t kRange = 8192;  // docs per CTA range: 32 KB of f32 accumulators
 constexpr uint32_t kTermChunk = 32; // query tokens whose metadata is staged at once
+constexpr uint32_t kMultiK = 128;   // up to this k every warp of the CTA keeps its own top-k list
 }
 
 struct veles_bm25 {
@@ -131,16 +132,40 @@ __global__ void __launch_bounds__(256) bm25_range_kernel(Bm25View v, const uint3
         }
         __syncthreads();
     }
-    // warp 0: the range's k best (score desc, doc asc) as ascending keys (~order(score) << 32 | doc)
-    if (threadIdx.x >= 32) return;
-    const uint32_t lane = threadIdx.x;
+    // The range's k best (score desc, doc asc) as ascending keys (~order(score) << 32 | doc).  For k <= kMultiK
+    // every warp scans its own slice of the accumulators into its own sorted list and warp 0 merges them;
+    // a single scanning warp would keep the CTA (and its 32 KB of shared memory) alive ~8x longer.
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const bool multi = k <= kMultiK;
+    if (!multi && warp != 0) return;
+    uint64_t* mine = res + (multi ? (size_t)warp * k : 0);
+    __shared__ uint32_t s_len[8];
     uint32_t len = 0;
     uint64_t worst = ~0ull;
+    auto offer = [&](uint64_t key) {
+        uint32_t msk = __ballot_sync(FULL_MASK, key < worst);
+        while (msk) {
+            const uint32_t src = __ffs(msk) - 1;
+            msk &= msk - 1;
+            const uint64_t kk = __shfl_sync(FULL_MASK, key, src);
+            if (kk >= worst) continue;
+            const uint32_t pos = lower_bound_warp(mine, len, kk, lane);
+            if (len < k) {
+                insert_at(mine, pos, len + 1, kk, lane);
+                ++len;
+            } else {
+                insert_at(mine, pos, len, kk, lane);
+            }
+            if (len == k) worst = mine[k - 1];
+        }
+    };
     if (touched) {
         // 128 accumulators per step (one float4 per lane); most are zero, so whole steps are skipped on one
         // ballot.  Padding docs past n_doc_slots never receive postings and stay 0.
         const float4* acc4 = reinterpret_cast<const float4*>(acc);
-        for (uint32_t i0 = 0; i0 < kRange; i0 += 128) {
+        const uint32_t per = multi ? kRange / nwarps : kRange;
+        const uint32_t i_begin = multi ? warp * per : 0;
+        for (uint32_t i0 = i_begin; i0 < i_begin + per; i0 += 128) {
             const float4 s4 = acc4[(i0 >> 2) + lane];
             const bool any = s4.x > 0.0f || s4.y > 0.0f || s4.z > 0.0f || s4.w > 0.0f;
             if (!__ballot_sync(FULL_MASK, any)) continue;
@@ -149,27 +174,26 @@ __global__ void __launch_bounds__(256) bm25_range_kernel(Bm25View v, const uint3
             for (int e = 0; e < 4; ++e) {
                 uint64_t key = ~0ull;
                 if (sv[e] > 0.0f) key = ((uint64_t)(~ord_key(sv[e])) << 32) | (base_doc + i0 + lane * 4 + e);
-                uint32_t msk = __ballot_sync(FULL_MASK, key < worst);
-                while (msk) {
-                    const uint32_t src = __ffs(msk) - 1;
-                    msk &= msk - 1;
-                    const uint64_t kk = __shfl_sync(FULL_MASK, key, src);
-                    if (kk >= worst) continue;
-                    const uint32_t pos = lower_bound_warp(res, len, kk, lane);
-                    if (len < k) {
-                        insert_at(res, pos, len + 1, kk, lane);
-                        ++len;
-                    } else {
-                        insert_at(res, pos, len, kk, lane);
-                    }
-                    if (len == k) worst = res[k - 1];
-                }
+                offer(key);
+            }
+        }
+    }
+    if (multi) {
+        if (lane == 0) s_len[warp] = len;
+        __syncthreads();
+        if (warp != 0) return;
+        for (uint32_t w = 1; w < nwarps; ++w) {
+            const uint64_t* other = res + (size_t)w * k;
+            const uint32_t olen = s_len[w];
+            for (uint32_t j0 = 0; j0 < olen; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                offer(j < olen ? other[j] : ~0ull);
             }
         }
     }
     __syncwarp();
     uint64_t* out = partial + ((size_t)q * v.n_ranges + r) * k;
-    for (uint32_t j = lane; j < k; j += 32) out[j] = j < len ? res[j] : ~0ull;
+    for (uint32_t j = lane; j < k; j += 32) out[j] = j < len ? mine[j] : ~0ull;
 }
 
 // one warp per query: k smallest keys over its n_ranges x k partial keys
@@ -350,7 +374,7 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
     v.k1 = ix->k1;
     v.b = ix->b;
     v.avgdl = ix->avgdl;
-    const size_t smem1 = (size_t)kRange * 4 + (size_t)k * 8;
+    const size_t smem1 = (size_t)kRange * 4 + (size_t)k * 8 * (k <= kMultiK ? 8 : 1);
     VELES_CUDA(cudaFuncSetAttribute(bm25_range_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     VELES_CUDA(cudaFuncSetAttribute(bm25_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(k * 8)));
     // gridDim.y <= 65535: chunk the queries; the partial buffer is bounded to ~512 MiB per pass
