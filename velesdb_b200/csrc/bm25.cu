@@ -55,6 +55,79 @@ struct Bm25View {
     float k1, b, avgdl;
 };
 
+// The range's k best (score desc, doc asc) as ascending keys (~order(score) << 32 | doc).  Every warp scans
+// its own slice of the accumulators into a register-resident sorted list (RegTopK), spills it to shared
+// memory, and warp 0 merges the lists.  k > 128 falls back to one warp with a shared-memory list.
+template <int R>
+__device__ __forceinline__ void bm25_topk_regs(const float* acc, uint64_t* res, bool touched, uint32_t base_doc, uint32_t k,
+                                               uint64_t* out) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    RegTopK<R> top;
+    top.init(k, lane);
+    if (touched) {
+        const float4* acc4 = reinterpret_cast<const float4*>(acc);
+        const uint32_t per = kRange / nwarps, i_begin = warp * per;
+        for (uint32_t i0 = i_begin; i0 < i_begin + per; i0 += 128) {
+            const float4 s4 = acc4[(i0 >> 2) + lane];
+            const bool any = s4.x > 0.0f || s4.y > 0.0f || s4.z > 0.0f || s4.w > 0.0f;
+            if (!__ballot_sync(FULL_MASK, any)) continue;  // most accumulators are zero
+            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint64_t key = ~0ull;
+                if (sv[e] > 0.0f) key = ((uint64_t)(~ord_key(sv[e])) << 32) | (base_doc + i0 + lane * 4 + e);
+                top.offer(key);
+            }
+        }
+    }
+    top.store(res + (size_t)warp * k, k);
+    __syncthreads();
+    if (warp != 0) return;
+    for (uint32_t w = 1; w < nwarps; ++w) {
+        const uint64_t* other = res + (size_t)w * k;
+        for (uint32_t j0 = 0; j0 < k; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            top.offer(j < k ? other[j] : ~0ull);
+        }
+    }
+    top.store(out, k);
+}
+
+__device__ __forceinline__ void bm25_range_topk(const float* acc, uint64_t* res, bool touched, uint32_t base_doc, uint32_t k,
+                                                uint64_t* out) {
+    if (k <= 32) return bm25_topk_regs<1>(acc, res, touched, base_doc, k, out);
+    if (k <= 64) return bm25_topk_regs<2>(acc, res, touched, base_doc, k, out);
+    if (k <= kMultiK) return bm25_topk_regs<4>(acc, res, touched, base_doc, k, out);
+    if (threadIdx.x >= 32) return;
+    const uint32_t lane = threadIdx.x;
+    uint32_t len = 0;
+    uint64_t worst = ~0ull;
+    if (touched) {
+        for (uint32_t i0 = 0; i0 < kRange; i0 += 32) {
+            const float s = acc[i0 + lane];
+            uint64_t key = ~0ull;
+            if (s > 0.0f) key = ((uint64_t)(~ord_key(s)) << 32) | (base_doc + i0 + lane);
+            uint32_t msk = __ballot_sync(FULL_MASK, key < worst);
+            while (msk) {
+                const uint32_t src = __ffs(msk) - 1;
+                msk &= msk - 1;
+                const uint64_t kk = __shfl_sync(FULL_MASK, key, src);
+                if (kk >= worst) continue;
+                const uint32_t pos = lower_bound_warp(res, len, kk, lane);
+                if (len < k) {
+                    insert_at(res, pos, len + 1, kk, lane);
+                    ++len;
+                } else {
+                    insert_at(res, pos, len, kk, lane);
+                }
+                if (len == k) worst = res[k - 1];
+            }
+        }
+    }
+    __syncwarp();
+    for (uint32_t j = lane; j < k; j += 32) out[j] = j < len ? res[j] : ~0ull;
+}
+
 __global__ void __launch_bounds__(256) bm25_range_kernel(Bm25View v, const uint32_t* __restrict__ q_ptr,
                                                          const uint32_t* __restrict__ q_terms, uint32_t k,
                                                          uint64_t* __restrict__ partial) {
@@ -132,68 +205,7 @@ __global__ void __launch_bounds__(256) bm25_range_kernel(Bm25View v, const uint3
         }
         __syncthreads();
     }
-    // The range's k best (score desc, doc asc) as ascending keys (~order(score) << 32 | doc).  For k <= kMultiK
-    // every warp scans its own slice of the accumulators into its own sorted list and warp 0 merges them;
-    // a single scanning warp would keep the CTA (and its 32 KB of shared memory) alive ~8x longer.
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const bool multi = k <= kMultiK;
-    if (!multi && warp != 0) return;
-    uint64_t* mine = res + (multi ? (size_t)warp * k : 0);
-    __shared__ uint32_t s_len[8];
-    uint32_t len = 0;
-    uint64_t worst = ~0ull;
-    auto offer = [&](uint64_t key) {
-        uint32_t msk = __ballot_sync(FULL_MASK, key < worst);
-        while (msk) {
-            const uint32_t src = __ffs(msk) - 1;
-            msk &= msk - 1;
-            const uint64_t kk = __shfl_sync(FULL_MASK, key, src);
-            if (kk >= worst) continue;
-            const uint32_t pos = lower_bound_warp(mine, len, kk, lane);
-            if (len < k) {
-                insert_at(mine, pos, len + 1, kk, lane);
-                ++len;
-            } else {
-                insert_at(mine, pos, len, kk, lane);
-            }
-            if (len == k) worst = mine[k - 1];
-        }
-    };
-    if (touched) {
-        // 128 accumulators per step (one float4 per lane); most are zero, so whole steps are skipped on one
-        // ballot.  Padding docs past n_doc_slots never receive postings and stay 0.
-        const float4* acc4 = reinterpret_cast<const float4*>(acc);
-        const uint32_t per = multi ? kRange / nwarps : kRange;
-        const uint32_t i_begin = multi ? warp * per : 0;
-        for (uint32_t i0 = i_begin; i0 < i_begin + per; i0 += 128) {
-            const float4 s4 = acc4[(i0 >> 2) + lane];
-            const bool any = s4.x > 0.0f || s4.y > 0.0f || s4.z > 0.0f || s4.w > 0.0f;
-            if (!__ballot_sync(FULL_MASK, any)) continue;
-            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                uint64_t key = ~0ull;
-                if (sv[e] > 0.0f) key = ((uint64_t)(~ord_key(sv[e])) << 32) | (base_doc + i0 + lane * 4 + e);
-                offer(key);
-            }
-        }
-    }
-    if (multi) {
-        if (lane == 0) s_len[warp] = len;
-        __syncthreads();
-        if (warp != 0) return;
-        for (uint32_t w = 1; w < nwarps; ++w) {
-            const uint64_t* other = res + (size_t)w * k;
-            const uint32_t olen = s_len[w];
-            for (uint32_t j0 = 0; j0 < olen; j0 += 32) {
-                const uint32_t j = j0 + lane;
-                offer(j < olen ? other[j] : ~0ull);
-            }
-        }
-    }
-    __syncwarp();
-    uint64_t* out = partial + ((size_t)q * v.n_ranges + r) * k;
-    for (uint32_t j = lane; j < k; j += 32) out[j] = j < len ? mine[j] : ~0ull;
+    bm25_range_topk(acc, res, touched, base_doc, k, partial + ((size_t)q * v.n_ranges + r) * k);
 }
 
 // one warp per query: k smallest keys over its n_ranges x k partial keys

@@ -331,6 +331,74 @@ __device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
     return v;
 }
 
+// ---- register-resident sorted list of the k smallest unique u64 keys (k <= 32 * R) ----
+// Position i lives in lane i % 32, slot i / 32; empty positions hold ~0.  An insert is one ballot per slot
+// (lower bound) plus one shuffle-up per slot, no shared memory and no barriers.
+template <int R>
+struct RegTopK {
+    uint64_t k[R];
+    uint64_t worst;  // key at position cap-1 once full, else ~0
+    uint32_t cap, lane;
+    __device__ __forceinline__ void init(uint32_t cap_, uint32_t lane_) {
+        cap = cap_;
+        lane = lane_;
+        worst = ~0ull;
+#pragma unroll
+        for (int s = 0; s < R; ++s) k[s] = ~0ull;
+    }
+    // all lanes pass the same key
+    __device__ __forceinline__ void insert(uint64_t key) {
+        uint32_t pos = 0;
+#pragma unroll
+        for (int s = 0; s < R; ++s) pos += __popc(__ballot_sync(FULL_MASK, k[s] < key));
+#pragma unroll
+        for (int s = R - 1; s >= 0; --s) {
+            uint64_t up = __shfl_up_sync(FULL_MASK, k[s], 1);
+            if (s > 0) {
+                const uint64_t carry = __shfl_sync(FULL_MASK, k[s - 1], 31);
+                up = lane == 0 ? carry : up;
+            }
+            const uint32_t i = 32u * s + lane;
+            uint64_t nv = i > pos ? up : k[s];
+            nv = i == pos ? key : nv;
+            nv = i >= cap ? ~0ull : nv;
+            k[s] = nv;
+        }
+        // key at position cap - 1
+        uint64_t w = ~0ull;
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            const uint64_t t = __shfl_sync(FULL_MASK, k[s], (cap - 1) & 31);
+            w = ((int)((cap - 1) >> 5) == s) ? t : w;
+        }
+        worst = w;
+    }
+    // each lane offers its own key (~0 = nothing); keys >= worst are dropped
+    __device__ __forceinline__ void offer(uint64_t key) {
+        uint32_t msk = __ballot_sync(FULL_MASK, key < worst);
+        while (msk) {
+            const uint32_t src = __ffs(msk) - 1;
+            msk &= msk - 1;
+            const uint64_t kk = __shfl_sync(FULL_MASK, key, src);
+            if (kk < worst) insert(kk);
+        }
+    }
+    __device__ __forceinline__ uint32_t size() const {
+        uint32_t n = 0;
+#pragma unroll
+        for (int s = 0; s < R; ++s) n += __popc(__ballot_sync(FULL_MASK, k[s] != ~0ull));
+        return n;
+    }
+    // writes positions [0, count) to out (count <= cap); positions past size() get ~0
+    __device__ __forceinline__ void store(uint64_t* out, uint32_t count) const {
+#pragma unroll
+        for (int s = 0; s < R; ++s) {
+            const uint32_t i = 32u * s + lane;
+            if (i < count) out[i] = k[s];
+        }
+    }
+};
+
 // the 8-wide and scalar tails of simd_avx512.rs:186-201 applied to a main-loop result (dim >= 16)
 template <int OP, typename TA, typename TB>
 __device__ __forceinline__ float warp_tree_tail(float result, const TA* __restrict__ a, const TB* __restrict__ b,
