@@ -29,7 +29,7 @@
 #include "common.cuh"
 
 namespace veles {
-constexpr uint32_t kRange = 8192;  // docs per CTA range: 32 KB of f32 accumulators
+constexpr uint32_t kRange = 7168;  // docs per range: 28 KB of f32 accumulators -> 7 query CTAs per SM (1036 >= 1024 resident)
 constexpr uint32_t kTermChunk = 32; // query tokens whose metadata is staged at once
 constexpr uint32_t kMultiK = 128;   // up to this k every warp of the CTA keeps its own top-k list
 }
