@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) bm25_range_kernel(Bm25View v, const uint3
 // merge kernel.  The skip entries of the next range are requested one range ahead.
 constexpr uint32_t kQueryTerms = 32;  // query tokens handled per pass over the ranges
 template <int R>
-__global__ void __launch_bounds__(256) bm25_query_kernel(Bm25View v, const uint32_t* __restrict__ q_ptr,
+__global__ void __launch_bounds__(256, 7) bm25_query_kernel(Bm25View v, const uint32_t* __restrict__ q_ptr,
                                                          const uint32_t* __restrict__ q_terms, uint32_t k,
                                                          uint32_t* __restrict__ out_doc, float* __restrict__ out_score,
                                                          uint32_t* __restrict__ out_cnt) {
