@@ -217,135 +217,153 @@ __global__ void __launch_bounds__(256) bm25_range_kernel(Bm25View v, const uint3
 // compare, so the scan costs ~8 loads per lane per range and inserts become rare; no per-range lists, no
 // merge kernel.  The skip entries of the next range are requested one range ahead.
 constexpr uint32_t kQueryTerms = 32;  // query tokens handled per pass over the ranges
+constexpr int kDepth = 4;             // posting chunks requested ahead of the one being applied
 template <int R>
-__global__ void __launch_bounds__(256, 7) bm25_query_kernel(Bm25View v, const uint32_t* __restrict__ q_ptr,
-                                                         const uint32_t* __restrict__ q_terms, uint32_t k,
-                                                         uint32_t* __restrict__ out_doc, float* __restrict__ out_score,
-                                                         uint32_t* __restrict__ out_cnt) {
+__global__ void __launch_bounds__(256, 5) bm25_query_kernel(Bm25View v, const uint32_t* __restrict__ q_ptr,
+                                                            const uint32_t* __restrict__ q_terms, uint32_t nq, uint32_t k,
+                                                            uint32_t* __restrict__ out_doc, float* __restrict__ out_score,
+                                                            uint32_t* __restrict__ out_cnt, uint32_t* __restrict__ work) {
     extern __shared__ __align__(16) uint8_t bq_smem[];
     float* acc = reinterpret_cast<float*>(bq_smem);
     uint64_t* lists = reinterpret_cast<uint64_t*>(bq_smem + kRange * 4);  // 8 x k keys for the final merge
     __shared__ uint64_t s_lo[kQueryTerms], s_hi[kQueryTerms];
     __shared__ float s_idf[kQueryTerms];
-    const uint32_t q = blockIdx.x;
+    __shared__ uint32_t s_q;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const uint32_t t0 = q_ptr[q], t1 = q_ptr[q + 1];
-    const uint32_t nt = min(kQueryTerms, t1 - t0);  // host guarantees t1 - t0 <= kQueryTerms on this path
     const float k1p1 = __fadd_rn(v.k1, 1.0f);
-    RegTopK<R> top;
-    top.init(k, lane);
-    // per-thread term metadata (threads < nt): term id, idf and the skip entry of the *next* range boundary
-    uint32_t my_term = VELES_INVALID_ID;
-    float my_idf = 0.0f;
-    uint64_t my_lo = 0, my_next = 0;
-    const uint64_t* my_skip = nullptr;
-    if (threadIdx.x < nt) {
-        my_term = q_terms[t0 + threadIdx.x];
-        if (my_term < v.n_terms) {
-            my_idf = v.idf[my_term];
-            my_skip = v.skip + (size_t)my_term * (v.n_ranges + 1);
-            my_lo = my_skip[0];
-            my_next = my_skip[1];
-        }
-        s_idf[threadIdx.x] = my_idf;
-    }
     const float4* acc4 = reinterpret_cast<const float4*>(acc);
-    for (uint32_t r = 0; r < v.n_ranges; ++r) {
-        const uint32_t base_doc = r * kRange;
-        if (threadIdx.x < nt) {
-            s_lo[threadIdx.x] = my_lo;
-            s_hi[threadIdx.x] = my_next;
-            my_lo = my_next;
-            if (my_skip && r + 2 <= v.n_ranges) my_next = my_skip[r + 2];  // boundary of the range after next
-        }
-        for (uint32_t i = threadIdx.x; i < kRange; i += blockDim.x) acc[i] = 0.0f;
+    for (;;) {  // persistent: queries are handed out by a global counter
+        if (threadIdx.x == 0) s_q = atomicAdd(work, 1u);
         __syncthreads();
-        // (term, 256-posting chunk) walk in query order, next chunk requested before the current is applied
-        bool touched = false;
-        uint32_t g = 0;
-        while (g < nt && s_hi[g] == s_lo[g]) ++g;
-        uint64_t base = g < nt ? s_lo[g] : 0;
-        uint32_t d_cur = VELES_INVALID_ID, tf_cur = 0;
-        float den_cur = 1.0f;
-        if (g < nt && base + threadIdx.x < s_hi[g]) {
-            d_cur = v.post_doc[base + threadIdx.x];
-            tf_cur = v.post_tf[base + threadIdx.x];
-            den_cur = v.post_den[base + threadIdx.x];
+        const uint32_t q = s_q;
+        if (q >= nq) return;
+        const uint32_t t0 = q_ptr[q], t1 = q_ptr[q + 1];
+        const uint32_t nt = min(kQueryTerms, t1 - t0);  // host guarantees t1 - t0 <= kQueryTerms on this path
+        RegTopK<R> top;
+        top.init(k, lane);
+        // per-thread term metadata (threads < nt): skip row of the term, boundaries of the current range
+        uint64_t my_lo = 0, my_next = 0;
+        const uint64_t* my_skip = nullptr;
+        if (threadIdx.x < nt) {
+            const uint32_t term = q_terms[t0 + threadIdx.x];
+            float idf = 0.0f;
+            if (term < v.n_terms) {
+                idf = v.idf[term];
+                my_skip = v.skip + (size_t)term * (v.n_ranges + 1);
+                my_lo = my_skip[0];
+                my_next = my_skip[1];
+            }
+            s_idf[threadIdx.x] = idf;
         }
-        while (g < nt) {
-            uint32_t g2 = g;
-            uint64_t base2 = base + blockDim.x;
-            if (base2 >= s_hi[g2]) {
-                ++g2;
-                while (g2 < nt && s_hi[g2] == s_lo[g2]) ++g2;
-                base2 = g2 < nt ? s_lo[g2] : 0;
+        for (uint32_t r = 0; r < v.n_ranges; ++r) {
+            const uint32_t base_doc = r * kRange;
+            if (threadIdx.x < nt) {
+                s_lo[threadIdx.x] = my_lo;
+                s_hi[threadIdx.x] = my_next;
+                my_lo = my_next;
+                if (my_skip && r + 2 <= v.n_ranges) my_next = my_skip[r + 2];  // boundary after the next range
             }
-            uint32_t d_nxt = VELES_INVALID_ID, tf_nxt = 0;
-            float den_nxt = 1.0f;
-            if (g2 < nt && base2 + threadIdx.x < s_hi[g2]) {
-                d_nxt = v.post_doc[base2 + threadIdx.x];
-                tf_nxt = v.post_tf[base2 + threadIdx.x];
-                den_nxt = v.post_den[base2 + threadIdx.x];
-            }
-            if (d_cur != VELES_INVALID_ID) {
-                const float num = __fmul_rn((float)tf_cur, k1p1);
-                const float contrib = __fdiv_rn(__fmul_rn(s_idf[g], num), den_cur);
-                acc[d_cur - base_doc] = __fadd_rn(acc[d_cur - base_doc], contrib);
-            }
-            touched = true;
-            if (g2 != g) __syncthreads();  // next term's contributions come after this term's, per document
-            g = g2;
-            base = base2;
-            d_cur = d_nxt;
-            tf_cur = tf_nxt;
-            den_cur = den_nxt;
-        }
-        // scan: this warp's slice of the range
-        if (touched) {
-            const uint32_t per = kRange / nwarps, i_begin = warp * per;
-            for (uint32_t i0 = i_begin; i0 < i_begin + per; i0 += 128) {
-                const float4 s4 = acc4[(i0 >> 2) + lane];
-                const bool any = s4.x > 0.0f || s4.y > 0.0f || s4.z > 0.0f || s4.w > 0.0f;
-                if (!__ballot_sync(FULL_MASK, any)) continue;
-                const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+            for (uint32_t i = threadIdx.x; i < kRange; i += blockDim.x) acc[i] = 0.0f;
+            __syncthreads();
+            // (term, 256-posting chunk) walk in query order with kDepth chunks in flight.  Chunks of one term
+            // touch distinct documents: a block barrier is only needed when the term changes.
+            uint32_t cg = 0;  // cursor: next chunk to request
+            while (cg < nt && s_hi[cg] == s_lo[cg]) ++cg;
+            uint64_t cbase = cg < nt ? s_lo[cg] : 0;
+            uint32_t qg[kDepth], qd[kDepth], qtf[kDepth];
+            float qden[kDepth];
+            auto request = [&](int slot) {
+                qg[slot] = cg;
+                qd[slot] = VELES_INVALID_ID;
+                qtf[slot] = 0;
+                qden[slot] = 1.0f;
+                if (cg < nt) {
+                    const uint64_t p = cbase + threadIdx.x;
+                    if (p < s_hi[cg]) {
+                        qd[slot] = v.post_doc[p];
+                        qtf[slot] = v.post_tf[p];
+                        qden[slot] = v.post_den[p];
+                    }
+                    cbase += blockDim.x;
+                    if (cbase >= s_hi[cg]) {
+                        ++cg;
+                        while (cg < nt && s_hi[cg] == s_lo[cg]) ++cg;
+                        cbase = cg < nt ? s_lo[cg] : 0;
+                    }
+                }
+            };
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    uint64_t key = ~0ull;
-                    if (sv[e] > 0.0f) key = ((uint64_t)(~ord_key(sv[e])) << 32) | (base_doc + i0 + lane * 4 + e);
-                    top.offer(key);
+            for (int i = 0; i < kDepth; ++i) request(i);
+            bool touched = false;
+            while (qg[0] < nt) {
+                if (qd[0] != VELES_INVALID_ID) {
+                    const float num = __fmul_rn((float)qtf[0], k1p1);
+                    const float contrib = __fdiv_rn(__fmul_rn(s_idf[qg[0]], num), qden[0]);
+                    acc[qd[0] - base_doc] = __fadd_rn(acc[qd[0] - base_doc], contrib);
+                }
+                touched = true;
+                if (qg[1] != qg[0]) __syncthreads();  // next term's contributions come after this term's
+#pragma unroll
+                for (int i = 0; i + 1 < kDepth; ++i) {
+                    qg[i] = qg[i + 1];
+                    qd[i] = qd[i + 1];
+                    qtf[i] = qtf[i + 1];
+                    qden[i] = qden[i + 1];
+                }
+                request(kDepth - 1);
+            }
+            // scan: this warp's slice of the range
+            if (touched) {
+                const uint32_t per = kRange / nwarps, i_begin = warp * per;
+                for (uint32_t i0 = i_begin; i0 < i_begin + per; i0 += 128) {
+                    const float4 s4 = acc4[(i0 >> 2) + lane];
+                    const bool any = s4.x > 0.0f || s4.y > 0.0f || s4.z > 0.0f || s4.w > 0.0f;
+                    if (!__ballot_sync(FULL_MASK, any)) continue;
+                    const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        uint64_t key = ~0ull;
+                        if (sv[e] > 0.0f) key = ((uint64_t)(~ord_key(sv[e])) << 32) | (base_doc + i0 + lane * 4 + e);
+                        top.offer(key);
+                    }
                 }
             }
+            __syncthreads();  // the accumulator is rewritten by the next range
         }
-        __syncthreads();  // the accumulator is rewritten by the next range
-    }
-    // merge the eight per-warp lists
-    top.store(lists + (size_t)warp * k, k);
-    __syncthreads();
-    if (warp != 0) return;
-    for (uint32_t w = 1; w < nwarps; ++w) {
-        const uint64_t* other = lists + (size_t)w * k;
-        for (uint32_t j0 = 0; j0 < k; j0 += 32) {
-            const uint32_t j = j0 + lane;
-            top.offer(j < k ? other[j] : ~0ull);
+        // merge the eight per-warp lists
+        top.store(lists + (size_t)warp * k, k);
+        __syncthreads();
+        if (warp == 0) {
+            for (uint32_t w = 1; w < nwarps; ++w) {
+                const uint64_t* other = lists + (size_t)w * k;
+                for (uint32_t j0 = 0; j0 < k; j0 += 32) {
+                    const uint32_t j = j0 + lane;
+                    top.offer(j < k ? other[j] : ~0ull);
+                }
+            }
+            top.store(lists, k);
+            __syncwarp();
+            uint32_t len = 0;
+            for (uint32_t j0 = 0; j0 < k; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                if (j < k) {
+                    const uint64_t key = lists[j];
+                    uint32_t doc = VELES_INVALID_ID;
+                    float sc = __uint_as_float(0x7fc00000u);
+                    if (key != ~0ull) {
+                        doc = (uint32_t)key;
+                        sc = ord_unkey(~(uint32_t)(key >> 32));
+                        ++len;
+                    }
+                    out_doc[(size_t)q * k + j] = doc;
+                    out_score[(size_t)q * k + j] = sc;
+                }
+            }
+            len = __reduce_add_sync(FULL_MASK, len);
+            if (lane == 0) out_cnt[q] = len;
         }
+        __syncthreads();  // `lists` and s_q are reused by the next query
     }
-    top.store(lists, k);
-    __syncwarp();
-    uint32_t len = 0;
-    for (uint32_t j = lane; j < k; j += 32) {
-        const uint64_t key = lists[j];
-        uint32_t doc = VELES_INVALID_ID;
-        float sc = __uint_as_float(0x7fc00000u);
-        if (key != ~0ull) {
-            doc = (uint32_t)key;
-            sc = ord_unkey(~(uint32_t)(key >> 32));
-            ++len;
-        }
-        out_doc[(size_t)q * k + j] = doc;
-        out_score[(size_t)q * k + j] = sc;
-    }
-    len = __reduce_add_sync(FULL_MASK, len);
-    if (lane == 0) out_cnt[q] = len;
 }
 
 // one warp per query: k smallest keys over its n_ranges x k partial keys
@@ -533,8 +551,17 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
         const size_t smem = (size_t)kRange * 4 + (size_t)8 * k * 8;
         auto kern = k <= 32 ? bm25_query_kernel<1> : k <= 64 ? bm25_query_kernel<2> : bm25_query_kernel<4>;
         VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<nq, 256, smem, st>>>(v, ix->q_ptr_d.as<uint32_t>(), ix->q_terms_d.as<uint32_t>(), k, ix->out_doc_d.as<uint32_t>(),
-                                    ix->out_score_d.as<float>(), ix->out_cnt_d.as<uint32_t>());
+        int per_sm = 0, dev = 0, sms = 0;
+        VELES_CUDA(cudaGetDevice(&dev));
+        VELES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        VELES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+        VELES_REQUIRE(per_sm >= 1, "bm25 query kernel does not fit on an SM");
+        VELES_TRY(ix->partial_d.ensure(64));
+        VELES_CUDA(cudaMemsetAsync(ix->partial_d.p, 0, 4, st));
+        const uint32_t grid = std::min<uint32_t>(nq, (uint32_t)(per_sm * sms));
+        kern<<<grid, 256, smem, st>>>(v, ix->q_ptr_d.as<uint32_t>(), ix->q_terms_d.as<uint32_t>(), nq, k,
+                                      ix->out_doc_d.as<uint32_t>(), ix->out_score_d.as<float>(), ix->out_cnt_d.as<uint32_t>(),
+                                      ix->partial_d.as<uint32_t>());
         count_launch();
         VELES_CUDA(cudaGetLastError());
     } else {
