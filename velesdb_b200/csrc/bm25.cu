@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) bm25_range_kernel(Bm25View v, const uint3
 // compare, so the scan costs ~8 loads per lane per range and inserts become rare; no per-range lists, no
 // merge kernel.  The skip entries of the next range are requested one range ahead.
 constexpr uint32_t kQueryTerms = 32;  // query tokens handled per pass over the ranges
-constexpr int kDepth = 4;             // posting chunks requested ahead of the one being applied
+constexpr int kDepth = 2;             // posting chunks in flight (the one being applied + one ahead)
 template <int R>
 __global__ void __launch_bounds__(256, 5) bm25_query_kernel(Bm25View v, const uint32_t* __restrict__ q_ptr,
                                                             const uint32_t* __restrict__ q_terms, uint32_t nq, uint32_t k,
@@ -263,7 +263,8 @@ __global__ void __launch_bounds__(256, 5) bm25_query_kernel(Bm25View v, const ui
                 my_lo = my_next;
                 if (my_skip && r + 2 <= v.n_ranges) my_next = my_skip[r + 2];  // boundary after the next range
             }
-            for (uint32_t i = threadIdx.x; i < kRange; i += blockDim.x) acc[i] = 0.0f;
+            for (uint32_t i = threadIdx.x; i < kRange / 4; i += blockDim.x)
+                reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             __syncthreads();
             // (term, 256-posting chunk) walk in query order with kDepth chunks in flight.  Chunks of one term
             // touch distinct documents: a block barrier is only needed when the term changes.
