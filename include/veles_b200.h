@@ -52,7 +52,9 @@ typedef enum veles_metric {
 typedef enum veles_dtype {
     VELES_F32 = 0,  /* reference layout: Vec<Vec<f32>> (native/graph.rs:22)                        */
     VELES_F16 = 1,  /* half::f16 round-to-nearest-even (core/half_precision.rs:97), f32 accumulate  */
-    VELES_BIN1 = 2  /* packed bits, LSB-first in u64 words (simd_explicit.rs:308-360); Hamming only */
+    VELES_BIN1 = 2, /* packed bits, LSB-first in u64 words (simd_explicit.rs:308-360); Hamming only */
+    VELES_SQ8 = 3   /* u8 codes of ScalarQuantizer (native/quantization.rs:236-250): only as the traversal store
+                       attached by veles_index_attach_sq8, never as store_dtype                      */
 } veles_dtype;
 
 /* SearchQuality (index/hnsw/params.rs:283-320) */
@@ -208,6 +210,36 @@ int32_t veles_index_build_graph(veles_index_t* idx, uint32_t M, uint32_t cand_k,
  * (graph.rs:592-639).  One warp, latency bound: meant for small/medium graphs and for build parity; f32
  * storage only.  Equal distances are ordered by node id (the reference: heap-internal order). */
 int32_t veles_index_build_graph_exact(veles_index_t* idx, uint32_t M, uint32_t ef_construction, void* stream);
+
+/* ---- SQ8 dual precision -------------------------------------------------- */
+/* DualPrecisionHnsw (native/dual_precision.rs:60-441): int8 traversal + exact f32 re-rank.
+ *
+ * veles_index_attach_sq8 trains the ScalarQuantizer (native/quantization.rs:190-233: per-dimension min/max,
+ * scale = 255 / range or 1.0 when |range| < 1e-10, inv_scale = 1 / scale) on the first `train_count` vectors of
+ * the snapshot -- the reference trains on its first min(1000, max_elements) inserts (dual_precision.rs:100,
+ * 134-137) or on everything inserted so far at force_train_quantizer (:172-176) -- and quantizes every vector
+ * (quantize, quantization.rs:236-250: ((v - min) * scale).round().clamp(0, 255) as u8) into a second, u8 store
+ * on the device.  Needs an f32 snapshot (the re-rank reads the original vectors, as the reference does). */
+int32_t veles_index_attach_sq8(veles_index_t* idx, uint64_t train_count, void* stream);
+int32_t veles_index_has_sq8(const veles_index_t* idx);
+/* Copies the quantizer (dim floats each) and, when `codes` is not NULL, the n * dim codes to the host. */
+int32_t veles_index_sq8_export(const veles_index_t* idx, float* min_vals, float* scales, float* inv_scales,
+                               uint8_t* codes);
+
+/* DualPrecisionHnsw::search_with_config on the int8 path (dual_precision.rs:284-325): the query is quantized,
+ * greedy_search_int8 (:407-441) descends the upper layers and search_layer_int8 (:327-405) runs the layer-0
+ * beam with ef = max(ef_search, k * oversampling), both on distance_l2_quantized (u32 sum of squared code
+ * differences, quantization.rs:42-92) whatever the index metric; the k * oversampling closest are re-ranked
+ * with the exact f32 graph distance of the index metric, stably sorted by total_cmp, and cut to k.
+ * Outputs as veles_search_batch, out_raw_dist = exact f32 distances.  Equal int8 distances are ordered by node
+ * id (the reference: heap-array order); out_stats as veles_search_batch.  The reference's size gate
+ * (min_index_size) and the use_int8_traversal switch stay with the host wrapper. */
+int32_t veles_search_batch_sq8(const veles_index_t* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef_search,
+                               uint32_t oversampling, uint32_t* out_node_ids, float* out_raw_dist, uint32_t* out_counts,
+                               uint32_t* out_stats, void* stream);
+int32_t veles_search_batch_sq8_d(const veles_index_t* idx, const float* queries_d, uint32_t nq, uint32_t k,
+                                 uint32_t ef_search, uint32_t oversampling, uint32_t* out_node_ids_d,
+                                 float* out_raw_dist_d, uint32_t* out_counts_d, uint32_t* out_stats_d, void* stream);
 
 /* ---- multi-GPU --------------------------------------------------------------------------------- */
 /* Queries shard by contiguous slices across ranks; the snapshot is replicated.  The only exchange

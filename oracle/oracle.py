@@ -107,6 +107,20 @@ _sig("vo_fuse", C.c_uint32,
      [C.c_int, _u32p, C.c_uint32, _u64p, _f32p, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_uint32, _u64p,
       _f32p])
 
+_sig("vo_sq8_train", C.c_void_p, [_f32p, C.c_uint64, C.c_uint32])
+_sig("vo_sq8_free", None, [C.c_void_p])
+_sig("vo_sq8_params", None, [C.c_void_p, _f32p, _f32p, _f32p])
+_sig("vo_sq8_quantize", None, [C.c_void_p, _f32p, C.c_uint64, _u8p])
+_sig("vo_sq8_push", None, [C.c_void_p, _f32p, C.c_uint64])
+_sig("vo_sq8_len", C.c_uint64, [C.c_void_p])
+_sig("vo_sq8_codes", C.POINTER(C.c_uint8), [C.c_void_p])
+_sig("vo_sq8_distance_quantized", C.c_uint32, [_u8p, _u8p, C.c_uint32])
+_sig("vo_sq8_distance_asymmetric", C.c_float, [C.c_void_p, _f32p, _u8p])
+_sig("vo_dual_search_int8", C.c_uint32,
+     [C.c_void_p, C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _u64p, _f32p, _u64p])
+_sig("vo_dual_search_int8_batch", None,
+     [C.c_void_p, C.c_void_p, _f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, _u64p, _f32p,
+      _u32p, _u64p])
 
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
@@ -302,6 +316,152 @@ class Hnsw:
         h = _lib.vo_hnsw_from_arrays(metric, dim, M, M0, ef_construction, int(fma), vectors, n, len(layers), rp_arr,
                                      c_arr, nodes, entry_point, max_layer)
         return cls(metric, dim, _handle=h, fma=fma)
+
+
+class ScalarQuantizer:
+    """ScalarQuantizer + QuantizedVectorStore restated (native/quantization.rs:160-374)."""
+
+    def __init__(self, train_vectors):
+        tv = _f32(train_vectors)
+        if tv.ndim != 2 or tv.shape[0] == 0:
+            raise ValueError("Cannot train on empty vectors")  # quantization.rs:191
+        self.dimension = tv.shape[1]
+        self._s = _lib.vo_sq8_train(tv, tv.shape[0], tv.shape[1])
+        self.min_vals = np.zeros(self.dimension, np.float32)
+        self.scales = np.zeros(self.dimension, np.float32)
+        self.inv_scales = np.zeros(self.dimension, np.float32)
+        _lib.vo_sq8_params(self._s, self.min_vals, self.scales, self.inv_scales)
+
+    def __del__(self):
+        if getattr(self, "_s", None) and _lib is not None:
+            _lib.vo_sq8_free(self._s)
+            self._s = None
+
+    def quantize(self, v) -> np.ndarray:
+        v = _f32(v)
+        one = v.ndim == 1
+        v2 = v.reshape(-1, self.dimension)
+        out = np.zeros(v2.shape, np.uint8)
+        _lib.vo_sq8_quantize(self._s, v2, v2.shape[0], out)
+        return out[0] if one else out
+
+    def dequantize(self, codes) -> np.ndarray:  # quantization.rs:254-268
+        return np.asarray(codes, np.uint8).astype(np.float32) * self.inv_scales + self.min_vals
+
+    def push(self, vs) -> None:
+        vs = _f32(vs).reshape(-1, self.dimension)
+        _lib.vo_sq8_push(self._s, vs, vs.shape[0])
+
+    def __len__(self):
+        return int(_lib.vo_sq8_len(self._s))
+
+    def codes(self) -> np.ndarray:
+        n = len(self)
+        if n == 0:
+            return np.zeros((0, self.dimension), np.uint8)
+        return np.ctypeslib.as_array(_lib.vo_sq8_codes(self._s), shape=(n, self.dimension)).copy()
+
+    @staticmethod
+    def distance_l2_quantized(a, b) -> int:
+        a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+        return int(_lib.vo_sq8_distance_quantized(a, b, a.size))
+
+    def distance_l2_asymmetric(self, q, codes) -> float:
+        return float(_lib.vo_sq8_distance_asymmetric(self._s, _f32(q), np.ascontiguousarray(codes, np.uint8)))
+
+
+class DualPrecisionHnsw:
+    """DualPrecisionHnsw<SimdDistance> restated (native/dual_precision.rs:60-441)."""
+
+    def __init__(self, metric, dimension, max_connections, ef_construction, max_elements, fma=True, graph=None):
+        self.inner = graph if graph is not None else Hnsw(metric, dimension, max_connections, ef_construction, fma=fma)
+        self.dimension = dimension
+        self.training_sample_size = min(1000, max_elements)  # dual_precision.rs:100
+        self.quantizer = None
+        self._buffer = []
+
+    @classmethod
+    def from_graph(cls, graph: Hnsw, train_count=None):
+        """Wraps an existing oracle graph as if its vectors had been inserted in id order."""
+        dp = cls(graph.metric, graph.dim, graph.M, 0, max(len(graph), 1), graph=graph)
+        vs = graph.vectors()
+        t = dp.training_sample_size if train_count is None else train_count
+        if len(vs) >= t > 0:
+            dp.quantizer = ScalarQuantizer(vs[:t])
+            dp.quantizer.push(vs)
+        else:
+            dp._buffer = [v for v in vs]
+        return dp
+
+    def __len__(self):
+        return len(self.inner)
+
+    def is_quantizer_trained(self) -> bool:
+        return self.quantizer is not None
+
+    def insert(self, v) -> int:  # dual_precision.rs:122-143
+        v = _f32(v)
+        node = self.inner.insert(v)
+        if self.quantizer is not None:
+            self.quantizer.push(v)
+        else:
+            self._buffer.append(v.copy())
+            if len(self._buffer) >= self.training_sample_size:
+                self._train()
+        return node
+
+    def _train(self):  # dual_precision.rs:146-169
+        if not self._buffer:
+            return
+        buf = np.stack(self._buffer)
+        self.quantizer = ScalarQuantizer(buf)
+        self.quantizer.push(buf)
+        self._buffer = []
+
+    def force_train_quantizer(self):  # dual_precision.rs:172-176
+        if self.quantizer is None and self._buffer:
+            self._train()
+
+    def search(self, q, k, ef_search):  # dual_precision.rs:179-228 (f32 traversal + exact re-rank = inner.search)
+        if self.quantizer is None:
+            return self.inner.search(q, k, ef_search)
+        rerank_k = max(ef_search * 2, k * 4)
+        ids, d = self.inner.search(q, rerank_k, ef_search)
+        order = np.argsort(np.array([_total_key(x) for x in d], dtype=np.int64), kind="stable")[:k]
+        return ids[order], d[order]
+
+    def search_with_config(self, q, k, ef_search, oversampling_ratio=4, use_int8_traversal=True, min_index_size=10_000,
+                           order="reference", with_stats=False):  # dual_precision.rs:263-325
+        if self.quantizer is None or not use_int8_traversal or len(self.inner) < min_index_size:
+            r = self.inner.search(q, k, ef_search, order=order, with_stats=with_stats)
+            return r
+        q = _f32(q)
+        ids = np.zeros(max(k, 1), dtype=np.uint64)
+        d = np.zeros(max(k, 1), dtype=np.float32)
+        st = np.zeros(6, dtype=np.uint64)
+        n = _lib.vo_dual_search_int8(self.inner._h, self.quantizer._s, q, k, ef_search, oversampling_ratio,
+                                     0 if order == "reference" else 1, ids, d, st)
+        if with_stats:
+            return ids[:n].copy(), d[:n].copy(), dict(zip(("ndc0", "hops0", "ndc_up", "hops_up", "tie_at_k", "adj0"),
+                                                          (int(x) for x in st)))
+        return ids[:n].copy(), d[:n].copy()
+
+    def search_int8_batch(self, qs, k, ef_search, oversampling_ratio=4, order="canonical", threads=1):
+        assert self.quantizer is not None
+        qs = _f32(qs)
+        nq = qs.shape[0]
+        ids = np.zeros((nq, k), dtype=np.uint64)
+        d = np.zeros((nq, k), dtype=np.float32)
+        cnt = np.zeros(nq, dtype=np.uint32)
+        st = np.zeros((nq, 6), dtype=np.uint64)
+        _lib.vo_dual_search_int8_batch(self.inner._h, self.quantizer._s, qs, nq, k, ef_search, oversampling_ratio,
+                                       0 if order == "reference" else 1, threads, ids, d, cnt, st)
+        return ids, d, cnt, st
+
+
+def _total_key(x) -> int:
+    b = int(np.float32(x).view(np.int32))
+    return b ^ (((b >> 31) & 0xFFFFFFFF) >> 1) if b < 0 else b
 
 
 def bruteforce(metric, vectors, q, k, fma=True):

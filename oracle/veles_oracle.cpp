@@ -751,6 +751,176 @@ struct Hnsw {
 };
 
 // ---------------------------------------------------------------------------
+// SQ8 dual precision (native/quantization.rs, native/dual_precision.rs)
+// ---------------------------------------------------------------------------
+// ScalarQuantizer (quantization.rs:160-233) + QuantizedVectorStore (:318-374)
+struct Sq8 {
+    uint32_t dim = 0;
+    std::vector<float> mn, scale, inv;
+    std::vector<uint8_t> codes;  // count * dim
+    uint64_t count = 0;
+
+    // ScalarQuantizer::train, quantization.rs:190-233
+    void train(const float* v, uint64_t n_train, uint32_t dim_) {
+        dim = dim_;
+        mn.assign(dim, std::numeric_limits<float>::max());
+        std::vector<float> mx(dim, std::numeric_limits<float>::lowest());
+        for (uint64_t r = 0; r < n_train; ++r)
+            for (uint32_t i = 0; i < dim; ++i) {
+                const float val = v[r * (size_t)dim + i];
+                mn[i] = std::fmin(mn[i], val);  // f32::min: NaN loses
+                mx[i] = std::fmax(mx[i], val);
+            }
+        scale.resize(dim);
+        inv.resize(dim);
+        for (uint32_t i = 0; i < dim; ++i) {
+            const float range = mx[i] - mn[i];
+            scale[i] = std::fabs(range) < 1e-10f ? 1.0f : 255.0f / range;
+            inv[i] = 1.0f / scale[i];
+        }
+    }
+    // ScalarQuantizer::quantize, quantization.rs:236-250: ((val - min) * scale).round().clamp(0, 255) as u8
+    void quantize(const float* v, uint8_t* out) const {
+        for (uint32_t i = 0; i < dim; ++i) {
+            float q = std::round((v[i] - mn[i]) * scale[i]);  // half away from zero, as f32::round
+            uint8_t b;
+            if (q != q) b = 0;  // NaN survives clamp; `as u8` maps it to 0
+            else b = (uint8_t)(q < 0.0f ? 0.0f : (q > 255.0f ? 255.0f : q));
+            out[i] = b;
+        }
+    }
+    void push(const float* v) {
+        codes.resize((count + 1) * (size_t)dim);
+        quantize(v, codes.data() + count * (size_t)dim);
+        ++count;
+    }
+    const uint8_t* row(uint64_t id) const { return codes.data() + id * (size_t)dim; }
+    // distance_l2_quantized_simd, quantization.rs:42-92 (u32 sums: the accumulator split cannot change the value)
+    static uint32_t dist_q(const uint8_t* a, const uint8_t* b, uint32_t dim) {
+        uint32_t s = 0;
+        for (uint32_t i = 0; i < dim; ++i) {
+            const int32_t d = (int32_t)a[i] - (int32_t)b[i];
+            s += (uint32_t)(d * d);
+        }
+        return s;
+    }
+    // distance_l2_asymmetric_simd, quantization.rs:98-147 (four f32 accumulators, element i -> sum[i % 4], no FMA)
+    float dist_asym(const float* q, const uint8_t* c) const {
+        float sum[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t chunks = dim / 4;
+        for (uint32_t i = 0; i < chunks * 4; ++i) {
+            const float dq = (float)c[i] * inv[i] + mn[i];
+            const float d = q[i] - dq;
+            sum[i & 3] += d * d;
+        }
+        for (uint32_t i = chunks * 4; i < dim; ++i) {
+            const float dq = (float)c[i] * inv[i] + mn[i];
+            const float d = q[i] - dq;
+            sum[0] += d * d;
+        }
+        return std::sqrt((sum[0] + sum[1] + sum[2] + sum[3]));
+    }
+};
+
+struct UN {
+    uint32_t d;
+    uint64_t n;
+};
+struct UNLess {  // (u32, NodeId) tuple order
+    bool operator()(const UN& a, const UN& b) const { return a.d != b.d ? a.d < b.d : a.n < b.n; }
+};
+struct UNGreater {
+    bool operator()(const UN& a, const UN& b) const { return UNLess()(b, a); }
+};
+
+// DualPrecisionHnsw::search_int8_traversal (dual_precision.rs:284-325) with search_layer_int8 (:327-405) and
+// greedy_search_int8 (:407-441).  order_mode 0: the reference's order (results.into_iter() = heap array, stable
+// sort by distance); 1: canonical coarse order (dist, id).  The exact re-rank is a stable sort by total_cmp over
+// the coarse order either way.  stats[4] = 1 when a tie makes the two orders differ observably: equal coarse
+// distances across the candidates_k cut, or equal exact distances among the first k+1 re-ranked.
+static std::vector<DN> dual_search_int8(const Hnsw& g, const Sq8& sq, const float* q, size_t k, size_t ef_search,
+                                        size_t oversampling, int order_mode, SearchStats* st) {
+    std::vector<DN> out;
+    if (!g.has_ep) return out;
+    std::vector<uint8_t> qq(g.dim);
+    sq.quantize(q, qq.data());
+    const size_t ck = k * oversampling;
+    auto dq = [&](uint64_t id) { return Sq8::dist_q(qq.data(), sq.row(id), g.dim); };
+
+    uint64_t cur = g.ep;
+    for (uint32_t l = g.max_layer; l >= 1; --l) {
+        uint32_t cur_d = dq(cur);
+        if (st) st->ndc_up++;
+        for (;;) {
+            std::vector<uint32_t> nb = g.neighbors(l, cur);
+            if (st) st->hops_up++;
+            bool improved = false;
+            for (uint32_t x : nb) {
+                const uint32_t d = dq(x);
+                if (st) st->ndc_up++;
+                if (d < cur_d) {
+                    cur = x;
+                    cur_d = d;
+                    improved = true;
+                }
+            }
+            if (!improved) break;
+        }
+    }
+
+    FxSet visited;
+    RustHeap<UN, UNGreater> cand;
+    RustHeap<UN, UNLess> res;
+    {
+        const uint32_t d = dq(cur);
+        if (st) st->ndc0++;
+        cand.push({d, cur});
+        res.push({d, cur});
+        visited.insert(cur);
+    }
+    const size_t ef = std::max(ef_search, ck);
+    while (!cand.empty()) {
+        const UN c = cand.pop();
+        const uint32_t furthest = res.empty() ? UINT32_MAX : res.peek().d;
+        if (c.d > furthest && res.size() >= ef) break;
+        const std::vector<uint32_t>& nb = g.neighbors(0, c.n);
+        if (st) {
+            st->hops0++;
+            st->adj0 += nb.size();
+        }
+        for (uint32_t x : nb) {
+            if (visited.insert(x)) {
+                const uint32_t d = dq(x);
+                if (st) st->ndc0++;
+                const uint32_t f = res.empty() ? UINT32_MAX : res.peek().d;
+                if (d < f || res.size() < ef) {
+                    cand.push({d, (uint64_t)x});
+                    res.push({d, (uint64_t)x});
+                    if (res.size() > ef) res.pop();
+                }
+            }
+        }
+    }
+    std::vector<UN> coarse = res.data;
+    if (order_mode == 1)
+        std::sort(coarse.begin(), coarse.end(), UNLess());
+    else
+        std::stable_sort(coarse.begin(), coarse.end(), [](const UN& a, const UN& b) { return a.d < b.d; });
+    if (st && coarse.size() > ck && ck > 0 && coarse[ck - 1].d == coarse[ck].d) st->tie_at_k = 1;
+    if (coarse.size() > ck) coarse.resize(ck);
+    if (coarse.empty()) return out;
+
+    out.reserve(coarse.size());
+    for (const UN& c : coarse) out.push_back({g.dist(q, g.vec(c.n)), c.n});
+    std::stable_sort(out.begin(), out.end(), [](const DN& a, const DN& b) { return total_cmp(a.d, b.d) < 0; });
+    if (st)
+        for (size_t i = 0; i + 1 < out.size() && i < k; ++i)
+            if (total_cmp(out[i].d, out[i + 1].d) == 0) st->tie_at_k = 1;
+    if (out.size() > k) out.resize(k);
+    return out;
+}
+
+// ---------------------------------------------------------------------------
 // BM25 (index/bm25.rs) on integer term ids.  Tokenisation lives in Python for
 // the tests (tokenize :114-120 is string handling, not arithmetic).
 // ---------------------------------------------------------------------------
@@ -1318,6 +1488,79 @@ uint32_t vo_fuse(int strategy, const uint32_t* list_ptr, uint32_t n_lists, const
         out_score[i] = fused[i].second;
     }
     return m;
+}
+
+// ---- SQ8 dual precision -------------------------------------------------------------------------
+void* vo_sq8_train(const float* v, uint64_t n_train, uint32_t dim) {
+    Sq8* s = new Sq8();
+    s->train(v, n_train, dim);
+    return s;
+}
+void vo_sq8_free(void* s) { delete (Sq8*)s; }
+void vo_sq8_params(void* s, float* mn, float* scale, float* inv) {
+    Sq8* q = (Sq8*)s;
+    std::memcpy(mn, q->mn.data(), q->dim * 4);
+    std::memcpy(scale, q->scale.data(), q->dim * 4);
+    std::memcpy(inv, q->inv.data(), q->dim * 4);
+}
+void vo_sq8_quantize(void* s, const float* v, uint64_t n, uint8_t* out) {
+    Sq8* q = (Sq8*)s;
+    for (uint64_t i = 0; i < n; ++i) q->quantize(v + i * (size_t)q->dim, out + i * (size_t)q->dim);
+}
+// appends n vectors to the store (QuantizedVectorStore::push)
+void vo_sq8_push(void* s, const float* v, uint64_t n) {
+    Sq8* q = (Sq8*)s;
+    for (uint64_t i = 0; i < n; ++i) q->push(v + i * (size_t)q->dim);
+}
+uint64_t vo_sq8_len(void* s) { return ((Sq8*)s)->count; }
+const uint8_t* vo_sq8_codes(void* s) { return ((Sq8*)s)->codes.data(); }
+uint32_t vo_sq8_distance_quantized(const uint8_t* a, const uint8_t* b, uint32_t dim) { return Sq8::dist_q(a, b, dim); }
+float vo_sq8_distance_asymmetric(void* s, const float* q, const uint8_t* c) { return ((Sq8*)s)->dist_asym(q, c); }
+
+// search_with_config on a trained index (dual_precision.rs:263-325).  stats layout as vo_hnsw_search.
+uint32_t vo_dual_search_int8(void* h, void* s, const float* q, uint32_t k, uint32_t ef_search, uint32_t oversampling,
+                             int order_mode, uint64_t* out_ids, float* out_dist, uint64_t* stats) {
+    SearchStats st;
+    std::vector<DN> r = dual_search_int8(*(Hnsw*)h, *(Sq8*)s, q, k, ef_search, oversampling, order_mode, &st);
+    for (size_t i = 0; i < r.size(); ++i) {
+        out_ids[i] = r[i].n;
+        out_dist[i] = r[i].d;
+    }
+    if (stats) {
+        stats[0] = st.ndc0;
+        stats[1] = st.hops0;
+        stats[2] = st.ndc_up;
+        stats[3] = st.hops_up;
+        stats[4] = st.tie_at_k;
+        stats[5] = st.adj0;
+    }
+    return (uint32_t)r.size();
+}
+void vo_dual_search_int8_batch(void* h, void* s, const float* q, uint64_t nq, uint32_t k, uint32_t ef_search,
+                               uint32_t oversampling, int order_mode, int threads, uint64_t* out_ids, float* out_dist,
+                               uint32_t* out_counts, uint64_t* stats) {
+    Hnsw* g = (Hnsw*)h;
+    std::atomic<uint64_t> next(0);
+    auto work = [&]() {
+        for (;;) {
+            uint64_t i = next.fetch_add(1);
+            if (i >= nq) break;
+            out_counts[i] = vo_dual_search_int8(g, s, q + i * (size_t)g->dim, k, ef_search, oversampling, order_mode,
+                                                out_ids + i * (size_t)k, out_dist + i * (size_t)k,
+                                                stats ? stats + i * 6 : nullptr);
+            for (uint32_t j = out_counts[i]; j < k; ++j) {
+                out_ids[i * (size_t)k + j] = UINT64_MAX;
+                out_dist[i * (size_t)k + j] = std::numeric_limits<float>::quiet_NaN();
+            }
+        }
+    };
+    if (threads <= 1) {
+        work();
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) pool.emplace_back(work);
+    for (auto& t : pool) t.join();
 }
 
 }  // extern "C"

@@ -226,6 +226,50 @@ def c5(n_docs=1_000_000, vocab=100_000, nq=1024, k=10):
           flush=True)
 
 
+def sq8(n=1_000_000, dim=768, nq=1024, k=10, ef=64, over=4, sample=128):
+    """C2 through DualPrecisionHnsw::search_with_config (dual_precision.rs:284-325): int8 traversal + exact re-rank."""
+    snap, x_h, q_d = hnsw_case("C2 f32 traversal (for comparison)", n, dim, "f32", DistanceMetric.Cosine, k, ef, nq, 24, sample=sample)
+    t0 = time.time()
+    snap.attach_sq8(1000)
+    torch.cuda.synchronize()
+    t_attach = time.time() - t0
+    stream = torch.cuda.current_stream().cuda_stream
+    out = {}
+    for batch in sorted({nq, 4 * nq}):
+        qb = q_d if batch == nq else gen_data(torch, batch, dim, 24, 1_000_003, DEV).contiguous()
+        ids = torch.empty((batch, k), dtype=torch.int32, device=DEV)
+        dist = torch.empty((batch, k), dtype=torch.float32, device=DEV)
+        cnt = torch.empty(batch, dtype=torch.int32, device=DEV)
+        st = torch.empty((batch, 4), dtype=torch.int32, device=DEV)
+        snap.search_batch_sq8_device(qb, k, ef, over, ids, dist, cnt, st, stream)
+        torch.cuda.synchronize()
+        ms = timed(lambda: snap.search_batch_sq8_device(qb, k, ef, over, ids, dist, cnt, None, stream), 20)
+        gi = torch.empty((batch, k), dtype=torch.int32, device=DEV)
+        gs = torch.empty((batch, k), dtype=torch.float32, device=DEV)
+        snap.bruteforce_batch_device(qb, k, gi, gs, stream)
+        torch.cuda.synchronize()
+        s = st.cpu().numpy().astype(np.int64)
+        ck = k * over
+        alg = int(((s[:, 0] + s[:, 2]) * dim + s[:, 1] * 64 * 4 + s[:, 3] * 32 * 4 + dim * 4 + ck * dim * 4 + k * 8).sum())
+        out[f"batch{batch}"] = {"ms_per_batch": ms, "queries_per_s": batch / ms * 1e3,
+                                "recall_at_k": recall(ids.cpu().numpy(), gi.cpu().numpy(), k),
+                                "ndc_per_query": float((s[:, 0] + s[:, 2]).mean()), "alg_GBps": alg / ms / 1e6,
+                                "frac_hbm": alg / ms / 1e6 / PEAK}
+        if batch == nq:
+            got_i, got_d = ids.cpu().numpy(), dist.cpu().numpy()
+    g = vo.Hnsw.from_arrays(int(DistanceMetric.Cosine), x_h, snap.export_graph(), 32, 64, snap.entry_point, snap.max_layer)
+    dp = vo.DualPrecisionHnsw.from_graph(g, train_count=1000)
+    qs = q_d[:sample].cpu().numpy()
+    t = time.time()
+    oi, od, oc, ost = dp.search_int8_batch(qs, k, ef, over, order="canonical", threads=NCORES)
+    cpu_qps = sample / (time.time() - t)
+    print(json.dumps({"config": "C2-sq8 DualPrecisionHnsw int8 traversal + exact re-rank", "n": n, "dim": dim, "k": k,
+                      "ef_search": ef, "oversampling": over, "attach_s": round(t_attach, 2), **out,
+                      "parity_ids_sample": bool(np.array_equal(got_i[:sample], oi.astype(np.int32))),
+                      "parity_dist_bits_sample": bool(np.array_equal(got_d[:sample].view(np.uint32), od.view(np.uint32))),
+                      "cpu_queries_per_s": cpu_qps, "cpu_threads": NCORES, "cpu_sample": sample, "peak_GBps": PEAK}), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("which", nargs="*", default=["c1", "c3", "c4", "c5"])
@@ -244,3 +288,5 @@ if __name__ == "__main__":
         torch.cuda.empty_cache()
     if "c5" in a.which:
         c5()
+    if "sq8" in a.which:
+        sq8()

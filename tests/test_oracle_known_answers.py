@@ -385,3 +385,119 @@ def test_hybrid_rrf_formula():
     # weight is clamped to [0,1]
     ids, sc = vo.rrf_hybrid([1], [2], k=2, vector_weight=7.0)
     assert ids.tolist() == [1, 2] and sc[1] == 0.0
+
+
+# ---- SQ8 dual precision (native/quantization_tests.rs, native/dual_precision_tests.rs) ----
+def test_sq8_quantizer_known_answers():
+    # quantization_tests.rs:13-29 train min / scale
+    q = vo.ScalarQuantizer([[0.0, 10.0, -5.0], [5.0, 20.0, 5.0], [2.5, 15.0, 0.0]])
+    assert q.dimension == 3
+    assert np.allclose(q.min_vals, [0.0, 10.0, -5.0], atol=1e-6)
+    assert np.allclose(q.scales, [255.0 / 5.0, 255.0 / 10.0, 255.0 / 10.0], atol=1e-4)
+    # :32-41 constant dimensions get scale 1
+    q = vo.ScalarQuantizer([[1.0, 5.0, 5.0], [2.0, 5.0, 5.0]])
+    assert q.scales[1] == 1.0 and q.scales[2] == 1.0
+    # :44-48 empty training set
+    with pytest.raises(ValueError, match="Cannot train on empty vectors"):
+        vo.ScalarQuantizer(np.zeros((0, 3), F))
+    # :54-62, :66-85 range mapping, :88-100 clamping
+    q = vo.ScalarQuantizer([[0.0, 100.0]])
+    assert q.quantize([0.0, 100.0])[0] == 0
+    q = vo.ScalarQuantizer([[0.0, 0.0], [10.0, 100.0]])
+    assert q.quantize([0.0, 0.0]).tolist() == [0, 0] and q.quantize([10.0, 100.0]).tolist() == [255, 255]
+    assert all(abs(int(v) - 127) <= 1 for v in q.quantize([5.0, 50.0]))
+    q = vo.ScalarQuantizer([[0.0], [10.0]])
+    assert q.quantize([-5.0])[0] == 0 and q.quantize([20.0])[0] == 255
+    assert q.quantize([float("nan")])[0] == 0  # NaN survives clamp, `as u8` saturates it to 0
+    # :103-124 dequantize within 1% of the range
+    q = vo.ScalarQuantizer([[0.0, -10.0, 100.0], [10.0, 10.0, 200.0]])
+    orig = np.array([5.0, 0.0, 150.0], F)
+    rec = q.dequantize(q.quantize(orig))
+    assert (np.abs(orig - rec) / np.array([10.0, 20.0, 100.0]) < 0.01).all()
+
+
+def test_sq8_distances_known_answers():
+    # quantization_tests.rs:129-147 identical -> 0, symmetry
+    q = vo.ScalarQuantizer([[0.0, 0.0], [10.0, 10.0]])
+    v = q.quantize([5.0, 5.0])
+    assert q.distance_l2_quantized(v, v) == 0
+    a, b = q.quantize([2.0, 3.0]), q.quantize([7.0, 8.0])
+    assert q.distance_l2_quantized(a, b) == q.distance_l2_quantized(b, a) > 0
+    # :150-177 asymmetric distance within 5% of exact
+    q = vo.ScalarQuantizer([np.zeros(128, F), np.full(128, 10.0, F)])
+    approx = q.distance_l2_asymmetric(np.full(128, 3.0, F), q.quantize(np.full(128, 7.0, F)))
+    exact = math.sqrt(128 * 16.0)
+    assert abs(approx - exact) / exact < 0.05
+    # u32 sum against a plain integer sum, 768 codes, extreme values
+    rng = np.random.default_rng(3)
+    x, y = rng.integers(0, 256, 771, dtype=np.uint8), rng.integers(0, 256, 771, dtype=np.uint8)
+    assert q.distance_l2_quantized(x, y) == int(((x.astype(np.int64) - y.astype(np.int64)) ** 2).sum())
+    assert q.distance_l2_quantized(np.zeros(768, np.uint8), np.full(768, 255, np.uint8)) == 768 * 65025
+    # :246-269 768-d reconstruction error
+    v1 = np.array([math.sin(i * 0.01) for i in range(768)], F)
+    v2 = np.array([math.cos(i * 0.01) for i in range(768)], F)
+    q = vo.ScalarQuantizer([v1, v2])
+    assert float(((v1 - q.dequantize(q.quantize(v1))) ** 2).mean()) < 1e-3
+
+
+def _ramp(i, dim):
+    return np.arange(i * dim, (i + 1) * dim, dtype=F)
+
+
+def test_dual_precision_training_lifecycle():
+    # dual_precision_tests.rs:12-77
+    dp = vo.DualPrecisionHnsw(vo.EUCLIDEAN, 32, 16, 100, 1000)
+    assert len(dp) == 0 and not dp.is_quantizer_trained()
+    for i in range(10):
+        dp.insert(_ramp(i, 32))
+    assert len(dp) == 10 and not dp.is_quantizer_trained()
+    dp.force_train_quantizer()
+    assert dp.is_quantizer_trained() and len(dp.quantizer) == 10
+    dp = vo.DualPrecisionHnsw(vo.EUCLIDEAN, 32, 16, 100, 100)  # training_sample_size = min(1000, 100)
+    for i in range(100):
+        dp.insert(np.array([math.sin((i * 32 + j) * 0.01) for j in range(32)], F))
+    assert dp.is_quantizer_trained() and len(dp.quantizer) == 100
+    dp.insert(np.zeros(32, F))  # :162-190 inserts after training are quantized too
+    assert len(dp.quantizer) == 101
+
+
+def test_dual_precision_search_known_answers():
+    # dual_precision_tests.rs:80-120: ramp vectors, nearest to the first ramp is node 0 before and after training
+    dp = vo.DualPrecisionHnsw(vo.EUCLIDEAN, 32, 16, 100, 1000)
+    for i in range(100):
+        dp.insert(_ramp(i, 32))
+    q = _ramp(0, 32)
+    ids, _ = dp.search(q, 10, 50)
+    assert len(ids) > 0 and ids[0] == 0
+    dp.force_train_quantizer()
+    ids, d = dp.search(q, 10, 50)
+    assert ids[0] == 0 and (np.diff(d) >= 0).all()
+    # :260-288 int8 traversal returns sorted results
+    dp = vo.DualPrecisionHnsw(vo.EUCLIDEAN, 64, 16, 100, 500)
+    for i in range(200):
+        dp.insert(np.array([math.sin((i * 64 + j) * 0.01) for j in range(64)], F))
+    dp.force_train_quantizer()
+    q = np.array([math.sin(j * 0.01) for j in range(64)], F)
+    ids, d = dp.search_with_config(q, 10, 50, min_index_size=0)
+    assert len(ids) > 0 and (np.diff(d) >= 0).all()
+    # the size gate (:275-277): below min_index_size the f32 path answers
+    a = dp.search_with_config(q, 10, 50)
+    b = dp.inner.search(q, 10, 50)
+    assert np.array_equal(a[0], b[0])
+
+
+def test_dual_precision_int8_recall_vs_f32():
+    # dual_precision_tests.rs:224-257, 291-334: 500 x 128 cos vectors, query = vector 0
+    dp = vo.DualPrecisionHnsw(vo.EUCLIDEAN, 128, 32, 200, 1000)
+    vs = np.array([[math.cos((i * 128 + j) * 0.001) for j in range(128)] for i in range(500)], F)
+    for v in vs:
+        dp.insert(v)
+    dp.force_train_quantizer()
+    f_ids, _ = dp.search(vs[0], 10, 100)
+    assert 0 in f_ids.tolist()
+    i_ids, i_d = dp.search_with_config(vs[0], 10, 100, oversampling_ratio=4, min_index_size=0)
+    assert len(set(f_ids.tolist()) & set(i_ids.tolist())) / max(len(f_ids), 1) >= 0.9
+    # canonical and reference coarse orders agree when no tie is flagged
+    r = dp.search_with_config(vs[0], 10, 100, min_index_size=0, order="canonical", with_stats=True)
+    if not r[2]["tie_at_k"]:
+        assert np.array_equal(r[0], i_ids)

@@ -10,16 +10,19 @@
 //   keep score > 0; order by score descending (total order), ties by doc id ascending (the reference's
 //   tie order is hash/roaring iteration + select_nth_unstable, i.e. unspecified -- SURVEY 8a a19).
 //
-// Layout in HBM: postings CSR by term, doc ids ascending within a term, (doc u32, tf u32) in two
-// arrays; doc_len[doc]; idf[term]; and a skip table skip[term][r] = first posting of `term` whose doc
-// id is >= r * kRange, so a CTA that owns the doc-id range r of one query reads exactly its slice of
-// every posting list, coalesced, with no search.
+// Layout in HBM: postings CSR by term, doc ids ascending within a term, (doc u32, tf u32, den f32) in
+// three arrays, den = tf + k1 * len_norm precomputed per posting (the snapshot is immutable); idf[term];
+// and a skip table skip[term][r] = first posting of `term` whose doc id is >= r * kRange, so the doc-id
+// range r of one query reads exactly its slice of every posting list, coalesced, with no search.
 //
-// Kernel 1 (bm25_range_kernel): one CTA per (doc range, query).  A dense f32 accumulator for the
-// range lives in shared memory; the query's terms are applied one after another with a block
-// barrier in between, so every document receives its term contributions in query order (a document
-// occurs at most once per posting list: no intra-term conflicts, no atomics).  Warp 0 then extracts
-// the range's k best.  Kernel 2 merges the per-range lists of a query.
+// bm25_query_kernel (k <= kMultiK, <= kQueryTerms tokens): one persistent CTA per query walks the
+// ranges in order.  A dense f32 accumulator for the range lives in shared memory; the query's terms
+// are applied one after another with a block barrier when the term changes, so every document
+// receives its term contributions in query order (a document occurs at most once per posting list:
+// no intra-term conflicts, no atomics).  Every warp keeps a register-resident top-k over its slice of
+// all ranges; the eight lists are merged once per query.
+// Fallback (larger k / longer queries): bm25_range_kernel, one CTA per (doc range, query), writes
+// per-range lists and bm25_merge_kernel merges them.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>

@@ -98,6 +98,8 @@ struct IndexView {
     int32_t metric;
     int32_t dtype;
     int32_t has_entry;
+    const float* sq_min;    // VELES_SQ8 views: the quantizer, to code the query (quantization.rs:236-250)
+    const float* sq_scale;
 };
 
 // ---------------------------------------------------------------------------------------------

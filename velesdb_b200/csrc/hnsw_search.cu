@@ -74,6 +74,15 @@ __device__ __forceinline__ uint64_t make_key(float d, uint32_t id) {
 __device__ __forceinline__ float key_dist(uint64_t key) { return ord_unkey((uint32_t)(key >> 32)); }
 __device__ __forceinline__ uint32_t key_id(uint64_t key) { return ((uint32_t)key) >> 1; }
 
+// distance_l2_quantized (native/quantization.rs:42-92) on four codes: sum of squared byte differences.  Integer
+// sums, so the reference's accumulator split is immaterial.  The u32 total travels through the beam as the
+// float with the same bit pattern: for values below 0x7f800000 (dim <= 32768) float order == integer order,
+// denormals included (no flush-to-zero in this build).
+__device__ __forceinline__ uint32_t sq8_word(uint32_t a, uint32_t b, uint32_t acc) {
+    const uint32_t d = __vabsdiffu4(a, b);
+    return __dp4a(d, d, acc);
+}
+
 template <int DT>
 __device__ __forceinline__ float row_distance(const SearchParams& p, const WarpCtx& c, const uint8_t* row) {
     if (DT == VELES_BIN1) {
@@ -83,6 +92,13 @@ __device__ __forceinline__ float row_distance(const SearchParams& p, const WarpC
         uint32_t d = 0;
         for (uint32_t i = c.lane; i < words; i += 32) d += __popc(qw[i] ^ rw[i]);
         return (float)__reduce_add_sync(FULL_MASK, d);
+    } else if (DT == VELES_SQ8) {
+        const uint32_t words = p.ix.row_bytes >> 2;  // zero padded on both sides
+        const uint32_t* qw = reinterpret_cast<const uint32_t*>(c.q);
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(row);
+        uint32_t d = 0;
+        for (uint32_t i = c.lane; i < words; i += 32) d = sq8_word(qw[i], rw[i], d);
+        return __uint_as_float(__reduce_add_sync(FULL_MASK, d));
     } else {
         float norm_b = 0.0f;
         if (p.ix.metric == VELES_COSINE) norm_b = *reinterpret_cast<const float*>(row + p.ix.norm_off);
@@ -198,6 +214,22 @@ __device__ __forceinline__ float quad_distance(const SearchParams& p, const Warp
         d += __shfl_xor_sync(FULL_MASK, d, 2);
         d += __shfl_xor_sync(FULL_MASK, d, 4);
         return (float)d;
+    } else if (DT == VELES_SQ8) {
+        const uint32_t n16 = p.ix.row_bytes >> 4;
+        const uint4* qw = reinterpret_cast<const uint4*>(c.q);
+        const uint4* rw = reinterpret_cast<const uint4*>(row);
+        uint32_t d = 0;
+        for (uint32_t w = t; w < n16; w += 8) {
+            const uint4 x = rw[w], y = qw[w];
+            d = sq8_word(x.x, y.x, d);
+            d = sq8_word(x.y, y.y, d);
+            d = sq8_word(x.z, y.z, d);
+            d = sq8_word(x.w, y.w, d);
+        }
+        d += __shfl_xor_sync(FULL_MASK, d, 1);
+        d += __shfl_xor_sync(FULL_MASK, d, 2);
+        d += __shfl_xor_sync(FULL_MASK, d, 4);
+        return __uint_as_float(d);
     } else {
         using TB = typename std::conditional<DT == VELES_F32, float, __half>::type;
         const TB* r = reinterpret_cast<const TB*>(row);
@@ -507,12 +539,22 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
                 for (uint32_t b = 0; b < 32; ++b) bits |= (qg[w * 32 + b] > 0.5f ? 1u : 0u) << b;
                 qw[w] = bits;
             }
+        } else if (DT == VELES_SQ8) {
+            // ScalarQuantizer::quantize (quantization.rs:236-250); padding bytes are zero like the rows'
+            for (uint32_t i = lane; i < p.ix.row_bytes; i += 32) {
+                uint32_t b = 0;
+                if (i < dim) {
+                    const float qv = roundf(__fmul_rn(__fsub_rn(qg[i], p.ix.sq_min[i]), p.ix.sq_scale[i]));
+                    b = (qv != qv) ? 0u : (uint32_t)fminf(fmaxf(qv, 0.0f), 255.0f);
+                }
+                c.q[i] = (uint8_t)b;
+            }
         } else {
             float* qs = reinterpret_cast<float*>(c.q);
             for (uint32_t i = lane; i < dim; i += 32) qs[i] = qg[i];
         }
         __syncwarp();
-        if (DT != VELES_BIN1 && p.ix.metric == VELES_COSINE) {
+        if ((DT == VELES_F32 || DT == VELES_F16) && p.ix.metric == VELES_COSINE) {
             const float* qs = reinterpret_cast<const float*>(c.q);
             c.norm_a = __fsqrt_rn(warp_tree_reduce<0>(qs, qs, dim, lane));
         }
@@ -786,14 +828,17 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
     return v && *v ? (uint32_t)std::strtoul(v, nullptr, 10) : dflt;
 }
 
-static int32_t launch_search(const veles_index* ix, const float* q_d, uint32_t nq, uint32_t k, uint32_t ef,
-                             uint32_t* ids_d, float* dist_d, uint32_t* cnt_d, uint32_t* stats_d, cudaStream_t st) {
+int32_t launch_search(const veles_index* ix, const IndexView& view, const float* q_d, uint32_t nq, uint32_t k, uint32_t ef,
+                      uint32_t* ids_d, float* dist_d, uint32_t* cnt_d, uint32_t* stats_d, cudaStream_t st) {
     VELES_REQUIRE(ix->has_graph, "snapshot has no graph; build or load one first");
+    VELES_REQUIRE(view.dtype != VELES_SQ8 || ix->dim <= 32768, "SQ8 traversal supports at most 32768 dimensions");
     VELES_REQUIRE(k >= 1 && k <= 65536, "k must be in 1..65536, got %u", k);
     VELES_REQUIRE(ef >= 1 && ef <= 16384, "ef must be in 1..16384, got %u", ef);
     if (nq == 0) return VELES_OK;
     SearchParams p;
-    p.ix = ix->view();
+    p.ix = view;
+    const int32_t dtype = view.dtype;
+    const uint32_t row_bytes = view.row_bytes;
     p.queries = q_d;
     p.nq = nq;
     p.k = k;
@@ -810,7 +855,7 @@ static int32_t launch_search(const veles_index* ix, const float* q_d, uint32_t n
     p.off_todo = p.off_res + res_bytes;
     const uint32_t todo_bytes = round_up(std::max(ix->stride0, ix->strideU) * 4, 16);
     p.off_q = p.off_todo + todo_bytes;
-    const uint32_t q_bytes = round_up(ix->dtype == VELES_BIN1 ? ix->dim / 8 : ix->dim * 4, 16);
+    const uint32_t q_bytes = dtype == VELES_SQ8 ? row_bytes : round_up(dtype == VELES_BIN1 ? ix->dim / 8 : ix->dim * 4, 16);
     p.off_ring = round_up(p.off_q + q_bytes, 128);
     int dev = 0, max_smem = 0, sms = 0;
     VELES_CUDA(cudaGetDevice(&dev));
@@ -819,12 +864,12 @@ static int32_t launch_search(const veles_index* ix, const float* q_d, uint32_t n
     int sm_smem = 0;
     VELES_CUDA(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
     // Quad path: four candidates per step (8 lanes each) when the row splits into 32-element blocks.
-    const bool can_quad = (ix->dtype == VELES_BIN1 && ix->dim % 128 == 0) ||
-                          (ix->dtype != VELES_BIN1 && ix->dim % 32 == 0 &&
+    const bool can_quad = (dtype == VELES_BIN1 && ix->dim % 128 == 0) || dtype == VELES_SQ8 ||
+                          ((dtype == VELES_F32 || dtype == VELES_F16) && ix->dim % 32 == 0 &&
                            (ix->metric == VELES_COSINE || ix->metric == VELES_EUCLIDEAN || ix->metric == VELES_DOT));
     p.quad = (can_quad && env_u32("VELES_SEARCH_QUAD", 1) != 0) ? 1 : 0;
     // packed rows of <= 128 bytes are read directly (no ring), see eval_list_bits
-    if (p.quad && ix->dtype == VELES_BIN1 && ix->dim <= 1024 && env_u32("VELES_SEARCH_BITS_DIRECT", 1) != 0) p.quad = 2;
+    if (p.quad && dtype == VELES_BIN1 && ix->dim <= 1024 && env_u32("VELES_SEARCH_BITS_DIRECT", 1) != 0) p.quad = 2;
     p.evict_first = env_u32("VELES_SEARCH_EVICT_FIRST", 1) != 0 ? 1 : 0;
     p.peek = env_u32("VELES_SEARCH_PEEK", 1) != 0 ? 1 : 0;
     p.row_prefetch = std::min(32u, env_u32("VELES_SEARCH_ROW_PREFETCH", 0));
@@ -833,25 +878,25 @@ static int32_t launch_search(const veles_index* ix, const float* q_d, uint32_t n
     // the batch time nearly doubles; 7 CTAs leave room for 2 stages of 4 rows each.
     // Batches larger than 7 x SMs prefer more resident queries with the minimal ring (two stages) over
     // deeper rings: measured on C3s (f16, 8192 queries) 7 -> 13 CTAs/SM = 173 K -> 222 K queries/s.
-    const uint32_t min_ring = (p.quad == 1 ? 8u : 2u) * ix->row_bytes;
+    const uint32_t min_ring = (p.quad == 1 ? 8u : 2u) * row_bytes;
     const uint32_t cmax = std::max(1u, (uint32_t)sm_smem / (p.off_ring + min_ring + 1024u));
     const uint32_t need = (nq + (uint32_t)sms - 1) / (uint32_t)sms;
     const uint32_t auto_ctas = std::min(std::min(cmax, 16u), std::max(need, p.quad ? 7u : 8u));
     const uint32_t want_ctas = std::max(1u, env_u32("VELES_SEARCH_CTAS_PER_SM", auto_ctas));
     const uint32_t per_cta_target = (uint32_t)sm_smem / want_ctas - 1024;
     uint32_t nslot = 2;
-    if (per_cta_target > p.off_ring + 2 * ix->row_bytes) nslot = (per_cta_target - p.off_ring) / ix->row_bytes;
+    if (per_cta_target > p.off_ring + 2 * row_bytes) nslot = (per_cta_target - p.off_ring) / row_bytes;
     nslot = std::min(std::max(nslot, 2u), kMaxSlots);
     if (p.quad) {
         nslot &= ~3u;
         if (nslot < 8) nslot = 8;  // at least two stages
-        if (p.off_ring + nslot * ix->row_bytes > (uint32_t)max_smem) {
+        if (p.off_ring + nslot * row_bytes > (uint32_t)max_smem) {
             p.quad = 0;
             nslot = 2;
         }
     }
     p.nslot = nslot;
-    const uint32_t smem_bytes = p.off_ring + nslot * ix->row_bytes;
+    const uint32_t smem_bytes = p.off_ring + nslot * row_bytes;
     VELES_REQUIRE((int)smem_bytes <= max_smem, "search needs %u bytes of shared memory per query (dim %u, ef %u); limit %d",
                   smem_bytes, ix->dim, ef, max_smem);
 
@@ -859,10 +904,12 @@ static int32_t launch_search(const veles_index* ix, const float* q_d, uint32_t n
     const uint32_t reg_mode = env_u32("VELES_SEARCH_REG_RESULTS", 1) == 0 ? 0 : (ef <= 64 ? 2 : (ef <= 256 ? 8 : 0));
     using KernT = void (*)(const SearchParams);
     KernT kern;
-    if (ix->dtype == VELES_F32)
+    if (dtype == VELES_F32)
         kern = reg_mode == 2 ? hnsw_search_kernel<VELES_F32, 2> : reg_mode == 8 ? hnsw_search_kernel<VELES_F32, 8> : hnsw_search_kernel<VELES_F32, 0>;
-    else if (ix->dtype == VELES_F16)
+    else if (dtype == VELES_F16)
         kern = reg_mode == 2 ? hnsw_search_kernel<VELES_F16, 2> : reg_mode == 8 ? hnsw_search_kernel<VELES_F16, 8> : hnsw_search_kernel<VELES_F16, 0>;
+    else if (dtype == VELES_SQ8)
+        kern = reg_mode == 2 ? hnsw_search_kernel<VELES_SQ8, 2> : reg_mode == 8 ? hnsw_search_kernel<VELES_SQ8, 8> : hnsw_search_kernel<VELES_SQ8, 0>;
     else
         kern = reg_mode == 2 ? hnsw_search_kernel<VELES_BIN1, 2> : reg_mode == 8 ? hnsw_search_kernel<VELES_BIN1, 8> : hnsw_search_kernel<VELES_BIN1, 0>;
     VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -893,7 +940,7 @@ static int32_t launch_search(const veles_index* ix, const float* q_d, uint32_t n
     return VELES_OK;
 }
 
-static int32_t check_error_flag(const veles_index* ix, cudaStream_t st) {
+int32_t check_search_error_flag(const veles_index* ix, cudaStream_t st) {
     uint32_t h[2] = {0, 0};
     VELES_CUDA(cudaMemcpyAsync(h, ix->counters.p, 8, cudaMemcpyDeviceToHost, st));
     VELES_CUDA(cudaStreamSynchronize(st));
@@ -916,7 +963,7 @@ int32_t veles_search_batch_d(const veles_index_t* idx, const float* queries_d, u
     VELES_REQUIRE(idx != nullptr, "index is NULL");
     VELES_REQUIRE(nq == 0 || (queries_d && out_node_ids_d && out_raw_dist_d && out_counts_d), "NULL buffer");
     std::lock_guard<std::mutex> g(idx->mu);
-    return launch_search(idx, queries_d, nq, k, ef, out_node_ids_d, out_raw_dist_d, out_counts_d, out_stats_d,
+    return launch_search(idx, idx->view(), queries_d, nq, k, ef, out_node_ids_d, out_raw_dist_d, out_counts_d, out_stats_d,
                          (cudaStream_t)stream);
 }
 
@@ -935,13 +982,13 @@ int32_t veles_search_batch(const veles_index_t* idx, const float* queries, uint3
     VELES_TRY(idx->out_cnt_d.ensure((size_t)nq * 4));
     if (out_stats) VELES_TRY(idx->out_stats_d.ensure((size_t)nq * 16));
     VELES_CUDA(cudaMemcpyAsync(idx->q_d.p, queries, qb, cudaMemcpyHostToDevice, st));
-    VELES_TRY(launch_search(idx, idx->q_d.as<float>(), nq, k, ef, idx->out_ids_d.as<uint32_t>(), idx->out_val_d.as<float>(),
+    VELES_TRY(launch_search(idx, idx->view(), idx->q_d.as<float>(), nq, k, ef, idx->out_ids_d.as<uint32_t>(), idx->out_val_d.as<float>(),
                             idx->out_cnt_d.as<uint32_t>(), out_stats ? idx->out_stats_d.as<uint32_t>() : nullptr, st));
     VELES_CUDA(cudaMemcpyAsync(out_node_ids, idx->out_ids_d.p, ob, cudaMemcpyDeviceToHost, st));
     VELES_CUDA(cudaMemcpyAsync(out_raw_dist, idx->out_val_d.p, ob, cudaMemcpyDeviceToHost, st));
     VELES_CUDA(cudaMemcpyAsync(out_counts, idx->out_cnt_d.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     if (out_stats) VELES_CUDA(cudaMemcpyAsync(out_stats, idx->out_stats_d.p, (size_t)nq * 16, cudaMemcpyDeviceToHost, st));
-    return check_error_flag(idx, st);
+    return check_search_error_flag(idx, st);
 }
 
 }  // extern "C"

@@ -24,6 +24,14 @@ struct veles_index {
 
     veles::DevBuf vecs, adj0, upper_ref, upper_adj;
 
+    // SQ8 traversal store (DualPrecisionHnsw, native/dual_precision.rs): u8 codes in rows of sq_row_bytes
+    // (dim codes, zero padded to 16) + the quantizer
+    veles::DevBuf sq_codes, sq_min, sq_scale, sq_inv;
+    uint32_t sq_row_bytes = 0;
+    uint64_t sq_train = 0;
+    bool has_sq8 = false;
+    mutable veles::DevBuf sq_ids_d, sq_dist_d, sq_cnt_d;  // coarse candidates between traversal and re-rank
+
     // search scratch, sized lazily and reused; guarded by `mu`
     mutable std::mutex mu;
     mutable veles::DevBuf visited, vlog, counters;
@@ -47,10 +55,23 @@ struct veles_index {
         v.metric = metric;
         v.dtype = dtype;
         v.has_entry = (has_entry && has_graph) ? 1 : 0;
+        v.sq_min = nullptr;
+        v.sq_scale = nullptr;
+        return v;
+    }
+    // the same graph over the u8 codes
+    veles::IndexView view_sq8() const {
+        veles::IndexView v = view();
+        v.vecs = sq_codes.as<uint8_t>();
+        v.row_bytes = sq_row_bytes;
+        v.norm_off = 0;
+        v.dtype = VELES_SQ8;
+        v.sq_min = sq_min.as<float>();
+        v.sq_scale = sq_scale.as<float>();
         return v;
     }
     uint64_t device_bytes() const {
-        return vecs.bytes + adj0.bytes + upper_ref.bytes + upper_adj.bytes + visited.bytes + vlog.bytes;
+        return vecs.bytes + adj0.bytes + upper_ref.bytes + upper_adj.bytes + visited.bytes + vlog.bytes + sq_codes.bytes;
     }
 };
 
@@ -66,4 +87,8 @@ int32_t install_graph_host(veles_index* ix, uint32_t num_layers, const uint64_t*
                            const uint32_t* const* cols, const uint64_t* layer_nodes, uint32_t M, uint32_t M0,
                            uint64_t entry_point, uint32_t max_layer);
 int device_sm_count();
+// batched traversal over `view` (the snapshot's own rows, or its SQ8 codes); hnsw_search.cu
+int32_t launch_search(const veles_index* ix, const IndexView& view, const float* q_d, uint32_t nq, uint32_t k,
+                      uint32_t ef, uint32_t* ids_d, float* dist_d, uint32_t* cnt_d, uint32_t* stats_d, cudaStream_t st);
+int32_t check_search_error_flag(const veles_index* ix, cudaStream_t st);
 }  // namespace veles

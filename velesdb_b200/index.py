@@ -202,6 +202,37 @@ class DeviceSnapshot:
         """NativeHnsw::insert for nodes 0..n-1 in order (graph.rs:158-237): the reference's deterministic graph."""
         nv.check(nv.lib().veles_index_build_graph_exact(self.h, M, ef_construction, stream))
 
+    # -- SQ8 dual precision (native/dual_precision.rs)
+    def attach_sq8(self, train_count, stream=None):
+        """Trains the ScalarQuantizer on the first `train_count` vectors and codes every vector."""
+        nv.check(nv.lib().veles_index_attach_sq8(self.h, train_count, stream))
+
+    @property
+    def has_sq8(self) -> bool:
+        return bool(nv.lib().veles_index_has_sq8(self.h))
+
+    def sq8_export(self, with_codes=True):
+        d = self.dim
+        mn, sc, inv = (np.empty(d, np.float32) for _ in range(3))
+        codes = np.empty((len(self), d), np.uint8) if with_codes else None
+        nv.check(nv.lib().veles_index_sq8_export(self.h, nv.ptr(mn), nv.ptr(sc), nv.ptr(inv), nv.ptr(codes)))
+        return mn, sc, inv, codes
+
+    def search_batch_sq8(self, queries, k, ef_search, oversampling=4, with_stats=False, stream=None):
+        q = _as_f32_2d(queries, self.dim, "Query")
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.uint32)
+        dist = np.empty((nq, k), dtype=np.float32)
+        cnt = np.zeros(nq, dtype=np.uint32)
+        st = np.zeros((nq, 4), dtype=np.uint32) if with_stats else None
+        nv.check(nv.lib().veles_search_batch_sq8(self.h, nv.ptr(q), nq, k, ef_search, oversampling, nv.ptr(ids),
+                                                 nv.ptr(dist), nv.ptr(cnt), nv.ptr(st), stream))
+        return (ids, dist, cnt, st) if with_stats else (ids, dist, cnt)
+
+    def search_batch_sq8_device(self, q_t, k, ef_search, oversampling, ids_t, dist_t, cnt_t, stats_t=None, stream=None):
+        nv.check(nv.lib().veles_search_batch_sq8_d(self.h, nv.ptr(q_t), q_t.shape[0], k, ef_search, oversampling,
+                                                   nv.ptr(ids_t), nv.ptr(dist_t), nv.ptr(cnt_t), nv.ptr(stats_t), stream))
+
     def export_layer(self, layer):
         nodes, edges = C.c_uint64(), C.c_uint64()
         nv.check(nv.lib().veles_index_export_layer(self.h, layer, C.byref(nodes), C.byref(edges), None, None))
