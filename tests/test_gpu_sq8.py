@@ -31,7 +31,7 @@ def test_quantizer_and_codes_bit_exact(dim):
         x[:, 1] = 0.25          # constant dimension -> scale 1.0
         x[1200:, 2] *= 40.0     # out of the trained range -> clamped
     x[1300, 0] = np.nan         # NaN after training -> code 0
-    snap = DeviceSnapshot.from_vectors(x, DistanceMetric.EUCLIDEAN)
+    snap = DeviceSnapshot.from_vectors(x, DistanceMetric.Euclidean)
     snap.attach_sq8(1000)
     assert snap.has_sq8
     mn, sc, inv, codes = snap.sq8_export()
@@ -113,7 +113,7 @@ def test_sq8_train_count_and_errors():
 
 def test_dual_precision_host_mirror_reference_tests():
     # dual_precision_tests.rs:12-120 through the host mirror (graph by the exact GPU builder)
-    dp = DualPrecisionHnsw.new(DistanceMetric.EUCLIDEAN, 32, 16, 100, 1000)
+    dp = DualPrecisionHnsw.new(DistanceMetric.Euclidean, 32, 16, 100, 1000)
     assert dp.is_empty() and not dp.is_quantizer_trained()
     assert dp.search(np.zeros(32, np.float32), 10, 50) == []
     for i in range(100):
@@ -127,7 +127,7 @@ def test_dual_precision_host_mirror_reference_tests():
     r = dp.search(q, 10, 50)
     assert r[0][0] == 0 and all(r[i][1] >= r[i - 1][1] for i in range(1, len(r)))
     # trains itself at the threshold (:36-54)
-    dp2 = DualPrecisionHnsw.new(DistanceMetric.EUCLIDEAN, 32, 16, 100, 100)
+    dp2 = DualPrecisionHnsw.new(DistanceMetric.Euclidean, 32, 16, 100, 100)
     for i in range(100):
         dp2.insert(np.array([math.sin((i * 32 + j) * 0.01) for j in range(32)], np.float32))
     assert dp2.is_quantizer_trained()
@@ -139,7 +139,7 @@ def test_dual_precision_host_mirror_reference_tests():
 def test_dual_precision_host_mirror_int8_vs_oracle():
     # dual_precision_tests.rs:260-334: 500 x 128 cos vectors; the mirror builds the same graph as the oracle
     vs = np.array([[math.cos((i * 128 + j) * 0.001) for j in range(128)] for i in range(500)], np.float32)
-    dp = DualPrecisionHnsw.new(DistanceMetric.EUCLIDEAN, 128, 32, 200, 1000)
+    dp = DualPrecisionHnsw.new(DistanceMetric.Euclidean, 128, 32, 200, 1000)
     odp = vo.DualPrecisionHnsw(vo.EUCLIDEAN, 128, 32, 200, 1000)
     for v in vs:
         dp.insert(v)

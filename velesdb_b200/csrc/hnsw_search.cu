@@ -51,7 +51,6 @@ struct SearchParams {
     uint32_t quad;        // 1: evaluate four candidates per step (8 lanes each), needs dim % 32 == 0
     uint32_t evict_first; // 1: vector rows are fetched with an L2 evict-first policy
     uint32_t peek;        // 1: speculative read-only visited test of the predicted next candidate's neighbours
-    uint32_t row_prefetch; // rows of the predicted next expansion warmed into L2 (0 = off)
     // shared-memory carve (bytes from base)
     uint32_t off_res, off_todo, off_q, off_ring;
 };
@@ -246,8 +245,13 @@ __device__ __forceinline__ float quad_distance(const SearchParams& p, const Warp
 }
 
 // Evaluates c.todo[0..m) in order, four rows per step; stage s uses slots 4s..4s+3 and barrier s.
-template <int DT, typename F>
-__device__ __forceinline__ void eval_list_quad(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
+// `maybe(d)` is a cheap, conservative accept test evaluated by every group on its own row at once; only rows
+// that pass are handed to `on_dist` (in list order), which applies the exact, order-dependent test.  The
+// caller guarantees that a row failing `maybe` at the start of a step would also fail `on_dist`'s test later
+// in the step (thresholds only tighten).  `tick(cnt)` runs once per step.
+template <int DT, typename M, typename F, typename T>
+__device__ __forceinline__ void eval_list_quad(const SearchParams& p, WarpCtx& c, uint32_t m, M&& maybe, F&& on_dist,
+                                               T&& tick) {
     const uint32_t stages = p.nslot >> 2;
     const uint32_t nquad = (m + 3) >> 2;
     // lanes 0..3 each issue one row copy of the quad (address arithmetic in parallel); lane 0 arms the barrier.
@@ -273,17 +277,22 @@ __device__ __forceinline__ void eval_list_quad(const SearchParams& p, WarpCtx& c
         const float d = quad_distance<DT>(p, c, c.ring + (size_t)(4 * s + gg) * p.ix.row_bytes);
         __syncwarp();
         if (j + stages < nquad) issue_quad(j + stages, s);
-        for (uint32_t e = 0; e < cnt; ++e) {
-            const float de = __shfl_sync(FULL_MASK, d, e * 8);
-            on_dist(c.todo[4 * j + e], de);
+        tick(cnt);
+        uint32_t mask = __ballot_sync(FULL_MASK, (c.lane & 7u) == 0 && g < cnt && maybe(d));
+        while (mask) {
+            const uint32_t src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float de = __shfl_sync(FULL_MASK, d, src);
+            on_dist(c.todo[4 * j + (src >> 3)], de);
         }
         s = (s + 1 == stages) ? 0 : s + 1;
     }
 }
 
 // Evaluates the distances of c.todo[0..m) in order, with up to nslot row fetches in flight.
-template <int DT, typename F>
-__device__ __forceinline__ void eval_list_single(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
+template <int DT, typename M, typename F, typename T>
+__device__ __forceinline__ void eval_list_single(const SearchParams& p, WarpCtx& c, uint32_t m, M&& maybe, F&& on_dist,
+                                                 T&& tick) {
     const uint32_t nslot = p.nslot;
     if (c.lane == 0) {
         uint32_t pre = m < nslot ? m : nslot;
@@ -297,7 +306,8 @@ __device__ __forceinline__ void eval_list_single(const SearchParams& p, WarpCtx&
         const float d = row_distance<DT>(p, c, c.ring + (size_t)slot * p.ix.row_bytes);
         __syncwarp();  // every lane is done reading the slot before it is refilled
         if (c.lane == 0 && i + nslot < m) issue_row(p, c, slot, c.todo[i + nslot]);
-        on_dist(id, d);
+        tick(1u);
+        if (maybe(d)) on_dist(id, d);  // d is warp-uniform
         slot = (slot + 1 == nslot) ? 0 : slot + 1;
     }
 }
@@ -305,8 +315,9 @@ __device__ __forceinline__ void eval_list_single(const SearchParams& p, WarpCtx&
 // Packed-bit rows of at most 1024 bits (128 bytes): no staging ring.  8 lanes x 16 bytes read one row with
 // a single 128-bit load per lane, 16 rows (4 groups x 4) are requested back to back before the first
 // popcount, so a whole neighbour list is ~4 rounds of independent loads.  Integer sums: order free.
-template <typename F>
-__device__ __forceinline__ void eval_list_bits(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
+template <typename M, typename F, typename T>
+__device__ __forceinline__ void eval_list_bits(const SearchParams& p, WarpCtx& c, uint32_t m, M&& maybe, F&& on_dist,
+                                               T&& tick) {
     const uint32_t g = c.lane >> 3, t = c.lane & 7;
     const uint32_t words4 = p.ix.dim >> 7;  // uint4 per row, <= 8
     const uint4* qw = reinterpret_cast<const uint4*>(c.q);
@@ -334,21 +345,22 @@ __device__ __forceinline__ void eval_list_bits(const SearchParams& p, WarpCtx& c
             for (uint32_t e = 0; e < 4; ++e) {
                 const uint32_t idx = base + 4 * u + e;
                 if (idx >= m) break;
-                const uint32_t de = __shfl_sync(FULL_MASK, d[u], e * 8);
-                on_dist(c.todo[idx], (float)de);
+                const float de = (float)__shfl_sync(FULL_MASK, d[u], e * 8);
+                tick(1u);
+                if (maybe(de)) on_dist(c.todo[idx], de);
             }
         }
     }
 }
 
-template <int DT, typename F>
-__device__ __forceinline__ void eval_list(const SearchParams& p, WarpCtx& c, uint32_t m, F&& on_dist) {
+template <int DT, typename M, typename F, typename T>
+__device__ __forceinline__ void eval_list(const SearchParams& p, WarpCtx& c, uint32_t m, M&& maybe, F&& on_dist, T&& tick) {
     if (DT == VELES_BIN1 && p.quad == 2)
-        eval_list_bits(p, c, m, on_dist);
+        eval_list_bits(p, c, m, maybe, on_dist, tick);
     else if (p.quad)
-        eval_list_quad<DT>(p, c, m, on_dist);
+        eval_list_quad<DT>(p, c, m, maybe, on_dist, tick);
     else
-        eval_list_single<DT>(p, c, m, on_dist);
+        eval_list_single<DT>(p, c, m, maybe, on_dist, tick);
 }
 
 // One 32-id chunk of an adjacency row (lane holds `nid`): optional visited test-and-set, then ordered
@@ -561,6 +573,8 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
 
         uint32_t ndc0 = 0, hops0 = 0, ndc_up = 0, hops_up = 0;
         uint32_t len = 0;
+        auto always = [](float) { return true; };
+        auto no_tick = [](uint32_t) {};
         res.init(c.res, lane);
 
         if (p.ix.has_entry) {
@@ -572,7 +586,7 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
                 float best_dist = 0.0f;
                 if (lane == 0) c.todo[0] = best;
                 __syncwarp();
-                eval_list<DT>(p, c, 1, [&](uint32_t, float d) { best_dist = d; });
+                eval_list<DT>(p, c, 1, always, [&](uint32_t, float d) { best_dist = d; }, no_tick);
                 ++ndc_up;
                 for (;;) {
                     const uint32_t ref = p.ix.upper_ref[best];
@@ -584,13 +598,16 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
                     ++hops_up;
                     ndc_up += m;
                     bool improved = false;
-                    eval_list<DT>(p, c, m, [&](uint32_t id, float d) {
-                        if (d < best_dist) {
-                            best = id;
-                            best_dist = d;
-                            improved = true;
-                        }
-                    });
+                    eval_list<DT>(
+                        p, c, m, [&](float d) { return d < best_dist; },
+                        [&](uint32_t id, float d) {
+                            if (d < best_dist) {
+                                best = id;
+                                best_dist = d;
+                                improved = true;
+                            }
+                        },
+                        no_tick);
                     __syncwarp();
                     if (!improved) break;
                 }
@@ -619,6 +636,30 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
                 pre_age = 1;
                 pre_peeked = false;
             };
+            // Runs once per evaluation step with the number of rows it covered: once the predicted node's adjacency
+            // row has had time to land, read the visited words of its neighbours (read-only); a little later
+            // they are usable.
+            auto tick = [&](uint32_t rows) {
+                if (pre_age == 0) return;
+                pre_age += rows;
+                if (pre_age < 100) {
+                    if (pre_age >= 10) {
+                        if (p.peek) {
+                            pre_va = pre_a != VELES_INVALID_ID ? __ldcg(&vis[pre_a >> 5]) : 0u;
+                            pre_vb = pre_b != VELES_INVALID_ID ? __ldcg(&vis[pre_b >> 5]) : 0u;
+                            pre_age = 100;
+                        } else {
+                            if (pre_a != VELES_INVALID_ID) prefetch_l2(&vis[pre_a >> 5]);
+                            if (pre_b != VELES_INVALID_ID) prefetch_l2(&vis[pre_b >> 5]);
+                            pre_age = 0;
+                        }
+                    }
+                } else if (pre_age >= 106) {
+                    pre_peeked = true;
+                    pre_age = 0;
+                }
+            };
+            bool full = false;  // len >= ef
             {
                 const uint32_t bit = 1u << (cur & 31);
                 if (lane == 0) {
@@ -629,10 +670,11 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
                 logn = 1;
                 __syncwarp();
                 float d0 = 0.0f;
-                eval_list<DT>(p, c, 1, [&](uint32_t, float d) { d0 = d; });
+                eval_list<DT>(p, c, 1, always, [&](uint32_t, float d) { d0 = d; }, no_tick);
                 ++ndc0;
                 res.set(0, make_key(d0, cur));
                 len = 1;
+                full = len >= ef;
                 worst = d0;
                 __syncwarp();
             }
@@ -684,48 +726,16 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
                 ndc0 += m;
                 pre_peeked = false;  // this expansion's marking invalidates any earlier peek
                 if (nxt < len) learn(key_id(res.get(nxt)));
-                eval_list<DT>(p, c, m, [&](uint32_t id, float d) {
-                    if (pre_age != 0) {
-                        ++pre_age;
-                        if (pre_age == 10) {  // the adjacency row landed long ago: fetch its visited words
-                            if (p.peek) {
-                                pre_va = pre_a != VELES_INVALID_ID ? __ldcg(&vis[pre_a >> 5]) : 0u;
-                                pre_vb = pre_b != VELES_INVALID_ID ? __ldcg(&vis[pre_b >> 5]) : 0u;
-                            } else {
-                                if (pre_a != VELES_INVALID_ID) prefetch_l2(&vis[pre_a >> 5]);
-                                if (pre_b != VELES_INVALID_ID) prefetch_l2(&vis[pre_b >> 5]);
-                                pre_age = 0;
-                            }
-                        } else if (pre_age == 16) {  // the words landed: the peek is usable; warm the first rows
-                            pre_peeked = true;
-                            pre_age = 0;
-                            if (p.row_prefetch) {
-                                const bool ka = pre_a != VELES_INVALID_ID && !((pre_va >> (pre_a & 31)) & 1u);
-                                const bool kb = pre_b != VELES_INVALID_ID && !((pre_vb >> (pre_b & 31)) & 1u);
-                                uint32_t ma = __ballot_sync(FULL_MASK, ka), mb = __ballot_sync(FULL_MASK, kb);
-                                for (uint32_t r = 0; r < p.row_prefetch && (ma | mb); ++r) {
-                                    uint32_t nid;
-                                    if (ma) {
-                                        const uint32_t src = __ffs(ma) - 1;
-                                        ma &= ma - 1;
-                                        nid = __shfl_sync(FULL_MASK, pre_a, src);
-                                    } else {
-                                        const uint32_t src = __ffs(mb) - 1;
-                                        mb &= mb - 1;
-                                        nid = __shfl_sync(FULL_MASK, pre_b, src);
-                                    }
-                                    if (lane * 128u < p.ix.row_bytes)
-                                        prefetch_l2(p.ix.vecs + (size_t)nid * p.ix.row_bytes + lane * 128u);
-                                }
-                            }
-                        }
-                    }
-                    if (d < worst || len < ef) {
+                eval_list<DT>(
+                    p, c, m, [&](float d) { return d < worst || !full; },
+                    [&](uint32_t id, float d) {
+                    if (d < worst || !full) {
                         const uint64_t key = make_key(d, id);
                         const uint32_t pos = res.lower_bound(len, key);
-                        if (len < ef) {
+                        if (!full) {
                             res.insert(pos, len + 1, ef, key);
                             ++len;
+                            full = len >= ef;
                             worst = key_dist(res.get(len - 1));
                             if (pos <= nxt) {
                                 nxt = pos;
@@ -779,13 +789,22 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
                             }
                         }
                     }
-                });
+                    },
+                    tick);
                 __syncwarp();
             }
 
             // ---- clear the visited bitmap for the next query of this slot ----
             if (logn <= kLogCap) {
-                for (uint32_t i = lane; i < logn; i += 32) vis[vlog[i] >> 5] = 0u;
+                // eight independent log reads in flight per lane (one at a time made this loop ~8% of a query)
+                for (uint32_t i = lane; i < logn; i += 32 * 8) {
+                    uint32_t v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = i + 32u * u < logn ? __ldcg(&vlog[i + 32u * u]) : VELES_INVALID_ID;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (v[u] != VELES_INVALID_ID) vis[v[u] >> 5] = 0u;
+                }
             } else {
                 for (uint32_t i = lane; i < p.vis_words; i += 32) vis[i] = 0u;
             }
@@ -872,7 +891,6 @@ int32_t launch_search(const veles_index* ix, const IndexView& view, const float*
     if (p.quad && dtype == VELES_BIN1 && ix->dim <= 1024 && env_u32("VELES_SEARCH_BITS_DIRECT", 1) != 0) p.quad = 2;
     p.evict_first = env_u32("VELES_SEARCH_EVICT_FIRST", 1) != 0 ? 1 : 0;
     p.peek = env_u32("VELES_SEARCH_PEEK", 1) != 0 ? 1 : 0;
-    p.row_prefetch = std::min(32u, env_u32("VELES_SEARCH_ROW_PREFETCH", 0));
     // resident warps (queries) per SM.  Measured on B200 (profiles/): every query of a 1024-batch must be
     // resident at once (7 x 148 = 1036 slots) -- with fewer slots a second wave of queries starts late and
     // the batch time nearly doubles; 7 CTAs leave room for 2 stages of 4 rows each.
