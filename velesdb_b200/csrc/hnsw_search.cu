@@ -353,9 +353,80 @@ __device__ __forceinline__ void eval_list_bits(const SearchParams& p, WarpCtx& c
     }
 }
 
-template <int DT, typename M, typename F, typename T>
-__device__ __forceinline__ void eval_list(const SearchParams& p, WarpCtx& c, uint32_t m, M&& maybe, F&& on_dist, T&& tick) {
-    if (DT == VELES_BIN1 && p.quad == 2)
+// SQ8 rows of at most 128 * QN bytes.  Group g = lane / 8 owns one row of the step, lane t = lane % 8 owns its
+// 16-byte chunks t, t + 8, ...: the lane copies exactly the bytes it later reads, so the ring is a per-lane
+// staging buffer filled by 16-byte async copies (no barrier object, no cross-lane hand-off) and the query's
+// chunks stay in registers for the whole query (`qreg`).  Stage s uses slots 4s..4s+3; one commit group per
+// step keeps the wait depth constant.
+template <int QN, typename M, typename F, typename T>
+__device__ __forceinline__ void eval_list_sq8(const SearchParams& p, WarpCtx& c, uint32_t m, const uint4 (&qreg)[QN > 0 ? QN : 1],
+                                              M&& maybe, F&& on_dist, T&& tick) {
+    const uint32_t stages = p.nslot >> 2;  // 2..4
+    const uint32_t nquad = (m + 3) >> 2;
+    const uint32_t g = c.lane >> 3, t = c.lane & 7;
+    const uint32_t n16 = p.ix.row_bytes >> 4;
+    auto issue = [&](uint32_t j, uint32_t s) {
+        if (4 * j + g < m) {
+            const uint8_t* src = p.ix.vecs + (size_t)c.todo[4 * j + g] * p.ix.row_bytes + t * 16;
+            uint8_t* dst = c.ring + (size_t)(4 * s + g) * p.ix.row_bytes + t * 16;
+#pragma unroll
+            for (int u = 0; u < QN; ++u)
+                if (t + 8 * u < n16) cp_async16(dst + 128 * u, src + 128 * u);
+        }
+    };
+    for (uint32_t j = 0; j < stages; ++j) {
+        if (j < nquad) issue(j, j);
+        cp_async_commit();
+    }
+    uint32_t s = 0;
+    for (uint32_t j = 0; j < nquad; ++j) {
+        if (stages == 4)
+            cp_async_wait<3>();
+        else if (stages == 3)
+            cp_async_wait<2>();
+        else
+            cp_async_wait<1>();
+        const uint32_t cnt = min(4u, m - 4 * j);
+        uint32_t d = 0;
+        if (g < cnt) {
+            const uint8_t* row = c.ring + (size_t)(4 * s + g) * p.ix.row_bytes + t * 16;
+            uint4 x[QN > 0 ? QN : 1];
+#pragma unroll
+            for (int u = 0; u < QN; ++u)
+                x[u] = (t + 8 * u < n16) ? *reinterpret_cast<const uint4*>(row + 128 * u) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < QN; ++u) {
+                d = sq8_word(x[u].x, qreg[u].x, d);
+                d = sq8_word(x[u].y, qreg[u].y, d);
+                d = sq8_word(x[u].z, qreg[u].z, d);
+                d = sq8_word(x[u].w, qreg[u].w, d);
+            }
+        }
+        if (j + stages < nquad) issue(j + stages, s);  // the lane is done with its own chunks of this stage
+        cp_async_commit();
+        d += __shfl_xor_sync(FULL_MASK, d, 1);
+        d += __shfl_xor_sync(FULL_MASK, d, 2);
+        d += __shfl_xor_sync(FULL_MASK, d, 4);
+        const float df = __uint_as_float(d);
+        tick(cnt);
+        uint32_t mask = __ballot_sync(FULL_MASK, t == 0 && g < cnt && maybe(df));
+        while (mask) {
+            const uint32_t src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float de = __shfl_sync(FULL_MASK, df, src);
+            on_dist(c.todo[4 * j + (src >> 3)], de);
+        }
+        s = (s + 1 == stages) ? 0 : s + 1;
+    }
+    cp_async_wait<0>();  // only empty groups can be pending here; keeps the group count clean for the next list
+}
+
+template <int DT, int QN, typename M, typename F, typename T>
+__device__ __forceinline__ void eval_list(const SearchParams& p, WarpCtx& c, uint32_t m, const uint4 (&qreg)[QN > 0 ? QN : 1],
+                                          M&& maybe, F&& on_dist, T&& tick) {
+    if (QN > 0)
+        eval_list_sq8<QN>(p, c, m, qreg, maybe, on_dist, tick);
+    else if (DT == VELES_BIN1 && p.quad == 2)
         eval_list_bits(p, c, m, maybe, on_dist, tick);
     else if (p.quad)
         eval_list_quad<DT>(p, c, m, maybe, on_dist, tick);
@@ -509,7 +580,7 @@ struct ResArr {
     }
 };
 
-template <int DT, int R>
+template <int DT, int R, int QN>
 __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     WarpCtx c;
@@ -566,6 +637,16 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
             for (uint32_t i = lane; i < dim; i += 32) qs[i] = qg[i];
         }
         __syncwarp();
+        uint4 qreg[QN > 0 ? QN : 1];
+        if (QN > 0) {
+#pragma unroll
+            for (int u = 0; u < QN; ++u) {
+                const uint32_t w = (lane & 7u) + 8u * u;
+                qreg[u] = w < (p.ix.row_bytes >> 4) ? reinterpret_cast<const uint4*>(c.q)[w] : make_uint4(0, 0, 0, 0);
+            }
+        } else {
+            qreg[0] = make_uint4(0, 0, 0, 0);
+        }
         if ((DT == VELES_F32 || DT == VELES_F16) && p.ix.metric == VELES_COSINE) {
             const float* qs = reinterpret_cast<const float*>(c.q);
             c.norm_a = __fsqrt_rn(warp_tree_reduce<0>(qs, qs, dim, lane));
@@ -586,7 +667,7 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
                 float best_dist = 0.0f;
                 if (lane == 0) c.todo[0] = best;
                 __syncwarp();
-                eval_list<DT>(p, c, 1, always, [&](uint32_t, float d) { best_dist = d; }, no_tick);
+                eval_list<DT, QN>(p, c, 1, qreg, always, [&](uint32_t, float d) { best_dist = d; }, no_tick);
                 ++ndc_up;
                 for (;;) {
                     const uint32_t ref = p.ix.upper_ref[best];
@@ -598,8 +679,8 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
                     ++hops_up;
                     ndc_up += m;
                     bool improved = false;
-                    eval_list<DT>(
-                        p, c, m, [&](float d) { return d < best_dist; },
+                    eval_list<DT, QN>(
+                        p, c, m, qreg, [&](float d) { return d < best_dist; },
                         [&](uint32_t id, float d) {
                             if (d < best_dist) {
                                 best = id;
@@ -670,7 +751,7 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
                 logn = 1;
                 __syncwarp();
                 float d0 = 0.0f;
-                eval_list<DT>(p, c, 1, always, [&](uint32_t, float d) { d0 = d; }, no_tick);
+                eval_list<DT, QN>(p, c, 1, qreg, always, [&](uint32_t, float d) { d0 = d; }, no_tick);
                 ++ndc0;
                 res.set(0, make_key(d0, cur));
                 len = 1;
@@ -726,8 +807,8 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
                 ndc0 += m;
                 pre_peeked = false;  // this expansion's marking invalidates any earlier peek
                 if (nxt < len) learn(key_id(res.get(nxt)));
-                eval_list<DT>(
-                    p, c, m, [&](float d) { return d < worst || !full; },
+                eval_list<DT, QN>(
+                    p, c, m, qreg, [&](float d) { return d < worst || !full; },
                     [&](uint32_t id, float d) {
                     if (d < worst || !full) {
                         const uint64_t key = make_key(d, id);
@@ -918,18 +999,32 @@ int32_t launch_search(const veles_index* ix, const IndexView& view, const float*
     VELES_REQUIRE((int)smem_bytes <= max_smem, "search needs %u bytes of shared memory per query (dim %u, ef %u); limit %d",
                   smem_bytes, ix->dim, ef, max_smem);
 
+    // SQ8: 16-byte chunks per lane (8 lanes per row), rounded up to an even count; 0 = rows too long, use the ring
+    uint32_t sq_qn = 0;
+    if (dtype == VELES_SQ8 && p.quad == 1 && env_u32("VELES_SEARCH_SQ8_ASYNC", 1) != 0) {
+        const uint32_t per_lane = (row_bytes / 16 + 7) / 8;
+        if (per_lane <= 8) sq_qn = (per_lane + 1) & ~1u;
+    }
     // result array in registers when ef allows (2 or 8 keys per lane), else in shared memory
     const uint32_t reg_mode = env_u32("VELES_SEARCH_REG_RESULTS", 1) == 0 ? 0 : (ef <= 64 ? 2 : (ef <= 256 ? 8 : 0));
     using KernT = void (*)(const SearchParams);
+#define VELES_PICK(DT, QN) \
+    (reg_mode == 2 ? hnsw_search_kernel<DT, 2, QN> : reg_mode == 8 ? hnsw_search_kernel<DT, 8, QN> : hnsw_search_kernel<DT, 0, QN>)
     KernT kern;
     if (dtype == VELES_F32)
-        kern = reg_mode == 2 ? hnsw_search_kernel<VELES_F32, 2> : reg_mode == 8 ? hnsw_search_kernel<VELES_F32, 8> : hnsw_search_kernel<VELES_F32, 0>;
+        kern = VELES_PICK(VELES_F32, 0);
     else if (dtype == VELES_F16)
-        kern = reg_mode == 2 ? hnsw_search_kernel<VELES_F16, 2> : reg_mode == 8 ? hnsw_search_kernel<VELES_F16, 8> : hnsw_search_kernel<VELES_F16, 0>;
+        kern = VELES_PICK(VELES_F16, 0);
     else if (dtype == VELES_SQ8)
-        kern = reg_mode == 2 ? hnsw_search_kernel<VELES_SQ8, 2> : reg_mode == 8 ? hnsw_search_kernel<VELES_SQ8, 8> : hnsw_search_kernel<VELES_SQ8, 0>;
+        // rows up to 1 KB: per-lane async copies, query chunks in registers (eval_list_sq8); else the TMA ring
+        kern = sq_qn == 2 ? VELES_PICK(VELES_SQ8, 2)
+             : sq_qn == 4 ? VELES_PICK(VELES_SQ8, 4)
+             : sq_qn == 6 ? VELES_PICK(VELES_SQ8, 6)
+             : sq_qn == 8 ? VELES_PICK(VELES_SQ8, 8)
+                          : VELES_PICK(VELES_SQ8, 0);
     else
-        kern = reg_mode == 2 ? hnsw_search_kernel<VELES_BIN1, 2> : reg_mode == 8 ? hnsw_search_kernel<VELES_BIN1, 8> : hnsw_search_kernel<VELES_BIN1, 0>;
+        kern = VELES_PICK(VELES_BIN1, 0);
+#undef VELES_PICK
     VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     int ctas_per_sm = 0;
     VELES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 32, smem_bytes));
