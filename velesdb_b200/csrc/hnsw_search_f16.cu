@@ -1,0 +1,6 @@
+// hnsw_search_f16.cu -- kernel instantiations of hnsw_search.cuh for one storage type
+#include "hnsw_search.cuh"
+
+namespace veles {
+SearchKernel search_kernel_f16(uint32_t reg_mode) { return VELES_PICK_KERNEL(VELES_F16, 0); }
+}  // namespace veles
