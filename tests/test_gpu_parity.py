@@ -71,6 +71,25 @@ def test_bruteforce_bit_exact(metric, dim):
     assert bits_equal(sc, rs)
 
 
+@pytest.mark.parametrize("metric", [vo.COSINE, vo.EUCLIDEAN, vo.DOT])
+@pytest.mark.parametrize("store", ["f32", "f16"])
+def test_bruteforce_few_queries_scan_path(metric, store):
+    # nq <= 8 takes the HBM-bound scan kernel (bf_scan_kernel); n >= 65536 the two-level top-k
+    for n, dim in ((3001, 768), (70_001, 64)):
+        x = latent_data(n, dim, seed=n % 97 + metric)
+        x[n // 2] = x[7]  # an exact duplicate: equal scores, ordered by id
+        snap = DeviceSnapshot.from_vectors(x, metric, store_dtype=store)
+        xo = x.astype(np.float16).astype(np.float32) if store == "f16" else x
+        for nq in (1, 2, 3, 5, 8):
+            q = queries_near(x, nq, seed=nq)
+            q[0] = x[7]
+            for k in (1, 10, 100):
+                ids, sc = snap.bruteforce_batch(q, k)
+                ri, rs = vo.bruteforce_batch(metric, xo, q, k, threads=8)
+                assert np.array_equal(ids, ri.astype(np.uint32)), (n, nq, k)
+                assert bits_equal(sc, rs), (n, nq, k)
+
+
 def test_bruteforce_edges():
     x = latent_data(5, 32)
     snap = DeviceSnapshot.from_vectors(x, vo.EUCLIDEAN)

@@ -10,6 +10,7 @@
 // Kernel 2 (topk_kernel) selects, per query, the k best by DistanceMetric::sort_results order
 // (core/distance.rs:95-103; ties by ascending node id) with a threshold filter over the score row.
 #include <algorithm>
+#include <cstdlib>
 
 #include "index.hpp"
 
@@ -217,6 +218,130 @@ __global__ void __launch_bounds__(kWarps * 32) bf_tile8_kernel(IndexView ix, con
     }
 }
 
+// ---- few queries (<= 8): the scan is HBM-bound, so it is laid out like a copy -----------------------------
+// "Quad" mapping of common.cuh: 8 lanes per row, lane t owns the reference accumulators 4t..4t+3 and reads
+// its row with one 128-bit load per 32 elements, so a warp-wide load covers 4 rows x 128 contiguous bytes.
+// A lane can work on RB rows at once (rows g, g + 4, ...) so that each 128-bit shared-memory read of a query
+// chunk feeds 4 * RB FMAs; measured on B200 RB = 1 is as fast or faster at every QT (more resident warps), so
+// that is what is launched.  QT queries (1, 2, 4 or 8) are scored per pass; the rows are read once per
+// launch whatever QT is: 5.8 TB/s at QT = 1, 5.4 at 2, 4.7 at 4 (1M x 768 f32), FMA/shared-memory bound at 8.
+// dim % 32 == 0.
+template <bool L2>
+__device__ __forceinline__ void scan_fma(const float4& x, const float4& y, float (&a)[4]) {
+    if (L2) {
+        const float d0 = __fsub_rn(y.x, x.x), d1 = __fsub_rn(y.y, x.y), d2 = __fsub_rn(y.z, x.z), d3 = __fsub_rn(y.w, x.w);
+        a[0] = __fmaf_rn(d0, d0, a[0]);
+        a[1] = __fmaf_rn(d1, d1, a[1]);
+        a[2] = __fmaf_rn(d2, d2, a[2]);
+        a[3] = __fmaf_rn(d3, d3, a[3]);
+    } else {
+        a[0] = __fmaf_rn(y.x, x.x, a[0]);
+        a[1] = __fmaf_rn(y.y, x.y, a[1]);
+        a[2] = __fmaf_rn(y.z, x.z, a[2]);
+        a[3] = __fmaf_rn(y.w, x.w, a[3]);
+    }
+}
+
+template <typename TB, int QT, int RB, int U, bool L2>
+__device__ __forceinline__ void scan_rows(const IndexView& ix, const float* qs, const TB* const (&r)[RB], uint32_t t,
+                                          float (&acc)[RB][QT][4]) {
+    const uint32_t dim = ix.dim;
+    uint32_t i = t * 4;
+    for (; i + 32 * (U - 1) < dim; i += 32 * U) {
+        float4 x[U][RB];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int b = 0; b < RB; ++b) x[u][b] = load4(r[b] + i + 32 * u);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < QT; ++q) {
+                const float4 y = *reinterpret_cast<const float4*>(qs + (size_t)q * dim + i + 32 * u);
+#pragma unroll
+                for (int b = 0; b < RB; ++b) scan_fma<L2>(x[u][b], y, acc[b][q]);
+            }
+    }
+    for (; i < dim; i += 32) {
+        float4 x[RB];
+#pragma unroll
+        for (int b = 0; b < RB; ++b) x[b] = load4(r[b] + i);
+#pragma unroll
+        for (int q = 0; q < QT; ++q) {
+            const float4 y = *reinterpret_cast<const float4*>(qs + (size_t)q * dim + i);
+#pragma unroll
+            for (int b = 0; b < RB; ++b) scan_fma<L2>(x[b], y, acc[b][q]);
+        }
+    }
+}
+
+template <typename TB, int QT, int RB>
+__global__ void __launch_bounds__(kWarps * 32) bf_scan_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq,
+                                                              float* __restrict__ scores, bool as_value) {
+    extern __shared__ __align__(16) float qs[];  // QT x dim, then QT norms
+    constexpr int U = RB >= 4 ? 2 : (RB == 2 ? 4 : 8);  // 8 row loads in flight per lane
+    const uint32_t dim = ix.dim;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* qnorm = qs + (size_t)QT * dim;
+    for (uint32_t i = threadIdx.x; i < QT * dim; i += blockDim.x) {
+        const uint32_t t = i / dim;
+        qs[i] = t < nq ? queries[(size_t)t * dim + (i - t * dim)] : 0.0f;
+    }
+    __syncthreads();
+    if (ix.metric == VELES_COSINE) {
+        for (uint32_t t = warp; t < QT; t += kWarps) {
+            const float* q = qs + (size_t)t * dim;
+            const float s = warp_tree_reduce<0>(q, q, dim, lane);
+            if (lane == 0) qnorm[t] = __fsqrt_rn(s);
+        }
+    }
+    __syncthreads();
+    const bool l2 = ix.metric == VELES_EUCLIDEAN;
+    const uint64_t n = ix.n;
+    const uint32_t g = lane >> 3, t = lane & 7;
+    const uint64_t tiles = (n + 4 * RB - 1) / (4 * RB);
+    for (uint64_t tile = blockIdx.x * (uint64_t)kWarps + warp; tile < tiles; tile += (uint64_t)gridDim.x * kWarps) {
+        const TB* r[RB];
+        uint64_t row[RB];
+#pragma unroll
+        for (int b = 0; b < RB; ++b) {
+            row[b] = tile * (4 * RB) + 4 * b + g;
+            const uint64_t rr = row[b] < n ? row[b] : n - 1;  // rows past the end alias the last row, not stored
+            r[b] = reinterpret_cast<const TB*>(ix.vecs + rr * ix.row_bytes);
+        }
+        float acc[RB][QT][4];
+#pragma unroll
+        for (int b = 0; b < RB; ++b)
+#pragma unroll
+            for (int q = 0; q < QT; ++q) acc[b][q][0] = acc[b][q][1] = acc[b][q][2] = acc[b][q][3] = 0.0f;
+        if (l2)
+            scan_rows<TB, QT, RB, U, true>(ix, qs, r, t, acc);
+        else
+            scan_rows<TB, QT, RB, U, false>(ix, qs, r, t, acc);
+#pragma unroll
+        for (int b = 0; b < RB; ++b) {
+            float nb = 0.0f;
+            if (ix.metric == VELES_COSINE) nb = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(r[b]) + ix.norm_off);
+            float mine = 0.0f;  // lane t of the group keeps query t's value
+#pragma unroll
+            for (int q = 0; q < QT; ++q) {
+                const float s = quad_tree_sum(acc[b][q][0], acc[b][q][1], acc[b][q][2], acc[b][q][3]);
+                float v;
+                if (l2) {
+                    v = __fsqrt_rn(s);
+                } else if (ix.metric == VELES_COSINE) {
+                    const float sim = cosine_from_parts(s, qnorm[q], nb);
+                    v = as_value ? sim : __fsub_rn(1.0f, sim);
+                } else {
+                    v = as_value ? s : -s;
+                }
+                mine = (int)t == q ? v : mine;
+            }
+            if (t < nq && t < QT && row[b] < n) scores[(size_t)t * n + row[b]] = mine;
+        }
+    }
+}
+
 // generic path: any metric, any dim >= 1, F32/F16 rows: one warp per (query, row) pair
 template <typename TB>
 __global__ void bf_generic_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq,
@@ -324,20 +449,26 @@ __global__ void __launch_bounds__(32) topk_kernel(const float* __restrict__ scor
 // k <= 512: one CTA of kTopWarps warps per query, each warp streams a slice of the score row (float4 loads)
 // through a threshold filter into its own sorted list; warp 0 merges the lists.
 constexpr int kTopWarps = 8;
+// With `partial` != NULL the grid is (queries, chunks): CTA (q, c) selects from elements [c * chunk, (c+1) * chunk)
+// of the row and writes its sorted keys (padded with ~0) to partial[(q * chunks + c) * k ..]; topk_merge_kernel
+// finishes.  That keeps the selection parallel when there are few queries and many rows.
 __global__ void __launch_bounds__(kTopWarps * 32) topk_cta_kernel(const float* __restrict__ scores, uint64_t n, uint32_t k,
                                                                  bool descending, uint32_t* __restrict__ out_ids,
-                                                                 float* __restrict__ out_score) {
+                                                                 float* __restrict__ out_score, uint64_t chunk,
+                                                                 uint64_t* __restrict__ partial) {
     extern __shared__ __align__(16) uint64_t tk_smem[];
     __shared__ uint32_t s_len[kTopWarps];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = blockIdx.x;
     const float* row = scores + (size_t)q * n;
     uint64_t* res = tk_smem + (size_t)warp * k;
+    const uint64_t r_begin = partial ? (uint64_t)blockIdx.y * chunk : 0;
+    const uint64_t r_end = partial ? min(n, r_begin + chunk) : n;
     // slices start at multiples of 128 elements past the row's 16-byte alignment point
     const uint64_t mis = (((uintptr_t)row) >> 2) & 3;       // elements until the next 16-byte boundary: (4 - mis) % 4
     const uint64_t head = (4 - mis) & 3;
-    uint64_t seg = (n + kTopWarps - 1) / kTopWarps;
+    uint64_t seg = (r_end - r_begin + kTopWarps - 1) / kTopWarps;
     seg = (seg + 127) & ~(uint64_t)127;
-    const uint64_t c_begin = warp * seg, c_end = min(n, c_begin + seg);
+    const uint64_t c_begin = min(r_end, r_begin + warp * seg), c_end = min(r_end, c_begin + seg);
     uint32_t len = 0;
     uint64_t worst = ~0ull;
     auto offer = [&](uint64_t key) {
@@ -394,12 +525,59 @@ __global__ void __launch_bounds__(kTopWarps * 32) topk_cta_kernel(const float* _
         }
     }
     __syncwarp();
+    if (partial) {
+        uint64_t* out = partial + ((size_t)q * gridDim.y + blockIdx.y) * k;
+        for (uint32_t i = lane; i < k; i += 32) out[i] = i < len ? res[i] : ~0ull;
+        return;
+    }
     for (uint32_t i = lane; i < k; i += 32) {
         uint32_t id = VELES_INVALID_ID;
         float sc = __uint_as_float(0x7fc00000u);
         if (i < len) {
             id = (uint32_t)res[i];
             sc = row[id];
+        }
+        out_ids[(size_t)q * k + i] = id;
+        out_score[(size_t)q * k + i] = sc;
+    }
+}
+
+// second level: one warp per query merges `chunks` sorted key lists of length k (k <= 512)
+__global__ void __launch_bounds__(32) topk_merge_kernel(const uint64_t* __restrict__ partial, uint32_t chunks, uint32_t k,
+                                                        const float* __restrict__ scores, uint64_t n,
+                                                        uint32_t* __restrict__ out_ids, float* __restrict__ out_score) {
+    extern __shared__ __align__(16) uint64_t res[];
+    const uint32_t lane = threadIdx.x, q = blockIdx.x;
+    const uint64_t* in = partial + (size_t)q * chunks * k;
+    uint32_t len = 0;
+    uint64_t worst = ~0ull;
+    const uint32_t total = chunks * k;
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t i = base + lane;
+        const uint64_t key = i < total ? in[i] : ~0ull;
+        uint32_t msk = __ballot_sync(FULL_MASK, key != ~0ull && (len < k || key < worst));
+        while (msk) {
+            const uint32_t src = __ffs(msk) - 1;
+            msk &= msk - 1;
+            const uint64_t kk = __shfl_sync(FULL_MASK, key, src);
+            if (len < k) {
+                const uint32_t pos = lower_bound_warp(res, len, kk, lane);
+                insert_at(res, pos, len + 1, kk, lane);
+                ++len;
+            } else if (kk < worst) {
+                const uint32_t pos = lower_bound_warp(res, len, kk, lane);
+                insert_at(res, pos, len, kk, lane);
+            }
+            if (len == k) worst = res[k - 1];
+        }
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < k; i += 32) {
+        uint32_t id = VELES_INVALID_ID;
+        float sc = __uint_as_float(0x7fc00000u);
+        if (i < len) {
+            id = (uint32_t)res[i];
+            sc = scores[(size_t)q * n + id];
         }
         out_ids[(size_t)q * k + i] = id;
         out_score[(size_t)q * k + i] = sc;
@@ -473,6 +651,31 @@ static int32_t launch_scores(const veles_index* ix, const float* q_d, uint32_t n
     } else if (ix->dim >= 16 && (ix->metric == VELES_COSINE || ix->metric == VELES_EUCLIDEAN || ix->metric == VELES_DOT)) {
         const size_t smem = ((size_t)kQT * ix->dim + kQT) * 4;
         const uint32_t qtiles = (nq + kQT - 1) / kQT;
+        if (ix->dim % 32 == 0 && nq <= 8) {
+            // few queries: HBM-bound scan, rows read once (bf_scan_kernel)
+            const uint32_t qt = nq <= 1 ? 1 : nq <= 2 ? 2 : nq <= 4 ? 4 : 8;
+            // one row per lane (RB = 1) measured best on B200 at every QT (RB = 2, 4 were no faster: fewer resident warps)
+            constexpr uint32_t rb = 1;
+            using ScanT = void (*)(IndexView, const float*, uint32_t, float*, bool);
+            ScanT ks;
+#define VELES_SCAN(TB) \
+    (qt == 1 ? bf_scan_kernel<TB, 1, 1> : qt == 2 ? bf_scan_kernel<TB, 2, 1> : qt == 4 ? bf_scan_kernel<TB, 4, 1> : bf_scan_kernel<TB, 8, 1>)
+            if (ix->dtype == VELES_F32)
+                ks = VELES_SCAN(float);
+            else
+                ks = VELES_SCAN(__half);
+#undef VELES_SCAN
+            const size_t smem_s = ((size_t)qt * ix->dim + qt) * 4;
+            VELES_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+            int per_sm = 1;
+            VELES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ks, kWarps * 32, smem_s));
+            const uint64_t tiles = (ix->n + 4 * rb - 1) / (4 * rb);
+            const uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((tiles + kWarps - 1) / kWarps, (uint64_t)sms * std::max(per_sm, 1)));
+            ks<<<(unsigned)gx, kWarps * 32, smem_s, st>>>(v, q_d, nq, scores_d, as_value);
+            count_launch();
+            VELES_CUDA(cudaGetLastError());
+            return VELES_OK;
+        }
         if (ix->dim % 32 == 0) {
             auto kern8 = ix->dtype == VELES_F32 ? bf_tile8_kernel<float> : bf_tile8_kernel<__half>;
             VELES_CUDA(cudaFuncSetAttribute(kern8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -541,9 +744,29 @@ static int32_t bruteforce_device(const veles_index* ix, const float* q_d, uint32
     for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
         const uint32_t nn = std::min(chunk, nq - q0);
         VELES_TRY(launch_scores(ix, q_d + (size_t)q0 * ix->dim, nn, ix->scores_d.as<float>(), true, st));
-        if (k <= 512) {
+        // few queries over many rows: split every row into chunks (first level), then merge (second level)
+        const int sms = device_sm_count();
+        uint32_t chunks = 1;
+        if (k <= 512 && (uint64_t)nn < (uint64_t)sms * 2 && ix->n >= 65536) {
+            const uint64_t want = ((uint64_t)sms * 4 + nn - 1) / nn;
+            const uint64_t most = std::max<uint64_t>(1, ix->n / std::max<uint64_t>(16384, (uint64_t)k * 64));
+            chunks = (uint32_t)std::min<uint64_t>(std::min(want, most), 4096);
+        }
+        if (chunks > 1) {
+            uint64_t chunk = (ix->n + chunks - 1) / chunks;
+            chunk = (chunk + 127) & ~(uint64_t)127;  // keeps float4 alignment of every chunk start
+            chunks = (uint32_t)((ix->n + chunk - 1) / chunk);
+            VELES_TRY(ix->aux_d.ensure((size_t)nn * chunks * k * 8));
+            dim3 grid(nn, chunks);
+            topk_cta_kernel<<<grid, kTopWarps * 32, (size_t)kTopWarps * k * 8, st>>>(ix->scores_d.as<float>(), ix->n, k, desc, nullptr,
+                                                                                    nullptr, chunk, ix->aux_d.as<uint64_t>());
+            count_launch();
+            topk_merge_kernel<<<nn, 32, (size_t)k * 8, st>>>(ix->aux_d.as<uint64_t>(), chunks, k, ix->scores_d.as<float>(), ix->n,
+                                                             ids_d + (size_t)q0 * k, score_d + (size_t)q0 * k);
+        } else if (k <= 512) {
             topk_cta_kernel<<<nn, kTopWarps * 32, (size_t)kTopWarps * k * 8, st>>>(ix->scores_d.as<float>(), ix->n, k, desc,
-                                                                                  ids_d + (size_t)q0 * k, score_d + (size_t)q0 * k);
+                                                                                  ids_d + (size_t)q0 * k, score_d + (size_t)q0 * k, 0,
+                                                                                  nullptr);
         } else {
             topk_kernel<<<nn, 32, (size_t)k * 8, st>>>(ix->scores_d.as<float>(), ix->n, k, desc, ids_d + (size_t)q0 * k,
                                                        score_d + (size_t)q0 * k);

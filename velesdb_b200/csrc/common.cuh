@@ -273,6 +273,37 @@ __device__ __forceinline__ float warp_metric(int metric, bool as_value, const fl
 }
 
 
+// ---- four rows per warp ("quad"): lane = 8*g + t, group g owns one row, sub-lane t owns elements
+// 32*it + 4t .. 4t+3 of it, i.e. the reference accumulators P[4t+e] = P[a][j] with a = t/2,
+// j = 4*(t%2) + e.  Combination order of simd_avx512.rs:182-184 + wide::reduce_add:
+//   xor 2 (a^1), xor 4 (a^2)  ->  C[j] = (P0+P1)+(P2+P3)
+//   xor 1                     ->  q[e] = C[e] + C[e+4]
+//   in-thread                 ->  (q0+q2) + (q1+q3)
+// Each step adds a commutative pair, so the result has the CPU's bits.
+__device__ __forceinline__ float quad_tree_sum(float a0, float a1, float a2, float a3) {
+    a0 = __fadd_rn(a0, __shfl_xor_sync(FULL_MASK, a0, 2));
+    a1 = __fadd_rn(a1, __shfl_xor_sync(FULL_MASK, a1, 2));
+    a2 = __fadd_rn(a2, __shfl_xor_sync(FULL_MASK, a2, 2));
+    a3 = __fadd_rn(a3, __shfl_xor_sync(FULL_MASK, a3, 2));
+    a0 = __fadd_rn(a0, __shfl_xor_sync(FULL_MASK, a0, 4));
+    a1 = __fadd_rn(a1, __shfl_xor_sync(FULL_MASK, a1, 4));
+    a2 = __fadd_rn(a2, __shfl_xor_sync(FULL_MASK, a2, 4));
+    a3 = __fadd_rn(a3, __shfl_xor_sync(FULL_MASK, a3, 4));
+    a0 = __fadd_rn(a0, __shfl_xor_sync(FULL_MASK, a0, 1));
+    a1 = __fadd_rn(a1, __shfl_xor_sync(FULL_MASK, a1, 1));
+    a2 = __fadd_rn(a2, __shfl_xor_sync(FULL_MASK, a2, 1));
+    a3 = __fadd_rn(a3, __shfl_xor_sync(FULL_MASK, a3, 1));
+    return __fadd_rn(__fadd_rn(a0, a2), __fadd_rn(a1, a3));
+}
+
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __half* p) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(p);
+    const __half2 lo = *reinterpret_cast<const __half2*>(&raw.x), hi = *reinterpret_cast<const __half2*>(&raw.y);
+    const float2 a = __half22float2(lo), b = __half22float2(hi);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
 // ---- warp-cooperative sorted array of unique u64 keys (ascending) in shared memory ----
 // position of the first key in res[0..len) that is >= key
 __device__ __forceinline__ uint32_t lower_bound_warp(const uint64_t* res, uint32_t len, uint64_t key, uint32_t lane) {
