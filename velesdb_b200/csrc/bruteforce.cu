@@ -10,6 +10,7 @@
 // Kernel 2 (topk_kernel) selects, per query, the k best by DistanceMetric::sort_results order
 // (core/distance.rs:95-103; ties by ascending node id) with a threshold filter over the score row.
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 
 #include "index.hpp"
@@ -141,62 +142,91 @@ __device__ __forceinline__ float butterfly32(float* v, uint32_t lane) {
 }
 
 constexpr int kRT8 = 8;
-template <typename TB>
-__global__ void __launch_bounds__(kWarps * 32) bf_tile8_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq,
+constexpr int kStepU = 2;  // steps per pointer advance
+// QW query tiles (of kQT queries) per CTA: warp w works on query tile w % QW and row tile w / QW, so the QW
+// warps that share a row tile read the same global addresses at about the same time -- one L2 read, QW - 1
+// L1 hits.  Only QW = 1 is launched (see launch_scores).
+template <typename TB, int QW>
+__global__ void __launch_bounds__(kWarps * 32, 2) bf_tile8_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq,
                                                                float* __restrict__ scores, bool as_value) {
-    extern __shared__ __align__(16) float qs[];  // kQT x dim, then kQT norms
+    extern __shared__ __align__(16) float qs_all[];  // QW x kQT x dim, then QW x kQT norms
     const uint32_t dim = ix.dim;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t qbase = blockIdx.y * kQT;
-    const uint32_t nqt = min((uint32_t)kQT, nq - qbase);
-    float* qnorm = qs + (size_t)kQT * dim;
-    for (uint32_t i = threadIdx.x; i < kQT * dim; i += blockDim.x) {
+    const uint32_t cta_q0 = blockIdx.y * (kQT * QW);
+    const uint32_t cta_nq = min((uint32_t)(kQT * QW), nq - cta_q0);
+    float* qnorm_all = qs_all + (size_t)QW * kQT * dim;
+    for (uint32_t i = threadIdx.x; i < QW * kQT * dim; i += blockDim.x) {
         const uint32_t t = i / dim;
-        qs[i] = t < nqt ? queries[(size_t)(qbase + t) * dim + (i - t * dim)] : 0.0f;
+        qs_all[i] = t < cta_nq ? queries[(size_t)(cta_q0 + t) * dim + (i - t * dim)] : 0.0f;
     }
     __syncthreads();
     if (ix.metric == VELES_COSINE) {
-        for (uint32_t t = warp; t < kQT; t += kWarps) {
-            const float* q = qs + (size_t)t * dim;
+        for (uint32_t t = warp; t < QW * kQT; t += kWarps) {
+            const float* q = qs_all + (size_t)t * dim;
             const float s = warp_tree_reduce<0>(q, q, dim, lane);
-            if (lane == 0) qnorm[t] = __fsqrt_rn(s);
+            if (lane == 0) qnorm_all[t] = __fsqrt_rn(s);
         }
     }
     __syncthreads();
+    const uint32_t qtile = warp % QW, rslot = warp / QW;
+    constexpr uint32_t kRowWarps = kWarps / QW;
+    const float* qs = qs_all + (size_t)qtile * kQT * dim;
+    const float* qnorm = qnorm_all + qtile * kQT;
+    const uint32_t qbase = cta_q0 + qtile * kQT;
+    const uint32_t nqt = qbase < nq ? min((uint32_t)kQT, nq - qbase) : 0u;
     const bool l2 = ix.metric == VELES_EUCLIDEAN;
     const uint64_t n = ix.n;
     const uint64_t tiles = (n + kRT8 - 1) / kRT8;
     // accumulator owned by this lane after the butterfly: row a/8 (within a half-tile of 4 rows), query a%8
     const uint32_t a = (lane & 1) | (lane & 2) | (lane & 4) | ((lane & 16) >> 1) | ((lane & 8) << 1);
     const uint32_t my_r = a >> 3, my_t = a & 7;
-    for (uint64_t tile = blockIdx.x * (uint64_t)kWarps + warp; tile < tiles; tile += (uint64_t)gridDim.x * kWarps) {
+    for (uint64_t tile = blockIdx.x * (uint64_t)kRowWarps + rslot; tile < tiles; tile += (uint64_t)gridDim.x * kRowWarps) {
         const uint64_t r0 = tile * kRT8;
         const uint8_t* base = ix.vecs + r0 * ix.row_bytes;
         const uint64_t last_off = (n - 1 - r0) * (uint64_t)ix.row_bytes;  // rows past the end alias the last row
         float acc[kRT8 * kQT];
 #pragma unroll
         for (int j = 0; j < kRT8 * kQT; ++j) acc[j] = 0.0f;
-        for (uint32_t i = lane; i < dim; i += 32) {
-            float x[kRT8], q[kQT];
+        // Row and query pointers advance once per block of kStepU steps, so every load inside the block is
+        // [pointer + immediate] (the index arithmetic was ~45 % of the loop's instructions otherwise).
+        const TB* rp[kRT8];
 #pragma unroll
-            for (int r = 0; r < kRT8; ++r) {
-                const uint64_t off = min((uint64_t)r * ix.row_bytes, last_off);
-                x[r] = load_elem(reinterpret_cast<const TB*>(base + off), i);
+        for (int r = 0; r < kRT8; ++r)
+            rp[r] = reinterpret_cast<const TB*>(base + min((uint64_t)r * ix.row_bytes, last_off)) + lane;
+        const float* qp[kQT];
+#pragma unroll
+        for (int t = 0; t < kQT; ++t) qp[t] = qs + (size_t)t * dim + lane;
+        auto steps = [&](auto un) {
+            constexpr int UN = decltype(un)::value;
+            float x[UN][kRT8], q[UN][kQT];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+#pragma unroll
+                for (int r = 0; r < kRT8; ++r) x[u][r] = load_elem(rp[r], 32 * u);
+#pragma unroll
+                for (int t = 0; t < kQT; ++t) q[u][t] = qp[t][32 * u];
             }
 #pragma unroll
-            for (int t = 0; t < kQT; ++t) q[t] = qs[(size_t)t * dim + i];
+            for (int u = 0; u < UN; ++u)
 #pragma unroll
-            for (int r = 0; r < kRT8; ++r)
+                for (int r = 0; r < kRT8; ++r)
 #pragma unroll
-                for (int t = 0; t < kQT; ++t) {
-                    if (l2) {
-                        const float d = __fsub_rn(q[t], x[r]);
-                        acc[r * kQT + t] = __fmaf_rn(d, d, acc[r * kQT + t]);
-                    } else {
-                        acc[r * kQT + t] = __fmaf_rn(q[t], x[r], acc[r * kQT + t]);
+                    for (int t = 0; t < kQT; ++t) {
+                        if (l2) {
+                            const float d = __fsub_rn(q[u][t], x[u][r]);
+                            acc[r * kQT + t] = __fmaf_rn(d, d, acc[r * kQT + t]);
+                        } else {
+                            acc[r * kQT + t] = __fmaf_rn(q[u][t], x[u][r], acc[r * kQT + t]);
+                        }
                     }
-                }
-        }
+#pragma unroll
+            for (int r = 0; r < kRT8; ++r) rp[r] += 32 * UN;
+#pragma unroll
+            for (int t = 0; t < kQT; ++t) qp[t] += 32 * UN;
+        };
+        uint32_t i = 0;
+        for (; i + 32 * kStepU <= dim; i += 32 * kStepU) steps(std::integral_constant<int, kStepU>{});
+        for (; i < dim; i += 32) steps(std::integral_constant<int, 1>{});
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const float s = butterfly32(acc + half * 32, lane);
@@ -677,18 +707,24 @@ static int32_t launch_scores(const veles_index* ix, const float* q_d, uint32_t n
             return VELES_OK;
         }
         if (ix->dim % 32 == 0) {
-            auto kern8 = ix->dtype == VELES_F32 ? bf_tile8_kernel<float> : bf_tile8_kernel<__half>;
-            VELES_CUDA(cudaFuncSetAttribute(kern8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // one query tile per CTA: sharing a row tile between the warps of a CTA (QW = 2, 4: one L2 read,
+            // QW - 1 L1 hits) measured 5-10 % slower on B200 -- the kernel is issue-bound, not L2-bound
+            constexpr uint32_t qw = 1;
+            auto kern8 = ix->dtype == VELES_F32 ? bf_tile8_kernel<float, 1> : bf_tile8_kernel<__half, 1>;
+            const size_t smem8 = ((size_t)qw * kQT * ix->dim + qw * kQT) * 4;
+            VELES_CUDA(cudaFuncSetAttribute(kern8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+            const uint32_t ctiles = (nq + kQT * qw - 1) / (kQT * qw);  // CTA-level query tiles
             const uint64_t row_tiles = (ix->n + kRT8 - 1) / kRT8;
-            uint64_t gx = (row_tiles + kWarps - 1) / kWarps;
-            const uint64_t want = std::max<uint64_t>(1, ((uint64_t)sms * 4 + qtiles - 1) / qtiles);
+            const uint32_t row_warps = kWarps / qw;
+            uint64_t gx = (row_tiles + row_warps - 1) / row_warps;
+            const uint64_t want = std::max<uint64_t>(1, ((uint64_t)sms * 4 + ctiles - 1) / ctiles);
             gx = std::max<uint64_t>(1, std::min(gx, want));
-            for (uint32_t t0 = 0; t0 < qtiles; t0 += 32768) {
-                const uint32_t nt = std::min(32768u, qtiles - t0);
-                const uint32_t qoff = t0 * kQT;
+            for (uint32_t t0 = 0; t0 < ctiles; t0 += 32768) {
+                const uint32_t nt = std::min(32768u, ctiles - t0);
+                const uint32_t qoff = t0 * kQT * qw;
                 dim3 grid((unsigned)gx, nt);
-                kern8<<<grid, kWarps * 32, smem, st>>>(v, q_d + (size_t)qoff * ix->dim, nq - qoff, scores_d + (size_t)qoff * ix->n,
-                                                      as_value);
+                kern8<<<grid, kWarps * 32, smem8, st>>>(v, q_d + (size_t)qoff * ix->dim, nq - qoff, scores_d + (size_t)qoff * ix->n,
+                                                       as_value);
                 count_launch();
             }
             VELES_CUDA(cudaGetLastError());
