@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <set>
 
+#include "dual_precision.hpp"
 #include "hnsw_index.hpp"
 
 using namespace veles::host;
@@ -106,6 +107,43 @@ int main(int argc, char** argv) {
     auto s = small.search(std::vector<float>(16, 0.0f), 5);
     CHECK(s.size() == 5 && s[0].first == 0 && s[0].second == 0.0f);
     for (size_t i = 1; i < s.size(); ++i) CHECK(s[i - 1].second <= s[i].second);  // distance metric: ascending
+    STEP("small index ok");
+    // DualPrecisionHnsw (native/dual_precision_tests.rs:12-120, 260-334)
+    {
+        DualPrecisionHnsw dp(DistanceMetric::Euclidean, 32, 16, 100, 1000);
+        CHECK(dp.is_empty() && !dp.is_quantizer_trained());
+        CHECK(dp.search(std::vector<float>(32, 0.0f), 10, 50).empty());
+        for (uint64_t i = 0; i < 100; ++i) {
+            std::vector<float> v(32);
+            for (size_t j = 0; j < 32; ++j) v[j] = (float)(i * 32 + j);
+            CHECK(dp.insert(v) == i);
+        }
+        CHECK(dp.len() == 100 && !dp.is_quantizer_trained());
+        std::vector<float> q0(32);
+        for (size_t j = 0; j < 32; ++j) q0[j] = (float)j;
+        auto r0 = dp.search(q0, 10, 50);
+        CHECK(!r0.empty() && r0[0].first == 0);
+        dp.force_train_quantizer();
+        CHECK(dp.is_quantizer_trained());
+        DualPrecisionConfig cfg;
+        CHECK(cfg.oversampling_ratio == 4 && cfg.use_int8_traversal && cfg.min_index_size == 10000);
+        auto gated = dp.search_with_config(q0, 10, 50, cfg);  // below min_index_size: the f32 path answers
+        CHECK(gated.size() == r0.size());
+        for (size_t i = 0; i < r0.size(); ++i) CHECK(gated[i] == r0[i]);
+        cfg.min_index_size = 0;
+        auto i8 = dp.search_with_config(q0, 10, 50, cfg);
+        CHECK(!i8.empty() && i8[0].first == 0 && i8[0].second == 0.0f);
+        for (size_t i = 1; i < i8.size(); ++i) CHECK(i8[i - 1].second <= i8[i].second);
+        // trains itself at the threshold
+        DualPrecisionHnsw dp2(DistanceMetric::Euclidean, 32, 16, 100, 100);
+        for (uint64_t i = 0; i < 100; ++i) {
+            std::vector<float> v(32);
+            for (size_t j = 0; j < 32; ++j) v[j] = std::sin((float)(i * 32 + j) * 0.01f);
+            dp2.insert(v);
+        }
+        CHECK(dp2.is_quantizer_trained());
+    }
+    STEP("dual precision ok");
     std::printf("host mirror ok\n");
     return 0;
 }
