@@ -251,3 +251,22 @@ def test_hnsw_search_f16_quad_path(metric):
     snap = DeviceSnapshot.from_arrays(x, metric, g.export_graph(), g.M, g.M0, g.entry_point, g.max_layer,
                                       store_dtype="f16")
     check_search(gh, snap, queries_near(x, 48, seed=13), 10, 64)
+
+
+@pytest.mark.parametrize("warps", ["1", "2", "4"])
+def test_hnsw_search_warps_per_query(warps, monkeypatch):
+    # one warp per query vs the cooperative multi-warp kernel (hnsw_search_kernel<.., COOP>): identical results,
+    # identical per-layer evaluation / expansion counts
+    monkeypatch.setenv("VELES_SEARCH_WARPS", warps)
+    for metric, dim in ((vo.COSINE, 768), (vo.EUCLIDEAN, 96), (vo.DOT, 96)):
+        x, g, snap = graph_case(metric, dim, n=2000 if dim < 768 else 1200)
+        q = queries_near(x, 64, seed=5)
+        for k, ef in ((10, 64), (1, 1), (100, 256), (10, 300)):
+            check_search(g, snap, q, k, ef)
+    x, g, snap = graph_case(vo.HAMMING, 64, n=1500, binary=True)  # ties everywhere (generic path: always one warp)
+    check_search(g, snap, (queries_near(x, 64, jitter=0.4, seed=9) > 0.5).astype(np.float32), 10, 64)
+    x, g, _ = graph_case(vo.COSINE, 96)
+    xh = x.astype(np.float16).astype(np.float32)
+    gh = vo.Hnsw.from_arrays(vo.COSINE, xh, g.export_graph(), g.M, g.M0, g.entry_point, g.max_layer)
+    snap = DeviceSnapshot.from_arrays(x, vo.COSINE, g.export_graph(), g.M, g.M0, g.entry_point, g.max_layer, store_dtype="f16")
+    check_search(gh, snap, queries_near(x, 48, seed=13), 10, 64)

@@ -173,3 +173,13 @@ def test_sq8_recall_close_to_f32():
     s_ids, _, _ = snap.search_batch_sq8(q, 10, 64, 4)
     rec = lambda a: np.mean([len(set(a[i].tolist()) & set(gt[i].tolist())) / 10 for i in range(len(q))])
     assert rec(s_ids) >= rec(f_ids) - 0.03, (rec(s_ids), rec(f_ids))
+
+
+@pytest.mark.parametrize("warps", ["1", "2", "4"])
+def test_sq8_warps_per_query(warps, monkeypatch):
+    monkeypatch.setenv("VELES_SEARCH_WARPS", warps)
+    for metric, dim in ((vo.COSINE, 768), (vo.EUCLIDEAN, 20)):
+        x, g, dp, snap = make_case(metric, dim, n=1200 if dim == 768 else 2000)
+        q = queries_near(x, 64, seed=5)
+        for k, ef, over in ((10, 64, 4), (50, 100, 4), (3, 600, 8)):
+            check_sq8(dp, snap, q, k, ef, over)

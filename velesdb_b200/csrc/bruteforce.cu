@@ -792,12 +792,12 @@ static int32_t bruteforce_device(const veles_index* ix, const float* q_d, uint32
             uint64_t chunk = (ix->n + chunks - 1) / chunks;
             chunk = (chunk + 127) & ~(uint64_t)127;  // keeps float4 alignment of every chunk start
             chunks = (uint32_t)((ix->n + chunk - 1) / chunk);
-            VELES_TRY(ix->aux_d.ensure((size_t)nn * chunks * k * 8));
+            VELES_TRY(ix->topk_d.ensure((size_t)nn * chunks * k * 8));
             dim3 grid(nn, chunks);
             topk_cta_kernel<<<grid, kTopWarps * 32, (size_t)kTopWarps * k * 8, st>>>(ix->scores_d.as<float>(), ix->n, k, desc, nullptr,
-                                                                                    nullptr, chunk, ix->aux_d.as<uint64_t>());
+                                                                                    nullptr, chunk, ix->topk_d.as<uint64_t>());
             count_launch();
-            topk_merge_kernel<<<nn, 32, (size_t)k * 8, st>>>(ix->aux_d.as<uint64_t>(), chunks, k, ix->scores_d.as<float>(), ix->n,
+            topk_merge_kernel<<<nn, 32, (size_t)k * 8, st>>>(ix->topk_d.as<uint64_t>(), chunks, k, ix->scores_d.as<float>(), ix->n,
                                                              ids_d + (size_t)q0 * k, score_d + (size_t)q0 * k);
         } else if (k <= 512) {
             topk_cta_kernel<<<nn, kTopWarps * 32, (size_t)kTopWarps * k * 8, st>>>(ix->scores_d.as<float>(), ix->n, k, desc,

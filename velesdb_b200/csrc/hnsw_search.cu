@@ -7,9 +7,11 @@
 
 namespace veles {
 
-SearchKernel search_kernel_sq8(uint32_t reg_mode, uint32_t qn) {
+SearchKernel search_kernel_sq8(uint32_t reg_mode, uint32_t qn, bool coop) {
     // rows up to 1 KB: per-lane async copies, query chunks in registers (eval_list_sq8); qn 0 = the TMA ring
-    return qn <= 2 ? search_kernel_sq8_a(reg_mode, qn) : qn <= 6 ? search_kernel_sq8_b(reg_mode, qn) : search_kernel_sq8_c(reg_mode, qn);
+    return qn <= 2   ? search_kernel_sq8_a(reg_mode, qn, coop)
+           : qn <= 6 ? search_kernel_sq8_b(reg_mode, qn, coop)
+                     : search_kernel_sq8_c(reg_mode, qn, coop);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -38,15 +40,19 @@ int32_t launch_search(const veles_index* ix, const IndexView& view, const float*
     p.out_counts = cnt_d;
     p.out_stats = stats_d;
 
-    // shared-memory carve
+    // shared-memory carve: [control words] results | todo | [distances, multi-warp only] | query | per warp: barriers + ring
     const uint32_t bar_bytes = kMaxSlots * 8;
-    p.off_res = bar_bytes;
+    p.off_res = 16;
     const uint32_t res_bytes = round_up(ef * 8, 16);
     p.off_todo = p.off_res + res_bytes;
     const uint32_t todo_bytes = round_up(std::max(ix->stride0, ix->strideU) * 4, 16);
-    p.off_q = p.off_todo + todo_bytes;
     const uint32_t q_bytes = dtype == VELES_SQ8 ? row_bytes : round_up(dtype == VELES_BIN1 ? ix->dim / 8 : ix->dim * 4, 16);
-    p.off_ring = round_up(p.off_q + q_bytes, 128);
+    auto carve = [&](bool coop) {
+        p.off_dist = p.off_todo + todo_bytes;
+        p.off_q = p.off_dist + (coop ? todo_bytes : 0u);
+        p.off_ring = round_up(p.off_q + q_bytes, 128);
+    };
+    carve(false);
     int dev = 0, max_smem = 0, sms = 0;
     VELES_CUDA(cudaGetDevice(&dev));
     VELES_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -62,33 +68,6 @@ int32_t launch_search(const veles_index* ix, const IndexView& view, const float*
     if (p.quad && dtype == VELES_BIN1 && ix->dim <= 1024 && env_u32("VELES_SEARCH_BITS_DIRECT", 1) != 0) p.quad = 2;
     p.evict_first = env_u32("VELES_SEARCH_EVICT_FIRST", 1) != 0 ? 1 : 0;
     p.peek = env_u32("VELES_SEARCH_PEEK", 1) != 0 ? 1 : 0;
-    // resident warps (queries) per SM.  Measured on B200 (profiles/): every query of a 1024-batch must be
-    // resident at once (7 x 148 = 1036 slots) -- with fewer slots a second wave of queries starts late and
-    // the batch time nearly doubles; 7 CTAs leave room for 2 stages of 4 rows each.
-    // Batches larger than 7 x SMs prefer more resident queries with the minimal ring (two stages) over
-    // deeper rings: measured on C3s (f16, 8192 queries) 7 -> 13 CTAs/SM = 173 K -> 222 K queries/s.
-    const uint32_t min_ring = (p.quad == 1 ? 8u : 2u) * row_bytes;
-    const uint32_t cmax = std::max(1u, (uint32_t)sm_smem / (p.off_ring + min_ring + 1024u));
-    const uint32_t need = (nq + (uint32_t)sms - 1) / (uint32_t)sms;
-    const uint32_t auto_ctas = std::min(std::min(cmax, 16u), std::max(need, p.quad ? 7u : 8u));
-    const uint32_t want_ctas = std::max(1u, env_u32("VELES_SEARCH_CTAS_PER_SM", auto_ctas));
-    const uint32_t per_cta_target = (uint32_t)sm_smem / want_ctas - 1024;
-    uint32_t nslot = 2;
-    if (per_cta_target > p.off_ring + 2 * row_bytes) nslot = (per_cta_target - p.off_ring) / row_bytes;
-    nslot = std::min(std::max(nslot, 2u), kMaxSlots);
-    if (p.quad) {
-        nslot &= ~3u;
-        if (nslot < 8) nslot = 8;  // at least two stages
-        if (p.off_ring + nslot * row_bytes > (uint32_t)max_smem) {
-            p.quad = 0;
-            nslot = 2;
-        }
-    }
-    p.nslot = nslot;
-    const uint32_t smem_bytes = p.off_ring + nslot * row_bytes;
-    VELES_REQUIRE((int)smem_bytes <= max_smem, "search needs %u bytes of shared memory per query (dim %u, ef %u); limit %d",
-                  smem_bytes, ix->dim, ef, max_smem);
-
     // SQ8: 16-byte chunks per lane (8 lanes per row), rounded up to an even count; 0 = rows too long, use the ring
     uint32_t sq_qn = 0;
     if (dtype == VELES_SQ8 && p.quad == 1 && env_u32("VELES_SEARCH_SQ8_ASYNC", 1) != 0) {
@@ -97,13 +76,69 @@ int32_t launch_search(const veles_index* ix, const IndexView& view, const float*
     }
     // result array in registers when ef allows (2 or 8 keys per lane), else in shared memory
     const uint32_t reg_mode = env_u32("VELES_SEARCH_REG_RESULTS", 1) == 0 ? 0 : (ef <= 64 ? 2 : (ef <= 256 ? 8 : 0));
-    SearchKernel kern = dtype == VELES_F32   ? search_kernel_f32(reg_mode)
-                        : dtype == VELES_F16 ? search_kernel_f16(reg_mode)
-                        : dtype == VELES_SQ8 ? search_kernel_sq8(reg_mode, sq_qn)
+
+    // Warps per query.  A lone warp's instruction chain bounds a query's latency (~1 ms at 1M x 768 f32), so a
+    // batch that cannot fill the GPU with one warp per query gets 4 or 2 warps per query (hnsw_search_kernel
+    // <.., COOP = true>): the largest count whose resident CTAs still hold the whole batch at once.
+    uint32_t warps = 1, nslot = 2;
+    const bool coop_ok = p.quad == 1 && reg_mode != 0 && dtype != VELES_BIN1;
+    const uint32_t coop_slots = (sq_qn != 0 && 16u * row_bytes <= 16384u) ? 16u : 8u;
+    auto coop_smem = [&](uint32_t w) { return p.off_ring + w * round_up(bar_bytes + coop_slots * row_bytes, 128); };
+    if (coop_ok) {
+        carve(true);
+        const uint32_t forced = env_u32("VELES_SEARCH_WARPS", 0);
+        for (uint32_t w = 4; w >= 2; w >>= 1) {
+            const uint32_t sb = coop_smem(w);
+            if (sb > (uint32_t)max_smem) continue;
+            const uint32_t per_sm = std::min((uint32_t)sm_smem / (sb + 1024u), 32u / w);
+            if (forced ? forced == w : (uint64_t)per_sm * (uint32_t)sms >= nq) {
+                warps = w;
+                break;
+            }
+        }
+        if (warps == 1) carve(false);
+    }
+    if (warps > 1) {
+        nslot = coop_slots;
+    } else {
+        // resident warps (queries) per SM.  Measured on B200 (profiles/): every query of a 1024-batch must be
+        // resident at once (7 x 148 = 1036 slots) -- with fewer slots a second wave of queries starts late and
+        // the batch time nearly doubles; 7 CTAs leave room for 2 stages of 4 rows each.
+        // Batches larger than 7 x SMs prefer more resident queries with the minimal ring (two stages) over
+        // deeper rings: measured on C3s (f16, 8192 queries) 7 -> 13 CTAs/SM = 173 K -> 222 K queries/s.
+        const uint32_t fixed = p.off_ring + bar_bytes;
+        const uint32_t min_ring = (p.quad == 1 ? 8u : 2u) * row_bytes;
+        const uint32_t cmax = std::max(1u, (uint32_t)sm_smem / (fixed + min_ring + 1024u));
+        const uint32_t need = (nq + (uint32_t)sms - 1) / (uint32_t)sms;
+        const uint32_t auto_ctas = std::min(std::min(cmax, 16u), std::max(need, p.quad ? 7u : 8u));
+        const uint32_t want_ctas = std::max(1u, env_u32("VELES_SEARCH_CTAS_PER_SM", auto_ctas));
+        const uint32_t per_cta_target = (uint32_t)sm_smem / want_ctas - 1024;
+        if (per_cta_target > fixed + 2 * row_bytes) nslot = (per_cta_target - fixed) / row_bytes;
+        nslot = std::min(std::max(nslot, 2u), kMaxSlots);
+        if (p.quad) {
+            nslot &= ~3u;
+            if (nslot < 8) nslot = 8;  // at least two stages
+            if (fixed + nslot * row_bytes > (uint32_t)max_smem) {
+                p.quad = 0;
+                sq_qn = 0;
+                nslot = 2;
+            }
+        }
+    }
+    p.nslot = nslot;
+    p.warp_bytes = round_up(bar_bytes + nslot * row_bytes, 128);
+    const uint32_t smem_bytes = p.off_ring + warps * p.warp_bytes;
+    VELES_REQUIRE((int)smem_bytes <= max_smem, "search needs %u bytes of shared memory per query (dim %u, ef %u); limit %d",
+                  smem_bytes, ix->dim, ef, max_smem);
+
+    const bool coop = warps > 1;
+    SearchKernel kern = dtype == VELES_F32   ? search_kernel_f32(reg_mode, coop)
+                        : dtype == VELES_F16 ? search_kernel_f16(reg_mode, coop)
+                        : dtype == VELES_SQ8 ? search_kernel_sq8(reg_mode, sq_qn, coop)
                                              : search_kernel_bin1(reg_mode);
     VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     int ctas_per_sm = 0;
-    VELES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 32, smem_bytes));
+    VELES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, (int)(32 * warps), smem_bytes));
     VELES_REQUIRE(ctas_per_sm >= 1, "search kernel does not fit on an SM");
     const uint32_t max_slots = (uint32_t)(ctas_per_sm * sms);
     const uint32_t grid = std::min(nq, max_slots);
@@ -123,7 +158,7 @@ int32_t launch_search(const veles_index* ix, const IndexView& view, const float*
     p.tie = ix->aux_d.as<uint64_t>();
     p.counters = ix->counters.as<uint32_t>();
     VELES_CUDA(cudaMemsetAsync(p.counters, 0, 8, st));
-    kern<<<grid, 32, smem_bytes, st>>>(p);
+    kern<<<grid, 32 * warps, smem_bytes, st>>>(p);
     count_launch();
     VELES_CUDA(cudaGetLastError());
     return VELES_OK;

@@ -54,7 +54,8 @@ struct SearchParams {
     uint32_t evict_first; // 1: vector rows are fetched with an L2 evict-first policy
     uint32_t peek;        // 1: speculative read-only visited test of the predicted next candidate's neighbours
     // shared-memory carve (bytes from base)
-    uint32_t off_res, off_todo, off_q, off_ring;
+    uint32_t off_res, off_todo, off_dist, off_q, off_ring;
+    uint32_t warp_bytes;  // per-warp block at off_ring: kMaxSlots barriers, then the ring
 };
 
 struct WarpCtx {
@@ -215,49 +216,67 @@ __device__ __forceinline__ float quad_distance(const SearchParams& p, const Warp
     }
 }
 
-// Evaluates c.todo[0..m) in order, four rows per step; stage s uses slots 4s..4s+3 and barrier s.
-// `maybe(d)` is a cheap, conservative accept test evaluated by every group on its own row at once; only rows
-// that pass are handed to `on_dist` (in list order), which applies the exact, order-dependent test.  The
-// caller guarantees that a row failing `maybe` at the start of a step would also fail `on_dist`'s test later
-// in the step (thresholds only tighten).  `tick(cnt)` runs once per step.
-template <int DT, typename M, typename F, typename T>
-__device__ __forceinline__ void eval_list_quad(const SearchParams& p, WarpCtx& c, uint32_t m, M&& maybe, F&& on_dist,
-                                               T&& tick) {
+// Evaluates quads first, first + step, ... of c.todo[0..m) (quad j = rows 4j..4j+3), four rows per evaluation
+// step; stage s uses slots 4s..4s+3 and barrier s.  `sink(j, cnt, d)` is called by all lanes after each step
+// with the quad's index, its row count and -- in the lanes of group g = lane / 8 -- the distance of row 4j + g.
+// One warp evaluating a whole list passes (0, 1); the warps of a cooperative CTA pass (warp, warps).
+template <int DT, typename S>
+__device__ __forceinline__ void eval_quads_ring(const SearchParams& p, WarpCtx& c, uint32_t m, uint32_t first, uint32_t step,
+                                                S&& sink) {
     const uint32_t stages = p.nslot >> 2;
-    const uint32_t nquad = (m + 3) >> 2;
+    const uint32_t nquad_all = (m + 3) >> 2;
+    const uint32_t nquad = nquad_all > first ? (nquad_all - first + step - 1) / step : 0;  // this warp's quads
     // lanes 0..3 each issue one row copy of the quad (address arithmetic in parallel); lane 0 arms the barrier.
     // The barrier's pending-arrival count stays at 1 until lane 0 arrives, so complete_tx from a copy that
     // lands before the expect_tx cannot complete the phase early.
-    auto issue_quad = [&](uint32_t j, uint32_t s) {
+    auto issue_quad = [&](uint32_t jl, uint32_t s) {
+        const uint32_t j = first + jl * step;
         const uint32_t cnt = min(4u, m - 4 * j);
         if (c.lane == 0) mbar_expect_tx(&c.bar[s], cnt * p.ix.row_bytes);
         if (c.lane < cnt) copy_row(p, c, 4 * s + c.lane, c.todo[4 * j + c.lane], &c.bar[s]);
     };
     {
         const uint32_t pre = nquad < stages ? nquad : stages;
-        for (uint32_t j = 0; j < pre; ++j) issue_quad(j, j);
+        for (uint32_t jl = 0; jl < pre; ++jl) issue_quad(jl, jl);
     }
     const uint32_t g = c.lane >> 3;
     uint32_t s = 0;
-    for (uint32_t j = 0; j < nquad; ++j) {
+    for (uint32_t jl = 0; jl < nquad; ++jl) {
         mbar_wait(&c.bar[s], (c.phases >> s) & 1u);
         c.phases ^= 1u << s;
+        const uint32_t j = first + jl * step;
         const uint32_t cnt = min(4u, m - 4 * j);
         // all 32 lanes run the shuffles; groups beyond a partial quad recompute row 0 and are ignored
         const uint32_t gg = g < cnt ? g : 0;
         const float d = quad_distance<DT>(p, c, c.ring + (size_t)(4 * s + gg) * p.ix.row_bytes);
         __syncwarp();
-        if (j + stages < nquad) issue_quad(j + stages, s);
-        tick(cnt);
-        uint32_t mask = __ballot_sync(FULL_MASK, (c.lane & 7u) == 0 && g < cnt && maybe(d));
-        while (mask) {
-            const uint32_t src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float de = __shfl_sync(FULL_MASK, d, src);
-            on_dist(c.todo[4 * j + (src >> 3)], de);
-        }
+        if (jl + stages < nquad) issue_quad(jl + stages, s);
+        sink(j, cnt, d);
         s = (s + 1 == stages) ? 0 : s + 1;
     }
+}
+
+// The single-warp sink: `maybe(d)` is a cheap, conservative accept test evaluated by every group on its own
+// row at once; only rows that pass are handed to `on_dist` (in list order), which applies the exact,
+// order-dependent test.  The caller guarantees that a row failing `maybe` at the start of a step would also
+// fail `on_dist`'s test later in the step (thresholds only tighten).  `tick(cnt)` runs once per step.
+template <typename M, typename F, typename T>
+__device__ __forceinline__ void consume_quad(const WarpCtx& c, uint32_t j, uint32_t cnt, float d, M&& maybe, F&& on_dist,
+                                             T&& tick) {
+    tick(cnt);
+    uint32_t mask = __ballot_sync(FULL_MASK, (c.lane & 7u) == 0 && (c.lane >> 3) < cnt && maybe(d));
+    while (mask) {
+        const uint32_t src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float de = __shfl_sync(FULL_MASK, d, src);
+        on_dist(c.todo[4 * j + (src >> 3)], de);
+    }
+}
+
+template <int DT, typename M, typename F, typename T>
+__device__ __forceinline__ void eval_list_quad(const SearchParams& p, WarpCtx& c, uint32_t m, M&& maybe, F&& on_dist,
+                                               T&& tick) {
+    eval_quads_ring<DT>(p, c, m, 0, 1, [&](uint32_t j, uint32_t cnt, float d) { consume_quad(c, j, cnt, d, maybe, on_dist, tick); });
 }
 
 // Evaluates the distances of c.todo[0..m) in order, with up to nslot row fetches in flight.
@@ -329,14 +348,16 @@ __device__ __forceinline__ void eval_list_bits(const SearchParams& p, WarpCtx& c
 // staging buffer filled by 16-byte async copies (no barrier object, no cross-lane hand-off) and the query's
 // chunks stay in registers for the whole query (`qreg`).  Stage s uses slots 4s..4s+3; one commit group per
 // step keeps the wait depth constant.
-template <int QN, typename M, typename F, typename T>
-__device__ __forceinline__ void eval_list_sq8(const SearchParams& p, WarpCtx& c, uint32_t m, const uint4 (&qreg)[QN > 0 ? QN : 1],
-                                              M&& maybe, F&& on_dist, T&& tick) {
+template <int QN, typename S>
+__device__ __forceinline__ void eval_quads_sq8(const SearchParams& p, WarpCtx& c, uint32_t m, const uint4 (&qreg)[QN > 0 ? QN : 1],
+                                               uint32_t first, uint32_t step, S&& sink) {
     const uint32_t stages = p.nslot >> 2;  // 2..4
-    const uint32_t nquad = (m + 3) >> 2;
+    const uint32_t nquad_all = (m + 3) >> 2;
+    const uint32_t nquad = nquad_all > first ? (nquad_all - first + step - 1) / step : 0;  // this warp's quads
     const uint32_t g = c.lane >> 3, t = c.lane & 7;
     const uint32_t n16 = p.ix.row_bytes >> 4;
-    auto issue = [&](uint32_t j, uint32_t s) {
+    auto issue = [&](uint32_t jl, uint32_t s) {
+        const uint32_t j = first + jl * step;
         if (4 * j + g < m) {
             const uint8_t* src = p.ix.vecs + (size_t)c.todo[4 * j + g] * p.ix.row_bytes + t * 16;
             uint8_t* dst = c.ring + (size_t)(4 * s + g) * p.ix.row_bytes + t * 16;
@@ -345,18 +366,19 @@ __device__ __forceinline__ void eval_list_sq8(const SearchParams& p, WarpCtx& c,
                 if (t + 8 * u < n16) cp_async16(dst + 128 * u, src + 128 * u);
         }
     };
-    for (uint32_t j = 0; j < stages; ++j) {
-        if (j < nquad) issue(j, j);
+    for (uint32_t jl = 0; jl < stages; ++jl) {
+        if (jl < nquad) issue(jl, jl);
         cp_async_commit();
     }
     uint32_t s = 0;
-    for (uint32_t j = 0; j < nquad; ++j) {
+    for (uint32_t jl = 0; jl < nquad; ++jl) {
         if (stages == 4)
             cp_async_wait<3>();
         else if (stages == 3)
             cp_async_wait<2>();
         else
             cp_async_wait<1>();
+        const uint32_t j = first + jl * step;
         const uint32_t cnt = min(4u, m - 4 * j);
         uint32_t d = 0;
         if (g < cnt) {
@@ -373,23 +395,21 @@ __device__ __forceinline__ void eval_list_sq8(const SearchParams& p, WarpCtx& c,
                 d = sq8_word(x[u].w, qreg[u].w, d);
             }
         }
-        if (j + stages < nquad) issue(j + stages, s);  // the lane is done with its own chunks of this stage
+        if (jl + stages < nquad) issue(jl + stages, s);  // the lane is done with its own chunks of this stage
         cp_async_commit();
         d += __shfl_xor_sync(FULL_MASK, d, 1);
         d += __shfl_xor_sync(FULL_MASK, d, 2);
         d += __shfl_xor_sync(FULL_MASK, d, 4);
-        const float df = __uint_as_float(d);
-        tick(cnt);
-        uint32_t mask = __ballot_sync(FULL_MASK, t == 0 && g < cnt && maybe(df));
-        while (mask) {
-            const uint32_t src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float de = __shfl_sync(FULL_MASK, df, src);
-            on_dist(c.todo[4 * j + (src >> 3)], de);
-        }
+        sink(j, cnt, __uint_as_float(d));
         s = (s + 1 == stages) ? 0 : s + 1;
     }
     cp_async_wait<0>();  // only empty groups can be pending here; keeps the group count clean for the next list
+}
+
+template <int QN, typename M, typename F, typename T>
+__device__ __forceinline__ void eval_list_sq8(const SearchParams& p, WarpCtx& c, uint32_t m, const uint4 (&qreg)[QN > 0 ? QN : 1],
+                                              M&& maybe, F&& on_dist, T&& tick) {
+    eval_quads_sq8<QN>(p, c, m, qreg, 0, 1, [&](uint32_t j, uint32_t cnt, float d) { consume_quad(c, j, cnt, d, maybe, on_dist, tick); });
 }
 
 template <int DT, int QN, typename M, typename F, typename T>
@@ -551,16 +571,28 @@ struct ResArr {
     }
 };
 
-template <int DT, int R, int QN>
-__global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p) {
+// COOP = false: one warp per query (CTA of 32 threads).  COOP = true: a CTA of 2..4 warps per query -- warp 0
+// (the leader) owns the result array and does everything order-dependent (pops, adjacency + visited filter,
+// inserts); the distance evaluations of each neighbour list are split across the warps, quad by quad, every
+// warp with its own ring, and handed back through shared memory.  Same arithmetic per row, same order of
+// inserts, so the results are identical; it exists for batches too small to fill the GPU with one warp per
+// query, where a query's latency is its single warp's instruction chain.
+template <int DT, int R, int QN, bool COOP>
+__global__ void __launch_bounds__(COOP ? 128 : 32, 1) hnsw_search_kernel(const SearchParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     WarpCtx c;
-    c.lane = threadIdx.x;
-    c.bar = reinterpret_cast<uint64_t*>(smem);
+    c.lane = threadIdx.x & 31;
+    const uint32_t tid = threadIdx.x, nthr = COOP ? blockDim.x : 32u;
+    const uint32_t warp = COOP ? threadIdx.x >> 5 : 0u, nwarp = COOP ? blockDim.x >> 5 : 1u;
+    const bool leader = warp == 0;
+    // layout: [COOP: control words, 16 B] results | todo | [COOP: distances] | query | per warp: barriers + ring
+    volatile uint32_t* ctrl = reinterpret_cast<volatile uint32_t*>(smem);
     c.res = reinterpret_cast<uint64_t*>(smem + p.off_res);
     c.todo = reinterpret_cast<uint32_t*>(smem + p.off_todo);
+    float* dists = reinterpret_cast<float*>(smem + p.off_dist);
     c.q = smem + p.off_q;
-    c.ring = smem + p.off_ring;
+    c.bar = reinterpret_cast<uint64_t*>(smem + p.off_ring + (size_t)warp * p.warp_bytes);
+    c.ring = reinterpret_cast<uint8_t*>(c.bar) + kMaxSlots * 8;
     c.phases = 0;
     c.norm_a = 0.0f;
     c.policy = make_evict_first_policy();
@@ -570,32 +602,52 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
         for (uint32_t i = 0; i < kMaxSlots; ++i) mbar_init(&c.bar[i], 1);
         fence_barrier_init();
     }
-    __syncwarp();
+    auto cta_sync = [&]() {
+        if (COOP)
+            __syncthreads();
+        else
+            __syncwarp();
+    };
+    // leader -> everyone, through alternating control words (a word is rewritten two barriers later at the earliest)
+    uint32_t bslot = 0;
+    auto bcast = [&](uint32_t v) -> uint32_t {
+        if (!COOP) return v;
+        if (leader && lane == 0) ctrl[bslot] = v;
+        __syncthreads();
+        v = ctrl[bslot];
+        bslot ^= 1u;
+        return v;
+    };
+    cta_sync();
 
     uint32_t* vis = p.visited + (size_t)blockIdx.x * p.vis_words;
     uint32_t* vlog = p.vlog + (size_t)blockIdx.x * kLogCap;
     uint64_t* tie = p.tie + (size_t)blockIdx.x * kTieCap;
     const uint32_t dim = p.ix.dim;
     const uint32_t ef = p.ef;
+    constexpr uint32_t kDone = 0xFFFFFFFFu;
 
     for (;;) {
         uint32_t qi = 0;
-        if (lane == 0) qi = atomicAdd(&p.counters[0], 1u);
-        qi = __shfl_sync(FULL_MASK, qi, 0);
+        if (leader) {
+            if (lane == 0) qi = atomicAdd(&p.counters[0], 1u);
+            qi = __shfl_sync(FULL_MASK, qi, 0);
+        }
+        qi = bcast(qi);
         if (qi >= p.nq) break;
 
         // ---- stage the query ----
         const float* qg = p.queries + (size_t)qi * dim;
         if (DT == VELES_BIN1) {
             uint32_t* qw = reinterpret_cast<uint32_t*>(c.q);
-            for (uint32_t w = lane; w < (dim >> 5); w += 32) {
+            for (uint32_t w = tid; w < (dim >> 5); w += nthr) {
                 uint32_t bits = 0;
                 for (uint32_t b = 0; b < 32; ++b) bits |= (qg[w * 32 + b] > 0.5f ? 1u : 0u) << b;
                 qw[w] = bits;
             }
         } else if (DT == VELES_SQ8) {
             // ScalarQuantizer::quantize (quantization.rs:236-250); padding bytes are zero like the rows'
-            for (uint32_t i = lane; i < p.ix.row_bytes; i += 32) {
+            for (uint32_t i = tid; i < p.ix.row_bytes; i += nthr) {
                 uint32_t b = 0;
                 if (i < dim) {
                     const float qv = roundf(__fmul_rn(__fsub_rn(qg[i], p.ix.sq_min[i]), p.ix.sq_scale[i]));
@@ -605,9 +657,9 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
             }
         } else {
             float* qs = reinterpret_cast<float*>(c.q);
-            for (uint32_t i = lane; i < dim; i += 32) qs[i] = qg[i];
+            for (uint32_t i = tid; i < dim; i += nthr) qs[i] = qg[i];
         }
-        __syncwarp();
+        cta_sync();
         uint4 qreg[QN > 0 ? QN : 1];
         if (QN > 0) {
 #pragma unroll
@@ -628,6 +680,37 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
         auto always = [](float) { return true; };
         auto no_tick = [](uint32_t) {};
         res.init(c.res, lane);
+        // Distances of c.todo[0..m) -> maybe / on_dist in list order (see consume_quad).  COOP: every warp calls it
+        // with the same m (after a bcast, which also publishes todo); the quads are dealt round-robin, the
+        // distances meet in `dists`, and the leader consumes them 32 at a time.
+        auto eval = [&](uint32_t m, auto&& maybe, auto&& on_dist, auto&& tick) {
+            if (!COOP) {
+                eval_list<DT, QN>(p, c, m, qreg, maybe, on_dist, tick);
+                return;
+            }
+            auto sink = [&](uint32_t j, uint32_t cnt, float d) {
+                if (leader) tick(cnt);
+                if ((lane & 7u) == 0 && (lane >> 3) < cnt) dists[4 * j + (lane >> 3)] = d;
+            };
+            if (QN > 0)
+                eval_quads_sq8<QN>(p, c, m, qreg, warp, nwarp, sink);
+            else
+                eval_quads_ring<DT>(p, c, m, warp, nwarp, sink);
+            __syncthreads();
+            if (leader) {
+                for (uint32_t base = 0; base < m; base += 32) {
+                    const uint32_t i = base + lane;
+                    const float d = i < m ? dists[i] : 0.0f;
+                    uint32_t mask = __ballot_sync(FULL_MASK, i < m && maybe(d));
+                    while (mask) {
+                        const uint32_t src = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const float de = __shfl_sync(FULL_MASK, d, src);
+                        on_dist(c.todo[base + src], de);
+                    }
+                }
+            }
+        };
 
         if (p.ix.has_entry) {
             // ---- greedy descent, layers max_layer..1 (graph.rs:259-263, 405-428) ----
@@ -636,22 +719,25 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
             for (uint32_t layer = p.ix.max_layer; layer >= 1; --layer) {
                 uint32_t best = cur;
                 float best_dist = 0.0f;
-                if (lane == 0) c.todo[0] = best;
-                __syncwarp();
-                eval_list<DT, QN>(p, c, 1, qreg, always, [&](uint32_t, float d) { best_dist = d; }, no_tick);
+                if (leader && lane == 0) c.todo[0] = best;
+                bcast(1u);
+                eval(1u, always, [&](uint32_t, float d) { best_dist = d; }, no_tick);
                 ++ndc_up;
                 for (;;) {
-                    const uint32_t ref = p.ix.upper_ref[best];
                     uint32_t m = 0;
-                    if (ref != VELES_INVALID_ID && layer <= (ref & 15u)) {
-                        const uint32_t* row = p.ix.upper_adj + ((size_t)(ref >> 4) + layer - 1) * p.ix.strideU;
-                        m = gather_row<false>(p, c, row, p.ix.strideU, nullptr, nullptr, dummy_logn, nread);
+                    if (leader) {
+                        const uint32_t ref = p.ix.upper_ref[best];
+                        if (ref != VELES_INVALID_ID && layer <= (ref & 15u)) {
+                            const uint32_t* row = p.ix.upper_adj + ((size_t)(ref >> 4) + layer - 1) * p.ix.strideU;
+                            m = gather_row<false>(p, c, row, p.ix.strideU, nullptr, nullptr, dummy_logn, nread);
+                        }
                     }
+                    m = bcast(m);
                     ++hops_up;
                     ndc_up += m;
                     bool improved = false;
-                    eval_list<DT, QN>(
-                        p, c, m, qreg, [&](float d) { return d < best_dist; },
+                    eval(
+                        m, [&](float d) { return d < best_dist; },
                         [&](uint32_t id, float d) {
                             if (d < best_dist) {
                                 best = id;
@@ -661,9 +747,9 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
                         },
                         no_tick);
                     __syncwarp();
-                    if (!improved) break;
+                    if (bcast(improved ? 1u : 0u) == 0u) break;
                 }
-                cur = best;
+                cur = best;  // meaningful in the leader only
             }
 
             // ---- layer 0 beam (graph.rs:266, 438-520) ----
@@ -713,73 +799,86 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
             };
             bool full = false;  // len >= ef
             {
-                const uint32_t bit = 1u << (cur & 31);
-                if (lane == 0) {
-                    atomicOr(&vis[cur >> 5], bit);
-                    vlog[0] = cur;
-                    c.todo[0] = cur;
+                if (leader) {
+                    const uint32_t bit = 1u << (cur & 31);
+                    if (lane == 0) {
+                        atomicOr(&vis[cur >> 5], bit);
+                        vlog[0] = cur;
+                        c.todo[0] = cur;
+                    }
                 }
                 logn = 1;
-                __syncwarp();
+                bcast(1u);
                 float d0 = 0.0f;
-                eval_list<DT, QN>(p, c, 1, qreg, always, [&](uint32_t, float d) { d0 = d; }, no_tick);
+                eval(1u, always, [&](uint32_t, float d) { d0 = d; }, no_tick);
                 ++ndc0;
-                res.set(0, make_key(d0, cur));
-                len = 1;
-                full = len >= ef;
-                worst = d0;
-                __syncwarp();
+                if (leader) {
+                    res.set(0, make_key(d0, cur));
+                    len = 1;
+                    full = len >= ef;
+                    worst = d0;
+                    __syncwarp();
+                }
             }
             for (;;) {
-                // pop the closest candidate: first unexpanded entry of res, else the smallest tie
-                uint32_t cnode = VELES_INVALID_ID;
-                if (nxt < len) {
-                    const uint64_t key = res.get(nxt);
-                    cnode = key_id(key);
-                    res.set(nxt, key | 1ull);
-                    nxt = res.next_unexpanded(nxt, false, len);  // the following unexpanded entry
-                } else if (tlen > 0) {
-                    // every tie has dist == worst result dist: popped without the break (graph.rs:474)
-                    uint64_t best = ~0ull;
-                    for (uint32_t i = lane; i < tlen; i += 32) {
-                        const uint64_t v = tie[i];
-                        best = v < best ? v : best;
+                uint32_t m = 0;
+                bool have = true;
+                if (leader) {
+                    // pop the closest candidate: first unexpanded entry of res, else the smallest tie
+                    uint32_t cnode = VELES_INVALID_ID;
+                    if (nxt < len) {
+                        const uint64_t key = res.get(nxt);
+                        cnode = key_id(key);
+                        res.set(nxt, key | 1ull);
+                        nxt = res.next_unexpanded(nxt, false, len);  // the following unexpanded entry
+                    } else if (tlen > 0) {
+                        // every tie has dist == worst result dist: popped without the break (graph.rs:474)
+                        uint64_t best = ~0ull;
+                        for (uint32_t i = lane; i < tlen; i += 32) {
+                            const uint64_t v = tie[i];
+                            best = v < best ? v : best;
+                        }
+                        best = warp_min_u64(best);
+                        cnode = key_id(best);
+                        // remove it: move the last entry into its place
+                        const uint64_t lastv = tie[tlen - 1];
+                        __syncwarp();
+                        for (uint32_t i = lane; i < tlen; i += 32)
+                            if (tie[i] == best) tie[i] = lastv;
+                        --tlen;
+                        __syncwarp();
+                    } else {
+                        have = false;  // candidates exhausted, or everything left is farther than the worst result
                     }
-                    best = warp_min_u64(best);
-                    cnode = key_id(best);
-                    // remove it: move the last entry into its place
-                    const uint64_t lastv = tie[tlen - 1];
-                    __syncwarp();
-                    for (uint32_t i = lane; i < tlen; i += 32)
-                        if (tie[i] == best) tie[i] = lastv;
-                    --tlen;
-                    __syncwarp();
-                } else {
-                    break;  // candidates exhausted, or everything left is farther than the worst result
+                    // expand cnode: adjacency from the prefetch registers when the prediction held
+                    uint32_t nread = 0;
+                    if (!have) {
+                    } else if (can_pre && cnode == pre_node && pre_peeked) {
+                        // The visited words were read after the previous expansion's marking and nothing has been
+                        // marked since: the peek is exact.  Mark now without waiting for the atomics' results.
+                        gather_peeked(c, pre_a, pre_va, vis, vlog, logn, m, nread);
+                        if (p.ix.stride0 > 32) gather_peeked(c, pre_b, pre_vb, vis, vlog, logn, m, nread);
+                        logn += m;
+                        __syncwarp();
+                    } else if (can_pre && cnode == pre_node) {
+                        if (gather_chunk<true>(c, pre_a, vis, vlog, logn, m, nread) && p.ix.stride0 > 32)
+                            gather_chunk<true>(c, pre_b, vis, vlog, logn, m, nread);
+                        logn += m;
+                        __syncwarp();
+                    } else {
+                        m = gather_row<true>(p, c, p.ix.adj0 + (size_t)cnode * p.ix.stride0, p.ix.stride0, vis, vlog, logn, nread);
+                    }
                 }
-                // expand cnode: adjacency from the prefetch registers when the prediction held
-                uint32_t nread = 0, m = 0;
-                if (can_pre && cnode == pre_node && pre_peeked) {
-                    // The visited words were read after the previous expansion's marking and nothing has been
-                    // marked since: the peek is exact.  Mark now without waiting for the atomics' results.
-                    gather_peeked(c, pre_a, pre_va, vis, vlog, logn, m, nread);
-                    if (p.ix.stride0 > 32) gather_peeked(c, pre_b, pre_vb, vis, vlog, logn, m, nread);
-                    logn += m;
-                    __syncwarp();
-                } else if (can_pre && cnode == pre_node) {
-                    if (gather_chunk<true>(c, pre_a, vis, vlog, logn, m, nread) && p.ix.stride0 > 32)
-                        gather_chunk<true>(c, pre_b, vis, vlog, logn, m, nread);
-                    logn += m;
-                    __syncwarp();
-                } else {
-                    m = gather_row<true>(p, c, p.ix.adj0 + (size_t)cnode * p.ix.stride0, p.ix.stride0, vis, vlog, logn, nread);
-                }
+                m = bcast(leader ? (have ? m : kDone) : 0u);
+                if (m == kDone) break;
                 ++hops0;
                 ndc0 += m;
-                pre_peeked = false;  // this expansion's marking invalidates any earlier peek
-                if (nxt < len) learn(key_id(res.get(nxt)));
-                eval_list<DT, QN>(
-                    p, c, m, qreg, [&](float d) { return d < worst || !full; },
+                if (leader) {
+                    pre_peeked = false;  // this expansion's marking invalidates any earlier peek
+                    if (nxt < len) learn(key_id(res.get(nxt)));
+                }
+                eval(
+                    m, [&](float d) { return d < worst || !full; },
                     [&](uint32_t id, float d) {
                     if (d < worst || !full) {
                         const uint64_t key = make_key(d, id);
@@ -846,65 +945,72 @@ __global__ void __launch_bounds__(32, 1) hnsw_search_kernel(const SearchParams p
                 __syncwarp();
             }
 
-            // ---- clear the visited bitmap for the next query of this slot ----
-            if (logn <= kLogCap) {
-                // eight independent log reads in flight per lane (one at a time made this loop ~8% of a query)
-                for (uint32_t i = lane; i < logn; i += 32 * 8) {
-                    uint32_t v[8];
+            if (leader) {
+                // ---- clear the visited bitmap for the next query of this slot ----
+                if (logn <= kLogCap) {
+                    // eight independent log reads in flight per lane (one at a time made this loop ~8% of a query)
+                    for (uint32_t i = lane; i < logn; i += 32 * 8) {
+                        uint32_t v[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = i + 32u * u < logn ? __ldcg(&vlog[i + 32u * u]) : VELES_INVALID_ID;
+                        for (int u = 0; u < 8; ++u) v[u] = i + 32u * u < logn ? __ldcg(&vlog[i + 32u * u]) : VELES_INVALID_ID;
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        if (v[u] != VELES_INVALID_ID) vis[v[u] >> 5] = 0u;
+                        for (int u = 0; u < 8; ++u)
+                            if (v[u] != VELES_INVALID_ID) vis[v[u] >> 5] = 0u;
+                    }
+                } else {
+                    for (uint32_t i = lane; i < p.vis_words; i += 32) vis[i] = 0u;
                 }
+                __syncwarp();
+            }
+        }
+
+        if (leader) {
+            // ---- write the first k results (graph.rs:269) ----
+            const uint32_t cnt = len < p.k ? len : p.k;
+            auto emit = [&](uint32_t i, uint64_t key) {
+                if (i < p.k) {
+                    const bool ok = i < cnt;
+                    p.out_ids[(size_t)qi * p.k + i] = ok ? key_id(key) : VELES_INVALID_ID;
+                    p.out_dist[(size_t)qi * p.k + i] = ok ? key_dist(key) : __uint_as_float(0x7fc00000u);
+                }
+            };
+            if (R == 0) {
+                for (uint32_t i = lane; i < p.k; i += 32) emit(i, i < cnt ? c.res[i] : 0ull);
             } else {
-                for (uint32_t i = lane; i < p.vis_words; i += 32) vis[i] = 0u;
+                // static slot indices only: position 32*s + lane lives in this lane's k[s]
+#pragma unroll
+                for (int s2 = 0; s2 < (R > 0 ? R : 1); ++s2) emit(32u * s2 + lane, res.k[s2]);
+                for (uint32_t i = 32u * R + lane; i < p.k; i += 32) emit(i, 0ull);
+            }
+            if (lane == 0) {
+                p.out_counts[qi] = cnt;
+                if (p.out_stats) {
+                    p.out_stats[(size_t)qi * 4 + 0] = ndc0;
+                    p.out_stats[(size_t)qi * 4 + 1] = hops0;
+                    p.out_stats[(size_t)qi * 4 + 2] = ndc_up;
+                    p.out_stats[(size_t)qi * 4 + 3] = hops_up;
+                }
             }
             __syncwarp();
         }
-
-        // ---- write the first k results (graph.rs:269) ----
-        const uint32_t cnt = len < p.k ? len : p.k;
-        auto emit = [&](uint32_t i, uint64_t key) {
-            if (i < p.k) {
-                const bool ok = i < cnt;
-                p.out_ids[(size_t)qi * p.k + i] = ok ? key_id(key) : VELES_INVALID_ID;
-                p.out_dist[(size_t)qi * p.k + i] = ok ? key_dist(key) : __uint_as_float(0x7fc00000u);
-            }
-        };
-        if (R == 0) {
-            for (uint32_t i = lane; i < p.k; i += 32) emit(i, i < cnt ? c.res[i] : 0ull);
-        } else {
-            // static slot indices only: position 32*s + lane lives in this lane's k[s]
-#pragma unroll
-            for (int s2 = 0; s2 < (R > 0 ? R : 1); ++s2) emit(32u * s2 + lane, res.k[s2]);
-            for (uint32_t i = 32u * R + lane; i < p.k; i += 32) emit(i, 0ull);
-        }
-        if (lane == 0) {
-            p.out_counts[qi] = cnt;
-            if (p.out_stats) {
-                p.out_stats[(size_t)qi * 4 + 0] = ndc0;
-                p.out_stats[(size_t)qi * 4 + 1] = hops0;
-                p.out_stats[(size_t)qi * 4 + 2] = ndc_up;
-                p.out_stats[(size_t)qi * 4 + 3] = hops_up;
-            }
-        }
-        __syncwarp();
     }
 }
 
 using SearchKernel = void (*)(const SearchParams);
 // one translation unit per storage type instantiates its kernels (hnsw_search_<type>.cu); reg_mode is the
 // result-array variant (2 or 8 keys per lane in registers, 0 = shared memory), qn the SQ8 chunk count
-SearchKernel search_kernel_f32(uint32_t reg_mode);
-SearchKernel search_kernel_f16(uint32_t reg_mode);
+SearchKernel search_kernel_f32(uint32_t reg_mode, bool coop);
+SearchKernel search_kernel_f16(uint32_t reg_mode, bool coop);
 SearchKernel search_kernel_bin1(uint32_t reg_mode);
-SearchKernel search_kernel_sq8(uint32_t reg_mode, uint32_t qn);
-SearchKernel search_kernel_sq8_a(uint32_t reg_mode, uint32_t qn);  // qn 0, 2
-SearchKernel search_kernel_sq8_b(uint32_t reg_mode, uint32_t qn);  // qn 4, 6
-SearchKernel search_kernel_sq8_c(uint32_t reg_mode, uint32_t qn);  // qn 8
+SearchKernel search_kernel_sq8(uint32_t reg_mode, uint32_t qn, bool coop);
+SearchKernel search_kernel_sq8_a(uint32_t reg_mode, uint32_t qn, bool coop);  // qn 0, 2
+SearchKernel search_kernel_sq8_b(uint32_t reg_mode, uint32_t qn, bool coop);  // qn 4, 6
+SearchKernel search_kernel_sq8_c(uint32_t reg_mode, uint32_t qn, bool coop);  // qn 8
 
-#define VELES_PICK_KERNEL(DT, QN) \
-    (reg_mode == 2 ? hnsw_search_kernel<DT, 2, QN> : reg_mode == 8 ? hnsw_search_kernel<DT, 8, QN> : hnsw_search_kernel<DT, 0, QN>)
+// coop: the multi-warp-per-query variant (result array in registers only: ef <= 256)
+#define VELES_PICK_KERNEL(DT, QN)                                                                                          \
+    (coop ? (reg_mode == 2 ? hnsw_search_kernel<DT, 2, QN, true> : hnsw_search_kernel<DT, 8, QN, true>)                   \
+          : (reg_mode == 2 ? hnsw_search_kernel<DT, 2, QN, false>                                                         \
+                           : reg_mode == 8 ? hnsw_search_kernel<DT, 8, QN, false> : hnsw_search_kernel<DT, 0, QN, false>))
 
 }  // namespace veles

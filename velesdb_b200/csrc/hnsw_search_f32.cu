@@ -2,5 +2,5 @@
 #include "hnsw_search.cuh"
 
 namespace veles {
-SearchKernel search_kernel_f32(uint32_t reg_mode) { return VELES_PICK_KERNEL(VELES_F32, 0); }
+SearchKernel search_kernel_f32(uint32_t reg_mode, bool coop) { return VELES_PICK_KERNEL(VELES_F32, 0); }
 }  // namespace veles

@@ -36,7 +36,7 @@ struct veles_index {
     mutable std::mutex mu;
     mutable veles::DevBuf visited, vlog, counters;
     mutable uint32_t scratch_slots = 0;
-    mutable veles::DevBuf q_d, out_ids_d, out_val_d, out_cnt_d, out_stats_d, scores_d, aux_d;
+    mutable veles::DevBuf q_d, out_ids_d, out_val_d, out_cnt_d, out_stats_d, scores_d, aux_d, topk_d;
 
     veles::IndexView view() const {
         veles::IndexView v;
