@@ -253,7 +253,7 @@ def test_hnsw_search_f16_quad_path(metric):
     check_search(gh, snap, queries_near(x, 48, seed=13), 10, 64)
 
 
-@pytest.mark.parametrize("warps", ["1", "2", "4"])
+@pytest.mark.parametrize("warps", ["1", "2", "4", "8"])
 def test_hnsw_search_warps_per_query(warps, monkeypatch):
     # one warp per query vs the cooperative multi-warp kernel (hnsw_search_kernel<.., COOP>): identical results,
     # identical per-layer evaluation / expansion counts

@@ -175,7 +175,7 @@ def test_sq8_recall_close_to_f32():
     assert rec(s_ids) >= rec(f_ids) - 0.03, (rec(s_ids), rec(f_ids))
 
 
-@pytest.mark.parametrize("warps", ["1", "2", "4"])
+@pytest.mark.parametrize("warps", ["1", "2", "4", "8"])
 def test_sq8_warps_per_query(warps, monkeypatch):
     monkeypatch.setenv("VELES_SEARCH_WARPS", warps)
     for metric, dim in ((vo.COSINE, 768), (vo.EUCLIDEAN, 20)):

@@ -78,7 +78,7 @@ int32_t launch_search(const veles_index* ix, const IndexView& view, const float*
     const uint32_t reg_mode = env_u32("VELES_SEARCH_REG_RESULTS", 1) == 0 ? 0 : (ef <= 64 ? 2 : (ef <= 256 ? 8 : 0));
 
     // Warps per query.  A lone warp's instruction chain bounds a query's latency (~1 ms at 1M x 768 f32), so a
-    // batch that cannot fill the GPU with one warp per query gets 4 or 2 warps per query (hnsw_search_kernel
+    // batch that cannot fill the GPU with one warp per query gets 8, 4 or 2 warps per query (hnsw_search_kernel
     // <.., COOP = true>): the largest count whose resident CTAs still hold the whole batch at once.
     uint32_t warps = 1, nslot = 2;
     const bool coop_ok = p.quad == 1 && reg_mode != 0 && dtype != VELES_BIN1;
@@ -87,7 +87,7 @@ int32_t launch_search(const veles_index* ix, const IndexView& view, const float*
     if (coop_ok) {
         carve(true);
         const uint32_t forced = env_u32("VELES_SEARCH_WARPS", 0);
-        for (uint32_t w = 4; w >= 2; w >>= 1) {
+        for (uint32_t w = 8; w >= 2; w >>= 1) {
             const uint32_t sb = coop_smem(w);
             if (sb > (uint32_t)max_smem) continue;
             const uint32_t per_sm = std::min((uint32_t)sm_smem / (sb + 1024u), 32u / w);

@@ -571,14 +571,14 @@ struct ResArr {
     }
 };
 
-// COOP = false: one warp per query (CTA of 32 threads).  COOP = true: a CTA of 2..4 warps per query -- warp 0
+// COOP = false: one warp per query (CTA of 32 threads).  COOP = true: a CTA of 2..8 warps per query -- warp 0
 // (the leader) owns the result array and does everything order-dependent (pops, adjacency + visited filter,
 // inserts); the distance evaluations of each neighbour list are split across the warps, quad by quad, every
 // warp with its own ring, and handed back through shared memory.  Same arithmetic per row, same order of
 // inserts, so the results are identical; it exists for batches too small to fill the GPU with one warp per
 // query, where a query's latency is its single warp's instruction chain.
 template <int DT, int R, int QN, bool COOP>
-__global__ void __launch_bounds__(COOP ? 128 : 32, 1) hnsw_search_kernel(const SearchParams p) {
+__global__ void __launch_bounds__(COOP ? 256 : 32, 1) hnsw_search_kernel(const SearchParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     WarpCtx c;
     c.lane = threadIdx.x & 31;
