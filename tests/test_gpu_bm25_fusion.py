@@ -168,3 +168,37 @@ def test_hybrid_search_end_to_end():
     ti, _ = ob.search("alpha gamma", 2 * k)
     oi, os_ = vo.rrf_hybrid([r[0] for r in vres], ti, k, 0.5)
     assert [g[0] for g in got] == oi.tolist() and bits_equal([g[1] for g in got], os_)
+
+
+def test_multi_query_search_and_search_with_filter_end_to_end():
+    # Collection::multi_query_search (collection/search/batch.rs:238-330) and Collection::search_with_filter
+    # (collection/search/vector.rs:164-239), minus the storage fetch
+    from velesdb_b200 import DistanceMetric, HnswIndex, SearchQuality, multi_query_search, overfetch_k, search_with_filter
+    from tests.gpu_util import latent_data
+
+    assert [overfetch_k(k) for k in (1, 10, 11, 50, 51, 100, 101)] == [20, 200, 110, 500, 255, 500, 202]
+    n, dim, k = 600, 32, 5
+    x = latent_data(n, dim, seed=4)
+    hx = HnswIndex(dim, DistanceMetric.Cosine)
+    for i in range(n):
+        hx.insert(i, x[i])
+    qs = [x[3] + 0.02, x[77] - 0.03, x[400] + 0.01]
+    even = lambda i: i % 2 == 0
+    for st, (kind, kw) in ((FusionStrategy.RRF(60), (vo.RRF, {"rrf_k": 60})), (FusionStrategy.Average(), (vo.AVERAGE, {}))):
+        for pred in (None, even):
+            got = multi_query_search(hx, qs, k, st, pred)
+            lists = hx.search_batch_parallel(qs, overfetch_k(k), SearchQuality.Balanced)
+            if pred:
+                lists = [[h for h in l if pred(h[0])] for l in lists]
+            oi, os_ = vo.fuse(kind, lists, **kw)
+            assert [g[0] for g in got] == oi[:k].tolist() and bits_equal([g[1] for g in got], os_[:k])
+            assert pred is None or all(even(g[0]) for g in got)
+    with pytest.raises(ValueError, match="at least one vector"):
+        multi_query_search(hx, [], k, FusionStrategy.RRF())
+    with pytest.raises(ValueError, match="at most 10 vectors"):
+        multi_query_search(hx, [x[0]] * 11, k, FusionStrategy.RRF())
+    # filtered search: first k matches among max(4k, k + 10) candidates, best first
+    got = search_with_filter(hx, qs[0], k, even)
+    cand = [h for h in hx.search(qs[0], max(4 * k, k + 10)) if even(h[0])][:k]
+    assert got == sorted(cand, key=lambda h: -h[1]) and len(got) == k and all(even(h[0]) for h in got)
+    assert search_with_filter(hx, qs[0], k, lambda i: False) == []

@@ -118,3 +118,17 @@ def test_empty_index_returns_nothing():
     assert ix.search_brute_force(np.zeros(8, np.float32), 3) == []
     assert ix.search_batch_parallel(np.zeros((0, 8), np.float32), 3, SearchQuality.Balanced) == []
     assert nv.lib().veles_ef_search(nv.BALANCED, 10, 0) == 128
+
+
+def test_search_with_filter_overfetch_and_order():
+    # collection/search/vector.rs:164-239: candidates_k = max(4k, k + 10), Balanced quality, first k matches
+    from velesdb_b200 import overfetch_k, search_with_filter
+    ix, snap, x, ids = make_index()
+    odd = lambda e: ((e - 1000) // 7) % 2 == 1
+    got = search_with_filter(ix, x[5], 3, odd)
+    assert snap.calls[-1] == ("search", 13, 128)            # max(12, 13) candidates; ef = max(128, 4 * 13)
+    assert len(got) == 3 and all(odd(e) for e, _ in got)
+    assert [s for _, s in got] == sorted((s for _, s in got), reverse=True)
+    search_with_filter(ix, x[5], 40, odd)
+    assert snap.calls[-1] == ("search", 160, 640)
+    assert [overfetch_k(k) for k in (10, 50, 100, 200)] == [200, 500, 500, 400]   # collection/search/batch.rs:270-275

@@ -100,3 +100,40 @@ def hybrid_search(index, text_index, vector_query, text_query, k, vector_weight=
     ti[0, :len(tres)] = [r[0] for r in tres]
     ids, sc, cnt = rrf_hybrid_batch(vi, [len(vres)], ti, [len(tres)], k, w)
     return [(int(ids[0, j]), float(sc[0, j])) for j in range(int(cnt[0]))]
+
+
+def search_with_filter(index, query, k, predicate):
+    """``Collection::search_with_filter`` (collection/search/vector.rs:164-239) minus the storage fetch:
+    post-filtering over ``candidates_k = max(4k, k + 10)`` index results (``index.search`` = Balanced), first k
+    matches in index order, then the reference's final sort by score (stable; descending for similarity
+    metrics).  ``predicate(id) -> bool`` stands for ``filter.matches(payload)``."""
+    candidates_k = max(k * 4, k + 10)
+    hits = [(i, s) for i, s in index.search(query, candidates_k) if predicate(i)][:k]
+    return sorted(hits, key=lambda h: -h[1] if index.metric().higher_is_better() else h[1])
+
+
+def overfetch_k(top_k: int) -> int:
+    """collection/search/batch.rs:270-275"""
+    if top_k <= 10:
+        return top_k * 20
+    if top_k <= 50:
+        return top_k * 10
+    if top_k <= 100:
+        return top_k * 5
+    return top_k * 2
+
+
+def multi_query_search(index, vectors, top_k, strategy: "FusionStrategy", predicate=None):
+    """``Collection::multi_query_search`` (collection/search/batch.rs:238-330) minus the storage fetch: at most 10
+    query vectors, one batched over-fetched search (Balanced), optional pre-fusion filter, ``FusionStrategy::fuse``
+    on the device, first ``top_k``.  Ids are the external ids of ``index`` (must fit u32)."""
+    from .index import SearchQuality
+    if len(vectors) == 0:
+        raise ValueError("multi_query_search requires at least one vector")      # batch.rs:241-245
+    if len(vectors) > 10:
+        raise ValueError(f"multi_query_search supports at most 10 vectors, got {len(vectors)}")  # batch.rs:247-253
+    batch = index.search_batch_parallel(vectors, overfetch_k(top_k), SearchQuality.Balanced)
+    if predicate is not None:
+        batch = [[(i, s) for i, s in r if predicate(i)] for r in batch]
+    fused = strategy.fuse(batch)
+    return fused[:top_k]
