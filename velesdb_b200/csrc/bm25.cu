@@ -321,7 +321,11 @@ __global__ void __launch_bounds__(256, 5) bm25_query_kernel(Bm25View v, const ui
                 const uint32_t per = kRange / nwarps, i_begin = warp * per;
                 for (uint32_t i0 = i_begin; i0 < i_begin + per; i0 += 128) {
                     const float4 s4 = acc4[(i0 >> 2) + lane];
-                    const bool any = s4.x > 0.0f || s4.y > 0.0f || s4.z > 0.0f || s4.w > 0.0f;
+                    // once the list is full only scores >= its k-th score can enter (ties go by document id, so
+                    // equality stays in): one compare per score skips nearly every step after the first ranges
+                    const float thr = top.worst == ~0ull ? 0.0f : ord_unkey(~(uint32_t)(top.worst >> 32));
+                    const bool any = (s4.x > 0.0f && s4.x >= thr) || (s4.y > 0.0f && s4.y >= thr) ||
+                                     (s4.z > 0.0f && s4.z >= thr) || (s4.w > 0.0f && s4.w >= thr);
                     if (!__ballot_sync(FULL_MASK, any)) continue;
                     const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
