@@ -611,7 +611,10 @@ __global__ void __launch_bounds__(COOP ? 256 : 32, 1) hnsw_search_kernel(const S
     // leader -> everyone, through alternating control words (a word is rewritten two barriers later at the earliest)
     uint32_t bslot = 0;
     auto bcast = [&](uint32_t v) -> uint32_t {
-        if (!COOP) return v;
+        if (!COOP) {
+            __syncwarp();  // publishes the leader lane's shared-memory writes (todo) to the warp
+            return v;
+        }
         if (leader && lane == 0) ctrl[bslot] = v;
         __syncthreads();
         v = ctrl[bslot];
