@@ -50,3 +50,27 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "veles_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f
+
+
+def test_committed_bench_lines_follow_the_contract():
+    # the JSON line bench.py printed on the B200 (profiles/), checked for the keys the driver reads
+    import glob
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lines = sorted(glob.glob(os.path.join(root, "profiles", "r1_bench_n*_v[34].json")))
+    assert lines
+    for path in lines:
+        j = json.load(open(path))
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                    "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+            assert key in j, (path, key)
+        assert j["higher_is_better"] is True and j["scaling"] == "weak" and j["vs_baseline"] is None
+        assert j["warmup"] >= 3 and j["gpu_launches"] == j["steps"] and "workload" in j["config"]
+        assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(j["e2e"])
+        assert j["e2e"]["h2d_bytes_per_step"] > 0 and j["e2e"]["value"] <= j["value"] * 1.02
+        r = j["roofline"]
+        assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0 < r["frac"] <= 1.0
+        assert r["traffic"] is None or r["traffic"] >= r["algorithmic_bytes_per_launch"] * 0.98
+        c = j["cpu_baseline"]
+        assert c["kind"] == "port" and c["cores"] >= 1 and c["ids_match_gpu"] is True
+        assert not set(j["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
