@@ -241,6 +241,22 @@ int32_t veles_search_batch_sq8_d(const veles_index_t* idx, const float* queries_
                                  uint32_t ef_search, uint32_t oversampling, uint32_t* out_node_ids_d,
                                  float* out_raw_dist_d, uint32_t* out_counts_d, uint32_t* out_stats_d, void* stream);
 
+/* ---- id map, tombstones, filtered search ---------------------------------- */
+/* ShardedMappings on the device (index/hnsw/sharded_mappings.rs:32-39): ext_ids[node] is the external id of
+ * node `node` (NULL = identity), live_bits has one bit per node, 0 for removed ids (HnswIndex::remove is a soft
+ * delete, trait_impl.rs:54-58; NULL = all live).  Call again after remove() with the new bitmap. */
+int32_t veles_index_set_id_map(veles_index_t* idx, const uint64_t* ext_ids, const uint32_t* live_bits);
+
+/* The per-query body of HnswIndex::search_batch_parallel (index/hnsw/index/batch.rs:178-196) in one call:
+ * NativeHnsw::search(query, k_fetch, ef), hits of removed nodes dropped (search.rs:86-91), node -> external id,
+ * transform_score (native/backend_adapter.rs:160-168), first k_out kept, traversal order preserved.
+ * With allow_bits (one bit per node, host pointer) it is also the candidate loop of
+ * Collection::search_with_filter (collection/search/vector.rs:182-211): k_fetch = max(4k, k + 10) over-fetched
+ * hits, filtered, take(k_out).  out_ids nq*k_out (padded with all-ones), out_scores nq*k_out (NaN padded). */
+int32_t veles_search_batch_mapped(const veles_index_t* idx, const float* queries, uint32_t nq, uint32_t k_fetch,
+                                  uint32_t k_out, uint32_t ef, const uint32_t* allow_bits, uint64_t* out_ids,
+                                  float* out_scores, uint32_t* out_counts, void* stream);
+
 /* ---- multi-GPU --------------------------------------------------------------------------------- */
 /* Queries shard by contiguous slices across ranks; the snapshot is replicated.  The only exchange
  * is the final gather of [nq_local, k] ids + distances, done by the host runtime with NCCL

@@ -270,3 +270,35 @@ def test_hnsw_search_warps_per_query(warps, monkeypatch):
     gh = vo.Hnsw.from_arrays(vo.COSINE, xh, g.export_graph(), g.M, g.M0, g.entry_point, g.max_layer)
     snap = DeviceSnapshot.from_arrays(x, vo.COSINE, g.export_graph(), g.M, g.M0, g.entry_point, g.max_layer, store_dtype="f16")
     check_search(gh, snap, queries_near(x, 48, seed=13), 10, 64)
+
+
+def test_mapped_search_id_map_tombstones_and_filter():
+    # veles_search_batch_mapped vs the host-side restatement of batch.rs:178-196 / search.rs:86-91 /
+    # collection/search/vector.rs:182-211 on top of the raw search
+    from velesdb_b200 import _native as nv
+    for metric in (vo.COSINE, vo.EUCLIDEAN, vo.DOT):
+        x, g, snap = graph_case(metric, 96)
+        n = len(x)
+        q = queries_near(x, 40, seed=21)
+        rng = np.random.default_rng(5)
+        ext = (rng.permutation(n).astype(np.uint64) * np.uint64(1_000_003) + np.uint64(1 << 40))  # ids beyond 32 bits
+        live = rng.random(n) > 0.3
+        allow = rng.random(n) > 0.5
+        pack = lambda b: np.packbits(b, bitorder="little").view(np.uint8).tobytes()
+        bits = lambda b: np.frombuffer(pack(np.concatenate([b, np.zeros((-len(b)) % 32, bool)])), np.uint32).copy()
+        snap.set_id_map(ext, bits(live))
+        k, kf, ef = 10, 50, 128
+        raw_i, raw_d, raw_c = snap.search_batch(q, kf, ef)
+        for use_allow in (False, True):
+            ids, sc, cnt = snap.search_batch_mapped(q, k, ef, k_fetch=kf, allow_bits=bits(allow) if use_allow else None)
+            for r in range(len(q)):
+                keep = [j for j in range(int(raw_c[r])) if live[raw_i[r, j]] and (not use_allow or allow[raw_i[r, j]])][:k]
+                assert cnt[r] == len(keep)
+                assert ids[r, :len(keep)].tolist() == [int(ext[raw_i[r, j]]) for j in keep]
+                want = np.array([nv.lib().veles_transform_score(int(metric), float(raw_d[r, j])) for j in keep], np.float32)
+                assert bits_equal(sc[r, :len(keep)], want)
+                assert (ids[r, len(keep):] == np.uint64(0xFFFFFFFFFFFFFFFF)).all() and np.isnan(sc[r, len(keep):]).all()
+        snap.set_id_map(None, None)  # back to identity / all live for the other tests sharing this snapshot
+        ids, sc, cnt = snap.search_batch_mapped(q, k, ef)
+        ri, rd, rc = snap.search_batch(q, k, ef)
+        assert np.array_equal(ids, ri.astype(np.uint64)) and np.array_equal(cnt, rc)

@@ -18,6 +18,7 @@ class OracleSnapshot:
         if len(self.x):
             self.g.insert_many(self.x)
         self.calls = []
+        self.ext, self.live = None, None
 
     def __len__(self):
         return len(self.x)
@@ -26,6 +27,28 @@ class OracleSnapshot:
         self.calls.append(("search", k, ef))
         ids, d, cnt, _ = self.g.search_batch(q, k, ef, order="canonical")
         return ids.astype(np.uint32), d, cnt
+
+    def set_id_map(self, ext_ids=None, live_bits=None):
+        self.ext, self.live = ext_ids, live_bits
+
+    def search_batch_mapped(self, q, k, ef, k_fetch=None, allow_bits=None, stream=None):
+        """veles_search_batch_mapped restated on the host: live filter, id map, transform_score, first k."""
+        ids, d, cnt = self.search_batch(q, k if k_fetch is None else k_fetch, ef)
+        out_i = np.full((len(q), k), 0xFFFFFFFFFFFFFFFF, np.uint64)
+        out_s = np.full((len(q), k), np.nan, np.float32)
+        out_c = np.zeros(len(q), np.uint32)
+        for r in range(len(q)):
+            w = 0
+            for j in range(int(cnt[r])):
+                node = int(ids[r, j])
+                if self.live is not None and not (int(self.live[node >> 5]) >> (node & 31)) & 1:
+                    continue
+                if w < k:
+                    out_i[r, w] = node if self.ext is None else self.ext[node]
+                    out_s[r, w] = vo.transform_score(int(self.metric_), float(d[r, j]))
+                w += 1
+            out_c[r] = min(w, k)
+        return out_i, out_s, out_c
 
     def bruteforce_batch(self, q, k):
         self.calls.append(("brute", k))

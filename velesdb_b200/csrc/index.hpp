@@ -32,6 +32,10 @@ struct veles_index {
     bool has_sq8 = false;
     mutable veles::DevBuf sq_ids_d, sq_dist_d, sq_cnt_d;  // coarse candidates between traversal and re-rank
 
+    // node index -> external id, live (not tombstoned) bitmap: ShardedMappings on the device (postfilter.cu)
+    veles::DevBuf id_map_d, live_d;
+    mutable veles::DevBuf allow_d, map_ids_d, map_score_d;
+
     // search scratch, sized lazily and reused; guarded by `mu`
     mutable std::mutex mu;
     mutable veles::DevBuf visited, vlog, counters;

@@ -233,6 +233,28 @@ class DeviceSnapshot:
         nv.check(nv.lib().veles_search_batch_sq8_d(self.h, nv.ptr(q_t), q_t.shape[0], k, ef_search, oversampling,
                                                    nv.ptr(ids_t), nv.ptr(dist_t), nv.ptr(cnt_t), nv.ptr(stats_t), stream))
 
+    # -- id map, tombstones, filtered search (ShardedMappings on the device)
+    def set_id_map(self, ext_ids=None, live_bits=None):
+        """ext_ids: u64[n] external id per node (None = identity); live_bits: one bit per node, 0 = removed."""
+        e = None if ext_ids is None else np.ascontiguousarray(ext_ids, dtype=np.uint64)
+        b = None if live_bits is None else np.ascontiguousarray(live_bits, dtype=np.uint32)
+        assert e is None or e.size == len(self)
+        assert b is None or b.size == (len(self) + 31) // 32
+        nv.check(nv.lib().veles_index_set_id_map(self.h, nv.ptr(e), nv.ptr(b)))
+
+    def search_batch_mapped(self, queries, k, ef, k_fetch=None, allow_bits=None, stream=None):
+        """search + tombstone/filter drop + node -> external id + transform_score in one call (batch.rs:178-196)."""
+        q = _as_f32_2d(queries, self.dim, "Query")
+        nq = q.shape[0]
+        kf = k if k_fetch is None else k_fetch
+        a = None if allow_bits is None else np.ascontiguousarray(allow_bits, dtype=np.uint32)
+        ids = np.empty((nq, k), dtype=np.uint64)
+        sc = np.empty((nq, k), dtype=np.float32)
+        cnt = np.zeros(nq, dtype=np.uint32)
+        nv.check(nv.lib().veles_search_batch_mapped(self.h, nv.ptr(q), nq, kf, k, ef, nv.ptr(a), nv.ptr(ids), nv.ptr(sc),
+                                                    nv.ptr(cnt), stream))
+        return ids, sc, cnt
+
     def export_layer(self, layer):
         nodes, edges = C.c_uint64(), C.c_uint64()
         nv.check(nv.lib().veles_index_export_layer(self.h, layer, C.byref(nodes), C.byref(edges), None, None))
@@ -286,6 +308,7 @@ class HnswIndex:
         self._staged = []          # vectors by node index
         self._snapshot = None
         self._dirty = False
+        self._map_dirty = True        # the device copy of the id map / live bitmap is stale
         self._bulk = False            # True once a batch of >= 100 vectors went through insert_batch_parallel
         self._vectors_present = True  # False after load(): ShardedVectors is left empty (constructors.rs:240)
 
@@ -328,6 +351,7 @@ class HnswIndex:
         self._idx_to_id[idx] = id
         self._staged.append(v.copy())
         self._dirty = True
+        self._map_dirty = True
 
     def insert_batch_parallel(self, vectors) -> int:
         """index/hnsw/index/batch.rs:82-108: (id, vector) pairs; returns how many were new.  Batches of fewer
@@ -348,6 +372,7 @@ class HnswIndex:
         if idx is None:
             return False
         del self._idx_to_id[idx]
+        self._map_dirty = True
         return True
 
     def len(self) -> int:
@@ -477,6 +502,7 @@ class HnswIndex:
             else:
                 snap.build_graph(self._params.max_connections)
             self._snapshot, self._dirty = snap, False
+            self._map_dirty = True
         return self._snapshot
 
     def _map(self, ids, vals, cnt, transform):
@@ -493,11 +519,27 @@ class HnswIndex:
             out.append(row)
         return out
 
+    def _sync_mappings(self, snap):
+        """Uploads node -> external id and the live bitmap when they changed (insert / remove / new snapshot)."""
+        if not self._map_dirty:
+            return
+        n = len(snap)
+        ext = np.zeros(n, np.uint64)
+        live = np.zeros((n + 31) // 32, np.uint32)
+        for idx, e in self._idx_to_id.items():
+            if idx < n:
+                ext[idx] = e
+                live[idx >> 5] |= np.uint32(1 << (idx & 31))
+        snap.set_id_map(ext, live)
+        self._map_dirty = False
+
     def _graph_search(self, q, k, ef):
         if self._next_idx == 0:
             return [[] for _ in range(q.shape[0])]
-        ids, dist, cnt = self._ensure_snapshot().search_batch(q, k, ef)
-        return self._map(ids, dist, cnt, True)
+        snap = self._ensure_snapshot()
+        self._sync_mappings(snap)
+        ids, sc, cnt = snap.search_batch_mapped(q, k, ef)   # id map, tombstone drop, transform_score on the device
+        return [[(int(ids[r, j]), float(sc[r, j])) for j in range(int(cnt[r]))] for r in range(q.shape[0])]
 
     def _brute(self, q, k):
         snap = self._ensure_snapshot()
