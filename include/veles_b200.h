@@ -241,6 +241,15 @@ int32_t veles_search_batch_sq8_d(const veles_index_t* idx, const float* queries_
                                  uint32_t ef_search, uint32_t oversampling, uint32_t* out_node_ids_d,
                                  float* out_raw_dist_d, uint32_t* out_counts_d, uint32_t* out_stats_d, void* stream);
 
+/* NativeHnsw::search_multi_entry (native/graph.rs:288-348): the layer-0 search starts from the greedy descent's
+ * result plus up to three extra entry points per query (extra_entries: nq*3 node ids, VELES_INVALID_ID padded;
+ * duplicates are dropped as `entry_points.contains` does).  The reference draws the extra ids from its shared
+ * xorshift64 state (`state % count`, only when count > 10 and num_probes > 1); that state lives with the host
+ * wrapper, which passes the ids in.  Needs ef >= 4.  Outputs as veles_search_batch. */
+int32_t veles_search_batch_multi_entry(const veles_index_t* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
+                                       const uint32_t* extra_entries, uint32_t* out_node_ids, float* out_raw_dist,
+                                       uint32_t* out_counts, uint32_t* out_stats, void* stream);
+
 /* ---- id map, tombstones, filtered search ---------------------------------- */
 /* ShardedMappings on the device (index/hnsw/sharded_mappings.rs:32-39): ext_ids[node] is the external id of
  * node `node` (NULL = identity), live_bits has one bit per node, 0 for removed ids (HnswIndex::remove is a soft

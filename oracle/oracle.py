@@ -82,6 +82,10 @@ _sig("vo_hnsw_from_arrays", C.c_void_p,
      [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _f32p, C.c_uint64, C.c_uint32,
       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _u64p, C.c_uint64, C.c_uint32])
 _sig("vo_hnsw_search", C.c_uint32, [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_int, _u64p, _f32p, _u64p])
+_sig("vo_hnsw_search_multi_entry", C.c_uint32,
+     [C.c_void_p, _f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, _u64p, _f32p, _u64p, _u64p])
+_sig("vo_hnsw_rng_state", C.c_uint64, [C.c_void_p])
+_sig("vo_hnsw_set_rng_state", None, [C.c_void_p, C.c_uint64])
 _sig("vo_hnsw_search_batch", None,
      [C.c_void_p, _f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_int, _u64p, _f32p, _u32p, _u64p])
 _sig("vo_hnsw_search_layer", C.c_uint32, [C.c_void_p, _f32p, C.c_uint64, C.c_uint32, C.c_uint32, _u64p, _f32p])
@@ -267,6 +271,25 @@ class Hnsw:
             return ids[:n].copy(), d[:n].copy(), dict(zip(("ndc0", "hops0", "ndc_up", "hops_up", "tie_at_k", "adj0"),
                                                           (int(x) for x in st)))
         return ids[:n].copy(), d[:n].copy()
+
+    def search_multi_entry(self, q, k, ef, num_probes, order="reference"):
+        """NativeHnsw::search_multi_entry (graph.rs:288-348).  Returns ids, dist, stats dict, entry points used."""
+        q = _f32(q)
+        ids = np.zeros(max(k, 1), dtype=np.uint64)
+        d = np.zeros(max(k, 1), dtype=np.float32)
+        st = np.zeros(6, dtype=np.uint64)
+        ent = np.zeros(4, dtype=np.uint64)
+        n = _lib.vo_hnsw_search_multi_entry(self._h, q, k, ef, num_probes, 0 if order == "reference" else 1, ids, d, st, ent)
+        stats = dict(zip(("ndc0", "hops0", "ndc_up", "hops_up", "tie_at_k", "adj0"), (int(x) for x in st)))
+        return ids[:n].copy(), d[:n].copy(), stats, [int(e) for e in ent if e != np.uint64(0xFFFFFFFFFFFFFFFF)]
+
+    @property
+    def rng_state(self) -> int:
+        return int(_lib.vo_hnsw_rng_state(self._h))
+
+    @rng_state.setter
+    def rng_state(self, s: int) -> None:
+        _lib.vo_hnsw_set_rng_state(self._h, s)
 
     def search_batch(self, qs, k, ef, order="canonical", threads=1):
         qs = _f32(qs)

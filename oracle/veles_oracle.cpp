@@ -735,6 +735,33 @@ struct Hnsw {
         return id;
     }
 
+    // graph.rs:288-348.  Advances rng_state like the reference's fetch_update; `used` receives the entry points.
+    std::vector<DN> search_multi_entry(const float* q, size_t k, size_t ef, size_t probes, int order_mode, SearchStats* st,
+                                       std::vector<uint64_t>* used) {
+        std::vector<DN> out;
+        if (!has_ep || n == 0) return out;
+        uint64_t cur = ep;
+        for (uint32_t l = max_layer; l >= 1; --l) cur = search_layer_single(q, cur, l, st);
+        std::vector<uint64_t> entries{cur};
+        if (probes > 1 && n > 10) {
+            for (size_t i = 1; i < std::min<size_t>(probes, 4); ++i) {
+                uint64_t s = rng_state;  // no zero replacement on this path (graph.rs:319-333)
+                s ^= s << 13;
+                s ^= s >> 7;
+                s ^= s << 17;
+                rng_state = s;
+                const uint64_t id = s % n;
+                if (std::find(entries.begin(), entries.end(), id) == entries.end()) entries.push_back(id);
+            }
+        }
+        if (used) *used = entries;
+        std::vector<DN> c = search_layer(q, entries, ef, 0, st);
+        if (order_mode == 1) std::sort(c.begin(), c.end(), DNLess());
+        if (st && c.size() > k && k > 0 && total_cmp(c[k - 1].d, c[k].d) == 0) st->tie_at_k = 1;
+        if (c.size() > k) c.resize(k);
+        return c;
+    }
+
     // graph.rs:251-270.  order_mode 0 = reference order (heap order among ties),
     // 1 = canonical (dist, id) order.
     std::vector<DN> search(const float* q, size_t k, size_t ef, int order_mode, SearchStats* st) const {
@@ -1140,6 +1167,30 @@ uint32_t vo_hnsw_search(void* h, const float* q, uint32_t k, uint32_t ef, int or
     }
     return (uint32_t)r.size();
 }
+
+// search_multi_entry; out_entries gets 4 slots (UINT64_MAX padded): the entry points actually used
+uint32_t vo_hnsw_search_multi_entry(void* h, const float* q, uint32_t k, uint32_t ef, uint32_t probes, int order_mode,
+                                    uint64_t* out_ids, float* out_dist, uint64_t* stats, uint64_t* out_entries) {
+    SearchStats st;
+    std::vector<uint64_t> used;
+    std::vector<DN> r = ((Hnsw*)h)->search_multi_entry(q, k, ef, probes, order_mode, &st, &used);
+    for (size_t i = 0; i < r.size(); ++i) {
+        out_ids[i] = r[i].n;
+        out_dist[i] = r[i].d;
+    }
+    for (size_t i = 0; i < 4; ++i) out_entries[i] = i < used.size() ? used[i] : UINT64_MAX;
+    if (stats) {
+        stats[0] = st.ndc0;
+        stats[1] = st.hops0;
+        stats[2] = st.ndc_up;
+        stats[3] = st.hops_up;
+        stats[4] = st.tie_at_k;
+        stats[5] = st.adj0;
+    }
+    return (uint32_t)r.size();
+}
+uint64_t vo_hnsw_rng_state(void* h) { return ((Hnsw*)h)->rng_state; }
+void vo_hnsw_set_rng_state(void* h, uint64_t s) { ((Hnsw*)h)->rng_state = s; }
 
 // rayon par_iter stand-in (index/hnsw/index/batch.rs:178-196): a static thread pool over queries.
 void vo_hnsw_search_batch(void* h, const float* q, uint64_t nq, uint32_t k, uint32_t ef, int order_mode, int threads,

@@ -302,3 +302,34 @@ def test_mapped_search_id_map_tombstones_and_filter():
         ids, sc, cnt = snap.search_batch_mapped(q, k, ef)
         ri, rd, rc = snap.search_batch(q, k, ef)
         assert np.array_equal(ids, ri.astype(np.uint64)) and np.array_equal(cnt, rc)
+
+
+@pytest.mark.parametrize("warps", ["1", "4"])
+def test_search_multi_entry_bit_exact(warps, monkeypatch):
+    # NativeHnsw::search_multi_entry (graph.rs:288-348): the oracle draws the probes from its xorshift state, the
+    # host helper reproduces the draws, the device starts layer 0 from the same entry points
+    from velesdb_b200 import multi_entry_probes
+    monkeypatch.setenv("VELES_SEARCH_WARPS", warps)
+    for metric, dim in ((vo.COSINE, 96), (vo.EUCLIDEAN, 768)):
+        x, g, snap = graph_case(metric, dim, n=2000 if dim < 768 else 1200)
+        q = queries_near(x, 24, seed=31)
+        n = len(x)
+        for probes, k, ef in ((3, 10, 64), (4, 5, 16), (2, 10, 100), (1, 10, 64)):
+            state = g.rng_state
+            rows, want = [], []
+            for r in range(len(q)):
+                row, state = multi_entry_probes(state, n, probes)
+                rows.append(row)
+                ids, d, st, ent = g.search_multi_entry(q[r], k, ef, probes, order="canonical")
+                assert set(ent[1:]) <= set(row)
+                want.append((ids, d, st))
+            assert state == g.rng_state
+            ids, dist, cnt, st = snap.search_batch_multi_entry(q, k, ef, np.array(rows, np.uint32), with_stats=True)
+            for r, (oi, od, ost) in enumerate(want):
+                assert cnt[r] == len(oi)
+                if not ost["tie_at_k"]:
+                    assert ids[r, :len(oi)].tolist() == oi.tolist(), (metric, probes, r)
+                assert bits_equal(dist[r, :len(oi)], od)
+                assert (st[r, 0], st[r, 1]) == (ost["ndc0"], ost["hops0"])
+    with pytest.raises(Exception, match="ef >= 4"):
+        snap.search_batch_multi_entry(q, 2, 2, np.full((len(q), 3), 0xFFFFFFFF, np.uint32))

@@ -501,3 +501,32 @@ def test_dual_precision_int8_recall_vs_f32():
     r = dp.search_with_config(vs[0], 10, 100, min_index_size=0, order="canonical", with_stats=True)
     if not r[2]["tie_at_k"]:
         assert np.array_equal(r[0], i_ids)
+
+
+def test_search_multi_entry_known_answers():
+    # native/tests.rs:217-256
+    g = vo.Hnsw(vo.COSINE, 32, M=16, ef_construction=100)
+    for i in range(50):
+        g.insert(np.array([math.sin((i + j) * 0.01) for j in range(32)], F))
+    q = np.array([math.sin(j * 0.01) for j in range(32)], F)
+    s0 = g.rng_state
+    ids, d, st, ent = g.search_multi_entry(q, 5, 50, 3)
+    assert 0 < len(ids) <= 5 and (np.diff(d) >= 0).all()
+    assert 1 <= len(ent) <= 3 and g.rng_state != s0          # two draws advanced the shared state
+    from velesdb_b200 import multi_entry_probes
+    row, s2 = multi_entry_probes(s0, 50, 3)
+    assert s2 == g.rng_state and set(ent[1:]) <= set(row)      # the host helper follows the same stream
+    g2 = vo.Hnsw(vo.EUCLIDEAN, 32, M=16, ef_construction=100)
+    for i in range(30):
+        g2.insert(np.array([(i + j) * 0.1 for j in range(32)], F))
+    q2 = np.array([j * 0.05 for j in range(32)], F)
+    std_ids, _ = g2.search(q2, 5, 50)
+    mi, _, _, _ = g2.search_multi_entry(q2, 5, 50, 2)
+    assert len(std_ids) > 0 and len(mi) > 0 and mi[0] == std_ids[0]   # ef covers the whole graph: same best hit
+    # count <= 10 or a single probe: no draw, same as the standard search
+    g3 = vo.Hnsw(vo.EUCLIDEAN, 4, M=8, ef_construction=20)
+    for i in range(8):
+        g3.insert(np.array([i, 0, 0, 1], F))
+    s3 = g3.rng_state
+    a, _, _, ent3 = g3.search_multi_entry(np.array([2.2, 0, 0, 1], F), 3, 16, 4)
+    assert g3.rng_state == s3 and len(ent3) == 1 and a.tolist() == g3.search(np.array([2.2, 0, 0, 1], F), 3, 16)[0].tolist()

@@ -60,6 +60,7 @@ SYMBOLS = [
     ("veles_index_sq8_export", _i32, [_vp, _vp, _vp, _vp, _vp]),
     ("veles_search_batch_sq8", _i32, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     ("veles_search_batch_sq8_d", _i32, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
+    ("veles_search_batch_multi_entry", _i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     ("veles_index_set_id_map", _i32, [_vp, _vp, _vp]),
     ("veles_search_batch_mapped", _i32, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
 ]

@@ -21,7 +21,8 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
 }
 
 int32_t launch_search(const veles_index* ix, const IndexView& view, const float* q_d, uint32_t nq, uint32_t k, uint32_t ef,
-                      uint32_t* ids_d, float* dist_d, uint32_t* cnt_d, uint32_t* stats_d, cudaStream_t st) {
+                      uint32_t* ids_d, float* dist_d, uint32_t* cnt_d, uint32_t* stats_d, cudaStream_t st,
+                      const uint32_t* extra_entries_d) {
     VELES_REQUIRE(ix->has_graph, "snapshot has no graph; build or load one first");
     VELES_REQUIRE(view.dtype != VELES_SQ8 || ix->dim <= 32768, "SQ8 traversal supports at most 32768 dimensions");
     VELES_REQUIRE(k >= 1 && k <= 65536, "k must be in 1..65536, got %u", k);
@@ -39,6 +40,7 @@ int32_t launch_search(const veles_index* ix, const IndexView& view, const float*
     p.out_dist = dist_d;
     p.out_counts = cnt_d;
     p.out_stats = stats_d;
+    p.extra_entries = extra_entries_d;
 
     // shared-memory carve: [control words] results | todo | [distances, multi-warp only] | query | per warp: barriers + ring
     const uint32_t bar_bytes = kMaxSlots * 8;
@@ -208,6 +210,34 @@ int32_t veles_search_batch(const veles_index_t* idx, const float* queries, uint3
     VELES_CUDA(cudaMemcpyAsync(idx->q_d.p, queries, qb, cudaMemcpyHostToDevice, st));
     VELES_TRY(launch_search(idx, idx->view(), idx->q_d.as<float>(), nq, k, ef, idx->out_ids_d.as<uint32_t>(), idx->out_val_d.as<float>(),
                             idx->out_cnt_d.as<uint32_t>(), out_stats ? idx->out_stats_d.as<uint32_t>() : nullptr, st));
+    VELES_CUDA(cudaMemcpyAsync(out_node_ids, idx->out_ids_d.p, ob, cudaMemcpyDeviceToHost, st));
+    VELES_CUDA(cudaMemcpyAsync(out_raw_dist, idx->out_val_d.p, ob, cudaMemcpyDeviceToHost, st));
+    VELES_CUDA(cudaMemcpyAsync(out_counts, idx->out_cnt_d.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    if (out_stats) VELES_CUDA(cudaMemcpyAsync(out_stats, idx->out_stats_d.p, (size_t)nq * 16, cudaMemcpyDeviceToHost, st));
+    return check_search_error_flag(idx, st);
+}
+
+int32_t veles_search_batch_multi_entry(const veles_index_t* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
+                                       const uint32_t* extra_entries, uint32_t* out_node_ids, float* out_raw_dist,
+                                       uint32_t* out_counts, uint32_t* out_stats, void* stream) {
+    VELES_REQUIRE(idx != nullptr, "index is NULL");
+    VELES_REQUIRE(nq == 0 || (queries && extra_entries && out_node_ids && out_raw_dist && out_counts), "NULL buffer");
+    VELES_REQUIRE(ef >= 4, "multi-entry search needs ef >= 4 (every entry point enters the result set), got %u", ef);
+    if (nq == 0) return VELES_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> g(idx->mu);
+    const size_t qb = (size_t)nq * idx->dim * 4, ob = (size_t)nq * k * 4;
+    VELES_TRY(idx->q_d.ensure(qb));
+    VELES_TRY(idx->out_ids_d.ensure(ob));
+    VELES_TRY(idx->out_val_d.ensure(ob));
+    VELES_TRY(idx->out_cnt_d.ensure((size_t)nq * 4));
+    VELES_TRY(idx->extra_d.ensure((size_t)nq * 12));
+    if (out_stats) VELES_TRY(idx->out_stats_d.ensure((size_t)nq * 16));
+    VELES_CUDA(cudaMemcpyAsync(idx->q_d.p, queries, qb, cudaMemcpyHostToDevice, st));
+    VELES_CUDA(cudaMemcpyAsync(idx->extra_d.p, extra_entries, (size_t)nq * 12, cudaMemcpyHostToDevice, st));
+    VELES_TRY(launch_search(idx, idx->view(), idx->q_d.as<float>(), nq, k, ef, idx->out_ids_d.as<uint32_t>(), idx->out_val_d.as<float>(),
+                            idx->out_cnt_d.as<uint32_t>(), out_stats ? idx->out_stats_d.as<uint32_t>() : nullptr, st,
+                            idx->extra_d.as<uint32_t>()));
     VELES_CUDA(cudaMemcpyAsync(out_node_ids, idx->out_ids_d.p, ob, cudaMemcpyDeviceToHost, st));
     VELES_CUDA(cudaMemcpyAsync(out_raw_dist, idx->out_val_d.p, ob, cudaMemcpyDeviceToHost, st));
     VELES_CUDA(cudaMemcpyAsync(out_counts, idx->out_cnt_d.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));

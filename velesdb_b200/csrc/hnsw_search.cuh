@@ -44,6 +44,7 @@ struct SearchParams {
     float* out_dist;
     uint32_t* out_counts;
     uint32_t* out_stats;  // may be null
+    const uint32_t* extra_entries;  // nq x 3 extra layer-0 entry points (INVALID padded), or null
     uint32_t* visited;    // slots x vis_words
     uint32_t* vlog;       // slots x kLogCap
     uint64_t* tie;        // slots x kTieCap
@@ -801,25 +802,107 @@ __global__ void __launch_bounds__(COOP ? 256 : 32, 1) hnsw_search_kernel(const S
                 }
             };
             bool full = false;  // len >= ef
-            {
-                if (leader) {
-                    const uint32_t bit = 1u << (cur & 31);
-                    if (lane == 0) {
-                        atomicOr(&vis[cur >> 5], bit);
-                        vlog[0] = cur;
-                        c.todo[0] = cur;
+            // the exact, order-dependent accept step of search_layer (graph.rs:499-515) for one evaluated neighbour
+            auto accept = [&](uint32_t id, float d) {
+                if (d < worst || !full) {
+                    const uint64_t key = make_key(d, id);
+                    const uint32_t pos = res.lower_bound(len, key);
+                    if (!full) {
+                        res.insert(pos, len + 1, ef, key);
+                        ++len;
+                        full = len >= ef;
+                        worst = key_dist(res.get(len - 1));
+                        if (pos <= nxt) {
+                            nxt = pos;
+                            learn(id);
+                        } else if (nxt == len - 1) {
+                            // there was no unexpanded entry: the new one (at pos) is now the first
+                            nxt = pos;
+                            learn(id);
+                        }
+                    } else {
+                        const uint64_t ev = res.get(len - 1);
+                        __syncwarp();
+                        res.insert(pos, len, ef, key);
+                        const float nworst = key_dist(res.get(len - 1));
+                        worst = nworst;
+                        // ties that are now farther than the worst result can only end the loop: drop them
+                        if (tlen > 0) {
+                            uint32_t w = 0;
+                            for (uint32_t base = 0; base < tlen; base += 32) {
+                                const uint32_t i = base + lane;
+                                uint64_t v = 0;
+                                bool keep = false;
+                                if (i < tlen) {
+                                    v = tie[i];
+                                    keep = !(key_dist(v) > nworst);
+                                }
+                                const uint32_t msk = __ballot_sync(FULL_MASK, keep);
+                                __syncwarp();
+                                if (keep) tie[w + __popc(msk & ((1u << lane) - 1u))] = v;
+                                w += __popc(msk);
+                                __syncwarp();
+                            }
+                            tlen = w;
+                        }
+                        if ((ev & 1ull) == 0 && !(key_dist(ev) > nworst)) {
+                            if (tlen < kTieCap) {
+                                if (lane == 0) tie[tlen] = ev;
+                                ++tlen;
+                            } else if (lane == 0) {
+                                atomicExch(&p.counters[1], 1u);
+                            }
+                            __syncwarp();
+                        }
+                        // index of the first unexpanded entry after the shift (the last entry fell off)
+                        if (pos <= nxt) {
+                            nxt = pos;
+                            learn(id);
+                        } else if (nxt >= len) {
+                            nxt = pos;
+                            learn(id);
+                        }
                     }
                 }
-                logn = 1;
-                bcast(1u);
-                float d0 = 0.0f;
-                eval(1u, always, [&](uint32_t, float d) { d0 = d; }, no_tick);
-                ++ndc0;
+            };
+            {
+                // entry points of the layer-0 search: the greedy descent's result, plus the caller's extra probes
+                // for NativeHnsw::search_multi_entry (graph.rs:288-348), duplicates dropped as `contains` does
+                uint32_t m0 = 1;
                 if (leader) {
-                    res.set(0, make_key(d0, cur));
-                    len = 1;
-                    full = len >= ef;
-                    worst = d0;
+                    if (lane == 0) {
+                        c.todo[0] = cur;
+                        if (p.extra_entries) {
+                            for (uint32_t e = 0; e < 3; ++e) {
+                                const uint32_t x = p.extra_entries[(size_t)qi * 3 + e];
+                                bool dup = x == VELES_INVALID_ID || x >= p.ix.n;
+                                for (uint32_t i = 0; i < m0 && !dup; ++i) dup = c.todo[i] == x;
+                                if (!dup) c.todo[m0++] = x;
+                            }
+                        }
+                        for (uint32_t i = 0; i < m0; ++i) {
+                            const uint32_t x = c.todo[i];
+                            atomicOr(&vis[x >> 5], 1u << (x & 31));
+                            vlog[i] = x;
+                        }
+                    }
+                    m0 = __shfl_sync(FULL_MASK, m0, 0);
+                }
+                m0 = bcast(m0);
+                logn = m0;
+                ndc0 += m0;
+                if (m0 == 1) {
+                    float d0 = 0.0f;
+                    eval(1u, always, [&](uint32_t, float d) { d0 = d; }, no_tick);
+                    if (leader) {
+                        res.set(0, make_key(d0, cur));
+                        len = 1;
+                        full = len >= ef;
+                        worst = d0;
+                        __syncwarp();
+                    }
+                } else {
+                    eval(m0, always, accept, no_tick);  // every entry enters both heaps (graph.rs:452-458); host checks ef >= 4
                     __syncwarp();
                 }
             }
@@ -880,71 +963,7 @@ __global__ void __launch_bounds__(COOP ? 256 : 32, 1) hnsw_search_kernel(const S
                     pre_peeked = false;  // this expansion's marking invalidates any earlier peek
                     if (nxt < len) learn(key_id(res.get(nxt)));
                 }
-                eval(
-                    m, [&](float d) { return d < worst || !full; },
-                    [&](uint32_t id, float d) {
-                    if (d < worst || !full) {
-                        const uint64_t key = make_key(d, id);
-                        const uint32_t pos = res.lower_bound(len, key);
-                        if (!full) {
-                            res.insert(pos, len + 1, ef, key);
-                            ++len;
-                            full = len >= ef;
-                            worst = key_dist(res.get(len - 1));
-                            if (pos <= nxt) {
-                                nxt = pos;
-                                learn(id);
-                            } else if (nxt == len - 1) {
-                                // there was no unexpanded entry: the new one (at pos) is now the first
-                                nxt = pos;
-                                learn(id);
-                            }
-                        } else {
-                            const uint64_t ev = res.get(len - 1);
-                            __syncwarp();
-                            res.insert(pos, len, ef, key);
-                            const float nworst = key_dist(res.get(len - 1));
-                            worst = nworst;
-                            // ties that are now farther than the worst result can only end the loop: drop them
-                            if (tlen > 0) {
-                                uint32_t w = 0;
-                                for (uint32_t base = 0; base < tlen; base += 32) {
-                                    const uint32_t i = base + lane;
-                                    uint64_t v = 0;
-                                    bool keep = false;
-                                    if (i < tlen) {
-                                        v = tie[i];
-                                        keep = !(key_dist(v) > nworst);
-                                    }
-                                    const uint32_t msk = __ballot_sync(FULL_MASK, keep);
-                                    __syncwarp();
-                                    if (keep) tie[w + __popc(msk & ((1u << lane) - 1u))] = v;
-                                    w += __popc(msk);
-                                    __syncwarp();
-                                }
-                                tlen = w;
-                            }
-                            if ((ev & 1ull) == 0 && !(key_dist(ev) > nworst)) {
-                                if (tlen < kTieCap) {
-                                    if (lane == 0) tie[tlen] = ev;
-                                    ++tlen;
-                                } else if (lane == 0) {
-                                    atomicExch(&p.counters[1], 1u);
-                                }
-                                __syncwarp();
-                            }
-                            // index of the first unexpanded entry after the shift (the last entry fell off)
-                            if (pos <= nxt) {
-                                nxt = pos;
-                                learn(id);
-                            } else if (nxt >= len) {
-                                nxt = pos;
-                                learn(id);
-                            }
-                        }
-                    }
-                    },
-                    tick);
+                eval(m, [&](float d) { return d < worst || !full; }, accept, tick);
                 __syncwarp();
             }
 

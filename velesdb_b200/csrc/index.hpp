@@ -34,7 +34,7 @@ struct veles_index {
 
     // node index -> external id, live (not tombstoned) bitmap: ShardedMappings on the device (postfilter.cu)
     veles::DevBuf id_map_d, live_d;
-    mutable veles::DevBuf allow_d, map_ids_d, map_score_d;
+    mutable veles::DevBuf allow_d, map_ids_d, map_score_d, extra_d;
 
     // search scratch, sized lazily and reused; guarded by `mu`
     mutable std::mutex mu;
@@ -93,6 +93,7 @@ int32_t install_graph_host(veles_index* ix, uint32_t num_layers, const uint64_t*
 int device_sm_count();
 // batched traversal over `view` (the snapshot's own rows, or its SQ8 codes); hnsw_search.cu
 int32_t launch_search(const veles_index* ix, const IndexView& view, const float* q_d, uint32_t nq, uint32_t k,
-                      uint32_t ef, uint32_t* ids_d, float* dist_d, uint32_t* cnt_d, uint32_t* stats_d, cudaStream_t st);
+                      uint32_t ef, uint32_t* ids_d, float* dist_d, uint32_t* cnt_d, uint32_t* stats_d, cudaStream_t st,
+                      const uint32_t* extra_entries_d = nullptr);
 int32_t check_search_error_flag(const veles_index* ix, cudaStream_t st);
 }  // namespace veles

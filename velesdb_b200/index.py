@@ -233,6 +233,20 @@ class DeviceSnapshot:
         nv.check(nv.lib().veles_search_batch_sq8_d(self.h, nv.ptr(q_t), q_t.shape[0], k, ef_search, oversampling,
                                                    nv.ptr(ids_t), nv.ptr(dist_t), nv.ptr(cnt_t), nv.ptr(stats_t), stream))
 
+    # -- NativeHnsw::search_multi_entry (native/graph.rs:288-348)
+    def search_batch_multi_entry(self, queries, k, ef, extra_entries, with_stats=False, stream=None):
+        """extra_entries: [nq, 3] node ids (INVALID padded) added to the greedy result as layer-0 entry points."""
+        q = _as_f32_2d(queries, self.dim, "Query")
+        nq = q.shape[0]
+        ex = np.ascontiguousarray(extra_entries, dtype=np.uint32).reshape(nq, 3)
+        ids = np.empty((nq, k), dtype=np.uint32)
+        dist = np.empty((nq, k), dtype=np.float32)
+        cnt = np.zeros(nq, dtype=np.uint32)
+        st = np.zeros((nq, 4), dtype=np.uint32) if with_stats else None
+        nv.check(nv.lib().veles_search_batch_multi_entry(self.h, nv.ptr(q), nq, k, ef, nv.ptr(ex), nv.ptr(ids), nv.ptr(dist),
+                                                         nv.ptr(cnt), nv.ptr(st), stream))
+        return (ids, dist, cnt, st) if with_stats else (ids, dist, cnt)
+
     # -- id map, tombstones, filtered search (ShardedMappings on the device)
     def set_id_map(self, ext_ids=None, live_bits=None):
         """ext_ids: u64[n] external id per node (None = identity); live_bits: one bit per node, 0 = removed."""
@@ -269,6 +283,21 @@ class DeviceSnapshot:
 
     def dump(self, directory, basename="native_hnsw"):
         nv.check(nv.lib().veles_index_dump(self.h, os.fsencode(directory), basename.encode()))
+
+
+def multi_entry_probes(rng_state: int, count: int, num_probes: int):
+    """The extra entry points NativeHnsw::search_multi_entry draws (graph.rs:313-340): xorshift64 (13, 7, 17) on the
+    shared state, `state % count`, only when count > 10 and num_probes > 1, at most 3 draws.  Returns the three-slot
+    row for veles_search_batch_multi_entry (INVALID padded) and the advanced state, which the caller keeps."""
+    m64 = (1 << 64) - 1
+    row = [nv.INVALID_ID] * 3
+    if num_probes > 1 and count > 10:
+        for i in range(min(num_probes, 4) - 1):
+            rng_state ^= (rng_state << 13) & m64
+            rng_state ^= rng_state >> 7
+            rng_state ^= (rng_state << 17) & m64
+            row[i] = rng_state % count
+    return row, rng_state
 
 
 def distance_pairs(metric, a, b, as_metric_value=False):
