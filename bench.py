@@ -293,7 +293,7 @@ def main():
         nv.check(nv.lib().veles_search_batch(snap.h, nv.ptr(qn), a.nq, a.k, a.ef, nv.ptr(out_ids), nv.ptr(out_dist),
                                              nv.ptr(out_cnt), None, stream))
 
-    for _ in range(3):
+    for _ in range(max(a.warmup, 5)):  # untimed: first touches of the pinned buffers, allocator and driver caches
         step_e2e()
     torch.cuda.synchronize()
     if use_dist:
