@@ -155,3 +155,23 @@ def test_search_with_filter_overfetch_and_order():
     search_with_filter(ix, x[5], 40, odd)
     assert snap.calls[-1] == ("search", 160, 640)
     assert [overfetch_k(k) for k in (10, 50, 100, 200)] == [200, 500, 500, 400]   # collection/search/batch.rs:270-275
+
+
+def test_vacuum_and_sequential_batch_bookkeeping():
+    # vacuum.rs:45-190, batch.rs:120-139: host-side state only (the snapshot is rebuilt lazily on the next search)
+    from velesdb_b200 import VacuumError
+    ix, snap, x, ids = make_index(n=120)
+    for e in ids[:30]:
+        assert ix.remove(e)
+    assert not ix.remove(ids[0])
+    assert ix.len() == 90 and ix.tombstone_count() == 30 and ix.needs_vacuum()
+    assert ix.vacuum() == 90
+    assert ix.len() == 90 and ix.tombstone_count() == 0 and not ix.needs_vacuum() and ix._dirty and ix._bulk
+    assert sorted(ix._id_to_idx) == sorted(ids[30:]) and sorted(ix._idx_to_id) == list(range(90))
+    assert all(np.array_equal(ix._staged[ix._id_to_idx[e]], x[i]) for i, e in enumerate(ids) if i >= 30)
+    ix2 = HnswIndex(16, DistanceMetric.Cosine, enable_vector_storage=False)
+    with pytest.raises(VacuumError, match="VectorStorageDisabled"):
+        ix2.vacuum()
+    ix3 = HnswIndex(16, DistanceMetric.Cosine)
+    assert ix3.vacuum() == 0
+    assert ix3.insert_batch_sequential([(1, x[0]), (2, x[1]), (1, x[2])]) == 2 and not ix3._bulk

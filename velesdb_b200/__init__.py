@@ -12,8 +12,8 @@ from .dual_precision import DualPrecisionConfig, DualPrecisionHnsw
 from .fusion import (FusionError, FusionStrategy, hybrid_search, multi_query_search, overfetch_k, rrf_hybrid_batch,
                      search_with_filter)
 from .index import (DeviceSnapshot, DimensionMismatch, DistanceMetric, HnswIndex, HnswParams, SearchQuality,
-                    distance_pairs, multi_entry_probes)
+                    VacuumError, distance_pairs, multi_entry_probes)
 
 __all__ = ["DualPrecisionConfig", "DualPrecisionHnsw", "Bm25Index", "Bm25Params", "Bm25Snapshot", "FusionError", "FusionStrategy", "hybrid_search", "multi_query_search", "overfetch_k", "search_with_filter",
            "rrf_hybrid_batch", "tokenize", "DeviceSnapshot", "DimensionMismatch", "DistanceMetric", "HnswIndex", "HnswParams", "SearchQuality",
-           "VelesError", "distance_pairs", "multi_entry_probes", "_native"]
+           "VacuumError", "VelesError", "distance_pairs", "multi_entry_probes", "_native"]

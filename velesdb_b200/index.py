@@ -66,6 +66,10 @@ class HnswParams:
         return HnswParams(24, 300) if dimension <= 256 else HnswParams(32, 400)
 
 
+class VacuumError(RuntimeError):
+    """index/hnsw/index/vacuum.rs:17-29"""
+
+
 class DimensionMismatch(ValueError):
     pass
 
@@ -395,6 +399,16 @@ class HnswIndex:
             count += len(self._id_to_idx) - before
         return count
 
+    def insert_batch_sequential(self, vectors) -> int:
+        """index/hnsw/index/batch.rs:120-139 (deprecated in the reference): one NativeHnsw::insert per new vector,
+        in order -- the exact sequential builder's path here."""
+        count = 0
+        for id, v in vectors:
+            before = len(self._id_to_idx)
+            self.insert(id, v)
+            count += len(self._id_to_idx) - before
+        return count
+
     def remove(self, id) -> bool:
         """Soft delete (trait_impl.rs:54-58): the mapping goes, the node stays in the graph."""
         idx = self._id_to_idx.pop(id, None)
@@ -514,6 +528,28 @@ class HnswIndex:
 
     def needs_vacuum(self) -> bool:
         return self.tombstone_ratio() > 0.2
+
+    def vacuum(self) -> int:
+        """index/hnsw/index/vacuum.rs:110-190: rebuild from the live vectors only -- new graph with
+        HnswParams::auto, `parallel_insert` (the bulk builder here), fresh dense node indices -- and return how many
+        vectors it kept.  The reference walks its DashMap (unspecified order); here live vectors keep their relative
+        insertion order.  The device snapshot is rebuilt on the next search."""
+        if not self.enable_vector_storage:
+            raise VacuumError("VectorStorageDisabled")
+        if not self._vectors_present:
+            return 0  # ShardedVectors is empty after load(): nothing is collected (vacuum.rs:116-126)
+        live = sorted(self._idx_to_id.items())
+        if not live:
+            return 0
+        self._staged = [self._staged[idx] for idx, _ in live]
+        self._idx_to_id = {i: e for i, (_, e) in enumerate(live)}
+        self._id_to_idx = {e: i for i, e in self._idx_to_id.items()}
+        self._next_idx = len(live)
+        self._params = HnswParams.auto(self._dimension)
+        self._bulk = True
+        self._dirty = True
+        self._map_dirty = True
+        return len(live)
 
     # ---- internals
     def _materialise_staged(self):
