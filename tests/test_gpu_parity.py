@@ -80,7 +80,7 @@ def test_bruteforce_few_queries_scan_path(metric, store):
         x[n // 2] = x[7]  # an exact duplicate: equal scores, ordered by id
         snap = DeviceSnapshot.from_vectors(x, metric, store_dtype=store)
         xo = x.astype(np.float16).astype(np.float32) if store == "f16" else x
-        for nq in (1, 2, 3, 5, 8):
+        for nq in (1, 2, 3, 5, 8, 20, 45):  # > 8: the tile kernels (shared-memory staged when dim % 128 == 0)
             q = queries_near(x, nq, seed=nq)
             q[0] = x[7]
             for k in (1, 10, 100):

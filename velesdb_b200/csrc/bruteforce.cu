@@ -248,6 +248,119 @@ __global__ void __launch_bounds__(kWarps * 32, 2) bf_tile8_kernel(IndexView ix, 
     }
 }
 
+// ---- many queries, dim % 128 == 0: rows staged in shared memory ------------------------------------------------
+// Same 8 x 8 register tile and lane <-> element-class mapping as bf_tile8_kernel, but a CTA (8 warps = 4 query
+// groups x 2 row groups) shares its operands: its 32 queries stay in shared memory for the CTA's lifetime and the
+// 16 rows of a tile stream through a double-buffered 128-element slab filled by per-thread 16-byte async copies
+// one slab ahead.  Every operand read in the FMA loop is then a conflict-free LDS with a short, hidden latency
+// (bf_tile8_kernel waits on L2 for its rows: 19 TFLOP/s), and a row element is fetched from L2 once per 32
+// queries instead of once per 8.  Arithmetic, summation order and results are unchanged.
+constexpr int kTsQ = 32, kTsR = 16, kTsK = 128;
+template <typename TB>
+__global__ void __launch_bounds__(kWarps * 32, 2) bf_tile_smem_kernel(IndexView ix, const float* __restrict__ queries,
+                                                                   uint32_t nq, float* __restrict__ scores, bool as_value) {
+    extern __shared__ __align__(16) uint8_t ts_smem[];
+    const uint32_t dim = ix.dim;
+    float* qs_all = reinterpret_cast<float*>(ts_smem);               // kTsQ x dim
+    float* qnorm_all = qs_all + (size_t)kTsQ * dim;                  // kTsQ
+    TB* slab = reinterpret_cast<TB*>(qnorm_all + kTsQ);              // 2 x kTsR x kTsK
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t cta_q0 = blockIdx.y * kTsQ;
+    const uint32_t cta_nq = min((uint32_t)kTsQ, nq - cta_q0);
+    for (uint32_t i = threadIdx.x; i < kTsQ * dim; i += blockDim.x) {
+        const uint32_t t = i / dim;
+        qs_all[i] = t < cta_nq ? queries[(size_t)(cta_q0 + t) * dim + (i - t * dim)] : 0.0f;
+    }
+    __syncthreads();
+    if (ix.metric == VELES_COSINE) {
+        for (uint32_t t = warp; t < kTsQ; t += kWarps) {
+            const float* q = qs_all + (size_t)t * dim;
+            const float s = warp_tree_reduce<0>(q, q, dim, lane);
+            if (lane == 0) qnorm_all[t] = __fsqrt_rn(s);
+        }
+    }
+    __syncthreads();
+    const uint32_t qg = warp & 3, rg = warp >> 2;
+    const float* qs = qs_all + (size_t)qg * kQT * dim;
+    const float* qnorm = qnorm_all + qg * kQT;
+    const uint32_t qbase = cta_q0 + qg * kQT;
+    const uint32_t nqt = qbase < nq ? min((uint32_t)kQT, nq - qbase) : 0u;
+    const bool l2 = ix.metric == VELES_EUCLIDEAN;
+    const uint64_t n = ix.n;
+    const uint64_t tiles = (n + kTsR - 1) / kTsR;
+    const uint32_t nslab = dim / kTsK;
+    constexpr uint32_t kChunksPerRow = kTsK * sizeof(TB) / 16;       // 16-byte chunks of one row's slab
+    constexpr uint32_t kChunks = kTsR * kChunksPerRow;               // per slab: 512 (f32) or 256 (f16)
+    const uint32_t a = (lane & 1) | (lane & 2) | (lane & 4) | ((lane & 16) >> 1) | ((lane & 8) << 1);
+    const uint32_t my_r = a >> 3, my_t = a & 7;
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint64_t r0 = tile * kTsR;
+        auto load_slab = [&](uint32_t s, uint32_t buf) {
+            for (uint32_t c = threadIdx.x; c < kChunks; c += blockDim.x) {
+                const uint32_t row = c / kChunksPerRow, off = c % kChunksPerRow;
+                const uint64_t rr = min(r0 + row, n - 1);  // rows past the end alias the last row, never stored
+                const uint8_t* src = ix.vecs + rr * ix.row_bytes + (size_t)s * kTsK * sizeof(TB) + off * 16;
+                uint8_t* dst = reinterpret_cast<uint8_t*>(slab + ((size_t)buf * kTsR + row) * kTsK) + off * 16;
+                cp_async16(dst, src);
+            }
+            cp_async_commit();
+        };
+        float acc[kRT8 * kQT];
+#pragma unroll
+        for (int j = 0; j < kRT8 * kQT; ++j) acc[j] = 0.0f;
+        load_slab(0, 0);
+        for (uint32_t s = 0; s < nslab; ++s) {
+            if (s + 1 < nslab) {
+                load_slab(s + 1, (s + 1) & 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();  // every thread's chunks of slab s have landed
+            const TB* xs = slab + ((size_t)(s & 1) * kTsR + rg * kRT8) * kTsK + lane;
+            const float* qp = qs + (size_t)s * kTsK + lane;
+#pragma unroll
+            for (int st = 0; st < kTsK / 32; ++st) {
+                float x[kRT8], q[kQT];
+#pragma unroll
+                for (int r = 0; r < kRT8; ++r) x[r] = load_elem(xs + r * kTsK, 32 * st);
+#pragma unroll
+                for (int t = 0; t < kQT; ++t) q[t] = qp[(size_t)t * dim + 32 * st];
+#pragma unroll
+                for (int r = 0; r < kRT8; ++r)
+#pragma unroll
+                    for (int t = 0; t < kQT; ++t) {
+                        if (l2) {
+                            const float d = __fsub_rn(q[t], x[r]);
+                            acc[r * kQT + t] = __fmaf_rn(d, d, acc[r * kQT + t]);
+                        } else {
+                            acc[r * kQT + t] = __fmaf_rn(q[t], x[r], acc[r * kQT + t]);
+                        }
+                    }
+            }
+            __syncthreads();  // buffer s & 1 is refilled by the load issued at the top of iteration s + 1
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const float sum = butterfly32(acc + half * 32, lane);
+            const uint64_t row = r0 + rg * kRT8 + half * 4 + my_r;
+            if (row < n && my_t < nqt) {
+                float v;
+                if (l2) {
+                    v = __fsqrt_rn(sum);
+                } else if (ix.metric == VELES_COSINE) {
+                    const float nb = *reinterpret_cast<const float*>(ix.vecs + row * ix.row_bytes + ix.norm_off);
+                    const float sim = cosine_from_parts(sum, qnorm[my_t], nb);
+                    v = as_value ? sim : __fsub_rn(1.0f, sim);
+                } else {
+                    v = as_value ? sum : -sum;
+                }
+                scores[(size_t)(qbase + my_t) * n + row] = v;
+            }
+        }
+    }
+}
+
 // ---- few queries (<= 8): the scan is HBM-bound, so it is laid out like a copy -----------------------------
 // "Quad" mapping of common.cuh: 8 lanes per row, lane t owns the reference accumulators 4t..4t+3 and reads
 // its row with one 128-bit load per 32 elements, so a warp-wide load covers 4 rows x 128 contiguous bytes.
@@ -705,6 +818,34 @@ static int32_t launch_scores(const veles_index* ix, const float* q_d, uint32_t n
             count_launch();
             VELES_CUDA(cudaGetLastError());
             return VELES_OK;
+        }
+        if (ix->dim % kTsK == 0 && nq >= 16 && std::getenv("VELES_BF_NO_SMEM_TILE") == nullptr) {
+            // many queries: operands staged in shared memory (bf_tile_smem_kernel)
+            const size_t tb = ix->dtype == VELES_F32 ? 4 : 2;
+            const size_t smem_t = ((size_t)kTsQ * ix->dim + kTsQ) * 4 + 2 * (size_t)kTsR * kTsK * tb;
+            int max_optin = 0, dev_id = 0;
+            VELES_CUDA(cudaGetDevice(&dev_id));
+            VELES_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev_id));
+            if (smem_t <= (size_t)max_optin) {
+                auto kt = ix->dtype == VELES_F32 ? bf_tile_smem_kernel<float> : bf_tile_smem_kernel<__half>;
+                VELES_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+                int per_sm = 1;
+                VELES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kt, kWarps * 32, smem_t));
+                const uint32_t qgroups = (nq + kTsQ - 1) / kTsQ;
+                const uint64_t tiles = (ix->n + kTsR - 1) / kTsR;
+                const uint64_t slots = (uint64_t)sms * std::max(per_sm, 1);
+                for (uint32_t g0 = 0; g0 < qgroups; g0 += 32768) {
+                    const uint32_t ng = std::min(32768u, qgroups - g0);
+                    const uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>(tiles, std::max<uint64_t>(1, slots / ng)));
+                    dim3 grid((unsigned)gx, ng);
+                    const uint32_t qoff = g0 * kTsQ;
+                    kt<<<grid, kWarps * 32, smem_t, st>>>(v, q_d + (size_t)qoff * ix->dim, nq - qoff, scores_d + (size_t)qoff * ix->n,
+                                                         as_value);
+                    count_launch();
+                }
+                VELES_CUDA(cudaGetLastError());
+                return VELES_OK;
+            }
         }
         if (ix->dim % 32 == 0) {
             // one query tile per CTA: sharing a row tile between the warps of a CTA (QW = 2, 4: one L2 read,
