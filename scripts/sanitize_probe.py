@@ -31,6 +31,15 @@ for dim, n in ((96, 1500), (100, 700)):
     h.build_graph(16)
     h.search_batch(q, 10, 64)
     h.bruteforce_batch(q[:2], 5)
+xs = rng.normal(size=(900, 128)).astype(np.float32)   # dim % 128 == 0: shared-memory staged brute-force tile
+for store in ("f32", "f16"):
+    t = DeviceSnapshot.from_vectors(xs, DistanceMetric.Cosine, store_dtype=store)
+    t.bruteforce_batch(xs[:37], 10)
+t = DeviceSnapshot.from_vectors(xs, DistanceMetric.Euclidean)
+t.build_graph(16)
+t.set_id_map(np.arange(900, dtype=np.uint64) + 7, np.full(29, 0xAAAAAAAA, np.uint32))
+t.search_batch_mapped(xs[:20], 5, 64, k_fetch=30, allow_bits=np.full(29, 0xF0F0F0F0, np.uint32))
+t.search_batch_multi_entry(xs[:20], 5, 32, np.tile(np.array([[3, 3, 800]], np.uint32), (20, 1)))
 small = DeviceSnapshot.from_vectors(x[:300], DistanceMetric.Euclidean)
 small.build_graph_exact(8, 40)
 small.search_batch(q, 5, 32)
