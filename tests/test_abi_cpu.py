@@ -74,3 +74,18 @@ def test_committed_bench_lines_follow_the_contract():
         c = j["cpu_baseline"]
         assert c["kind"] == "port" and c["cores"] >= 1 and c["ids_match_gpu"] is True
         assert not set(j["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_integration_md_ffi_block_matches_the_header():
+    # every `pub fn veles_*` INTEGRATION.md shows a maintainer exists in include/veles_b200.h with the same arity
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", open(os.path.join(root, "include", "veles_b200.h")).read(), flags=re.S)
+    rust = re.findall(r"pub fn (veles_\w+)\s*\((.*?)\)\s*->", md, flags=re.S)
+    assert len(rust) >= 20
+    for name, args in rust:
+        m = re.search(r"\b%s\s*\((.*?)\)\s*;" % name, hdr, flags=re.S)
+        assert m, f"{name} is in INTEGRATION.md but not in the header"
+        c_args = [a for a in m.group(1).split(",") if a.strip() and a.strip() != "void"]
+        r_args = [a for a in args.split(",") if a.strip()]
+        assert len(c_args) == len(r_args), (name, len(c_args), len(r_args))
