@@ -295,14 +295,23 @@ __global__ void __launch_bounds__(kWarps * 32, 2) bf_tile_smem_kernel(IndexView 
     const uint32_t my_r = a >> 3, my_t = a & 7;
     for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const uint64_t r0 = tile * kTsR;
+        // a thread copies the same (row, 16-byte column) chunks of every slab: addresses are set up once per tile
+        constexpr uint32_t kPerThread = (kChunks + kWarps * 32 - 1) / (kWarps * 32);  // 2 (f32) or 1 (f16)
+        const uint8_t* csrc[kPerThread];
+        uint32_t cdst[kPerThread];  // byte offset inside one slab buffer, ~0 = no chunk
+#pragma unroll
+        for (uint32_t i = 0; i < kPerThread; ++i) {
+            const uint32_t c = threadIdx.x + i * kWarps * 32;
+            const uint32_t row = c / kChunksPerRow, off = c % kChunksPerRow;
+            const uint64_t rr = min(r0 + row, n - 1);  // rows past the end alias the last row, never stored
+            csrc[i] = ix.vecs + rr * ix.row_bytes + off * 16;
+            cdst[i] = c < kChunks ? (uint32_t)((row * kTsK) * sizeof(TB) + off * 16) : ~0u;
+        }
         auto load_slab = [&](uint32_t s, uint32_t buf) {
-            for (uint32_t c = threadIdx.x; c < kChunks; c += blockDim.x) {
-                const uint32_t row = c / kChunksPerRow, off = c % kChunksPerRow;
-                const uint64_t rr = min(r0 + row, n - 1);  // rows past the end alias the last row, never stored
-                const uint8_t* src = ix.vecs + rr * ix.row_bytes + (size_t)s * kTsK * sizeof(TB) + off * 16;
-                uint8_t* dst = reinterpret_cast<uint8_t*>(slab + ((size_t)buf * kTsR + row) * kTsK) + off * 16;
-                cp_async16(dst, src);
-            }
+            uint8_t* base = reinterpret_cast<uint8_t*>(slab + (size_t)buf * kTsR * kTsK);
+#pragma unroll
+            for (uint32_t i = 0; i < kPerThread; ++i)
+                if (cdst[i] != ~0u) cp_async16(base + cdst[i], csrc[i] + (size_t)s * kTsK * sizeof(TB));
             cp_async_commit();
         };
         float acc[kRT8 * kQT];
