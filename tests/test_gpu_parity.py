@@ -333,3 +333,20 @@ def test_search_multi_entry_bit_exact(warps, monkeypatch):
                 assert (st[r, 0], st[r, 1]) == (ost["ndc0"], ost["hops0"])
     with pytest.raises(Exception, match="ef >= 4"):
         snap.search_batch_multi_entry(q, 2, 2, np.full((len(q), 3), 0xFFFFFFFF, np.uint32))
+
+
+@pytest.mark.parametrize("dim", [16, 17, 40, 100, 771])
+def test_hnsw_search_dims_with_tails_on_the_quad_path(dim, monkeypatch):
+    # dims that are not multiples of 32: 32-element blocks, then the reference's 8-wide and scalar tails
+    # (simd_avx512.rs:186-201) inside the four-rows-per-step evaluator, f32 and f16 rows, 1 and 4 warps per query
+    for metric in (vo.COSINE, vo.EUCLIDEAN, vo.DOT):
+        x, g, snap = graph_case(metric, dim, n=1200)
+        q = queries_near(x, 32, seed=dim)
+        for warps in ("1", "4"):
+            monkeypatch.setenv("VELES_SEARCH_WARPS", warps)
+            check_search(g, snap, q, 10, 64)
+        monkeypatch.delenv("VELES_SEARCH_WARPS")
+    xh = x.astype(np.float16).astype(np.float32)
+    gh = vo.Hnsw.from_arrays(vo.DOT, xh, g.export_graph(), g.M, g.M0, g.entry_point, g.max_layer)
+    sh = DeviceSnapshot.from_arrays(x, vo.DOT, g.export_graph(), g.M, g.M0, g.entry_point, g.max_layer, store_dtype="f16")
+    check_search(gh, sh, q, 10, 64)

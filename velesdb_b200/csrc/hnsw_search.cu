@@ -61,9 +61,10 @@ int32_t launch_search(const veles_index* ix, const IndexView& view, const float*
     VELES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int sm_smem = 0;
     VELES_CUDA(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
-    // Quad path: four candidates per step (8 lanes each) when the row splits into 32-element blocks.
+    // Quad path: four candidates per step (8 lanes each); f32 / f16 rows from 16 dimensions up (the reference's
+    // wide16 regime: 32-element blocks, then its 8-wide and scalar tails).
     const bool can_quad = (dtype == VELES_BIN1 && ix->dim % 128 == 0) || dtype == VELES_SQ8 ||
-                          ((dtype == VELES_F32 || dtype == VELES_F16) && ix->dim % 32 == 0 &&
+                          ((dtype == VELES_F32 || dtype == VELES_F16) && ix->dim >= 16 &&
                            (ix->metric == VELES_COSINE || ix->metric == VELES_EUCLIDEAN || ix->metric == VELES_DOT));
     p.quad = (can_quad && env_u32("VELES_SEARCH_QUAD", 1) != 0) ? 1 : 0;
     // packed rows of <= 128 bytes are read directly (no ring), see eval_list_bits

@@ -157,18 +157,47 @@ __device__ __forceinline__ void quad_block(const TB* __restrict__ r, const float
     }
 }
 
+// Main loop over the 32-element blocks (simd_avx512.rs:166-184), then -- when dim is not a multiple of 32 -- the
+// reference's tails on top of the reduced main-loop sum: whole 8-element blocks, each reduced with the f32x8
+// tree (the group's eight lanes are the eight SIMD lanes) and added, then the remaining elements one by one
+// (simd_avx512.rs:186-201; same arithmetic as warp_tree_tail).  All eight lanes of a group return the same value.
 template <bool L2, typename TB>
 __device__ __forceinline__ float quad_accumulate(const TB* __restrict__ r, const float* __restrict__ q, uint32_t dim,
                                                  uint32_t t) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const uint32_t main_len = dim & ~31u;
     uint32_t i = t * 4;
-    for (; i + 32 * 7 < dim; i += 32 * 8) quad_block<8, L2>(r, q, i, a0, a1, a2, a3);
-    for (; i + 32 * 3 < dim; i += 32 * 4) quad_block<4, L2>(r, q, i, a0, a1, a2, a3);
-    for (; i < dim; i += 32) quad_block<1, L2>(r, q, i, a0, a1, a2, a3);
-    return quad_tree_sum(a0, a1, a2, a3);
+    for (; i + 32 * 7 < main_len; i += 32 * 8) quad_block<8, L2>(r, q, i, a0, a1, a2, a3);
+    for (; i + 32 * 3 < main_len; i += 32 * 4) quad_block<4, L2>(r, q, i, a0, a1, a2, a3);
+    for (; i < main_len; i += 32) quad_block<1, L2>(r, q, i, a0, a1, a2, a3);
+    float result = quad_tree_sum(a0, a1, a2, a3);
+    if (main_len != dim) {
+        uint32_t pos = main_len;
+        for (; pos + 8 <= dim; pos += 8) {
+            const float x = q[pos + t], y = load_elem(r, pos + t);
+            float v;
+            if (L2) {
+                const float d = __fsub_rn(x, y);
+                v = __fmaf_rn(d, d, 0.0f);
+            } else {
+                v = __fmaf_rn(x, y, 0.0f);
+            }
+            result = __fadd_rn(result, warp_tree_sum8(v));  // xor 4, 2, 1 stay inside the 8-lane group
+        }
+        for (; pos < dim; ++pos) {
+            const float x = q[pos], y = load_elem(r, pos);
+            if (L2) {
+                const float d = __fsub_rn(x, y);
+                result = __fadd_rn(result, __fmul_rn(d, d));
+            } else {
+                result = __fadd_rn(result, __fmul_rn(x, y));
+            }
+        }
+    }
+    return result;
 }
 
-// distance of the row owned by this lane's group (dim % 32 == 0, dim >= 32)
+// distance of the row owned by this lane's group (f32 / f16 rows: dim >= 16, the reference's wide16 regime)
 template <int DT>
 __device__ __forceinline__ float quad_distance(const SearchParams& p, const WarpCtx& c, const uint8_t* row) {
     const uint32_t t = c.lane & 7;
