@@ -141,6 +141,25 @@ int32_t veles_search_batch_d(const veles_index_t* idx, const float* queries_d, u
                              uint32_t* out_node_ids_d, float* out_raw_dist_d, uint32_t* out_counts_d,
                              uint32_t* out_stats_d, void* stream);
 
+/* Outcome of the `_d` searches enqueued on `stream` so far.  `_d` calls only enqueue work, so a tie-list overflow
+ * (VELES_ERR_OVERFLOW: more than 4096 evicted candidates tied with the worst result of one query) cannot be returned
+ * by them; this call waits for `stream` and reports -- and clears -- it.  Every launch has its own scratch (visited
+ * bitmaps, tie lists, work counter), so `_d` calls on different streams and host-pointer calls from different host
+ * threads run concurrently on one index, as the reference's searches do under its read lock
+ * (index/hnsw/index/search.rs:59-94; HnswIndex is Send + Sync). */
+int32_t veles_search_status(const veles_index_t* idx, void* stream);
+
+/* Pipelined form of veles_search_batch for a serving loop (the rayon pool of
+ * HnswIndex::search_batch_parallel, index/hnsw/index/batch.rs:159-197, keeps every core busy across batches; this
+ * keeps the GPU busy across batches).  veles_search_submit enqueues the batch's H2D copy, the search and the D2H
+ * copies on a stream owned by the library and returns a ticket; veles_search_wait blocks until that batch's outputs
+ * are in the host buffers and returns its status.  Several tickets (up to 16) may be in flight: batch i+1's copies
+ * and first queries overlap batch i's last queries and copies back.  Buffers must stay valid until the wait; pinned
+ * host memory makes the copies asynchronous.  Results are identical to veles_search_batch. */
+int32_t veles_search_submit(const veles_index_t* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
+                            uint32_t* out_node_ids, float* out_raw_dist, uint32_t* out_counts, uint64_t* ticket);
+int32_t veles_search_wait(const veles_index_t* idx, uint64_t ticket);
+
 /* ---- brute force -------------------------------------------------------------------------- */
 /* HnswIndex::search_brute_force / brute_force_search_parallel (index/hnsw/index/search.rs:176-219,
  * batch.rs:223-244) for a batch: metric value (compute_distance, search.rs:30-38) against every
@@ -197,11 +216,14 @@ int32_t veles_fuse(int32_t strategy, const uint32_t* list_ptr, uint32_t n_lists,
 /* ---- graph construction (the path's producer) ---------------------------- */
 /* Bulk construction of the HNSW graph on the GPU for the vectors of `idx` -- the role of
  * HnswIndex::insert_batch_parallel (index/hnsw/index/batch.rs:82-108), whose result the reference
- * itself leaves order-dependent (rayon).  Levels follow the reference PRNG (graph.rs:368-403) in
- * node-id order, so level assignment and entry point equal the reference's; neighbour lists follow
- * select_neighbors (graph.rs:526-581) over the exact `cand_k` nearest nodes of each layer, plus
- * reverse links pruned closest-first (graph.rs:592-639).  Replaces any graph held by `idx`. */
-int32_t veles_index_build_graph(veles_index_t* idx, uint32_t M, uint32_t cand_k, void* stream);
+ * itself leaves order dependent (rayon).  Nodes are inserted in id order, a block at a time: every node of a
+ * block runs NativeHnsw::insert's searches (graph.rs:190-223: greedy descent, then search_layer with
+ * ef_construction on each of its layers) on the graph built so far -- layer 0 through the production search
+ * kernel -- then select_neighbors (graph.rs:526-581) and add_bidirectional_connection (graph.rs:592-639: a
+ * full row keeps its max_conn closest).  Levels follow the reference PRNG (graph.rs:368-403) in node-id
+ * order, so level assignment and entry point equal the reference's.  O(N log N); no library calls.
+ * ef_construction 0 = 200.  Replaces any graph held by `idx`. */
+int32_t veles_index_build_graph(veles_index_t* idx, uint32_t M, uint32_t ef_construction, void* stream);
 
 /* The reference's *sequential* construction, exactly: NativeHnsw::insert (native/graph.rs:158-237) for nodes
  * 0..n-1 in id order -- what HnswIndex::insert (index/hnsw/index/trait_impl.rs:10-36) builds, the one path on

@@ -147,6 +147,20 @@ def test_fusion_strategies_bit_exact():
     assert d1 > 0.04
 
 
+def test_fusion_of_ten_lists_of_five_hundred_disjoint_hits():
+    """multi_query_search allows 10 vectors x overfetch_k(top_k) = 500 hits each (collection/search/batch.rs:238,
+    270-275): 5000 distinct documents in one request must fuse, not overflow."""
+    rng = np.random.default_rng(9)
+    lists = [[(l * 500 + i, float(np.float32(1.0 - i / 600.0))) for i in range(500)] for l in range(10)]
+    lists[3] += [(7, 0.31), (1200, 0.5)]  # a few cross-list repeats
+    for st, (kind, kw) in ((FusionStrategy.RRF(60), (vo.RRF, {"rrf_k": 60})), (FusionStrategy.Average(), (vo.AVERAGE, {})),
+                           (FusionStrategy.weighted(0.6, 0.3, 0.1), (vo.WEIGHTED, {"avg_w": 0.6, "max_w": 0.3, "hit_w": 0.1}))):
+        got = st.fuse(lists)
+        oi, os_ = vo.fuse(kind, lists, **kw)
+        assert len(got) == 5000 and [g[0] for g in got] == oi.tolist()
+        assert bits_equal([g[1] for g in got], os_)
+
+
 def test_hybrid_search_end_to_end():
     # Collection::hybrid_search (text.rs:113-203): vector top-2k + BM25 top-2k -> RRF -> top-k
     from velesdb_b200 import DistanceMetric, HnswIndex

@@ -20,6 +20,7 @@ def test_host_mirror_cpp(tmp_path):
     assert "host mirror ok" in r.stdout
 
 
+@pytest.mark.gpu
 def test_vacuum_rebuilds_a_searchable_index():
     # index/hnsw/index/vacuum.rs:110-190 end to end: tombstones gone, ids kept, searches still find their vectors
     import numpy as np

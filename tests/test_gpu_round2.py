@@ -1,0 +1,178 @@
+"""Round-2 parity and API tests on the GPU: the re-rank kernel against the oracle, the overflow flag of the
+asynchronous entry points, the pipelined submit/wait ABI, and searches racing on one index."""
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import oracle as vo
+from tests.gpu_util import bits_equal, build_oracle, latent_data, queries_near
+from velesdb_b200 import DeviceSnapshot, DistanceMetric
+from velesdb_b200 import _native as nv
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("metric", [vo.COSINE, vo.EUCLIDEAN, vo.DOT, vo.HAMMING, vo.JACCARD])
+@pytest.mark.parametrize("dim,store", [(768, "f32"), (100, "f32"), (13, "f32"), (96, "f16")])
+def test_rerank_values_equal_the_oracle(metric, dim, store):
+    """veles_rerank_batch = the exact-metric step of HnswIndex::search_with_rerank (index/hnsw/index/search.rs:118-160):
+    compute_distance (search.rs:30-38) of the query against each candidate.  Values must have the oracle's bits."""
+    rng = np.random.default_rng(5)
+    n, nq, m = 300, 7, 24
+    if metric in (vo.HAMMING, vo.JACCARD):
+        x = (rng.random((n, dim)) > 0.5).astype(np.float32)
+        q = (rng.random((nq, dim)) > 0.5).astype(np.float32)
+    else:
+        x = latent_data(n, dim, seed=2)
+        q = queries_near(x, nq, seed=3)
+    snap = DeviceSnapshot.from_vectors(x, metric, store_dtype=store)
+    cand = rng.integers(0, n, size=(nq, m)).astype(np.uint32)
+    cand[1, 3] = nv.INVALID_ID
+    cand[4, :] = nv.INVALID_ID
+    got = snap.rerank_batch(q, cand)
+    xs = x.astype(np.float16).astype(np.float32) if store == "f16" else x
+    want = np.full((nq, m), np.nan, np.float32)
+    for i in range(nq):
+        for j in range(m):
+            if cand[i, j] != nv.INVALID_ID:
+                want[i, j] = vo.metric_value(metric, q[i], xs[cand[i, j]])
+    assert bits_equal(got[~np.isnan(want)], want[~np.isnan(want)])
+    assert np.isnan(got[np.isnan(want)]).all()
+
+
+TIE_EF = 5000
+
+
+def _tie_index():
+    """A graph on which one query's tie list outgrows its 4096 entries.  6000 identical `far` vectors in a 64-ary tree
+    laid out in BFS order (so the beam fills its TIE_EF results with far nodes 0..4999, all at distance 1), and 5000
+    identical `near` vectors (= the query, distance 0) in a second tree hanging off far node 100.  Every near node
+    that enters the results evicts an unexpanded far node whose distance still equals the worst result's: by
+    graph.rs:474 it stays poppable, so it goes to the tie list -- ~4900 of them."""
+    F, N, dim, M = 6000, 5000, 16, 32
+    x = np.zeros((F + N, dim), np.float32)
+    x[:F, 0] = 1.0
+    rows, cols = [0], []
+    for i in range(F):
+        if i == 100:
+            cols.extend(range(F, F + 64))
+        else:
+            cols.extend(c for c in range(64 * i + 1, 64 * i + 65) if c < F)
+        rows.append(len(cols))
+    for j in range(N):
+        cols.extend(F + c for c in range(64 * j + 1, 64 * j + 65) if c < N)
+        rows.append(len(cols))
+    layers = [(np.array(rows, np.uint64), np.array(cols, np.uint32))]
+    return DeviceSnapshot.from_arrays(x, DistanceMetric.Euclidean, layers, M, 2 * M, 0, 0), x[F:F + 4].copy()
+
+
+def test_tie_overflow_is_reported_by_host_and_device_entry_points():
+    import torch
+
+    snap, q = _tie_index()
+    ids, dist, cnt = snap.search_batch(q, 5, 64)   # a small beam never gets there
+    assert (dist == 1.0).all()
+    with pytest.raises(nv.VelesError) as e:
+        snap.search_batch(q, 5, TIE_EF)
+    assert e.value.status == nv.ERR_OVERFLOW
+    dev = torch.device("cuda", 0)
+    q_d = torch.from_numpy(q).to(dev)
+    ids = torch.empty((4, 5), dtype=torch.int32, device=dev)
+    dist = torch.empty((4, 5), dtype=torch.float32, device=dev)
+    cnt = torch.empty(4, dtype=torch.int32, device=dev)
+    st = torch.cuda.Stream()
+    snap.search_batch_device(q_d, 5, TIE_EF, ids, dist, cnt, None, st.cuda_stream)   # enqueues only: no error yet
+    with pytest.raises(nv.VelesError) as e:
+        snap.search_status(st.cuda_stream)
+    assert e.value.status == nv.ERR_OVERFLOW
+    snap.search_status(st.cuda_stream)  # reported once, then clear
+    # the pipelined ABI reports it at wait
+    out = [np.empty((4, 5), np.uint32), np.empty((4, 5), np.float32), np.empty(4, np.uint32)]
+    t = snap.search_submit(q, 5, TIE_EF, *out)
+    with pytest.raises(nv.VelesError) as e:
+        snap.search_wait(t)
+    assert e.value.status == nv.ERR_OVERFLOW
+
+
+def test_submit_wait_equals_search_batch_with_tickets_in_flight():
+    x = latent_data(5000, 64, seed=21)
+    g = build_oracle(vo.COSINE, x, M=16, ef_c=100)
+    snap = DeviceSnapshot.from_arrays(x, DistanceMetric.Cosine, g.export_graph(), g.M, g.M0, g.entry_point, g.max_layer)
+    batches = [queries_near(x, 300, seed=s) for s in range(6)]
+    want = [snap.search_batch(b, 10, 64) for b in batches]
+    outs = [(np.empty((300, 10), np.uint32), np.empty((300, 10), np.float32), np.empty(300, np.uint32)) for _ in batches]
+    tickets = []
+    for b, o in zip(batches, outs):          # three in flight at most
+        tickets.append(snap.search_submit(b, 10, 64, *o))
+        if len(tickets) >= 3:
+            snap.search_wait(tickets.pop(0))
+    for t in tickets:
+        snap.search_wait(t)
+    for w, o in zip(want, outs):
+        assert np.array_equal(w[0], o[0]) and bits_equal(w[1], o[1]) and np.array_equal(w[2], o[2])
+    with pytest.raises(nv.VelesError):
+        snap.search_wait(12345)              # unknown ticket
+
+
+def test_concurrent_searches_on_one_index_do_not_share_scratch():
+    """HnswIndex is Send + Sync and searches take a read lock (index/hnsw/index/search.rs:59-94): host threads and
+    streams must be able to search one snapshot at the same time."""
+    import torch
+
+    x = latent_data(8000, 48, seed=33)
+    g = build_oracle(vo.COSINE, x, M=16, ef_c=100)
+    snap = DeviceSnapshot.from_arrays(x, DistanceMetric.Cosine, g.export_graph(), g.M, g.M0, g.entry_point, g.max_layer)
+    qs = [queries_near(x, 700, seed=100 + s) for s in range(4)]
+    want = [snap.search_batch(q, 10, 64) for q in qs]
+    # (a) host threads, each with its own stream
+    got = [None] * 4
+
+    def work(i):
+        st = torch.cuda.Stream()
+        for _ in range(5):
+            got[i] = snap.search_batch(qs[i], 10, 64, stream=st.cuda_stream)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for w, o in zip(want, got):
+        assert np.array_equal(w[0], o[0]) and bits_equal(w[1], o[1])
+    # (b) device-pointer calls on four streams, all enqueued before any completes
+    dev = torch.device("cuda", 0)
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    q_d = [torch.from_numpy(q).to(dev) for q in qs]
+    ids = [torch.empty((700, 10), dtype=torch.int32, device=dev) for _ in range(4)]
+    dist = [torch.empty((700, 10), dtype=torch.float32, device=dev) for _ in range(4)]
+    cnt = [torch.empty(700, dtype=torch.int32, device=dev) for _ in range(4)]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for i in range(4):
+            snap.search_batch_device(q_d[i], 10, 64, ids[i], dist[i], cnt[i], None, streams[i].cuda_stream)
+    for i in range(4):
+        snap.search_status(streams[i].cuda_stream)
+        assert np.array_equal(want[i][0], ids[i].cpu().numpy().astype(np.uint32))
+        assert bits_equal(want[i][1], dist[i].cpu().numpy())
+
+
+def test_index_directory_round_trip_in_the_reference_layout(tmp_path):
+    """HnswIndex::save / load (constructors.rs:190-287): graph + vectors in file format v1, mappings and meta as
+    bincode.  After load the searches answer as before and ShardedVectors is empty (rerank finds nothing)."""
+    import struct
+
+    from velesdb_b200 import HnswIndex, SearchQuality
+
+    x = latent_data(300, 24, seed=6)
+    ix = HnswIndex(24, DistanceMetric.Euclidean)
+    for i in range(300):
+        ix.insert(5_000_000_000 + i, x[i])
+    ix.remove(5_000_000_007)
+    want = ix.search_batch_parallel(x[:20], 5, SearchQuality.Balanced)
+    ix.save(str(tmp_path))
+    meta = open(tmp_path / "native_meta.bin", "rb").read()
+    assert meta == struct.pack("<QBB", 24, 1, 1)
+    assert len(open(tmp_path / "native_mappings.bin", "rb").read()) == 8 + 299 * 16 + 8 + 299 * 16 + 8
+    back = HnswIndex.load(str(tmp_path), 999, DistanceMetric.Cosine)   # both arguments are ignored, as in the reference
+    assert back.dimension() == 24 and back.metric() == DistanceMetric.Euclidean and back.len() == 299
+    assert back.search_batch_parallel(x[:20], 5, SearchQuality.Balanced) == want
+    assert back.search_with_rerank(x[3], 3, 10) == []

@@ -175,3 +175,24 @@ def test_vacuum_and_sequential_batch_bookkeeping():
     ix3 = HnswIndex(16, DistanceMetric.Cosine)
     assert ix3.vacuum() == 0
     assert ix3.insert_batch_sequential([(1, x[0]), (2, x[1]), (1, x[2])]) == 2 and not ix3._bulk
+
+
+def test_mappings_and_meta_files_follow_the_reference_bincode_layout():
+    """constructors.rs:190-287 writes native_mappings.bin / native_meta.bin with bincode 1.3 (Cargo.lock): fixed-width
+    little-endian integers, usize as u64, HashMap = u64 length + (key, value) pairs, bool = one byte.  The bytes below
+    are written by hand from that spec; the mirror must parse them and write the same layout back."""
+    import struct
+
+    from velesdb_b200.index import _bincode_mappings, _parse_bincode_mappings
+
+    raw = (struct.pack("<Q", 2) + struct.pack("<QQ", 1000, 0) + struct.pack("<QQ", 2 ** 40 + 7, 2) +
+           struct.pack("<Q", 2) + struct.pack("<QQ", 0, 1000) + struct.pack("<QQ", 2, 2 ** 40 + 7) + struct.pack("<Q", 3))
+    a, b, nxt = _parse_bincode_mappings(raw)
+    assert a == {1000: 0, 2 ** 40 + 7: 2} and b == {0: 1000, 2: 2 ** 40 + 7} and nxt == 3
+    assert _bincode_mappings(a, b, nxt) == raw
+    import pytest
+
+    with pytest.raises(OSError):
+        _parse_bincode_mappings(raw[:-3])
+    with pytest.raises(OSError):
+        _parse_bincode_mappings(struct.pack("<Q", 2 ** 60) + raw[8:])   # absurd length: rejected before allocating

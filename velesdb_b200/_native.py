@@ -44,6 +44,9 @@ SYMBOLS = [
     ("veles_index_export_layer", _i32, [_vp, _u32, C.POINTER(_u64), C.POINTER(_u64), _vp, _vp]),
     ("veles_search_batch", _i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     ("veles_search_batch_d", _i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
+    ("veles_search_status", _i32, [_vp, _vp]),
+    ("veles_search_submit", _i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, C.POINTER(_u64)]),
+    ("veles_search_wait", _i32, [_vp, _u64]),
     ("veles_bruteforce_batch", _i32, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     ("veles_bruteforce_batch_d", _i32, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     ("veles_rerank_batch", _i32, [_vp, _vp, _u32, _vp, _u32, _vp, _vp]),

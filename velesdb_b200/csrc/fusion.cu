@@ -92,11 +92,13 @@ __global__ void __launch_bounds__(32) rrf_hybrid_kernel(const uint32_t* __restri
 }
 
 // ---- FusionStrategy::fuse ----------------------------------------------------------------------
-// One request is tiny (<= 10 lists x a few hundred hits, collection/search/batch.rs:238,270-275) and
+// One request is small (<= 10 lists x overfetch_k hits, collection/search/batch.rs:238,270-275: up to 10 x 500) and
 // the reference semantics are sequential per document (contributions in list order), so thread 0
-// walks the lists with an open-addressing table in shared memory and the block then sorts.
-constexpr uint32_t kFuseCap = 4096;   // distinct documents
-constexpr uint32_t kFuseHash = 8192;  // table slots (power of two)
+// walks the lists with an open-addressing table and the block then sorts.  The tables are sized from the request
+// (docs = total hits, slots = the power of two >= 2 x that): in shared memory up to kFuseSmemDocs documents, in
+// global memory above.
+constexpr uint32_t kFuseSmemDocs = 4096;
+constexpr uint32_t kFuseMaxDocs = 1u << 20;
 
 struct FuseDoc {
     uint32_t id;
@@ -112,13 +114,15 @@ __global__ void __launch_bounds__(256) fuse_kernel(int strategy, const uint32_t*
                                                    const uint32_t* __restrict__ ids, const float* __restrict__ scores,
                                                    float rrf_k, float avg_w, float max_w, float hit_w, uint32_t cap,
                                                    uint32_t* __restrict__ out_ids, float* __restrict__ out_score,
-                                                   uint32_t* __restrict__ out_count, uint32_t* __restrict__ err) {
+                                                   uint32_t* __restrict__ out_count, uint32_t* __restrict__ err,
+                                                   uint32_t doc_cap, uint32_t hash_slots, uint8_t* __restrict__ work) {
     extern __shared__ __align__(16) uint8_t fz_smem[];
-    FuseDoc* docs = reinterpret_cast<FuseDoc*>(fz_smem);
-    uint32_t* table = reinterpret_cast<uint32_t*>(fz_smem + sizeof(FuseDoc) * kFuseCap);
-    uint64_t* keys = reinterpret_cast<uint64_t*>(fz_smem + sizeof(FuseDoc) * kFuseCap + kFuseHash * 4);
+    uint8_t* mem = work ? work : fz_smem;  // work: global-memory tables for requests beyond kFuseSmemDocs
+    FuseDoc* docs = reinterpret_cast<FuseDoc*>(mem);
+    uint32_t* table = reinterpret_cast<uint32_t*>(mem + sizeof(FuseDoc) * doc_cap);
+    uint64_t* keys = reinterpret_cast<uint64_t*>(mem + sizeof(FuseDoc) * doc_cap + (size_t)hash_slots * 4);
     __shared__ uint32_t s_n;
-    for (uint32_t i = threadIdx.x; i < kFuseHash; i += blockDim.x) table[i] = 0xffffffffu;
+    for (uint32_t i = threadIdx.x; i < hash_slots; i += blockDim.x) table[i] = 0xffffffffu;
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t n = 0;
@@ -142,15 +146,15 @@ __global__ void __launch_bounds__(256) fuse_kernel(int strategy, const uint32_t*
             const uint32_t tag = l + 1;
             for (uint32_t e = list_ptr[l]; e < list_ptr[l + 1]; ++e) {
                 const uint32_t id = ids[e];
-                uint32_t h = (id * 2654435761u) & (kFuseHash - 1);
+                uint32_t h = (id * 2654435761u) & (hash_slots - 1);
                 uint32_t slot;
                 for (;;) {
                     slot = table[h];
                     if (slot == 0xffffffffu || docs[slot].id == id) break;
-                    h = (h + 1) & (kFuseHash - 1);
+                    h = (h + 1) & (hash_slots - 1);
                 }
                 if (slot == 0xffffffffu) {
-                    if (n == kFuseCap) {
+                    if (n == doc_cap) {
                         overflow = true;
                         break;
                     }
@@ -280,30 +284,40 @@ int32_t veles_fuse(int32_t strategy, const uint32_t* list_ptr, uint32_t n_lists,
     VELES_REQUIRE(ids && scores && out_ids && out_score, "NULL buffer");
     VELES_REQUIRE(cap >= 1, "cap must be >= 1");
     cudaStream_t st = (cudaStream_t)stream;
-    DevBuf dp, di, ds, oi, os, oc;
+    VELES_REQUIRE(total <= kFuseMaxDocs, "veles_fuse: at most %u hits per request, got %u", kFuseMaxDocs, total);
+    // distinct documents <= total hits; the sort works on the next power of two
+    uint32_t doc_cap = 1;
+    while (doc_cap < total) doc_cap <<= 1;
+    const uint32_t hash_slots = doc_cap * 2;
+    DevBuf dp, di, ds, oi, os, oc, work;
     VELES_TRY(dp.alloc(((size_t)n_lists + 1) * 4));
     VELES_TRY(di.alloc((size_t)total * 4));
     VELES_TRY(ds.alloc((size_t)total * 4));
-    VELES_TRY(oi.alloc((size_t)kFuseCap * 4));
-    VELES_TRY(os.alloc((size_t)kFuseCap * 4));
+    VELES_TRY(oi.alloc((size_t)doc_cap * 4));
+    VELES_TRY(os.alloc((size_t)doc_cap * 4));
     VELES_TRY(oc.alloc(8));
     VELES_CUDA(cudaMemsetAsync(oc.p, 0, 8, st));
     VELES_CUDA(cudaMemcpyAsync(dp.p, list_ptr, ((size_t)n_lists + 1) * 4, cudaMemcpyHostToDevice, st));
     VELES_CUDA(cudaMemcpyAsync(di.p, ids, (size_t)total * 4, cudaMemcpyHostToDevice, st));
     VELES_CUDA(cudaMemcpyAsync(ds.p, scores, (size_t)total * 4, cudaMemcpyHostToDevice, st));
-    const size_t smem = sizeof(FuseDoc) * kFuseCap + kFuseHash * 4 + (size_t)kFuseCap * 8;
-    VELES_CUDA(cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint32_t dcap = std::min(cap, kFuseCap);
+    const size_t table_bytes = sizeof(FuseDoc) * doc_cap + (size_t)hash_slots * 4 + (size_t)doc_cap * 8;
+    size_t smem = table_bytes;
+    if (doc_cap > kFuseSmemDocs) {
+        VELES_TRY(work.alloc(table_bytes));
+        smem = 0;
+    }
+    VELES_CUDA(cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    const uint32_t dcap = std::min(cap, doc_cap);
     fuse_kernel<<<1, 256, smem, st>>>(strategy, dp.as<uint32_t>(), n_lists, di.as<uint32_t>(), ds.as<float>(), (float)rrf_k, avg_w,
                                       max_w, hit_w, dcap, oi.as<uint32_t>(), os.as<float>(), oc.as<uint32_t>(),
-                                      oc.as<uint32_t>() + 1);
+                                      oc.as<uint32_t>() + 1, doc_cap, hash_slots, smem ? nullptr : work.as<uint8_t>());
     count_launch();
     VELES_CUDA(cudaGetLastError());
     uint32_t h[2] = {0, 0};
     VELES_CUDA(cudaMemcpyAsync(h, oc.p, 8, cudaMemcpyDeviceToHost, st));
     VELES_CUDA(cudaStreamSynchronize(st));
     if (h[1]) {
-        set_error("veles_fuse: more than %u distinct documents in one request", kFuseCap);
+        set_error("veles_fuse: internal table overflow (%u documents)", doc_cap);
         return VELES_ERR_OVERFLOW;
     }
     if (h[0]) {

@@ -20,8 +20,67 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
     return v && *v ? (uint32_t)std::strtoul(v, nullptr, 10) : dflt;
 }
 
-int32_t launch_search(const veles_index* ix, const IndexView& view, const float* q_d, uint32_t nq, uint32_t k, uint32_t ef,
-                      uint32_t* ids_d, float* dist_d, uint32_t* cnt_d, uint32_t* stats_d, cudaStream_t st,
+constexpr size_t kMaxCtx = 16;
+
+static int32_t harvest_flag(const veles_index* ix, SearchCtx* c) {
+    // the context's previous work is complete (its event was waited on or queried): a plain copy sees the final flag
+    if (!c->launched || !c->counters.p) return VELES_OK;
+    uint32_t h[2] = {0, 0};
+    VELES_CUDA(cudaMemcpy(h, c->counters.p, 8, cudaMemcpyDeviceToHost));
+    if (h[1] != 0) {
+        ix->overflowed.push_back(c->bound);
+        VELES_CUDA(cudaMemset(c->counters.as<uint32_t>() + 1, 0, 4));
+    }
+    return VELES_OK;
+}
+
+int32_t acquire_ctx(const veles_index* ix, cudaStream_t st, bool exclusive, SearchCtx** out) {
+    SearchCtx* pick = nullptr;
+    for (auto& c : ix->ctxs)
+        if (!c->in_use && c->launched && c->bound == st) {
+            pick = c.get();
+            break;
+        }
+    if (!pick) {
+        for (auto& c : ix->ctxs) {
+            if (c->in_use) continue;
+            if (!c->launched || cudaEventQuery(c->done) == cudaSuccess) {
+                pick = c.get();
+                break;
+            }
+        }
+        (void)cudaGetLastError();  // cudaErrorNotReady from the queries above is not an error
+        if (!pick && ix->ctxs.size() < kMaxCtx) {
+            ix->ctxs.emplace_back(new SearchCtx());
+            pick = ix->ctxs.back().get();
+            VELES_CUDA(cudaEventCreateWithFlags(&pick->done, cudaEventDisableTiming));
+        }
+        if (!pick) {
+            for (auto& c : ix->ctxs)
+                if (!c->in_use) {
+                    pick = c.get();
+                    break;
+                }
+            if (!pick) {
+                set_error("all %zu search contexts of this index are checked out", ix->ctxs.size());
+                return VELES_ERR_OVERFLOW;
+            }
+            VELES_CUDA(cudaEventSynchronize(pick->done));
+        }
+        if (pick->launched && pick->bound != st) VELES_TRY(harvest_flag(ix, pick));
+    }
+    pick->in_use = exclusive;
+    *out = pick;
+    return VELES_OK;
+}
+
+void release_ctx(const veles_index* ix, SearchCtx* c) {
+    std::lock_guard<std::mutex> g(ix->mu);
+    c->in_use = false;
+}
+
+int32_t launch_search(const veles_index* ix, const IndexView& view, SearchCtx* ctx, const float* q_d, uint32_t nq, uint32_t k,
+                      uint32_t ef, uint32_t* ids_d, float* dist_d, uint32_t* cnt_d, uint32_t* stats_d, cudaStream_t st,
                       const uint32_t* extra_entries_d) {
     VELES_REQUIRE(ix->has_graph, "snapshot has no graph; build or load one first");
     VELES_REQUIRE(view.dtype != VELES_SQ8 || ix->dim <= 32768, "SQ8 traversal supports at most 32768 dimensions");
@@ -147,33 +206,46 @@ int32_t launch_search(const veles_index* ix, const IndexView& view, const float*
     const uint32_t grid = std::min(nq, max_slots);
 
     // scratch: visited bitmaps, logs, tie lists for `max_slots` resident queries
-    p.vis_words = (uint32_t)((ix->n + 31) / 32);
-    if (ix->scratch_slots < max_slots || !ix->visited.p) {
-        VELES_TRY(ix->visited.alloc((size_t)max_slots * std::max(p.vis_words, 1u) * 4));
-        VELES_CUDA(cudaMemsetAsync(ix->visited.p, 0, ix->visited.bytes, st));
-        VELES_TRY(ix->vlog.alloc((size_t)max_slots * kLogCap * 4));
-        VELES_TRY(ix->aux_d.alloc((size_t)max_slots * kTieCap * 8));
-        VELES_TRY(ix->counters.alloc(64));
-        ix->scratch_slots = max_slots;
+    p.vis_words = std::max((uint32_t)((ix->n + 31) / 32), 1u);
+    if (ctx->slots < max_slots || ctx->vis_words != p.vis_words || !ctx->visited.p) {
+        // (re)allocation: cudaFree waits for the device, so an earlier launch still using the old buffers is safe
+        VELES_TRY(ctx->visited.alloc((size_t)max_slots * p.vis_words * 4));
+        VELES_CUDA(cudaMemsetAsync(ctx->visited.p, 0, ctx->visited.bytes, st));
+        VELES_TRY(ctx->vlog.alloc((size_t)max_slots * kLogCap * 4));
+        VELES_TRY(ctx->tie.alloc((size_t)max_slots * kTieCap * 8));
+        if (!ctx->counters.p) {
+            VELES_TRY(ctx->counters.alloc(64));
+            VELES_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+        }
+        ctx->slots = max_slots;
+        ctx->vis_words = p.vis_words;
     }
-    p.visited = ix->visited.as<uint32_t>();
-    p.vlog = ix->vlog.as<uint32_t>();
-    p.tie = ix->aux_d.as<uint64_t>();
-    p.counters = ix->counters.as<uint32_t>();
-    VELES_CUDA(cudaMemsetAsync(p.counters, 0, 8, st));
+    p.visited = ctx->visited.as<uint32_t>();
+    p.vlog = ctx->vlog.as<uint32_t>();
+    p.tie = ctx->tie.as<uint64_t>();
+    p.counters = ctx->counters.as<uint32_t>();
+    VELES_CUDA(cudaMemsetAsync(p.counters, 0, 4, st));  // the work counter; the overflow flag [1] is sticky
     kern<<<grid, 32 * warps, smem_bytes, st>>>(p);
     count_launch();
     VELES_CUDA(cudaGetLastError());
+    ctx->bound = st;
+    ctx->launched = true;
+    VELES_CUDA(cudaEventRecord(ctx->done, st));
     return VELES_OK;
 }
 
-int32_t check_search_error_flag(const veles_index* ix, cudaStream_t st) {
+static int32_t overflow_error() {
+    set_error("tie list overflow (> %u equal-distance evicted candidates in one query)", kTieCap);
+    return VELES_ERR_OVERFLOW;
+}
+
+int32_t check_search_error_flag(SearchCtx* ctx, cudaStream_t st) {
     uint32_t h[2] = {0, 0};
-    VELES_CUDA(cudaMemcpyAsync(h, ix->counters.p, 8, cudaMemcpyDeviceToHost, st));
+    VELES_CUDA(cudaMemcpyAsync(h, ctx->counters.p, 8, cudaMemcpyDeviceToHost, st));
     VELES_CUDA(cudaStreamSynchronize(st));
     if (h[1] != 0) {
-        set_error("tie list overflow (> %u equal-distance evicted candidates in one query)", kTieCap);
-        return VELES_ERR_OVERFLOW;
+        VELES_CUDA(cudaMemsetAsync(ctx->counters.as<uint32_t>() + 1, 0, 4, st));
+        return overflow_error();
     }
     return VELES_OK;
 }
@@ -190,8 +262,77 @@ int32_t veles_search_batch_d(const veles_index_t* idx, const float* queries_d, u
     VELES_REQUIRE(idx != nullptr, "index is NULL");
     VELES_REQUIRE(nq == 0 || (queries_d && out_node_ids_d && out_raw_dist_d && out_counts_d), "NULL buffer");
     std::lock_guard<std::mutex> g(idx->mu);
-    return launch_search(idx, idx->view(), queries_d, nq, k, ef, out_node_ids_d, out_raw_dist_d, out_counts_d, out_stats_d,
+    SearchCtx* ctx = nullptr;
+    VELES_TRY(acquire_ctx(idx, (cudaStream_t)stream, false, &ctx));
+    return launch_search(idx, idx->view(), ctx, queries_d, nq, k, ef, out_node_ids_d, out_raw_dist_d, out_counts_d, out_stats_d,
                          (cudaStream_t)stream);
+}
+
+// Outcome of the `_d` searches enqueued on `stream` so far: waits for the stream, then reports (and clears) a tie-list
+// overflow of any of them.  `_d` calls only enqueue, so this is how their callers learn about VELES_ERR_OVERFLOW.
+int32_t veles_search_status(const veles_index_t* idx, void* stream) {
+    VELES_REQUIRE(idx != nullptr, "index is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    VELES_CUDA(cudaStreamSynchronize(st));
+    std::lock_guard<std::mutex> g(idx->mu);
+    bool bad = false;
+    for (auto it = idx->overflowed.begin(); it != idx->overflowed.end();) {
+        if (*it == st) {
+            bad = true;
+            it = idx->overflowed.erase(it);
+        } else {
+            ++it;
+        }
+    }
+    for (auto& c : idx->ctxs) {
+        if (!c->launched || c->bound != st || !c->counters.p) continue;
+        uint32_t h[2] = {0, 0};
+        VELES_CUDA(cudaMemcpy(h, c->counters.p, 8, cudaMemcpyDeviceToHost));
+        if (h[1] != 0) {
+            bad = true;
+            VELES_CUDA(cudaMemset(c->counters.as<uint32_t>() + 1, 0, 4));
+        }
+    }
+    return bad ? overflow_error() : VELES_OK;
+}
+
+// host-pointer search on `st` with an exclusive context: staging + launch + copies back; does not synchronise
+static int32_t enqueue_host_search(const veles_index_t* idx, SearchCtx* ctx, const float* queries, uint32_t nq, uint32_t k,
+                                   uint32_t ef, const uint32_t* extra_entries, uint32_t* out_node_ids, float* out_raw_dist,
+                                   uint32_t* out_counts, uint32_t* out_stats, cudaStream_t st) {
+    const size_t qb = (size_t)nq * idx->dim * 4, ob = (size_t)nq * k * 4;
+    VELES_TRY(ctx->q_d.ensure(qb));
+    VELES_TRY(ctx->ids_d.ensure(ob));
+    VELES_TRY(ctx->val_d.ensure(ob));
+    VELES_TRY(ctx->cnt_d.ensure((size_t)nq * 4));
+    if (out_stats) VELES_TRY(ctx->stats_d.ensure((size_t)nq * 16));
+    if (extra_entries) VELES_TRY(ctx->extra_d.ensure((size_t)nq * 12));
+    VELES_CUDA(cudaMemcpyAsync(ctx->q_d.p, queries, qb, cudaMemcpyHostToDevice, st));
+    if (extra_entries) VELES_CUDA(cudaMemcpyAsync(ctx->extra_d.p, extra_entries, (size_t)nq * 12, cudaMemcpyHostToDevice, st));
+    VELES_TRY(launch_search(idx, idx->view(), ctx, ctx->q_d.as<float>(), nq, k, ef, ctx->ids_d.as<uint32_t>(), ctx->val_d.as<float>(),
+                            ctx->cnt_d.as<uint32_t>(), out_stats ? ctx->stats_d.as<uint32_t>() : nullptr, st,
+                            extra_entries ? ctx->extra_d.as<uint32_t>() : nullptr));
+    VELES_CUDA(cudaMemcpyAsync(out_node_ids, ctx->ids_d.p, ob, cudaMemcpyDeviceToHost, st));
+    VELES_CUDA(cudaMemcpyAsync(out_raw_dist, ctx->val_d.p, ob, cudaMemcpyDeviceToHost, st));
+    VELES_CUDA(cudaMemcpyAsync(out_counts, ctx->cnt_d.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    if (out_stats) VELES_CUDA(cudaMemcpyAsync(out_stats, ctx->stats_d.p, (size_t)nq * 16, cudaMemcpyDeviceToHost, st));
+    return VELES_OK;
+}
+
+static int32_t host_search(const veles_index_t* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
+                           const uint32_t* extra_entries, uint32_t* out_node_ids, float* out_raw_dist, uint32_t* out_counts,
+                           uint32_t* out_stats, cudaStream_t st) {
+    SearchCtx* ctx = nullptr;
+    {
+        std::lock_guard<std::mutex> g(idx->mu);
+        VELES_TRY(acquire_ctx(idx, st, true, &ctx));
+    }
+    // the context is checked out: other host threads search concurrently with their own contexts
+    int32_t s = enqueue_host_search(idx, ctx, queries, nq, k, ef, extra_entries, out_node_ids, out_raw_dist, out_counts,
+                                    out_stats, st);
+    if (s == VELES_OK) s = check_search_error_flag(ctx, st);
+    release_ctx(idx, ctx);
+    return s;
 }
 
 int32_t veles_search_batch(const veles_index_t* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
@@ -200,22 +341,7 @@ int32_t veles_search_batch(const veles_index_t* idx, const float* queries, uint3
     VELES_REQUIRE(idx != nullptr, "index is NULL");
     VELES_REQUIRE(nq == 0 || (queries && out_node_ids && out_raw_dist && out_counts), "NULL buffer");
     if (nq == 0) return VELES_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    std::lock_guard<std::mutex> g(idx->mu);
-    const size_t qb = (size_t)nq * idx->dim * 4, ob = (size_t)nq * k * 4;
-    VELES_TRY(idx->q_d.ensure(qb));
-    VELES_TRY(idx->out_ids_d.ensure(ob));
-    VELES_TRY(idx->out_val_d.ensure(ob));
-    VELES_TRY(idx->out_cnt_d.ensure((size_t)nq * 4));
-    if (out_stats) VELES_TRY(idx->out_stats_d.ensure((size_t)nq * 16));
-    VELES_CUDA(cudaMemcpyAsync(idx->q_d.p, queries, qb, cudaMemcpyHostToDevice, st));
-    VELES_TRY(launch_search(idx, idx->view(), idx->q_d.as<float>(), nq, k, ef, idx->out_ids_d.as<uint32_t>(), idx->out_val_d.as<float>(),
-                            idx->out_cnt_d.as<uint32_t>(), out_stats ? idx->out_stats_d.as<uint32_t>() : nullptr, st));
-    VELES_CUDA(cudaMemcpyAsync(out_node_ids, idx->out_ids_d.p, ob, cudaMemcpyDeviceToHost, st));
-    VELES_CUDA(cudaMemcpyAsync(out_raw_dist, idx->out_val_d.p, ob, cudaMemcpyDeviceToHost, st));
-    VELES_CUDA(cudaMemcpyAsync(out_counts, idx->out_cnt_d.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
-    if (out_stats) VELES_CUDA(cudaMemcpyAsync(out_stats, idx->out_stats_d.p, (size_t)nq * 16, cudaMemcpyDeviceToHost, st));
-    return check_search_error_flag(idx, st);
+    return host_search(idx, queries, nq, k, ef, nullptr, out_node_ids, out_raw_dist, out_counts, out_stats, (cudaStream_t)stream);
 }
 
 int32_t veles_search_batch_multi_entry(const veles_index_t* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
@@ -225,25 +351,78 @@ int32_t veles_search_batch_multi_entry(const veles_index_t* idx, const float* qu
     VELES_REQUIRE(nq == 0 || (queries && extra_entries && out_node_ids && out_raw_dist && out_counts), "NULL buffer");
     VELES_REQUIRE(ef >= 4, "multi-entry search needs ef >= 4 (every entry point enters the result set), got %u", ef);
     if (nq == 0) return VELES_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    std::lock_guard<std::mutex> g(idx->mu);
-    const size_t qb = (size_t)nq * idx->dim * 4, ob = (size_t)nq * k * 4;
-    VELES_TRY(idx->q_d.ensure(qb));
-    VELES_TRY(idx->out_ids_d.ensure(ob));
-    VELES_TRY(idx->out_val_d.ensure(ob));
-    VELES_TRY(idx->out_cnt_d.ensure((size_t)nq * 4));
-    VELES_TRY(idx->extra_d.ensure((size_t)nq * 12));
-    if (out_stats) VELES_TRY(idx->out_stats_d.ensure((size_t)nq * 16));
-    VELES_CUDA(cudaMemcpyAsync(idx->q_d.p, queries, qb, cudaMemcpyHostToDevice, st));
-    VELES_CUDA(cudaMemcpyAsync(idx->extra_d.p, extra_entries, (size_t)nq * 12, cudaMemcpyHostToDevice, st));
-    VELES_TRY(launch_search(idx, idx->view(), idx->q_d.as<float>(), nq, k, ef, idx->out_ids_d.as<uint32_t>(), idx->out_val_d.as<float>(),
-                            idx->out_cnt_d.as<uint32_t>(), out_stats ? idx->out_stats_d.as<uint32_t>() : nullptr, st,
-                            idx->extra_d.as<uint32_t>()));
-    VELES_CUDA(cudaMemcpyAsync(out_node_ids, idx->out_ids_d.p, ob, cudaMemcpyDeviceToHost, st));
-    VELES_CUDA(cudaMemcpyAsync(out_raw_dist, idx->out_val_d.p, ob, cudaMemcpyDeviceToHost, st));
-    VELES_CUDA(cudaMemcpyAsync(out_counts, idx->out_cnt_d.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
-    if (out_stats) VELES_CUDA(cudaMemcpyAsync(out_stats, idx->out_stats_d.p, (size_t)nq * 16, cudaMemcpyDeviceToHost, st));
-    return check_search_error_flag(idx, st);
+    return host_search(idx, queries, nq, k, ef, extra_entries, out_node_ids, out_raw_dist, out_counts, out_stats,
+                       (cudaStream_t)stream);
+}
+
+// ---- asynchronous, pipelined form of veles_search_batch ------------------------------------------------------------
+// submit: the batch's H2D copy, search and D2H copies are enqueued on a stream owned by one of the index's contexts
+// and the call returns; wait: blocks until that batch is complete.  Several tickets can be in flight: batch i+1's
+// copies and first queries overlap batch i's tail and copies back (each launch is a persistent grid that thins out as
+// its last queries finish).  Results are identical to veles_search_batch.
+int32_t veles_search_submit(const veles_index_t* idx, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
+                            uint32_t* out_node_ids, float* out_raw_dist, uint32_t* out_counts, uint64_t* ticket) {
+    VELES_REQUIRE(idx != nullptr && ticket != nullptr, "NULL argument");
+    VELES_REQUIRE(nq >= 1 && queries && out_node_ids && out_raw_dist && out_counts, "NULL buffer or empty batch");
+    *ticket = 0;
+    SearchCtx* ctx = nullptr;
+    size_t slot = 0;
+    {
+        std::lock_guard<std::mutex> g(idx->mu);
+        // prefer a context that already owns a stream
+        for (size_t i = 0; i < idx->ctxs.size() && !ctx; ++i) {
+            SearchCtx* c = idx->ctxs[i].get();
+            if (!c->in_use && c->own && (!c->launched || c->bound == c->own)) ctx = c;
+        }
+        if (ctx)
+            ctx->in_use = true;
+        else
+            VELES_TRY(acquire_ctx(idx, nullptr, true, &ctx));
+        for (size_t i = 0; i < idx->ctxs.size(); ++i)
+            if (idx->ctxs[i].get() == ctx) slot = i;
+        ctx->generation += 1;
+    }
+    int32_t s = VELES_OK;
+    auto body = [&]() -> int32_t {
+        if (!ctx->own) VELES_CUDA(cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking));
+        if (!ctx->h_flag) VELES_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_flag), 8, cudaHostAllocDefault));
+        if (ctx->launched && ctx->bound != ctx->own) VELES_CUDA(cudaEventSynchronize(ctx->done));
+        VELES_TRY(enqueue_host_search(idx, ctx, queries, nq, k, ef, nullptr, out_node_ids, out_raw_dist, out_counts, nullptr,
+                                      ctx->own));
+        VELES_CUDA(cudaMemcpyAsync(ctx->h_flag, ctx->counters.p, 8, cudaMemcpyDeviceToHost, ctx->own));
+        VELES_CUDA(cudaMemsetAsync(ctx->counters.as<uint32_t>() + 1, 0, 4, ctx->own));
+        VELES_CUDA(cudaEventRecord(ctx->done, ctx->own));
+        return VELES_OK;
+    };
+    s = body();
+    if (s != VELES_OK) {
+        release_ctx(idx, ctx);
+        return s;
+    }
+    *ticket = (ctx->generation << 8) | (uint64_t)(slot + 1);
+    return VELES_OK;
+}
+
+int32_t veles_search_wait(const veles_index_t* idx, uint64_t ticket) {
+    VELES_REQUIRE(idx != nullptr, "index is NULL");
+    SearchCtx* ctx = nullptr;
+    {
+        std::lock_guard<std::mutex> g(idx->mu);
+        const size_t slot = (size_t)(ticket & 0xff);
+        VELES_REQUIRE(slot >= 1 && slot <= idx->ctxs.size(), "unknown ticket");
+        ctx = idx->ctxs[slot - 1].get();
+        VELES_REQUIRE(ctx->in_use && ctx->generation == (ticket >> 8), "stale ticket");
+    }
+    int32_t s = VELES_OK;
+    cudaError_t e = cudaEventSynchronize(ctx->done);
+    if (e != cudaSuccess) {
+        set_error("cudaEventSynchronize failed: %s", cudaGetErrorString(e));
+        s = VELES_ERR_CUDA;
+    } else if (ctx->h_flag[1] != 0) {
+        s = overflow_error();
+    }
+    release_ctx(idx, ctx);
+    return s;
 }
 
 }  // extern "C"

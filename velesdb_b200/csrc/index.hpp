@@ -1,9 +1,39 @@
 // index.hpp -- host-side handle of a device snapshot (one NativeHnsw, native/graph.rs:18-44).
 #pragma once
 
+#include <memory>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
+
+namespace veles {
+// Everything one search launch writes besides its outputs: visited bitmaps, logs, tie lists and the work counter /
+// error flag, plus the device staging buffers of the host-pointer entry points.  An index owns a small pool of these
+// (veles_index::ctxs); a context serves one stream at a time, so launches on different streams or from different
+// host threads never share scratch (the reference's HnswIndex is Send + Sync behind an Arc; searches only take a
+// read lock, index/hnsw/index/search.rs:59-94).
+struct SearchCtx {
+    DevBuf visited, vlog, tie, counters;  // counters: [0] work counter (zeroed per launch), [1] sticky overflow flag
+    uint32_t slots = 0, vis_words = 0;
+    DevBuf q_d, ids_d, val_d, cnt_d, stats_d, extra_d;  // staging of host-pointer calls
+    cudaStream_t bound = nullptr;   // stream of the last launch
+    cudaEvent_t done = nullptr;     // recorded after the last launch
+    cudaStream_t own = nullptr;     // this context's stream, for veles_search_submit / _wait
+    uint32_t* h_flag = nullptr;     // pinned: the overflow flag read back by a submitted batch
+    uint64_t generation = 0;        // ticket check
+    bool launched = false;          // `done` has been recorded at least once
+    bool in_use = false;            // checked out by a host-pointer call or a pending ticket
+    SearchCtx() = default;
+    SearchCtx(const SearchCtx&) = delete;
+    SearchCtx& operator=(const SearchCtx&) = delete;
+    ~SearchCtx() {
+        if (done) cudaEventDestroy(done);
+        if (own) cudaStreamDestroy(own);
+        if (h_flag) cudaFreeHost(h_flag);
+    }
+};
+}  // namespace veles
 
 struct veles_index {
     int device = 0;
@@ -36,11 +66,11 @@ struct veles_index {
     veles::DevBuf id_map_d, live_d;
     mutable veles::DevBuf allow_d, map_ids_d, map_score_d, extra_d;
 
-    // search scratch, sized lazily and reused; guarded by `mu`
+    // `mu` guards the context pool and the shared staging buffers below
     mutable std::mutex mu;
-    mutable veles::DevBuf visited, vlog, counters;
-    mutable uint32_t scratch_slots = 0;
-    mutable veles::DevBuf q_d, out_ids_d, out_val_d, out_cnt_d, out_stats_d, scores_d, aux_d, topk_d;
+    mutable std::vector<std::unique_ptr<veles::SearchCtx>> ctxs;
+    mutable std::vector<cudaStream_t> overflowed;  // streams whose overflow flag was harvested when a context moved on
+    mutable veles::DevBuf q_d, out_ids_d, out_val_d, out_cnt_d, out_stats_d, scores_d, topk_d;
 
     veles::IndexView view() const {
         veles::IndexView v;
@@ -75,7 +105,9 @@ struct veles_index {
         return v;
     }
     uint64_t device_bytes() const {
-        return vecs.bytes + adj0.bytes + upper_ref.bytes + upper_adj.bytes + visited.bytes + vlog.bytes + sq_codes.bytes;
+        uint64_t b = vecs.bytes + adj0.bytes + upper_ref.bytes + upper_adj.bytes + sq_codes.bytes;
+        for (const auto& c : ctxs) b += c->visited.bytes + c->vlog.bytes + c->tie.bytes;
+        return b;
     }
 };
 
@@ -91,9 +123,15 @@ int32_t install_graph_host(veles_index* ix, uint32_t num_layers, const uint64_t*
                            const uint32_t* const* cols, const uint64_t* layer_nodes, uint32_t M, uint32_t M0,
                            uint64_t entry_point, uint32_t max_layer);
 int device_sm_count();
-// batched traversal over `view` (the snapshot's own rows, or its SQ8 codes); hnsw_search.cu
-int32_t launch_search(const veles_index* ix, const IndexView& view, const float* q_d, uint32_t nq, uint32_t k,
+// A context for a launch on `st` (hnsw_search.cu); the caller holds ix->mu.  Prefers the context already bound to
+// `st` (stream order makes reuse safe), then an idle one, then a new one (at most kMaxCtx, after that it waits for
+// the oldest).  `exclusive` marks it in_use until release_ctx.
+int32_t acquire_ctx(const veles_index* ix, cudaStream_t st, bool exclusive, SearchCtx** out);
+void release_ctx(const veles_index* ix, SearchCtx* c);
+// batched traversal over `view` (the snapshot's own rows, or its SQ8 codes) with `ctx`'s scratch; records ctx->done
+int32_t launch_search(const veles_index* ix, const IndexView& view, SearchCtx* ctx, const float* q_d, uint32_t nq, uint32_t k,
                       uint32_t ef, uint32_t* ids_d, float* dist_d, uint32_t* cnt_d, uint32_t* stats_d, cudaStream_t st,
                       const uint32_t* extra_entries_d = nullptr);
-int32_t check_search_error_flag(const veles_index* ix, cudaStream_t st);
+// synchronises `st`, reads and clears the context's overflow flag
+int32_t check_search_error_flag(SearchCtx* ctx, cudaStream_t st);
 }  // namespace veles

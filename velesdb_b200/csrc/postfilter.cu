@@ -103,7 +103,9 @@ int32_t veles_search_batch_mapped(const veles_index_t* idx, const float* queries
     }
     uint32_t* raw_cnt = idx->out_cnt_d.as<uint32_t>();
     uint32_t* map_cnt = raw_cnt + nq;
-    VELES_TRY(launch_search(idx, idx->view(), idx->q_d.as<float>(), nq, k_fetch, ef, idx->out_ids_d.as<uint32_t>(),
+    SearchCtx* ctx = nullptr;
+    VELES_TRY(acquire_ctx(idx, st, false, &ctx));
+    VELES_TRY(launch_search(idx, idx->view(), ctx, idx->q_d.as<float>(), nq, k_fetch, ef, idx->out_ids_d.as<uint32_t>(),
                             idx->out_val_d.as<float>(), raw_cnt, nullptr, st));
     map_results_kernel<<<(nq + 3) / 4, 128, 0, st>>>(idx->out_ids_d.as<uint32_t>(), idx->out_val_d.as<float>(), raw_cnt, nq, k_fetch,
                                                     k_out, idx->id_map_d.as<uint64_t>(), idx->live_d.as<uint32_t>(),
@@ -114,7 +116,7 @@ int32_t veles_search_batch_mapped(const veles_index_t* idx, const float* queries
     VELES_CUDA(cudaMemcpyAsync(out_ids, idx->map_ids_d.p, (size_t)nq * k_out * 8, cudaMemcpyDeviceToHost, st));
     VELES_CUDA(cudaMemcpyAsync(out_scores, idx->map_score_d.p, (size_t)nq * k_out * 4, cudaMemcpyDeviceToHost, st));
     VELES_CUDA(cudaMemcpyAsync(out_counts, map_cnt, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
-    return check_search_error_flag(idx, st);
+    return check_search_error_flag(ctx, st);
 }
 
 }  // extern "C"

@@ -98,7 +98,7 @@ __global__ void sq8_rerank_kernel(const IndexView ix, const float* __restrict__ 
 
 static int32_t sq8_search(const veles_index* ix, const float* q_d, uint32_t nq, uint32_t k, uint32_t ef_search,
                           uint32_t oversampling, uint32_t* ids_d, float* dist_d, uint32_t* cnt_d, uint32_t* stats_d,
-                          cudaStream_t st) {
+                          cudaStream_t st, SearchCtx** ctx_out = nullptr) {
     VELES_REQUIRE(ix->has_sq8, "snapshot has no SQ8 store; call veles_index_attach_sq8 first");
     VELES_REQUIRE(k >= 1 && oversampling >= 1, "k and oversampling must be >= 1");
     const uint64_t ck64 = (uint64_t)k * oversampling;
@@ -109,7 +109,10 @@ static int32_t sq8_search(const veles_index* ix, const float* q_d, uint32_t nq, 
     VELES_TRY(ix->sq_ids_d.ensure((size_t)nq * ck * 4));
     VELES_TRY(ix->sq_dist_d.ensure((size_t)nq * ck * 4));
     VELES_TRY(ix->sq_cnt_d.ensure((size_t)nq * 4));
-    VELES_TRY(launch_search(ix, ix->view_sq8(), q_d, nq, ck, ef, ix->sq_ids_d.as<uint32_t>(), ix->sq_dist_d.as<float>(),
+    SearchCtx* ctx = nullptr;
+    VELES_TRY(acquire_ctx(ix, st, false, &ctx));  // the caller holds ix->mu
+    if (ctx_out) *ctx_out = ctx;
+    VELES_TRY(launch_search(ix, ix->view_sq8(), ctx, q_d, nq, ck, ef, ix->sq_ids_d.as<uint32_t>(), ix->sq_dist_d.as<float>(),
                             ix->sq_cnt_d.as<uint32_t>(), stats_d, st));
     const uint32_t warps = ck <= 512 ? 4 : 1;
     const size_t smem = (size_t)warps * ck * 8;
@@ -200,14 +203,15 @@ int32_t veles_search_batch_sq8(const veles_index_t* idx, const float* queries, u
     VELES_TRY(idx->out_cnt_d.ensure((size_t)nq * 4));
     if (out_stats) VELES_TRY(idx->out_stats_d.ensure((size_t)nq * 16));
     VELES_CUDA(cudaMemcpyAsync(idx->q_d.p, queries, qb, cudaMemcpyHostToDevice, st));
+    SearchCtx* ctx = nullptr;
     VELES_TRY(sq8_search(idx, idx->q_d.as<float>(), nq, k, ef_search, oversampling, idx->out_ids_d.as<uint32_t>(),
                          idx->out_val_d.as<float>(), idx->out_cnt_d.as<uint32_t>(),
-                         out_stats ? idx->out_stats_d.as<uint32_t>() : nullptr, st));
+                         out_stats ? idx->out_stats_d.as<uint32_t>() : nullptr, st, &ctx));
     VELES_CUDA(cudaMemcpyAsync(out_node_ids, idx->out_ids_d.p, ob, cudaMemcpyDeviceToHost, st));
     VELES_CUDA(cudaMemcpyAsync(out_raw_dist, idx->out_val_d.p, ob, cudaMemcpyDeviceToHost, st));
     VELES_CUDA(cudaMemcpyAsync(out_counts, idx->out_cnt_d.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     if (out_stats) VELES_CUDA(cudaMemcpyAsync(out_stats, idx->out_stats_d.p, (size_t)nq * 16, cudaMemcpyDeviceToHost, st));
-    return check_search_error_flag(idx, st);
+    return check_search_error_flag(ctx, st);
 }
 
 }  // extern "C"

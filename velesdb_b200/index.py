@@ -13,7 +13,7 @@ from __future__ import annotations
 import ctypes as C
 import enum
 import os
-import pickle
+import struct
 
 import numpy as np
 
@@ -199,8 +199,23 @@ class DeviceSnapshot:
                                              stream))
         return out
 
-    def build_graph(self, M, cand_k=0, stream=None):
-        nv.check(nv.lib().veles_index_build_graph(self.h, M, cand_k, stream))
+    def build_graph(self, M, ef_construction=0, stream=None):
+        """Bulk construction by block insertion (insert_batch_parallel's role, batch.rs:82-108); 0 = library default."""
+        nv.check(nv.lib().veles_index_build_graph(self.h, M, ef_construction, stream))
+
+    def search_status(self, stream=None):
+        """Waits for `stream`; raises VelesError(OVERFLOW) if a `_d` search enqueued on it overflowed its tie list."""
+        nv.check(nv.lib().veles_search_status(self.h, stream))
+
+    def search_submit(self, q, k, ef, ids, dist, cnt):
+        """veles_search_submit: host arrays (pinned for true overlap) in/out, returns a ticket for search_wait."""
+        t = C.c_uint64()
+        nv.check(nv.lib().veles_search_submit(self.h, nv.ptr(q), q.shape[0], k, ef, nv.ptr(ids), nv.ptr(dist), nv.ptr(cnt),
+                                              C.byref(t)))
+        return t.value
+
+    def search_wait(self, ticket):
+        nv.check(nv.lib().veles_search_wait(self.h, ticket))
 
     def build_graph_exact(self, M, ef_construction, stream=None):
         """NativeHnsw::insert for nodes 0..n-1 in order (graph.rs:158-237): the reference's deterministic graph."""
@@ -316,6 +331,34 @@ def distance_pairs(metric, a, b, as_metric_value=False):
     nv.check(nv.lib().veles_distance_pairs(int(metric), nv.ptr(a), nv.ptr(b), a.shape[0], a.shape[1],
                                            1 if as_metric_value else 0, nv.ptr(out), None))
     return out
+
+
+def _bincode_mappings(id_to_idx, idx_to_id, next_idx) -> bytes:
+    out = [struct.pack("<Q", len(id_to_idx))]
+    out += [struct.pack("<QQ", int(k), int(v)) for k, v in id_to_idx.items()]
+    out.append(struct.pack("<Q", len(idx_to_id)))
+    out += [struct.pack("<QQ", int(k), int(v)) for k, v in idx_to_id.items()]
+    out.append(struct.pack("<Q", int(next_idx)))
+    return b"".join(out)
+
+
+def _parse_bincode_mappings(raw: bytes):
+    def read_map(off):
+        if off + 8 > len(raw):
+            raise OSError("native_mappings.bin is truncated")
+        (n,) = struct.unpack_from("<Q", raw, off)
+        off += 8
+        if n > (len(raw) - off) // 16:
+            raise OSError("native_mappings.bin is truncated")
+        flat = np.frombuffer(raw, dtype="<u8", count=2 * n, offset=off)
+        return {int(flat[2 * i]): int(flat[2 * i + 1]) for i in range(n)}, off + 16 * n
+
+    a, off = read_map(0)
+    b, off = read_map(off)
+    if off + 8 > len(raw):
+        raise OSError("native_mappings.bin is truncated")
+    (next_idx,) = struct.unpack_from("<Q", raw, off)
+    return a, b, int(next_idx)
 
 
 class HnswIndex:
@@ -497,24 +540,41 @@ class HnswIndex:
         self._ensure_snapshot()
 
     # ---- persistence (constructors.rs:190-287)
+    # native_mappings.bin / native_meta.bin are the reference's bincode 1.3 files (fixed-width little-endian
+    # integers, usize as u64, a HashMap as its u64 length followed by the (key, value) pairs, bool as one byte):
+    #   mappings = (HashMap<u64, usize> id_to_idx, HashMap<usize, u64> idx_to_id, usize next_idx)
+    #   meta     = (usize dimension, u8 metric, bool enable_vector_storage)
+    # so a directory written by either side opens on the other.
     def save(self, path):
         os.makedirs(path, exist_ok=True)
         snap = self._ensure_snapshot()
         snap.dump(path, "native_hnsw")
         with open(os.path.join(path, "native_mappings.bin"), "wb") as f:
-            pickle.dump((self._id_to_idx, self._idx_to_id, self._next_idx), f)
+            f.write(_bincode_mappings(self._id_to_idx, self._idx_to_id, self._next_idx))
         with open(os.path.join(path, "native_meta.bin"), "wb") as f:
-            pickle.dump((self._dimension, int(self._metric), self.enable_vector_storage), f)
+            f.write(struct.pack("<QBB", self._dimension, int(self._metric), 1 if self.enable_vector_storage else 0))
 
     @classmethod
-    def load(cls, path, dimension, metric):
-        for name in ("native_hnsw.vectors", "native_hnsw.graph", "native_mappings.bin"):
+    def load(cls, path, dimension=None, metric=None):
+        """`dimension` and `metric` are kept for API compatibility, as in the reference: both are read from
+        native_meta.bin (constructors.rs:190-217)."""
+        for name in ("native_meta.bin", "native_hnsw.vectors", "native_hnsw.graph", "native_mappings.bin"):
             if not os.path.exists(os.path.join(path, name)):
                 raise FileNotFoundError(f"{name} not found in {path}")
-        snap = DeviceSnapshot.from_reference_files(path, metric)
-        ix = cls(dimension, metric)
+        with open(os.path.join(path, "native_meta.bin"), "rb") as f:
+            raw = f.read()
+        if len(raw) < 10:
+            raise OSError("native_meta.bin is truncated")
+        dim_file, metric_u8, evs = struct.unpack_from("<QBB", raw)
+        if metric_u8 > 4:
+            raise OSError("Unknown distance metric")  # constructors.rs:211-216
         with open(os.path.join(path, "native_mappings.bin"), "rb") as f:
-            ix._id_to_idx, ix._idx_to_id, ix._next_idx = pickle.load(f)
+            id_to_idx, idx_to_id, next_idx = _parse_bincode_mappings(f.read())
+        snap = DeviceSnapshot.from_reference_files(path, DistanceMetric(metric_u8))
+        if len(snap) and snap.dim != dim_file:
+            raise OSError(f"native_meta.bin says dimension {dim_file}, native_hnsw.vectors holds {snap.dim}")
+        ix = cls(dim_file, DistanceMetric(metric_u8), enable_vector_storage=bool(evs))
+        ix._id_to_idx, ix._idx_to_id, ix._next_idx = id_to_idx, idx_to_id, next_idx
         ix._snapshot = snap
         ix._vectors_present = False  # ShardedVectors stays empty after load (constructors.rs:240)
         return ix
