@@ -105,6 +105,15 @@ int32_t veles_index_from_arrays(const void* vectors, uint64_t n, uint32_t dim, i
  * of veles_index_build_graph. */
 int32_t veles_index_from_vectors(const void* vectors, uint64_t n, uint32_t dim, int32_t src_dtype, int32_t store_dtype,
                                  int32_t metric, veles_index_t** out);
+/* The same for hosts whose vectors are already on the device (or are produced there): an empty snapshot of n
+ * zero rows, then rows [first, first + count) from device memory -- src_dtype F32 (converted like
+ * veles_index_from_vectors does) or the store type itself.  veles_index_get_rows copies rows back to the host in the
+ * store type (what HnswIndex::load leaves out: ShardedVectors stays empty after load, constructors.rs:240, but the
+ * graph's own vectors are there, native/backend_adapter.rs:286-307). */
+int32_t veles_index_create(uint64_t n, uint32_t dim, int32_t store_dtype, int32_t metric, veles_index_t** out);
+int32_t veles_index_set_rows_d(veles_index_t* idx, uint64_t first, uint64_t count, const void* rows_d, int32_t src_dtype,
+                               void* stream);
+int32_t veles_index_get_rows(const veles_index_t* idx, uint64_t first, uint64_t count, void* out);
 int32_t veles_index_free(veles_index_t* idx);
 
 uint64_t veles_index_len(const veles_index_t* idx);       /* NativeHnsw::len  graph.rs:130 */
@@ -117,6 +126,8 @@ uint64_t veles_index_device_bytes(const veles_index_t* idx);
 /* NativeHnsw::file_dump (native/backend_adapter.rs:184-261): writes the snapshot back in
  * format v1 (vectors are written as f32). */
 int32_t veles_index_dump(const veles_index_t* idx, const char* dir, const char* basename);
+/* only `{basename}.graph` (native/backend_adapter.rs:213-261), for snapshots of any storage type */
+int32_t veles_index_dump_graph(const veles_index_t* idx, const char* dir, const char* basename);
 /* copies the layer-`l` adjacency out as CSR (row_ptr may be NULL to query sizes only) */
 int32_t veles_index_export_layer(const veles_index_t* idx, uint32_t layer, uint64_t* out_nodes, uint64_t* out_edges,
                                  uint64_t* row_ptr, uint32_t* cols);
@@ -169,6 +180,21 @@ int32_t veles_bruteforce_batch(const veles_index_t* idx, const float* queries, u
                                uint32_t* out_ids, float* out_score, void* stream);
 int32_t veles_bruteforce_batch_d(const veles_index_t* idx, const float* queries_d, uint32_t nq, uint32_t k,
                                  uint32_t* out_ids_d, float* out_score_d, void* stream);
+/* Relaxed-mode brute force for large query batches: the candidate stage runs on the tensor cores, the final scores
+ * are exact.  An fp16 copy of the collection (built on first use) is multiplied with the fp16 queries by a
+ * hand-written tcgen05 GEMM (accumulators in TMEM, operands staged by TMA); its epilogue keeps the rows whose fp16
+ * score reaches a per-query threshold -- the (k * oversample)-th best score of a sample of the collection, which can
+ * only be looser than the true one -- and the exact metric value (compute_distance, index/hnsw/index/search.rs:30-38,
+ * reference summation order) of those candidates decides the top k.  This is the role of the reference's GPU hook
+ * search_brute_force_gpu (search.rs:229-279 -> gpu/gpu_backend.rs:300-340) and of the re-rank in search_with_rerank
+ * (search.rs:118-160).  Ordering and padding as veles_bruteforce_batch; results equal it unless fp16 rounding pushes a
+ * true neighbour below rank k * oversample (judged by recall; cosine, euclidean and dot; f32 or f16 storage).
+ * gemm_ms (may be NULL): device time of the two GEMM passes, for the roofline. */
+int32_t veles_bruteforce_batch_relaxed(const veles_index_t* idx, const float* queries, uint32_t nq, uint32_t k,
+                                       uint32_t oversample, uint32_t* out_ids, float* out_score, void* stream);
+int32_t veles_bruteforce_batch_relaxed_d(const veles_index_t* idx, const float* queries_d, uint32_t nq, uint32_t k,
+                                         uint32_t oversample, uint32_t* out_ids_d, float* out_score_d, float* gemm_ms,
+                                         void* stream);
 /* exact metric value of explicit (query, node) pairs: the re-rank step of
  * HnswIndex::search_with_rerank (index/hnsw/index/search.rs:118-160).  cand is nq*m node ids
  * (VELES_INVALID_ID entries give NaN). */
@@ -288,10 +314,33 @@ int32_t veles_search_batch_mapped(const veles_index_t* idx, const float* queries
                                   uint32_t k_out, uint32_t ef, const uint32_t* allow_bits, uint64_t* out_ids,
                                   float* out_scores, uint32_t* out_counts, void* stream);
 
-/* ---- multi-GPU --------------------------------------------------------------------------------- */
-/* Queries shard by contiguous slices across ranks; the snapshot is replicated.  The only exchange
- * is the final gather of [nq_local, k] ids + distances, done by the host runtime with NCCL
- * all-gather (velesdb_b200/dist.py) on the buffers the `_d` calls fill. */
+/* ---- multi-GPU ----------------------------------------------------------------------------------- */
+/* Queries shard by contiguous slices across the GPUs of one NVSwitch box (one process per GPU); the snapshot is
+ * replicated.  The reference's one strategy is rayon over queries in one process
+ * (index/hnsw/index/batch.rs:159-197); its per-query results simply land in one Vec.  Here the only exchange is the
+ * final gather of [nq, k] ids + distances, and it is done by the library itself, fused into the search: each rank
+ * owns a gather window in its HBM, peers map it through CUDA IPC, and the search kernel's epilogue stores every
+ * finished query's top-k into slot `rank` of every window (peer stores over NVLink); a flag exchange closes the epoch.
+ *
+ *   veles_comm_create    allocates this rank's window for `nq_per_rank` x `k` results per rank and writes an opaque
+ *                        handle blob of veles_comm_handle_bytes() bytes
+ *   veles_comm_connect   takes all ranks' blobs (rank-major; the host moves them over any channel it has) and maps the
+ *                        peers' windows
+ *   veles_search_batch_gather_d   veles_search_batch_d + gather; collective (every rank, same order, same nq / k / ef);
+ *                        only enqueues on `stream`; mid_event (cudaEvent_t or NULL) is recorded between the search
+ *                        kernel and the flag exchange
+ *   veles_comm_window    device pointers of the local window of the latest epoch: [world*nq*k] ids, distances,
+ *                        [world*nq] counts = the whole batch in query order, valid once `stream` has run
+ *   veles_comm_status    waits for `stream`; error if a peer never arrived */
+typedef struct veles_comm veles_comm_t;
+int32_t veles_comm_handle_bytes(void);
+int32_t veles_comm_create(int32_t rank, int32_t world, uint32_t nq_per_rank, uint32_t k, veles_comm_t** out, void* handle_out);
+int32_t veles_comm_connect(veles_comm_t* comm, const void* all_handles);
+int32_t veles_search_batch_gather_d(const veles_index_t* idx, veles_comm_t* comm, const float* queries_d, uint32_t nq,
+                                    uint32_t k, uint32_t ef, void* stream, void* mid_event);
+int32_t veles_comm_window(veles_comm_t* comm, uint32_t** ids_d, float** dist_d, uint32_t** counts_d);
+int32_t veles_comm_status(veles_comm_t* comm, void* stream);
+int32_t veles_comm_destroy(veles_comm_t* comm);
 
 #ifdef __cplusplus
 }

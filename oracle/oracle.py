@@ -97,6 +97,10 @@ _sig("vo_bruteforce_batch", None,
 _sig("vo_bruteforce_binary", C.c_uint32, [_u64p, C.c_uint64, C.c_uint32, _u64p, C.c_uint32, _u64p, _u32p])
 _sig("vo_hnsw_dump", C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p])
 _sig("vo_hnsw_load", C.c_void_p, [C.c_char_p, C.c_char_p, C.c_int, C.c_int])
+_sig("vo_hnsw_frozen", C.c_void_p,
+     [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_uint32,
+      C.c_void_p, C.c_void_p, _u64p, C.c_uint64, C.c_uint32])
+_sig("vo_hnsw_open", C.c_void_p, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_uint32])
 _sig("vo_bm25_new", C.c_void_p, [C.c_float, C.c_float])
 _sig("vo_bm25_free", None, [C.c_void_p])
 _sig("vo_bm25_add", None, [C.c_void_p, C.c_uint64, _u32p, C.c_uint64])
@@ -339,6 +343,52 @@ class Hnsw:
         h = _lib.vo_hnsw_from_arrays(metric, dim, M, M0, ef_construction, int(fma), vectors, n, len(layers), rp_arr,
                                      c_arr, nodes, entry_point, max_layer)
         return cls(metric, dim, _handle=h, fma=fma)
+
+
+STORE_F32, STORE_F16, STORE_BIN = 0, 1, 2
+_STORE_OF = {np.dtype(np.float32): STORE_F32, np.dtype(np.float16): STORE_F16, np.dtype(np.uint64): STORE_BIN}
+
+
+def frozen(metric, vectors, layers, M, M0, entry_point, max_layer, dim=None, ef_construction=400, fma=True):
+    """A search-only index over the caller's arrays, nothing copied: CSR adjacency per layer and `vectors` as
+    float32 [n, dim], float16 [n, dim] (up-converted per evaluation) or uint64 [n, dim/64] (packed bits, Hamming).
+    For the CPU arm of the 10M / 50M node configs, where per-node lists and f32 lanes would not fit."""
+    vectors = np.ascontiguousarray(vectors)
+    store = _STORE_OF[vectors.dtype]
+    n = vectors.shape[0]
+    d = dim if dim is not None else (vectors.shape[1] * 64 if store == STORE_BIN else vectors.shape[1])
+    rps = [np.ascontiguousarray(rp, dtype=np.uint64) for rp, _ in layers]
+    cols = [np.ascontiguousarray(c if len(c) else np.zeros(1, np.uint32), dtype=np.uint32) for _, c in layers]
+    nodes = np.array([rp.size - 1 for rp in rps], dtype=np.uint64)
+    rp_arr = (C.c_void_p * len(layers))(*[rp.ctypes.data for rp in rps])
+    c_arr = (C.c_void_p * len(layers))(*[c.ctypes.data for c in cols])
+    h = _lib.vo_hnsw_frozen(metric, d, M, M0, ef_construction, int(fma), store, vectors.ctypes.data, n, len(layers),
+                            C.cast(rp_arr, C.c_void_p), C.cast(c_arr, C.c_void_p), nodes, entry_point, max_layer)
+    if not h:
+        raise ValueError("oracle: unsupported storage / metric combination")
+    g = Hnsw(metric, d, _handle=h, fma=fma)
+    g._keep = (vectors, rps, cols, nodes, rp_arr, c_arr)  # borrowed by the C side
+    return g
+
+
+def open_index(directory, metric, basename="native_hnsw", vectors=None, dim=None, fma=True):
+    """Search-only index from a format-v1 `.graph` file; vectors from `{basename}.vectors` (f32) or, when given, from
+    the caller's array in float32 / float16 / packed uint64 form (borrowed)."""
+    if vectors is None:
+        h = _lib.vo_hnsw_open(os.fsencode(directory), basename.encode(), metric, int(fma), STORE_F32, None, 0, 0)
+        keep = None
+    else:
+        vectors = np.ascontiguousarray(vectors)
+        store = _STORE_OF[vectors.dtype]
+        d = dim if dim is not None else (vectors.shape[1] * 64 if store == STORE_BIN else vectors.shape[1])
+        h = _lib.vo_hnsw_open(os.fsencode(directory), basename.encode(), metric, int(fma), store, vectors.ctypes.data,
+                              vectors.shape[0], d)
+        keep = vectors
+    if not h:
+        raise OSError("oracle: open failed")
+    g = Hnsw(metric, 0, _handle=h, fma=fma)
+    g._keep = keep
+    return g
 
 
 class ScalarQuantizer:

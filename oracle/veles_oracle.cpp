@@ -531,6 +531,48 @@ struct SearchStats {
     uint64_t adj0 = 0;       // adjacency ids read on layer 0
 };
 
+// read-only view of one adjacency list (a Vec<usize> in the reference, native/layer.rs:12-15)
+struct Span {
+    const uint32_t* p = nullptr;
+    size_t n = 0;
+    const uint32_t* begin() const { return p; }
+    const uint32_t* end() const { return p + n; }
+    size_t size() const { return n; }
+    uint32_t operator[](size_t i) const { return p[i]; }
+    operator std::vector<uint32_t>() const { return std::vector<uint32_t>(p, p + n); }  // get_neighbors clones
+};
+
+// Storage of the vectors the traversal reads.  STORE_F32 is the reference (Vec<Vec<f32>>, graph.rs:22).  The two
+// compact forms exist for the BASELINE configs that exceed what the reference HNSW stores (SURVEY finding 0.5):
+//   STORE_F16   half::f16 values (core/half_precision.rs:97), up-converted to f32 before the reference's f32 distance
+//   STORE_BIN   packed bits, u64 words LSB first: hamming_distance_binary (simd_explicit.rs:308-360), whose count
+//               equals the f32-lane Hamming (simd_explicit.rs:256-287) on {0,1} data; the query is thresholded > 0.5
+enum { STORE_F32 = 0, STORE_F16 = 1, STORE_BIN = 2 };
+
+static inline float half_to_float(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t exp = (h >> 10) & 0x1f, man = h & 0x3ffu, bits;
+    if (exp == 0) {
+        if (man == 0) {
+            bits = sign;
+        } else {  // subnormal half -> normal float
+            int e = -1;
+            do {
+                man <<= 1;
+                ++e;
+            } while (!(man & 0x400u));
+            bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3ffu) << 13);
+        }
+    } else if (exp == 31) {
+        bits = sign | 0x7f800000u | (man << 13);
+    } else {
+        bits = sign | ((exp + 112) << 23) | (man << 13);
+    }
+    float f;
+    std::memcpy(&f, &bits, 4);
+    return f;
+}
+
 struct Hnsw {
     int metric;
     uint32_t dim;
@@ -542,6 +584,18 @@ struct Hnsw {
     std::vector<float> vectors;  // contiguous n*dim
     uint64_t n = 0;
     std::vector<std::vector<std::vector<uint32_t>>> layers;  // [layer][node] -> ids
+    // frozen form (search only): CSR adjacency per layer and, optionally, compact vector storage.  Pointers are either
+    // owned (the own_* vectors) or borrowed from the caller, who keeps them alive.
+    bool frozen = false;
+    int store = STORE_F32;
+    const void* ext_vectors = nullptr;
+    std::vector<const uint64_t*> csr_rp;
+    std::vector<const uint32_t*> csr_cols;
+    std::vector<uint64_t> csr_nodes;
+    std::vector<std::vector<uint64_t>> own_rp;
+    std::vector<std::vector<uint32_t>> own_cols;
+    std::vector<float> own_f32;
+    uint32_t num_layers() const { return frozen ? (uint32_t)csr_nodes.size() : (uint32_t)layers.size(); }
     bool has_ep = false;
     uint64_t ep = 0;
     uint32_t max_layer = 0;
@@ -552,8 +606,46 @@ struct Hnsw {
         level_mult = 1.0 / std::log((double)M_);
         layers.emplace_back();
     }
-    const float* vec(uint64_t id) const { return vectors.data() + id * (size_t)dim; }
+    const float* vec(uint64_t id) const {
+        return (frozen ? static_cast<const float*>(ext_vectors) : vectors.data()) + id * (size_t)dim;
+    }
     float dist(const float* a, const float* b) const { return graph_distance(metric, a, b, dim, fma); }
+    // distance of the query to stored node x, whatever the storage
+    float qdist(const float* q, uint64_t x) const {
+        if (store == STORE_F32) return dist(q, vec(x));
+        if (store == STORE_F16) {
+            static thread_local std::vector<float> row;
+            row.resize(dim);
+            const uint16_t* h = static_cast<const uint16_t*>(ext_vectors) + x * (size_t)dim;
+            for (uint32_t i = 0; i < dim; ++i) row[i] = half_to_float(h[i]);
+            return dist(q, row.data());
+        }
+        const uint64_t* a = packed_query(q);
+        const uint64_t* b = static_cast<const uint64_t*>(ext_vectors) + x * (size_t)(dim / 64);
+        uint32_t d = 0;
+        for (uint32_t w = 0; w < dim / 64; ++w) d += (uint32_t)__builtin_popcountll(a[w] ^ b[w]);
+        return (float)d;
+    }
+    // the query as packed bits (threshold > 0.5, simd_explicit.rs:256-287), cached per thread and per query pointer;
+    // begin_query() drops the cache at the start of every search
+    static const float*& packed_for() {
+        static thread_local const float* p = nullptr;
+        return p;
+    }
+    const uint64_t* packed_query(const float* q) const {
+        static thread_local std::vector<uint64_t> bits;
+        if (packed_for() != q) {
+            bits.assign(dim / 64, 0);
+            for (uint32_t i = 0; i < dim; ++i)
+                if (q[i] > 0.5f) bits[i >> 6] |= 1ull << (i & 63);
+            packed_for() = q;
+        }
+        return bits.data();
+    }
+    void begin_query() const { packed_for() = nullptr; }
+    void prefetch_node(uint64_t x) const {
+        if (store == STORE_F32) prefetch_vector(vec(x));
+    }
 
     // graph.rs:368-403
     uint32_t random_layer() {
@@ -570,23 +662,28 @@ struct Hnsw {
         return (uint32_t)std::min<uint64_t>(level, 15);
     }
 
-    const std::vector<uint32_t>& neighbors(uint32_t layer, uint64_t node) const {
-        static const std::vector<uint32_t> empty;
-        if (layer >= layers.size() || node >= layers[layer].size()) return empty;
-        return layers[layer][node];
+    Span neighbors(uint32_t layer, uint64_t node) const {
+        if (frozen) {
+            if (layer >= csr_nodes.size() || node >= csr_nodes[layer]) return Span{};
+            const uint64_t a = csr_rp[layer][node], b = csr_rp[layer][node + 1];
+            return Span{csr_cols[layer] + a, (size_t)(b - a)};
+        }
+        if (layer >= layers.size() || node >= layers[layer].size()) return Span{};
+        const std::vector<uint32_t>& v = layers[layer][node];
+        return Span{v.data(), v.size()};
     }
 
     // graph.rs:405-428
     uint64_t search_layer_single(const float* q, uint64_t entry, uint32_t layer, SearchStats* st) const {
         uint64_t best = entry;
-        float best_dist = dist(q, vec(entry));
+        float best_dist = qdist(q, entry);
         if (st) st->ndc_up++;
         for (;;) {
             std::vector<uint32_t> nb = neighbors(layer, best);  // snapshot, as get_neighbors clones
             if (st) st->hops_up++;
             bool improved = false;
             for (uint32_t x : nb) {
-                float d = dist(q, vec(x));
+                float d = qdist(q, x);
                 if (st) st->ndc_up++;
                 if (d < best_dist) {
                     best = x;
@@ -608,7 +705,7 @@ struct Hnsw {
         const size_t pd = prefetch_distance(dim);
         RustHeap<DN, DNLess> res;      // max-heap
         for (uint64_t e : entries) {
-            float d = dist(q, vec(e));
+            float d = qdist(q, e);
             if (st) st->ndc0++;
             cand.push({d, e});
             res.push({d, e});
@@ -618,7 +715,7 @@ struct Hnsw {
             DN c = cand.pop();
             float furthest = res.empty() ? std::numeric_limits<float>::max() : res.peek().d;
             if (c.d > furthest && res.size() >= ef) break;
-            const std::vector<uint32_t>& nb = neighbors(layer, c.n);
+            const Span nb = neighbors(layer, c.n);
             if (st) {
                 st->hops0++;
                 st->adj0 += nb.size();
@@ -626,12 +723,12 @@ struct Hnsw {
             // graph.rs:480-497: software prefetch of upcoming neighbour vectors for dim >= 384
             if (dim >= 384 && nb.size() > pd)
                 for (size_t i = 0; i < pd; ++i)
-                    if (nb[i] < n) prefetch_vector(vec(nb[i]));
+                    if (nb[i] < n) prefetch_node(nb[i]);
             for (size_t i = 0; i < nb.size(); ++i) {
                 const uint32_t x = nb[i];
-                if (dim >= 384 && i + pd < nb.size() && nb[i + pd] < n) prefetch_vector(vec(nb[i + pd]));
+                if (dim >= 384 && i + pd < nb.size() && nb[i + pd] < n) prefetch_node(nb[i + pd]);
                 if (visited.insert(x)) {
-                    float d = dist(q, vec(x));
+                    float d = qdist(q, x);
                     if (st) st->ndc0++;
                     float f = res.empty() ? std::numeric_limits<float>::max() : res.peek().d;
                     if (d < f || res.size() < ef) {
@@ -740,6 +837,7 @@ struct Hnsw {
                                        std::vector<uint64_t>* used) {
         std::vector<DN> out;
         if (!has_ep || n == 0) return out;
+        begin_query();
         uint64_t cur = ep;
         for (uint32_t l = max_layer; l >= 1; --l) cur = search_layer_single(q, cur, l, st);
         std::vector<uint64_t> entries{cur};
@@ -767,6 +865,7 @@ struct Hnsw {
     std::vector<DN> search(const float* q, size_t k, size_t ef, int order_mode, SearchStats* st) const {
         std::vector<DN> out;
         if (!has_ep) return out;
+        begin_query();
         uint64_t cur = ep;
         for (uint32_t l = max_layer; l >= 1; --l) cur = search_layer_single(q, cur, l, st);
         std::vector<DN> c = search_layer(q, {cur}, ef, 0, st);
@@ -910,7 +1009,7 @@ static std::vector<DN> dual_search_int8(const Hnsw& g, const Sq8& sq, const floa
         const UN c = cand.pop();
         const uint32_t furthest = res.empty() ? UINT32_MAX : res.peek().d;
         if (c.d > furthest && res.size() >= ef) break;
-        const std::vector<uint32_t>& nb = g.neighbors(0, c.n);
+        const Span nb = g.neighbors(0, c.n);
         if (st) {
             st->hops0++;
             st->adj0 += nb.size();
@@ -1098,7 +1197,7 @@ void vo_hnsw_insert_many(void* h, const float* v, uint64_t n) {
 }
 uint64_t vo_hnsw_len(void* h) { return ((Hnsw*)h)->n; }
 uint32_t vo_hnsw_dim(void* h) { return ((Hnsw*)h)->dim; }
-uint32_t vo_hnsw_num_layers(void* h) { return (uint32_t)((Hnsw*)h)->layers.size(); }
+uint32_t vo_hnsw_num_layers(void* h) { return ((Hnsw*)h)->num_layers(); }
 uint32_t vo_hnsw_max_layer(void* h) { return ((Hnsw*)h)->max_layer; }
 uint32_t vo_hnsw_M(void* h) { return ((Hnsw*)h)->M; }
 uint32_t vo_hnsw_M0(void* h) { return ((Hnsw*)h)->M0; }
@@ -1120,7 +1219,10 @@ void vo_hnsw_export_layer(void* h, uint32_t l, uint64_t* row_ptr, uint32_t* cols
     }
     row_ptr[L.size()] = e;
 }
-const float* vo_hnsw_vectors(void* h) { return ((Hnsw*)h)->vectors.data(); }
+const float* vo_hnsw_vectors(void* h) {
+    Hnsw* g = (Hnsw*)h;
+    return g->frozen ? (g->store == STORE_F32 ? static_cast<const float*>(g->ext_vectors) : nullptr) : g->vectors.data();
+}
 // the first `count` levels the reference PRNG would assign (graph.rs:368-403)
 void vo_levels(uint32_t M, uint64_t count, uint8_t* out) {
     Hnsw g(0, 1, M, 1, 1.0f, true);
@@ -1145,6 +1247,120 @@ void* vo_hnsw_from_arrays(int metric, uint32_t dim, uint32_t M, uint32_t M0, uin
     g->has_ep = n > 0;
     g->ep = entry_point;
     g->max_layer = max_layer;
+    return g;
+}
+
+// A search-only index over caller-held arrays: CSR adjacency per layer and vectors in `storage` form (STORE_*).
+// Nothing is copied: the caller keeps `vectors`, `row_ptrs[l]` and `cols[l]` alive as long as the handle.  This is
+// how the CPU arm holds 10M+ node graphs (no per-node allocations) and the f16 / packed-bit configs.
+void* vo_hnsw_frozen(int metric, uint32_t dim, uint32_t M, uint32_t M0, uint32_t ef_c, int fma, int storage,
+                     const void* vectors, uint64_t n, uint32_t num_layers, const uint64_t* const* row_ptrs,
+                     const uint32_t* const* cols, const uint64_t* layer_nodes, uint64_t entry_point, uint32_t max_layer) {
+    if (storage < STORE_F32 || storage > STORE_BIN) return nullptr;
+    if (storage == STORE_BIN && (dim % 64 != 0 || metric != HAMMING)) return nullptr;
+    Hnsw* g = new Hnsw(metric, dim, M, ef_c, 1.0f, fma != 0);
+    g->M0 = M0;
+    g->n = n;
+    g->frozen = true;
+    g->store = storage;
+    g->ext_vectors = vectors;
+    for (uint32_t l = 0; l < num_layers; ++l) {
+        g->csr_rp.push_back(row_ptrs[l]);
+        g->csr_cols.push_back(cols[l]);
+        g->csr_nodes.push_back(layer_nodes[l]);
+    }
+    g->has_ep = n > 0;
+    g->ep = entry_point;
+    g->max_layer = max_layer;
+    return g;
+}
+
+// The same from a format-v1 `.graph` file (native/backend_adapter.rs:213-261), adjacency owned as CSR.  `vectors`
+// NULL: the f32 vectors are read from `{basename}.vectors` (storage must be STORE_F32); otherwise borrowed as above.
+void* vo_hnsw_open(const char* dir, const char* basename, int metric, int fma, int storage, const void* vectors,
+                   uint64_t n_vectors, uint32_t dim_vectors) {
+    const std::string vp = std::string(dir) + "/" + basename + ".vectors";
+    const std::string gp = std::string(dir) + "/" + basename + ".graph";
+    uint32_t version = 0, dim = dim_vectors;
+    uint64_t count = n_vectors;
+    std::vector<float> vecs;
+    if (!vectors) {
+        if (storage != STORE_F32) return nullptr;
+        FILE* f = std::fopen(vp.c_str(), "rb");
+        if (!f) return nullptr;
+        bool okv = std::fread(&version, 4, 1, f) == 1 && version == 1 && std::fread(&count, 8, 1, f) == 1 &&
+                   std::fread(&dim, 4, 1, f) == 1;
+        if (okv) {
+            vecs.resize(count * (size_t)dim);
+            okv = std::fread(vecs.data(), 4, vecs.size(), f) == vecs.size();
+        }
+        std::fclose(f);
+        if (!okv) return nullptr;
+    }
+    FILE* f = std::fopen(gp.c_str(), "rb");
+    if (!f) return nullptr;
+    uint32_t nl, M, M0, efc, maxl;
+    uint64_t ep, cnt2;
+    bool ok = std::fread(&version, 4, 1, f) == 1 && version == 1 && std::fread(&nl, 4, 1, f) == 1 &&
+              std::fread(&M, 4, 1, f) == 1 && std::fread(&M0, 4, 1, f) == 1 && std::fread(&efc, 4, 1, f) == 1 &&
+              std::fread(&ep, 8, 1, f) == 1 && std::fread(&maxl, 4, 1, f) == 1 && std::fread(&cnt2, 8, 1, f) == 1;
+    if (!ok || nl == 0 || nl > 16) {
+        std::fclose(f);
+        return nullptr;
+    }
+    Hnsw* g = new Hnsw(metric, dim, M, efc, 1.0f, fma != 0);
+    g->M0 = M0;
+    g->n = count;
+    g->frozen = true;
+    g->store = storage;
+    g->own_rp.resize(nl);
+    g->own_cols.resize(nl);
+    for (uint32_t l = 0; l < nl && ok; ++l) {
+        uint64_t nn;
+        if (std::fread(&nn, 8, 1, f) != 1 || nn > count) {
+            ok = false;
+            break;
+        }
+        auto& rp = g->own_rp[l];
+        auto& cl = g->own_cols[l];
+        rp.resize(nn + 1);
+        rp[0] = 0;
+        if (l == 0) cl.reserve(nn * (size_t)M0);
+        for (uint64_t i = 0; i < nn; ++i) {
+            uint32_t deg;
+            if (std::fread(&deg, 4, 1, f) != 1 || deg > 4096) {
+                ok = false;
+                break;
+            }
+            const size_t base = cl.size();
+            cl.resize(base + deg);
+            if (deg && std::fread(cl.data() + base, 4, deg, f) != deg) {
+                ok = false;
+                break;
+            }
+            rp[i + 1] = base + deg;
+        }
+        g->csr_nodes.push_back(nn);
+    }
+    std::fclose(f);
+    if (!ok) {
+        delete g;
+        return nullptr;
+    }
+    for (uint32_t l = 0; l < nl; ++l) {
+        if (g->own_cols[l].empty()) g->own_cols[l].push_back(0);
+        g->csr_rp.push_back(g->own_rp[l].data());
+        g->csr_cols.push_back(g->own_cols[l].data());
+    }
+    if (vectors) {
+        g->ext_vectors = vectors;
+    } else {
+        g->own_f32 = std::move(vecs);
+        g->ext_vectors = g->own_f32.data();
+    }
+    g->has_ep = true;  // file_load always sets Some(entry_point) (backend_adapter.rs:368)
+    g->ep = ep;
+    g->max_layer = maxl;
     return g;
 }
 

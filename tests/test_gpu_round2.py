@@ -176,3 +176,47 @@ def test_index_directory_round_trip_in_the_reference_layout(tmp_path):
     assert back.dimension() == 24 and back.metric() == DistanceMetric.Euclidean and back.len() == 299
     assert back.search_batch_parallel(x[:20], 5, SearchQuality.Balanced) == want
     assert back.search_with_rerank(x[3], 3, 10) == []
+
+
+@pytest.mark.parametrize("metric,store,n,dim,nq,k", [(vo.COSINE, "f32", 20000, 768, 300, 10), (vo.EUCLIDEAN, "f32", 5000, 100, 130, 5),
+                                                    (vo.DOT, "f16", 9000, 64, 64, 20), (vo.COSINE, "f32", 300, 48, 7, 10)])
+def test_tensor_core_relaxed_brute_force(metric, store, n, dim, nq, k):
+    """veles_bruteforce_batch_relaxed: candidates from the tcgen05 fp16 GEMM, exact re-rank.  Recall-gated against the
+    exact path (fp16 rounding may only move rows near rank k * oversample); every returned score must be the exact
+    metric value of its row, bit for bit, and the order must be the exact path's order."""
+    x = latent_data(n, dim, latent=12, noise=0.3, seed=41, normalize=(metric == vo.COSINE))
+    q = queries_near(x, nq, jitter=0.2, seed=42)
+    snap = DeviceSnapshot.from_vectors(x, metric, store_dtype=store)
+    ei, es = snap.bruteforce_batch(q, k)
+    ri, rs = snap.bruteforce_batch_relaxed(q, k, oversample=4)
+    rec = np.mean([len(set(ei[i].tolist()) & set(ri[i].tolist())) / k for i in range(nq)])
+    assert rec >= 0.99, rec
+    same = ei == ri
+    assert bits_equal(es[same], rs[same])                 # same row => same exact score
+    exact_of = snap.rerank_batch(q, ri)                     # every score is the exact metric value of its row
+    assert bits_equal(exact_of, rs)
+    sign = -1.0 if metric in (vo.COSINE, vo.DOT) else 1.0
+    assert (np.diff(sign * rs.astype(np.float64), axis=1) >= 0).all()
+
+
+@pytest.mark.parametrize("metric,dim,nq,k", [(vo.COSINE, 64, 40, 10), (vo.EUCLIDEAN, 96, 9, 5), (vo.DOT, 128, 33, 20),
+                                            (vo.HAMMING, 64, 12, 10), (vo.COSINE, 64, 3, 10), (vo.EUCLIDEAN, 64, 8, 100)])
+def test_fused_brute_force_equals_the_matrix_path_and_the_oracle(metric, dim, nq, k, monkeypatch):
+    """The exact scan without the [nq, n] score matrix: <= 8 queries select inside the scan kernel, larger batches go
+    sample -> bound -> filtered scan -> select.  Both must return exactly what the matrix path and the oracle do."""
+    n = 70_000
+    rng = np.random.default_rng(77)
+    if metric == vo.HAMMING:
+        x = (rng.random((n, dim)) > 0.5).astype(np.float32)
+        q = (rng.random((nq, dim)) > 0.5).astype(np.float32)
+    else:
+        x = latent_data(n, dim, latent=10, noise=0.3, seed=5)
+        q = queries_near(x, nq, jitter=0.2, seed=6)
+    snap = DeviceSnapshot.from_vectors(x, metric)
+    fi, fs = snap.bruteforce_batch(q, k)
+    monkeypatch.setenv("VELES_BF_NO_FUSE", "1")
+    mi, ms = snap.bruteforce_batch(q, k)
+    monkeypatch.delenv("VELES_BF_NO_FUSE")
+    assert np.array_equal(fi, mi) and bits_equal(fs, ms)
+    oi, os_ = vo.bruteforce_batch(metric, x, q[:6], k, threads=8)
+    assert np.array_equal(fi[:6], oi.astype(np.uint32)) and bits_equal(fs[:6], os_)

@@ -33,6 +33,9 @@ SYMBOLS = [
      [_vp, _u64, _u32, _i32, _i32, _i32, _u32, C.POINTER(_vp), C.POINTER(_vp), _vp, _u32, _u32, _u64, _u32,
       C.POINTER(_vp)]),
     ("veles_index_from_vectors", _i32, [_vp, _u64, _u32, _i32, _i32, _i32, C.POINTER(_vp)]),
+    ("veles_index_create", _i32, [_u64, _u32, _i32, _i32, C.POINTER(_vp)]),
+    ("veles_index_set_rows_d", _i32, [_vp, _u64, _u64, _vp, _i32, _vp]),
+    ("veles_index_get_rows", _i32, [_vp, _u64, _u64, _vp]),
     ("veles_index_free", _i32, [_vp]),
     ("veles_index_len", _u64, [_vp]),
     ("veles_index_dim", _u32, [_vp]),
@@ -41,6 +44,7 @@ SYMBOLS = [
     ("veles_index_entry_point", _u64, [_vp]),
     ("veles_index_device_bytes", _u64, [_vp]),
     ("veles_index_dump", _i32, [_vp, C.c_char_p, C.c_char_p]),
+    ("veles_index_dump_graph", _i32, [_vp, C.c_char_p, C.c_char_p]),
     ("veles_index_export_layer", _i32, [_vp, _u32, C.POINTER(_u64), C.POINTER(_u64), _vp, _vp]),
     ("veles_search_batch", _i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     ("veles_search_batch_d", _i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
@@ -49,6 +53,8 @@ SYMBOLS = [
     ("veles_search_wait", _i32, [_vp, _u64]),
     ("veles_bruteforce_batch", _i32, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     ("veles_bruteforce_batch_d", _i32, [_vp, _vp, _u32, _u32, _vp, _vp, _vp]),
+    ("veles_bruteforce_batch_relaxed", _i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
+    ("veles_bruteforce_batch_relaxed_d", _i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, C.POINTER(_f), _vp]),
     ("veles_rerank_batch", _i32, [_vp, _vp, _u32, _vp, _u32, _vp, _vp]),
     ("veles_distance_pairs", _i32, [_i32, _vp, _vp, _u32, _u32, _i32, _vp, _vp]),
     ("veles_bm25_from_csr", _i32, [_u32, _vp, _vp, _vp, _vp, _u32, _vp, _u64, _u64, _f, _f, C.POINTER(_vp)]),
@@ -65,6 +71,13 @@ SYMBOLS = [
     ("veles_search_batch_sq8_d", _i32, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     ("veles_search_batch_multi_entry", _i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     ("veles_index_set_id_map", _i32, [_vp, _vp, _vp]),
+    ("veles_comm_handle_bytes", _i32, []),
+    ("veles_comm_create", _i32, [_i32, _i32, _u32, _u32, C.POINTER(_vp), _vp]),
+    ("veles_comm_connect", _i32, [_vp, _vp]),
+    ("veles_search_batch_gather_d", _i32, [_vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp]),
+    ("veles_comm_window", _i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    ("veles_comm_status", _i32, [_vp, _vp]),
+    ("veles_comm_destroy", _i32, [_vp]),
     ("veles_search_batch_mapped", _i32, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
 ]
 

@@ -17,6 +17,49 @@
 
 namespace veles {
 
+// Where a score kernel's results go.  STORE: the [nq, ld] matrix of metric values.  FILTER (thr != NULL): no matrix --
+// a result is kept only if its sort key (order(score) << 32 | row, smaller = better in DistanceMetric::sort_results
+// order) does not exceed the query's bound, and is appended to the query's candidate list.  The bound is the k-th best
+// key of a strided sample of the collection (any subset's k-th best is no better than the collection's), so the true
+// top k always pass; see bruteforce_device.
+struct ScoreSink {
+    float* scores = nullptr;
+    uint64_t ld = 0;
+    const uint32_t* thr = nullptr;  // per query: order bits of the bound
+    uint32_t* cnt = nullptr;        // per query candidate count
+    uint64_t* cand = nullptr;       // nq x cap keys
+    uint32_t cap = 0;
+    uint32_t* err = nullptr;        // [0] set when a list overflowed
+    uint32_t desc = 0;
+    __host__ __device__ ScoreSink at(uint32_t q0) const {
+        ScoreSink o = *this;
+        if (scores) o.scores = scores + (size_t)q0 * ld;
+        if (thr) {
+            o.thr = thr + q0;
+            o.cnt = cnt + q0;
+            o.cand = cand + (size_t)q0 * cap;
+        }
+        return o;
+    }
+#ifdef __CUDACC__
+    __device__ __forceinline__ void emit(uint32_t q, uint64_t row, float v) const {
+        if (!thr) {
+            scores[(size_t)q * ld + row] = v;
+            return;
+        }
+        uint32_t o = ord_key(v);
+        if (desc) o = ~o;
+        if (o <= thr[q]) {
+            const uint32_t slot = atomicAdd(&cnt[q], 1u);
+            if (slot < cap)
+                cand[(size_t)q * cap + slot] = ((uint64_t)o << 32) | (uint32_t)row;
+            else
+                atomicExch(err, 1u);
+        }
+    }
+#endif
+};
+
 constexpr int kRT = 4;   // rows per warp tile
 constexpr int kQT = 8;   // queries per warp tile
 constexpr int kWarps = 8;
@@ -25,7 +68,7 @@ constexpr int kWarps = 8;
 // Fast path: F32/F16 rows, COSINE / EUCLIDEAN / DOT, dim >= 16.
 template <typename TB>
 __global__ void __launch_bounds__(kWarps * 32) bf_tile_kernel(IndexView ix, const float* __restrict__ queries,
-                                                              uint32_t nq, uint32_t q0, float* __restrict__ scores,
+                                                              uint32_t nq, uint32_t q0, ScoreSink out,
                                                               bool as_value) {
     extern __shared__ __align__(16) float qs[];  // kQT x dim, then kQT norms
     const uint32_t dim = ix.dim;
@@ -109,7 +152,7 @@ __global__ void __launch_bounds__(kWarps * 32) bf_tile_kernel(IndexView ix, cons
                         v = as_value ? s : -s;
                     }
                 }
-                if (lane == 0 && row_ok && t < (int)nqt) scores[(size_t)(qbase - q0 + t) * n + (r0 + r)] = v;
+                if (lane == 0 && row_ok && t < (int)nqt) out.emit(qbase - q0 + t, r0 + r, v);
             }
         }
     }
@@ -148,7 +191,7 @@ constexpr int kStepU = 2;  // steps per pointer advance
 // L1 hits.  Only QW = 1 is launched (see launch_scores).
 template <typename TB, int QW>
 __global__ void __launch_bounds__(kWarps * 32, 2) bf_tile8_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq,
-                                                               float* __restrict__ scores, bool as_value) {
+                                                               ScoreSink out, bool as_value) {
     extern __shared__ __align__(16) float qs_all[];  // QW x kQT x dim, then QW x kQT norms
     const uint32_t dim = ix.dim;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -242,7 +285,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) bf_tile8_kernel(IndexView ix, 
                 } else {
                     v = as_value ? s : -s;
                 }
-                scores[(size_t)(qbase + my_t) * n + row] = v;
+                out.emit(qbase + my_t, row, v);
             }
         }
     }
@@ -258,7 +301,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) bf_tile8_kernel(IndexView ix, 
 constexpr int kTsQ = 32, kTsR = 16, kTsK = 128;
 template <typename TB>
 __global__ void __launch_bounds__(kWarps * 32, 2) bf_tile_smem_kernel(IndexView ix, const float* __restrict__ queries,
-                                                                   uint32_t nq, float* __restrict__ scores, bool as_value) {
+                                                                   uint32_t nq, ScoreSink out, bool as_value) {
     extern __shared__ __align__(16) uint8_t ts_smem[];
     const uint32_t dim = ix.dim;
     float* qs_all = reinterpret_cast<float*>(ts_smem);               // kTsQ x dim
@@ -364,7 +407,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) bf_tile_smem_kernel(IndexView 
                 } else {
                     v = as_value ? sum : -sum;
                 }
-                scores[(size_t)(qbase + my_t) * n + row] = v;
+                out.emit(qbase + my_t, row, v);
             }
         }
     }
@@ -427,10 +470,42 @@ __device__ __forceinline__ void scan_rows(const IndexView& ix, const float* qs, 
     }
 }
 
+// Fused selection for the scan kernel (fuse.k != 0): every warp keeps, per query, a sorted list of its k best keys
+// in shared memory (a ballot per tile decides whether anything can enter -- after the first tiles almost nothing
+// does), the CTA merges its warps' lists, writes one list per (query, CTA) and the last CTA to finish merges those
+// and writes the result: the scan and the top-k are ONE launch and no score matrix exists.
+struct ScanFuse {
+    uint32_t k = 0;             // 0 = not fused (scores go to the sink)
+    uint32_t desc = 0;
+    uint64_t* partial = nullptr;  // nq x gridDim.x x k keys
+    uint32_t* done = nullptr;     // CTA counter (self-resetting)
+    uint32_t* out_ids = nullptr;
+    float* out_score = nullptr;
+};
+
+// all lanes of the warp call it; inserts `key` into the ascending list res[0..len) capped at k
+__device__ __forceinline__ void list_offer(uint64_t* res, uint32_t& len, uint64_t& worst, uint32_t k, uint64_t key, uint32_t lane) {
+    uint32_t msk = __ballot_sync(FULL_MASK, key < worst);
+    while (msk) {
+        const uint32_t src = __ffs(msk) - 1;
+        msk &= msk - 1;
+        const uint64_t kk = __shfl_sync(FULL_MASK, key, src);
+        if (kk >= worst) continue;
+        const uint32_t pos = lower_bound_warp(res, len, kk, lane);
+        if (len < k) {
+            insert_at(res, pos, len + 1, kk, lane);
+            ++len;
+        } else {
+            insert_at(res, pos, len, kk, lane);
+        }
+        if (len == k) worst = res[k - 1];
+    }
+}
+
 template <typename TB, int QT, int RB>
 __global__ void __launch_bounds__(kWarps * 32) bf_scan_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq,
-                                                              float* __restrict__ scores, bool as_value) {
-    extern __shared__ __align__(16) float qs[];  // QT x dim, then QT norms
+                                                              ScoreSink out, bool as_value, ScanFuse fuse) {
+    extern __shared__ __align__(16) float qs[];  // QT x dim, then QT norms, then (fused) kWarps x QT lists of k keys
     constexpr int U = RB >= 4 ? 2 : (RB == 2 ? 4 : 8);  // 8 row loads in flight per lane
     const uint32_t dim = ix.dim;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -452,6 +527,15 @@ __global__ void __launch_bounds__(kWarps * 32) bf_scan_kernel(IndexView ix, cons
     const uint64_t n = ix.n;
     const uint32_t g = lane >> 3, t = lane & 7;
     const uint64_t tiles = (n + 4 * RB - 1) / (4 * RB);
+    // fused selection state: list q of this warp at lists + (warp * QT + q) * k
+    uint64_t* lists = reinterpret_cast<uint64_t*>(qs + (((size_t)QT * dim + QT + 3) & ~(size_t)3));
+    uint32_t flen[QT];
+    uint64_t fworst[QT];
+#pragma unroll
+    for (int q = 0; q < QT; ++q) {
+        flen[q] = 0;
+        fworst[q] = ~0ull;
+    }
     for (uint64_t tile = blockIdx.x * (uint64_t)kWarps + warp; tile < tiles; tile += (uint64_t)gridDim.x * kWarps) {
         const TB* r[RB];
         uint64_t row[RB];
@@ -489,15 +573,86 @@ __global__ void __launch_bounds__(kWarps * 32) bf_scan_kernel(IndexView ix, cons
                 }
                 mine = (int)t == q ? v : mine;
             }
-            if (t < nq && t < QT && row[b] < n) scores[(size_t)t * n + row[b]] = mine;
+            if (fuse.k == 0) {
+                if (t < nq && t < QT && row[b] < n) out.emit(t, row[b], mine);
+            } else {
+                uint64_t key = ~0ull;
+                if (t < nq && t < QT && row[b] < n) {
+                    uint32_t o = ord_key(mine);
+                    if (fuse.desc) o = ~o;
+                    key = ((uint64_t)o << 32) | (uint32_t)row[b];
+                }
+#pragma unroll
+                for (int q = 0; q < QT; ++q) {
+                    // lane t of each group holds query t's key for the group's row
+                    const uint64_t kq = (int)t == q ? key : ~0ull;
+                    if (__any_sync(FULL_MASK, kq < fworst[q]))
+                        list_offer(lists + ((size_t)warp * QT + q) * fuse.k, flen[q], fworst[q], fuse.k, kq, lane);
+                }
+            }
         }
     }
+    if (fuse.k == 0) return;
+    // ---- CTA merge: warp q % kWarps merges query q's kWarps lists into warp 0's list of that query ----
+    __shared__ uint32_t s_len[kWarps][QT];
+    __shared__ uint32_t s_last;
+    if (lane == 0)
+        for (int q = 0; q < QT; ++q) s_len[warp][q] = flen[q];
+    __syncthreads();
+    for (uint32_t q = warp; q < (uint32_t)QT && q < nq; q += kWarps) {
+        uint64_t* dst = lists + (size_t)q * fuse.k;  // warp 0's list of query q
+        uint32_t len = s_len[0][q];
+        uint64_t worst = len == fuse.k ? dst[fuse.k - 1] : ~0ull;
+        for (uint32_t w = 1; w < kWarps; ++w) {
+            const uint64_t* src = lists + ((size_t)w * QT + q) * fuse.k;
+            const uint32_t sl = s_len[w][q];
+            for (uint32_t j0 = 0; j0 < sl; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                list_offer(dst, len, worst, fuse.k, j < sl ? src[j] : ~0ull, lane);
+            }
+        }
+        __syncwarp();
+        uint64_t* po = fuse.partial + ((size_t)q * gridDim.x + blockIdx.x) * fuse.k;
+        for (uint32_t i = lane; i < fuse.k; i += 32) po[i] = i < len ? dst[i] : ~0ull;
+    }
+    // ---- the last CTA merges the per-CTA lists ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(fuse.done, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (uint32_t q = warp; q < nq; q += kWarps) {
+        uint64_t* dst = lists + (size_t)warp * QT * fuse.k;  // reuse this warp's list space
+        uint32_t len = 0;
+        uint64_t worst = ~0ull;
+        const uint64_t* in = fuse.partial + (size_t)q * gridDim.x * fuse.k;
+        const uint32_t total = gridDim.x * fuse.k;
+        for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            list_offer(dst, len, worst, fuse.k, j < total ? __ldcg(in + j) : ~0ull, lane);
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < fuse.k; i += 32) {
+            uint32_t id = VELES_INVALID_ID;
+            float sc = __uint_as_float(0x7fc00000u);
+            if (i < len) {
+                id = (uint32_t)dst[i];
+                const uint32_t o = (uint32_t)(dst[i] >> 32);
+                sc = ord_unkey(fuse.desc ? ~o : o);
+            }
+            fuse.out_ids[(size_t)q * fuse.k + i] = id;
+            fuse.out_score[(size_t)q * fuse.k + i] = sc;
+        }
+        __syncwarp();
+    }
+    if (threadIdx.x == 0) *fuse.done = 0u;  // ready for the next launch
 }
 
 // generic path: any metric, any dim >= 1, F32/F16 rows: one warp per (query, row) pair
 template <typename TB>
 __global__ void bf_generic_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq,
-                                  float* __restrict__ scores, bool as_value) {
+                                  ScoreSink out, bool as_value) {
     extern __shared__ __align__(16) float qs[];  // one query
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const uint32_t q = blockIdx.y;
@@ -510,12 +665,12 @@ __global__ void bf_generic_kernel(IndexView ix, const float* __restrict__ querie
         const uint8_t* row = ix.vecs + r * ix.row_bytes;
         float nb = ix.metric == VELES_COSINE ? *reinterpret_cast<const float*>(row + ix.norm_off) : 0.0f;
         float v = warp_metric(ix.metric, as_value, qs, reinterpret_cast<const TB*>(row), dim, na, nb, lane);
-        if (lane == 0) scores[(size_t)q * ix.n + r] = v;
+        if (lane == 0) out.emit(q, r, v);
     }
 }
 
 // packed-bit rows: Hamming count of (query > 0.5) bits vs row bits; one thread per row chunk
-__global__ void bf_bin_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq, float* __restrict__ scores) {
+__global__ void bf_bin_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq, ScoreSink out) {
     extern __shared__ __align__(16) uint32_t qw[];  // dim/32 words
     const uint32_t q = blockIdx.y, words = ix.dim >> 5;
     for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) {
@@ -545,7 +700,7 @@ __global__ void bf_bin_kernel(IndexView ix, const float* __restrict__ queries, u
         d += __shfl_xor_sync(FULL_MASK, d, 4);
         d += __shfl_xor_sync(FULL_MASK, d, 2);
         d += __shfl_xor_sync(FULL_MASK, d, 1);
-        if (sub == 0 && r < ix.n) scores[(size_t)q * ix.n + r] = (float)d;
+        if (sub == 0 && r < ix.n) out.emit(q, r, (float)d);
     }
 }
 
@@ -792,13 +947,19 @@ __global__ void pairs_kernel(int metric, const float* __restrict__ a, const floa
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-static int32_t launch_scores(const veles_index* ix, const float* q_d, uint32_t nq, float* scores_d, bool as_value,
-                             cudaStream_t st) {
-    IndexView v = ix->view();
+// `v`: the snapshot's view, or a strided view of it (row_bytes multiplied: every S-th row) for the sample pass
+static int32_t launch_scores(const veles_index* ixh, const IndexView& v, const float* q_d, uint32_t nq, const ScoreSink& sink,
+                             bool as_value, cudaStream_t st, const ScanFuse* fuse = nullptr) {
+    struct {
+        uint64_t n;
+        uint32_t dim;
+        int32_t dtype, metric;
+    } view{v.n, v.dim, v.dtype, v.metric}, *ix = &view;
+    (void)ixh;
     const int sms = device_sm_count();
     if (ix->dtype == VELES_BIN1) {
         dim3 grid((unsigned)std::min<uint64_t>((ix->n + 31) / 32 + 1, (uint64_t)sms * 8), nq);
-        bf_bin_kernel<<<grid, 256, (ix->dim / 32) * 4, st>>>(v, q_d, nq, scores_d);
+        bf_bin_kernel<<<grid, 256, (ix->dim / 32) * 4, st>>>(v, q_d, nq, sink);
         count_launch();
     } else if (ix->dim >= 16 && (ix->metric == VELES_COSINE || ix->metric == VELES_EUCLIDEAN || ix->metric == VELES_DOT)) {
         const size_t smem = ((size_t)kQT * ix->dim + kQT) * 4;
@@ -808,7 +969,7 @@ static int32_t launch_scores(const veles_index* ix, const float* q_d, uint32_t n
             const uint32_t qt = nq <= 1 ? 1 : nq <= 2 ? 2 : nq <= 4 ? 4 : 8;
             // one row per lane (RB = 1) measured best on B200 at every QT (RB = 2, 4 were no faster: fewer resident warps)
             constexpr uint32_t rb = 1;
-            using ScanT = void (*)(IndexView, const float*, uint32_t, float*, bool);
+            using ScanT = void (*)(IndexView, const float*, uint32_t, ScoreSink, bool, ScanFuse);
             ScanT ks;
 #define VELES_SCAN(TB) \
     (qt == 1 ? bf_scan_kernel<TB, 1, 1> : qt == 2 ? bf_scan_kernel<TB, 2, 1> : qt == 4 ? bf_scan_kernel<TB, 4, 1> : bf_scan_kernel<TB, 8, 1>)
@@ -817,13 +978,14 @@ static int32_t launch_scores(const veles_index* ix, const float* q_d, uint32_t n
             else
                 ks = VELES_SCAN(__half);
 #undef VELES_SCAN
-            const size_t smem_s = ((size_t)qt * ix->dim + qt) * 4;
+            const ScanFuse fz = fuse ? *fuse : ScanFuse();
+            const size_t smem_s = ((((size_t)qt * ix->dim + qt) + 3) & ~(size_t)3) * 4 + (size_t)kWarps * qt * fz.k * 8;
             VELES_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
             int per_sm = 1;
             VELES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ks, kWarps * 32, smem_s));
             const uint64_t tiles = (ix->n + 4 * rb - 1) / (4 * rb);
             const uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((tiles + kWarps - 1) / kWarps, (uint64_t)sms * std::max(per_sm, 1)));
-            ks<<<(unsigned)gx, kWarps * 32, smem_s, st>>>(v, q_d, nq, scores_d, as_value);
+            ks<<<(unsigned)gx, kWarps * 32, smem_s, st>>>(v, q_d, nq, sink, as_value, fz);
             count_launch();
             VELES_CUDA(cudaGetLastError());
             return VELES_OK;
@@ -848,8 +1010,7 @@ static int32_t launch_scores(const veles_index* ix, const float* q_d, uint32_t n
                     const uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>(tiles, std::max<uint64_t>(1, slots / ng)));
                     dim3 grid((unsigned)gx, ng);
                     const uint32_t qoff = g0 * kTsQ;
-                    kt<<<grid, kWarps * 32, smem_t, st>>>(v, q_d + (size_t)qoff * ix->dim, nq - qoff, scores_d + (size_t)qoff * ix->n,
-                                                         as_value);
+                    kt<<<grid, kWarps * 32, smem_t, st>>>(v, q_d + (size_t)qoff * ix->dim, nq - qoff, sink.at(qoff), as_value);
                     count_launch();
                 }
                 VELES_CUDA(cudaGetLastError());
@@ -873,8 +1034,7 @@ static int32_t launch_scores(const veles_index* ix, const float* q_d, uint32_t n
                 const uint32_t nt = std::min(32768u, ctiles - t0);
                 const uint32_t qoff = t0 * kQT * qw;
                 dim3 grid((unsigned)gx, nt);
-                kern8<<<grid, kWarps * 32, smem8, st>>>(v, q_d + (size_t)qoff * ix->dim, nq - qoff, scores_d + (size_t)qoff * ix->n,
-                                                       as_value);
+                kern8<<<grid, kWarps * 32, smem8, st>>>(v, q_d + (size_t)qoff * ix->dim, nq - qoff, sink.at(qoff), as_value);
                 count_launch();
             }
             VELES_CUDA(cudaGetLastError());
@@ -892,8 +1052,7 @@ static int32_t launch_scores(const veles_index* ix, const float* q_d, uint32_t n
             const uint32_t nt = std::min(32768u, qtiles - t0);
             const uint32_t qoff = t0 * kQT;
             dim3 grid((unsigned)gx, nt);
-            kern<<<grid, kWarps * 32, smem, st>>>(v, q_d + (size_t)qoff * ix->dim, nq - qoff, 0,
-                                                 scores_d + (size_t)qoff * ix->n, as_value);
+            kern<<<grid, kWarps * 32, smem, st>>>(v, q_d + (size_t)qoff * ix->dim, nq - qoff, 0, sink.at(qoff), as_value);
             count_launch();
         }
     } else {
@@ -901,8 +1060,7 @@ static int32_t launch_scores(const veles_index* ix, const float* q_d, uint32_t n
         for (uint32_t q0 = 0; q0 < nq; q0 += 32768) {
             const uint32_t nn = std::min(32768u, nq - q0);
             dim3 grid((unsigned)std::min<uint64_t>((ix->n + 7) / 8 + 1, (uint64_t)sms * 4), nn);
-            kern<<<grid, 256, (size_t)ix->dim * 4, st>>>(v, q_d + (size_t)q0 * ix->dim, nn, scores_d + (size_t)q0 * ix->n,
-                                                         as_value);
+            kern<<<grid, 256, (size_t)ix->dim * 4, st>>>(v, q_d + (size_t)q0 * ix->dim, nn, sink.at(q0), as_value);
             count_launch();
         }
     }
@@ -910,8 +1068,157 @@ static int32_t launch_scores(const veles_index* ix, const float* q_d, uint32_t n
     return VELES_OK;
 }
 
+// per query: order bits of the kp-th best of its `m` sample scores (0xffffffff = no bound: fewer than kp samples)
+__global__ void bf_threshold_kernel(const float* __restrict__ scores, uint64_t ld, uint32_t m, uint32_t nq, uint32_t kp, bool descending,
+                                    uint32_t* __restrict__ thr) {
+    extern __shared__ __align__(16) uint64_t bt_smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (q >= nq) return;
+    uint64_t* res = bt_smem + (size_t)warp * kp;
+    uint32_t len = 0;
+    uint64_t worst = ~0ull;
+    for (uint32_t base = 0; base < m; base += 32) {
+        const uint32_t i = base + lane;
+        uint64_t key = ~0ull;
+        if (i < m) {
+            uint32_t o = ord_key(scores[(size_t)q * ld + i]);
+            if (descending) o = ~o;
+            key = ((uint64_t)o << 32) | i;
+        }
+        if (__any_sync(FULL_MASK, key < worst)) list_offer(res, len, worst, kp, key, lane);
+    }
+    if (lane == 0) thr[q] = len == kp ? (uint32_t)(res[kp - 1] >> 32) : 0xffffffffu;
+}
+
+// per query: the k best of its candidate keys, written as (row, score); one warp per query
+__global__ void bf_select_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t nq, uint32_t k,
+                                 bool descending, uint32_t* __restrict__ out_ids, float* __restrict__ out_score) {
+    extern __shared__ __align__(16) uint64_t bs_smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (q >= nq) return;
+    uint64_t* res = bs_smem + (size_t)warp * k;
+    uint32_t len = 0;
+    uint64_t worst = ~0ull;
+    const uint32_t m = min(cnt[q], cap);
+    const uint64_t* in = cand + (size_t)q * cap;
+    for (uint32_t base = 0; base < m; base += 32) {
+        const uint32_t i = base + lane;
+        const uint64_t key = i < m ? in[i] : ~0ull;
+        if (__any_sync(FULL_MASK, key < worst)) list_offer(res, len, worst, k, key, lane);
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < k; i += 32) {
+        uint32_t id = VELES_INVALID_ID;
+        float sc = __uint_as_float(0x7fc00000u);
+        if (i < len) {
+            id = (uint32_t)res[i];
+            const uint32_t o = (uint32_t)(res[i] >> 32);
+            sc = ord_unkey(descending ? ~o : o);
+        }
+        out_ids[(size_t)q * k + i] = id;
+        out_score[(size_t)q * k + i] = sc;
+    }
+}
+
+// The exact scan without the [nq, n] score matrix (north_star: selection merged into the distance kernel).
+//   <= 8 queries   bf_scan_kernel keeps per-warp lists and finishes inside the same launch (ScanFuse)
+//   more queries   two passes of the same exact kernels: a strided sample of the collection into a small matrix ->
+//                  per query, the key of its kp-th best sample (a bound no true top-k row can miss), then the full
+//                  scan whose results go through the bound into per-query candidate lists (ScoreSink FILTER), then
+//                  bf_select_kernel.  Same scores, same order as the matrix path; a list overflow (a collection whose
+//                  strided sample is unrepresentative) falls back to the matrix path.
+// Returns 1 when the fused path ran, 0 when the caller should use the matrix path.
+static int32_t bruteforce_fused(const veles_index* ix, const float* q_d, uint32_t nq, uint32_t k, uint32_t* ids_d, float* score_d,
+                                bool desc, cudaStream_t st, int* ran) {
+    *ran = 0;
+    const int sms = device_sm_count();
+    const IndexView v = ix->view();
+    const bool fast_metric = ix->dtype != VELES_BIN1 && ix->dim >= 16 &&
+                             (ix->metric == VELES_COSINE || ix->metric == VELES_EUCLIDEAN || ix->metric == VELES_DOT);
+    if (std::getenv("VELES_BF_NO_FUSE")) return VELES_OK;
+    if (fast_metric && ix->dim % 32 == 0 && nq <= 8 && k <= 128) {
+        const uint32_t qt = nq <= 1 ? 1 : nq <= 2 ? 2 : nq <= 4 ? 4 : 8;
+        if ((size_t)kWarps * qt * k * 8 > 96 * 1024) return VELES_OK;
+        const size_t max_ctas = (size_t)sms * 16;
+        VELES_TRY(ix->topk_d.ensure((size_t)nq * max_ctas * k * 8 + 64));
+        if (!ix->bf_done.p) {
+            VELES_TRY(ix->bf_done.alloc(64));
+            VELES_CUDA(cudaMemsetAsync(ix->bf_done.p, 0, 64, st));
+        }
+        ScanFuse fz;
+        fz.k = k;
+        fz.desc = desc ? 1u : 0u;
+        fz.partial = ix->topk_d.as<uint64_t>();
+        fz.done = ix->bf_done.as<uint32_t>();
+        fz.out_ids = ids_d;
+        fz.out_score = score_d;
+        VELES_TRY(launch_scores(ix, v, q_d, nq, ScoreSink(), true, st, &fz));
+        *ran = 1;
+        return VELES_OK;
+    }
+    if (nq <= 8 || ix->n < 65536 || k > 1024) return VELES_OK;
+    const uint32_t kp = std::max(k, 16u);
+    // sample every S-th row; ~n/64 rows but at least 8192: expected candidates per query ~ kp * S
+    const uint64_t s_rows = std::min<uint64_t>(ix->n, std::max<uint64_t>(8192, ix->n / 64));
+    const uint64_t S = ix->n / s_rows;
+    if (S < 4 || (uint64_t)ix->row_bytes * S > 0xffffffffull) return VELES_OK;
+    const uint64_t m = ix->n / S;
+    const uint32_t cap = (uint32_t)std::min<uint64_t>(ix->n, 4 * (uint64_t)kp * S + 256);
+    // queries per pass: sample matrix <= 256 MiB, candidate lists <= 512 MiB
+    const uint32_t chunk = (uint32_t)std::max<uint64_t>(
+        9, std::min<uint64_t>(nq, std::min<uint64_t>((256ull << 20) / (m * 4), (512ull << 20) / ((uint64_t)cap * 8))));
+    if (chunk <= 8) return VELES_OK;
+    VELES_TRY(ix->scores_d.ensure((size_t)chunk * m * 4));
+    VELES_TRY(ix->topk_d.ensure((size_t)chunk * cap * 8));
+    VELES_TRY(ix->bf_aux.ensure((size_t)chunk * 8 + 64));
+    uint32_t* thr = ix->bf_aux.as<uint32_t>();
+    uint32_t* cnt = thr + chunk;
+    uint32_t* err = cnt + chunk;
+    IndexView vs = v;
+    vs.row_bytes = (uint32_t)(ix->row_bytes * S);
+    vs.n = m;
+    // equal passes, so that none falls into the <= 8 query (scan kernel) regime
+    const uint32_t passes = (nq + chunk - 1) / chunk;
+    if (nq / passes < 9) return VELES_OK;
+    uint32_t q0 = 0;
+    for (uint32_t pass = 0; pass < passes; ++pass) {
+        const uint32_t nn = nq / passes + (pass < nq % passes ? 1u : 0u);
+        VELES_CUDA(cudaMemsetAsync(cnt, 0, (size_t)chunk * 4 + 16, st));
+        ScoreSink store;
+        store.scores = ix->scores_d.as<float>();
+        store.ld = m;
+        VELES_TRY(launch_scores(ix, vs, q_d + (size_t)q0 * ix->dim, nn, store, true, st));
+        const uint32_t tw = kp <= 128 ? 8 : 2;
+        bf_threshold_kernel<<<(nn + tw - 1) / tw, tw * 32, (size_t)tw * kp * 8, st>>>(ix->scores_d.as<float>(), m, (uint32_t)m, nn, kp, desc, thr);
+        count_launch();
+        ScoreSink filt;
+        filt.thr = thr;
+        filt.cnt = cnt;
+        filt.cand = ix->topk_d.as<uint64_t>();
+        filt.cap = cap;
+        filt.err = err;
+        filt.desc = desc ? 1u : 0u;
+        VELES_TRY(launch_scores(ix, v, q_d + (size_t)q0 * ix->dim, nn, filt, true, st));
+        const uint32_t sw = k <= 128 ? 8 : 2;
+        bf_select_kernel<<<(nn + sw - 1) / sw, sw * 32, (size_t)sw * k * 8, st>>>(ix->topk_d.as<uint64_t>(), cnt, cap, nn, k, desc,
+                                                                                ids_d + (size_t)q0 * k, score_d + (size_t)q0 * k);
+        count_launch();
+        VELES_CUDA(cudaGetLastError());
+        uint32_t h = 0;
+        VELES_CUDA(cudaMemcpyAsync(&h, err, 4, cudaMemcpyDeviceToHost, st));
+        VELES_CUDA(cudaStreamSynchronize(st));
+        if (h != 0) return VELES_OK;  // a candidate list overflowed: the caller redoes the batch on the matrix path
+        q0 += nn;
+    }
+    *ran = 1;
+    return VELES_OK;
+}
+
 static int32_t bruteforce_device(const veles_index* ix, const float* q_d, uint32_t nq, uint32_t k, uint32_t* ids_d,
                                  float* score_d, cudaStream_t st) {
+    NvtxRange nvtx_range("veles::bruteforce (HnswIndex::search_brute_force)");
     VELES_REQUIRE(k >= 1 && k <= 16384, "k must be in 1..16384, got %u", k);
     if (nq == 0) return VELES_OK;
     if (ix->n == 0) {
@@ -919,17 +1226,25 @@ static int32_t bruteforce_device(const veles_index* ix, const float* q_d, uint32
         VELES_CUDA(cudaMemsetAsync(score_d, 0xff, (size_t)nq * k * 4, st));  // 0xffffffff is a NaN
         return VELES_OK;
     }
-    // bound the score matrix to ~1 GiB per pass
+    const bool desc = ix->metric == VELES_COSINE || ix->metric == VELES_DOT || ix->metric == VELES_JACCARD;
+    {
+        int ran = 0;
+        VELES_TRY(bruteforce_fused(ix, q_d, nq, k, ids_d, score_d, desc, st, &ran));
+        if (ran) return VELES_OK;
+    }
+    // matrix path: [nq, n] metric values (<= ~1 GiB per pass), then a top-k kernel per query
     const uint64_t per_q = ix->n * 4;
     const uint32_t chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(nq, (1ull << 30) / per_q));
     VELES_TRY(ix->scores_d.ensure((size_t)chunk * per_q));
-    const bool desc = ix->metric == VELES_COSINE || ix->metric == VELES_DOT || ix->metric == VELES_JACCARD;
     VELES_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(k * 8)));
     if (k <= 512)
         VELES_CUDA(cudaFuncSetAttribute(topk_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTopWarps * k * 8)));
     for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
         const uint32_t nn = std::min(chunk, nq - q0);
-        VELES_TRY(launch_scores(ix, q_d + (size_t)q0 * ix->dim, nn, ix->scores_d.as<float>(), true, st));
+        ScoreSink store;
+        store.scores = ix->scores_d.as<float>();
+        store.ld = ix->n;
+        VELES_TRY(launch_scores(ix, ix->view(), q_d + (size_t)q0 * ix->dim, nn, store, true, st));
         // few queries over many rows: split every row into chunks (first level), then merge (second level)
         const int sms = device_sm_count();
         uint32_t chunks = 1;

@@ -601,6 +601,7 @@ static uint32_t env_u32b(const char* name, uint32_t dflt) {
 using namespace veles;
 
 extern "C" int32_t veles_index_build_graph(veles_index_t* ix, uint32_t M, uint32_t ef_construction, void* stream) {
+    NvtxRange nvtx_range("veles::build_graph (NativeHnsw::insert, block insertion)");
     VELES_REQUIRE(ix != nullptr, "index is NULL");
     VELES_REQUIRE(M >= 2 && M <= 128, "M must be in 2..128, got %u", M);
     if (ef_construction == 0) ef_construction = env_u32b("VELES_BUILD_EF", 200);

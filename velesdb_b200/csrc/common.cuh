@@ -3,6 +3,7 @@
 
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <atomic>
 #include <cstdarg>
@@ -23,6 +24,15 @@ namespace veles {
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
 inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// NVTX range around each kernel group, named after the reference function it stands for: the tracing counterpart of
+// the reference's spans (core/metrics.rs:977-1058).  Header-only NVTX 3: a no-op unless a profiler is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 #define VELES_CUDA(expr)                                                                          \
     do {                                                                                          \

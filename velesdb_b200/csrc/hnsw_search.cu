@@ -81,7 +81,8 @@ void release_ctx(const veles_index* ix, SearchCtx* c) {
 
 int32_t launch_search(const veles_index* ix, const IndexView& view, SearchCtx* ctx, const float* q_d, uint32_t nq, uint32_t k,
                       uint32_t ef, uint32_t* ids_d, float* dist_d, uint32_t* cnt_d, uint32_t* stats_d, cudaStream_t st,
-                      const uint32_t* extra_entries_d) {
+                      const uint32_t* extra_entries_d, const PeerOut* peers) {
+    NvtxRange nvtx_range("veles::hnsw_search_kernel (NativeHnsw::search)");
     VELES_REQUIRE(ix->has_graph, "snapshot has no graph; build or load one first");
     VELES_REQUIRE(view.dtype != VELES_SQ8 || ix->dim <= 32768, "SQ8 traversal supports at most 32768 dimensions");
     VELES_REQUIRE(k >= 1 && k <= 65536, "k must be in 1..65536, got %u", k);
@@ -100,6 +101,12 @@ int32_t launch_search(const veles_index* ix, const IndexView& view, SearchCtx* c
     p.out_counts = cnt_d;
     p.out_stats = stats_d;
     p.extra_entries = extra_entries_d;
+    p.n_peers = peers ? std::min(peers->n, kMaxPeers) : 0u;
+    for (uint32_t r = 0; r < kMaxPeers; ++r) {
+        p.peer_ids[r] = r < p.n_peers ? peers->ids[r] : nullptr;
+        p.peer_dist[r] = r < p.n_peers ? peers->dist[r] : nullptr;
+        p.peer_cnt[r] = r < p.n_peers ? peers->cnt[r] : nullptr;
+    }
 
     // shared-memory carve: [control words] results | todo | [distances, multi-warp only] | query | per warp: barriers + ring
     const uint32_t bar_bytes = kMaxSlots * 8;

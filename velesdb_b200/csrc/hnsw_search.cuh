@@ -35,6 +35,7 @@ namespace veles {
 constexpr uint32_t kMaxSlots = 16;      // ring slots per warp (upper bound)
 constexpr uint32_t kTieCap = 4096;      // per-query tie-list capacity (keys), lives in global scratch
 constexpr uint32_t kLogCap = 16384;     // visited-log entries per query slot before falling back to a full clear
+constexpr uint32_t kMaxPeers = 7;       // other GPUs of one NVSwitch box
 
 struct SearchParams {
     IndexView ix;
@@ -45,6 +46,12 @@ struct SearchParams {
     uint32_t* out_counts;
     uint32_t* out_stats;  // may be null
     const uint32_t* extra_entries;  // nq x 3 extra layer-0 entry points (INVALID padded), or null
+    // multi-GPU gather fused into the epilogue (comm.cu): every query's results are also stored into the same
+    // position of up to kMaxPeers peer windows -- peer-mapped memory, i.e. posted stores over NVLink
+    uint32_t n_peers;
+    uint32_t* peer_ids[kMaxPeers];
+    float* peer_dist[kMaxPeers];
+    uint32_t* peer_cnt[kMaxPeers];
     uint32_t* visited;    // slots x vis_words
     uint32_t* vlog;       // slots x kLogCap
     uint64_t* tie;        // slots x kTieCap
@@ -1021,8 +1028,14 @@ __global__ void __launch_bounds__(COOP ? 256 : 32, 1) hnsw_search_kernel(const S
             auto emit = [&](uint32_t i, uint64_t key) {
                 if (i < p.k) {
                     const bool ok = i < cnt;
-                    p.out_ids[(size_t)qi * p.k + i] = ok ? key_id(key) : VELES_INVALID_ID;
-                    p.out_dist[(size_t)qi * p.k + i] = ok ? key_dist(key) : __uint_as_float(0x7fc00000u);
+                    const uint32_t id = ok ? key_id(key) : VELES_INVALID_ID;
+                    const float d = ok ? key_dist(key) : __uint_as_float(0x7fc00000u);
+                    p.out_ids[(size_t)qi * p.k + i] = id;
+                    p.out_dist[(size_t)qi * p.k + i] = d;
+                    for (uint32_t r = 0; r < p.n_peers; ++r) {
+                        p.peer_ids[r][(size_t)qi * p.k + i] = id;
+                        p.peer_dist[r][(size_t)qi * p.k + i] = d;
+                    }
                 }
             };
             if (R == 0) {
@@ -1035,6 +1048,7 @@ __global__ void __launch_bounds__(COOP ? 256 : 32, 1) hnsw_search_kernel(const S
             }
             if (lane == 0) {
                 p.out_counts[qi] = cnt;
+                for (uint32_t r = 0; r < p.n_peers; ++r) p.peer_cnt[r][qi] = cnt;
                 if (p.out_stats) {
                     p.out_stats[(size_t)qi * 4 + 0] = ndc0;
                     p.out_stats[(size_t)qi * 4 + 1] = hops0;

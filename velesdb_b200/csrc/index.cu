@@ -248,6 +248,77 @@ int32_t veles_index_from_vectors(const void* vectors, uint64_t n, uint32_t dim, 
     return VELES_OK;
 }
 
+// An empty snapshot of n zero rows, to be filled by veles_index_set_rows_d: for hosts that produce (or already
+// hold) the vectors on the device, so that 10M+ row collections never pass through host memory.
+int32_t veles_index_create(uint64_t n, uint32_t dim, int32_t store_dtype, int32_t metric, veles_index_t** out) {
+    VELES_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    static const float dummy = 0.0f;
+    VELES_TRY(check_common(n, dim, store_dtype, store_dtype, metric, &dummy));
+    VELES_REQUIRE(n < (1ull << 31), "at most 2^31-1 nodes per snapshot");
+    std::unique_ptr<veles_index> ix(new veles_index());
+    VELES_CUDA(cudaGetDevice(&ix->device));
+    ix->metric = metric;
+    ix->dtype = store_dtype;
+    ix->dim = dim;
+    ix->n = n;
+    compute_row_layout(ix.get());
+    VELES_TRY(ix->vecs.alloc((size_t)n * ix->row_bytes));
+    if (n) VELES_CUDA(cudaMemset(ix->vecs.p, 0, (size_t)n * ix->row_bytes));
+    *out = ix.release();
+    return VELES_OK;
+}
+
+// Rows [first, first + count) from device memory: src_dtype F32 (count*dim floats, converted to the store type as
+// veles_index_from_vectors does) or the store type itself (F16: count*dim halves; BIN1: count*(dim/64) u64 words).
+// Cosine norms of those rows are recomputed.  Any graph held by the snapshot is left alone.
+int32_t veles_index_set_rows_d(veles_index_t* ix, uint64_t first, uint64_t count, const void* rows_d, int32_t src_dtype,
+                               void* stream) {
+    VELES_REQUIRE(ix != nullptr, "index is NULL");
+    VELES_REQUIRE(first <= ix->n && count <= ix->n - first, "rows [%llu, +%llu) outside the snapshot (%llu rows)",
+                  (unsigned long long)first, (unsigned long long)count, (unsigned long long)ix->n);
+    if (count == 0) return VELES_OK;
+    VELES_REQUIRE(rows_d != nullptr, "rows_d is NULL");
+    VELES_REQUIRE(src_dtype == ix->dtype || src_dtype == VELES_F32, "unsupported conversion: src dtype %d -> store dtype %d",
+                  src_dtype, ix->dtype);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> g(ix->mu);
+    const int sms = device_sm_count();
+    uint8_t* dst = ix->vecs.as<uint8_t>() + first * ix->row_bytes;
+    if (src_dtype == ix->dtype) {
+        const size_t width = ix->dtype == VELES_BIN1 ? (size_t)(ix->dim / 64) * 8 : (size_t)ix->dim * elt_bytes(ix->dtype);
+        VELES_CUDA(cudaMemcpy2DAsync(dst, ix->row_bytes, rows_d, width, width, count, cudaMemcpyDeviceToDevice, st));
+    } else if (ix->dtype == VELES_F16) {
+        f32_to_f16_rows<<<sms * 8, 256, 0, st>>>(static_cast<const float*>(rows_d), dst, count, ix->dim, ix->row_bytes);
+        count_launch();
+    } else {
+        f32_to_bits_rows<<<sms * 8, 256, 0, st>>>(static_cast<const float*>(rows_d), dst, count, ix->dim, ix->row_bytes);
+        count_launch();
+    }
+    VELES_CUDA(cudaGetLastError());
+    if (ix->metric == VELES_COSINE && ix->dtype != VELES_BIN1) {
+        if (ix->dtype == VELES_F32)
+            row_norms_kernel<float><<<sms * 4, 256, 0, st>>>(dst, count, ix->dim, ix->row_bytes, ix->norm_off);
+        else
+            row_norms_kernel<__half><<<sms * 4, 256, 0, st>>>(dst, count, ix->dim, ix->row_bytes, ix->norm_off);
+        count_launch();
+        VELES_CUDA(cudaGetLastError());
+    }
+    return VELES_OK;
+}
+
+// Rows [first, first + count) back to the host in the store type (F32: floats, F16: halves, BIN1: u64 words), without
+// the row trailer -- what a host needs to re-stage the vectors of a snapshot it loaded from files.
+int32_t veles_index_get_rows(const veles_index_t* ix, uint64_t first, uint64_t count, void* out) {
+    VELES_REQUIRE(ix != nullptr && (count == 0 || out != nullptr), "NULL argument");
+    VELES_REQUIRE(first <= ix->n && count <= ix->n - first, "rows outside the snapshot");
+    if (count == 0) return VELES_OK;
+    const size_t width = ix->dtype == VELES_BIN1 ? (size_t)(ix->dim / 64) * 8 : (size_t)ix->dim * elt_bytes(ix->dtype);
+    VELES_CUDA(cudaMemcpy2D(out, width, ix->vecs.as<uint8_t>() + first * ix->row_bytes, ix->row_bytes, width, count,
+                            cudaMemcpyDeviceToHost));
+    return VELES_OK;
+}
+
 int32_t veles_index_from_arrays(const void* vectors, uint64_t n, uint32_t dim, int32_t src_dtype, int32_t store_dtype,
                                 int32_t metric, uint32_t num_layers, const uint64_t* const* row_ptr,
                                 const uint32_t* const* cols, const uint64_t* layer_nodes, uint32_t M, uint32_t M0,
@@ -286,7 +357,27 @@ int32_t veles_index_from_reference_files(const char* dir, const char* basename, 
         std::fclose(f);
         return io_fail(ok ? "Unsupported version: " + std::to_string(version) : "truncated header in " + vp);
     }
-    std::vector<float> vecs((size_t)count * dim);
+    // sizes come from the file: validate them against the file itself before allocating anything
+    long fsize = 0;
+    {
+        const long here = std::ftell(f);
+        std::fseek(f, 0, SEEK_END);
+        fsize = std::ftell(f);
+        std::fseek(f, here, SEEK_SET);
+    }
+    if (dim > 65536 || count >= (1ull << 31) || (count > 0 && dim == 0) ||
+        (uint64_t)count * dim > ((uint64_t)(fsize > 16 ? fsize - 16 : 0)) / 4) {
+        std::fclose(f);
+        return io_fail("corrupt header in " + vp + " (count/dimension do not fit the file)");
+    }
+    std::vector<float> vecs;
+    try {
+        vecs.resize((size_t)count * dim);
+    } catch (const std::exception&) {
+        std::fclose(f);
+        set_error("out of host memory reading %s", vp.c_str());
+        return VELES_ERR_OOM;
+    }
     if (!vecs.empty() && std::fread(vecs.data(), 4, vecs.size(), f) != vecs.size()) {
         std::fclose(f);
         return io_fail("truncated vector data in " + vp);
@@ -310,31 +401,48 @@ int32_t veles_index_from_reference_files(const char* dir, const char* basename, 
     std::vector<std::vector<uint64_t>> rps(nl);
     std::vector<std::vector<uint32_t>> cls(nl);
     std::vector<uint64_t> nodes(nl);
-    for (uint32_t l = 0; l < nl && ok; ++l) {
-        uint64_t nn = 0;
-        if (std::fread(&nn, 8, 1, f) != 1) {
-            ok = false;
-            break;
-        }
-        nodes[l] = nn;
-        rps[l].resize(nn + 1);
-        rps[l][0] = 0;
-        for (uint64_t i = 0; i < nn; ++i) {
-            uint32_t deg = 0;
-            if (std::fread(&deg, 4, 1, f) != 1) {
+    std::string bad;
+    try {
+        for (uint32_t l = 0; l < nl && ok; ++l) {
+            uint64_t nn = 0;
+            if (std::fread(&nn, 8, 1, f) != 1) {
                 ok = false;
                 break;
             }
-            size_t base = cls[l].size();
-            cls[l].resize(base + deg);
-            if (deg && std::fread(cls[l].data() + base, 4, deg, f) != deg) {
-                ok = false;
+            if (nn > count) {  // Layer::new(num_nodes) never exceeds the vector count (graph.rs:173-178)
+                bad = "layer " + std::to_string(l) + " claims more nodes than there are vectors in " + gp;
                 break;
             }
-            rps[l][i + 1] = base + deg;
+            nodes[l] = nn;
+            rps[l].resize(nn + 1);
+            rps[l][0] = 0;
+            for (uint64_t i = 0; i < nn; ++i) {
+                uint32_t deg = 0;
+                if (std::fread(&deg, 4, 1, f) != 1) {
+                    ok = false;
+                    break;
+                }
+                if (deg > 4096) {
+                    bad = "adjacency row longer than 4096 in " + gp;
+                    break;
+                }
+                size_t base = cls[l].size();
+                cls[l].resize(base + deg);
+                if (deg && std::fread(cls[l].data() + base, 4, deg, f) != deg) {
+                    ok = false;
+                    break;
+                }
+                rps[l][i + 1] = base + deg;
+            }
+            if (!bad.empty()) break;
         }
+    } catch (const std::exception&) {
+        std::fclose(f);
+        set_error("out of host memory reading %s", gp.c_str());
+        return VELES_ERR_OOM;
     }
     std::fclose(f);
+    if (!bad.empty()) return io_fail(bad);
     if (!ok) return io_fail("truncated graph data in " + gp);
     std::vector<const uint64_t*> rp(nl);
     std::vector<const uint32_t*> cp(nl);
@@ -403,67 +511,113 @@ int32_t veles_index_export_layer(const veles_index_t* idx, uint32_t layer, uint6
     return VELES_OK;
 }
 
+// the `.graph` half of NativeHnsw::file_dump (native/backend_adapter.rs:213-261); any storage type
+int32_t veles_index_dump_graph(const veles_index_t* idx, const char* dir, const char* basename) {
+    VELES_REQUIRE(idx && dir && basename, "NULL argument");
+    VELES_REQUIRE(idx->has_graph, "snapshot has no graph");
+    const uint64_t n = idx->n;
+    const std::string gp = std::string(dir) + "/" + basename + ".graph";
+    FILE* f = std::fopen(gp.c_str(), "wb");
+    if (!f) {
+        set_error("cannot create %s", gp.c_str());
+        return VELES_ERR_IO;
+    }
+    bool ok = true;
+    auto put = [&](const void* p, size_t sz, size_t cnt) { ok = ok && std::fwrite(p, sz, cnt, f) == cnt; };
+    const uint32_t version = 1, nl = idx->num_layers, maxl = idx->max_layer, efc = idx->ef_construction;
+    const uint64_t ep = idx->has_entry ? idx->entry : 0;
+    put(&version, 4, 1);
+    put(&nl, 4, 1);
+    put(&idx->M, 4, 1);
+    put(&idx->M0, 4, 1);
+    put(&efc, 4, 1);
+    put(&ep, 8, 1);
+    put(&maxl, 4, 1);
+    put(&n, 8, 1);
+    try {
+        for (uint32_t l = 0; l < nl && ok; ++l) {
+            uint64_t nodes = 0, edges = 0;
+            int32_t s = veles_index_export_layer(idx, l, &nodes, &edges, nullptr, nullptr);
+            std::vector<uint64_t> rp;
+            std::vector<uint32_t> cl;
+            if (s == VELES_OK) {
+                rp.resize(nodes + 1);
+                cl.resize(std::max<uint64_t>(edges, 1));
+                s = veles_index_export_layer(idx, l, &nodes, &edges, rp.data(), cl.data());
+            }
+            if (s != VELES_OK) {
+                std::fclose(f);
+                return s;
+            }
+            put(&nodes, 8, 1);
+            // one buffered record stream per layer: deg, ids, deg, ids, ...
+            std::vector<uint32_t> rec;
+            rec.reserve((size_t)1 << 20);
+            for (uint64_t i = 0; i < nodes && ok; ++i) {
+                const uint32_t deg = (uint32_t)(rp[i + 1] - rp[i]);
+                rec.push_back(deg);
+                rec.insert(rec.end(), cl.begin() + rp[i], cl.begin() + rp[i] + deg);
+                if (rec.size() >= ((size_t)1 << 20) - 4200) {
+                    put(rec.data(), 4, rec.size());
+                    rec.clear();
+                }
+            }
+            if (!rec.empty()) put(rec.data(), 4, rec.size());
+        }
+    } catch (const std::exception&) {
+        std::fclose(f);
+        set_error("out of host memory writing %s", gp.c_str());
+        return VELES_ERR_OOM;
+    }
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) {
+        set_error("short write to %s (disk full?)", gp.c_str());
+        return VELES_ERR_IO;
+    }
+    return VELES_OK;
+}
+
 // NativeHnsw::file_dump, native/backend_adapter.rs:184-261
 int32_t veles_index_dump(const veles_index_t* idx, const char* dir, const char* basename) {
     VELES_REQUIRE(idx && dir && basename, "NULL argument");
     VELES_REQUIRE(idx->dtype == VELES_F32, "file format v1 stores f32 vectors; this snapshot holds dtype %d", idx->dtype);
     VELES_REQUIRE(idx->has_graph, "snapshot has no graph");
     const uint64_t n = idx->n;
-    std::vector<float> vecs((size_t)n * idx->dim);
-    if (n)
-        VELES_CUDA(cudaMemcpy2D(vecs.data(), (size_t)idx->dim * 4, idx->vecs.p, idx->row_bytes, (size_t)idx->dim * 4, n,
-                                cudaMemcpyDeviceToHost));
-    std::string vp = std::string(dir) + "/" + basename + ".vectors";
-    std::string gp = std::string(dir) + "/" + basename + ".graph";
+    const std::string vp = std::string(dir) + "/" + basename + ".vectors";
     FILE* f = std::fopen(vp.c_str(), "wb");
     if (!f) {
         set_error("cannot create %s", vp.c_str());
         return VELES_ERR_IO;
     }
-    uint32_t version = 1, dim = n ? idx->dim : 0;
-    std::fwrite(&version, 4, 1, f);
-    std::fwrite(&n, 8, 1, f);
-    std::fwrite(&dim, 4, 1, f);
-    if (!vecs.empty()) std::fwrite(vecs.data(), 4, vecs.size(), f);
-    std::fclose(f);
-    f = std::fopen(gp.c_str(), "wb");
-    if (!f) {
-        set_error("cannot create %s", gp.c_str());
+    bool ok = true;
+    const uint32_t version = 1, dim = n ? idx->dim : 0;
+    ok = ok && std::fwrite(&version, 4, 1, f) == 1 && std::fwrite(&n, 8, 1, f) == 1 && std::fwrite(&dim, 4, 1, f) == 1;
+    try {
+        // 64 MiB of rows at a time
+        const uint64_t chunk = std::max<uint64_t>(1, ((uint64_t)64 << 20) / ((uint64_t)idx->dim * 4));
+        std::vector<float> buf((size_t)std::min<uint64_t>(chunk, std::max<uint64_t>(n, 1)) * idx->dim);
+        for (uint64_t r0 = 0; r0 < n && ok; r0 += chunk) {
+            const uint64_t rows = std::min<uint64_t>(chunk, n - r0);
+            cudaError_t e = cudaMemcpy2D(buf.data(), (size_t)idx->dim * 4, idx->vecs.as<uint8_t>() + r0 * idx->row_bytes,
+                                         idx->row_bytes, (size_t)idx->dim * 4, rows, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) {
+                std::fclose(f);
+                set_error("cudaMemcpy2D failed: %s", cudaGetErrorString(e));
+                return VELES_ERR_CUDA;
+            }
+            ok = ok && std::fwrite(buf.data(), 4, (size_t)rows * idx->dim, f) == (size_t)rows * idx->dim;
+        }
+    } catch (const std::exception&) {
+        std::fclose(f);
+        set_error("out of host memory writing %s", vp.c_str());
+        return VELES_ERR_OOM;
+    }
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) {
+        set_error("short write to %s (disk full?)", vp.c_str());
         return VELES_ERR_IO;
     }
-    uint32_t nl = idx->num_layers, maxl = idx->max_layer, efc = idx->ef_construction;
-    uint64_t ep = idx->has_entry ? idx->entry : 0;
-    std::fwrite(&version, 4, 1, f);
-    std::fwrite(&nl, 4, 1, f);
-    std::fwrite(&idx->M, 4, 1, f);
-    std::fwrite(&idx->M0, 4, 1, f);
-    std::fwrite(&efc, 4, 1, f);
-    std::fwrite(&ep, 8, 1, f);
-    std::fwrite(&maxl, 4, 1, f);
-    std::fwrite(&n, 8, 1, f);
-    for (uint32_t l = 0; l < nl; ++l) {
-        uint64_t nodes = 0, edges = 0;
-        int32_t s = veles_index_export_layer(idx, l, &nodes, &edges, nullptr, nullptr);
-        if (s != VELES_OK) {
-            std::fclose(f);
-            return s;
-        }
-        std::vector<uint64_t> rp(nodes + 1);
-        std::vector<uint32_t> cl(std::max<uint64_t>(edges, 1));
-        s = veles_index_export_layer(idx, l, &nodes, &edges, rp.data(), cl.data());
-        if (s != VELES_OK) {
-            std::fclose(f);
-            return s;
-        }
-        std::fwrite(&nodes, 8, 1, f);
-        for (uint64_t i = 0; i < nodes; ++i) {
-            uint32_t deg = (uint32_t)(rp[i + 1] - rp[i]);
-            std::fwrite(&deg, 4, 1, f);
-            if (deg) std::fwrite(cl.data() + rp[i], 4, deg, f);
-        }
-    }
-    std::fclose(f);
-    return VELES_OK;
+    return veles_index_dump_graph(idx, dir, basename);
 }
 
 }  // extern "C"

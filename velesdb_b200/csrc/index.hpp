@@ -62,6 +62,11 @@ struct veles_index {
     bool has_sq8 = false;
     mutable veles::DevBuf sq_ids_d, sq_dist_d, sq_cnt_d;  // coarse candidates between traversal and re-rank
 
+    // fp16 copy of the collection for the tensor-core candidate GEMM (gemm_tc.cu), built on first use: rows of
+    // x16_dpad halves (dim padded to 64), cosine rows pre-normalised; x16_bias = |row16|^2 (L2)
+    mutable veles::DevBuf x16, x16_bias;
+    mutable uint32_t x16_dpad = 0;
+
     // node index -> external id, live (not tombstoned) bitmap: ShardedMappings on the device (postfilter.cu)
     veles::DevBuf id_map_d, live_d;
     mutable veles::DevBuf allow_d, map_ids_d, map_score_d, extra_d;
@@ -70,7 +75,7 @@ struct veles_index {
     mutable std::mutex mu;
     mutable std::vector<std::unique_ptr<veles::SearchCtx>> ctxs;
     mutable std::vector<cudaStream_t> overflowed;  // streams whose overflow flag was harvested when a context moved on
-    mutable veles::DevBuf q_d, out_ids_d, out_val_d, out_cnt_d, out_stats_d, scores_d, topk_d;
+    mutable veles::DevBuf q_d, out_ids_d, out_val_d, out_cnt_d, out_stats_d, scores_d, topk_d, bf_aux, bf_done;
 
     veles::IndexView view() const {
         veles::IndexView v;
@@ -128,10 +133,17 @@ int device_sm_count();
 // the oldest).  `exclusive` marks it in_use until release_ctx.
 int32_t acquire_ctx(const veles_index* ix, cudaStream_t st, bool exclusive, SearchCtx** out);
 void release_ctx(const veles_index* ix, SearchCtx* c);
+// extra destinations of a launch's results (peer GPUs' gather windows, comm.cu)
+struct PeerOut {
+    uint32_t n = 0;
+    uint32_t* ids[7];
+    float* dist[7];
+    uint32_t* cnt[7];
+};
 // batched traversal over `view` (the snapshot's own rows, or its SQ8 codes) with `ctx`'s scratch; records ctx->done
 int32_t launch_search(const veles_index* ix, const IndexView& view, SearchCtx* ctx, const float* q_d, uint32_t nq, uint32_t k,
                       uint32_t ef, uint32_t* ids_d, float* dist_d, uint32_t* cnt_d, uint32_t* stats_d, cudaStream_t st,
-                      const uint32_t* extra_entries_d = nullptr);
+                      const uint32_t* extra_entries_d = nullptr, const PeerOut* peers = nullptr);
 // synchronises `st`, reads and clears the context's overflow flag
 int32_t check_search_error_flag(SearchCtx* ctx, cudaStream_t st);
 }  // namespace veles

@@ -354,6 +354,7 @@ static void exact_levels(uint64_t n, uint32_t M, std::vector<uint8_t>& level) {
 using namespace veles;
 
 extern "C" int32_t veles_index_build_graph_exact(veles_index_t* ix, uint32_t M, uint32_t ef_construction, void* stream) {
+    NvtxRange nvtx_range("veles::build_graph_exact (NativeHnsw::insert, sequential)");
     VELES_REQUIRE(ix != nullptr, "index is NULL");
     VELES_REQUIRE(M >= 2 && M <= 128, "M must be in 2..128, got %u", M);
     VELES_REQUIRE(ef_construction >= 1 && ef_construction <= 4096, "ef_construction must be in 1..4096");

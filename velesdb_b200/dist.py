@@ -65,3 +65,89 @@ class ShardedSearcher:
         lo, hi = shard_bounds(nq, world, rank)
         ids, vals, cnt = self.local_search(queries[lo:hi], k, ef)
         return gather_topk(ids, vals, cnt, nq, self.group)
+
+
+class PeerGather:
+    """The library's own gather (csrc/comm.cu, include/veles_b200.h "multi-GPU"): the search kernel stores every
+    query's top-k straight into each rank's gather window over NVLink, and a flag exchange closes the step.
+    ``torch.distributed`` is used once, to hand the IPC handle blobs around."""
+
+    def __init__(self, snapshot, rank, world, nq, k, device):
+        import ctypes as C
+
+        import numpy as np
+
+        from . import _native as nv
+
+        self.snap, self.rank, self.world, self.nq, self.k, self.device = snapshot, rank, world, nq, k, device
+        lib = nv.lib()
+        nb = lib.veles_comm_handle_bytes()
+        blob = np.zeros(nb, np.uint8)
+        h = C.c_void_p()
+        nv.check(lib.veles_comm_create(rank, world, nq, k, C.byref(h), nv.ptr(blob)))
+        self.h = h
+        mine = torch.from_numpy(blob).to(device)
+        every = torch.empty(world * nb, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(every, mine)
+        self._blobs = every.cpu().numpy()
+        nv.check(lib.veles_comm_connect(self.h, nv.ptr(self._blobs)))
+        dist.barrier()
+
+    def search_gather(self, q_t, ef, stream=None, mid_event=None):
+        from . import _native as nv
+
+        ev = None if mid_event is None else mid_event.cuda_event
+        if mid_event is not None and not ev:  # a torch event is created lazily by its first record()
+            mid_event.record()
+            ev = mid_event.cuda_event
+        nv.check(nv.lib().veles_search_batch_gather_d(self.snap.h, self.h, nv.ptr(q_t), q_t.shape[0], self.k, ef, stream, ev))
+
+    def window(self):
+        """(ids [world*nq, k] int32, dist [world*nq, k] f32, counts [world*nq] int32) as torch views of the window."""
+        import ctypes as C
+
+        from . import _native as nv
+
+        pi, pd, pc = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nv.check(nv.lib().veles_comm_window(self.h, C.byref(pi), C.byref(pd), C.byref(pc)))
+        n = self.world * self.nq
+
+        return (_device_view(pi.value, (n, self.k), torch.int32, self.device),
+                _device_view(pd.value, (n, self.k), torch.float32, self.device),
+                _device_view(pc.value, (n,), torch.int32, self.device))
+
+    def status(self, stream=None):
+        from . import _native as nv
+
+        nv.check(nv.lib().veles_comm_status(self.h, stream))
+
+    def check(self, ids_t, dist_t, rank):
+        """After a step: the local window must hold every rank's results, in rank order.  `ids_t` / `dist_t` are this
+        rank's results of the same queries from a plain veles_search_batch_d call; they are all-gathered with NCCL
+        (the check, not the product path) and compared bit for bit with the window the library filled."""
+        self.status(None)
+        ids, dd, cnt = self.window()
+        want_ids = torch.empty_like(ids)
+        want_dd = torch.empty_like(dd)
+        dist.all_gather_into_tensor(want_ids, ids_t.contiguous())
+        dist.all_gather_into_tensor(want_dd, dist_t.contiguous())
+        torch.cuda.synchronize()
+        ok = torch.equal(ids, want_ids) and torch.equal(dd.view(torch.int32), want_dd.view(torch.int32))
+        return bool(ok) and bool((cnt >= 0).all().item()) and bool((cnt <= self.k).all().item())
+
+    def close(self):
+        from . import _native as nv
+
+        if self.h:
+            nv.lib().veles_comm_destroy(self.h)
+            self.h = None
+
+
+class _CudaArray:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def _device_view(ptr, shape, dtype, device):
+    typestr = {torch.int32: "<i4", torch.float32: "<f4"}[dtype]
+    return torch.as_tensor(_CudaArray(ptr, shape, typestr), device=device)

@@ -112,6 +112,28 @@ class DeviceSnapshot:
         return DeviceSnapshot(h)
 
     @staticmethod
+    def create(n, dim, metric, store_dtype="f32"):
+        """An empty snapshot of n zero rows, to be filled from device memory with set_rows_device."""
+        nv.init()
+        h = C.c_void_p()
+        nv.check(nv.lib().veles_index_create(n, dim, _DT[store_dtype], int(metric), C.byref(h)))
+        return DeviceSnapshot(h)
+
+    def set_rows_device(self, first, rows_t, src_dtype="f32", stream=None):
+        """rows_t: a contiguous CUDA tensor holding rows [first, first + len(rows_t)) as f32, or in the store type."""
+        nv.check(nv.lib().veles_index_set_rows_d(self.h, first, rows_t.shape[0], nv.ptr(rows_t), _DT[src_dtype], stream))
+
+    def get_rows(self, first, count, dtype):
+        """Rows back on the host in the store type: dtype np.float32 / np.float16 / np.uint64 (packed bits)."""
+        width = {np.dtype(np.float32): self.dim, np.dtype(np.float16): self.dim, np.dtype(np.uint64): self.dim // 64}[np.dtype(dtype)]
+        out = np.empty((count, width), dtype=dtype)
+        nv.check(nv.lib().veles_index_get_rows(self.h, first, count, nv.ptr(out)))
+        return out
+
+    def dump_graph(self, directory, basename="native_hnsw"):
+        nv.check(nv.lib().veles_index_dump_graph(self.h, os.fsencode(directory), basename.encode()))
+
+    @staticmethod
     def from_arrays(vectors, metric, layers, M, M0, entry_point, max_layer, store_dtype="f32", src_dtype="f32",
                     dim=None):
         """layers: [(row_ptr u64[nodes+1], cols u32[edges])] per layer (CSR)."""
@@ -190,6 +212,21 @@ class DeviceSnapshot:
     def bruteforce_batch_device(self, q_t, k, ids_t, score_t, stream=None):
         nv.check(nv.lib().veles_bruteforce_batch_d(self.h, nv.ptr(q_t), q_t.shape[0], k, nv.ptr(ids_t), nv.ptr(score_t),
                                                    stream))
+
+    def bruteforce_batch_relaxed(self, queries, k, oversample=4, stream=None):
+        """Tensor-core candidate GEMM (fp16) + exact re-rank: veles_bruteforce_batch_relaxed."""
+        q = _as_f32_2d(queries, self.dim, "Query")
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.uint32)
+        sc = np.empty((nq, k), dtype=np.float32)
+        nv.check(nv.lib().veles_bruteforce_batch_relaxed(self.h, nv.ptr(q), nq, k, oversample, nv.ptr(ids), nv.ptr(sc), stream))
+        return ids, sc
+
+    def bruteforce_batch_relaxed_device(self, q_t, k, oversample, ids_t, score_t, stream=None, want_gemm_ms=False):
+        ms = C.c_float(0.0)
+        nv.check(nv.lib().veles_bruteforce_batch_relaxed_d(self.h, nv.ptr(q_t), q_t.shape[0], k, oversample, nv.ptr(ids_t),
+                                                           nv.ptr(score_t), C.byref(ms) if want_gemm_ms else None, stream))
+        return ms.value
 
     def rerank_batch(self, queries, cand, stream=None):
         q = _as_f32_2d(queries, self.dim, "Query")
