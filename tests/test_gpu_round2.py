@@ -220,3 +220,28 @@ def test_fused_brute_force_equals_the_matrix_path_and_the_oracle(metric, dim, nq
     assert np.array_equal(fi, mi) and bits_equal(fs, ms)
     oi, os_ = vo.bruteforce_batch(metric, x, q[:6], k, threads=8)
     assert np.array_equal(fi[:6], oi.astype(np.uint32)) and bits_equal(fs[:6], os_)
+
+
+def test_insert_after_load_and_sparse_bm25_ids(tmp_path):
+    """(a) HnswIndex::load then insert (constructors.rs:190-253 + trait_impl.rs:10-36): the vectors come back from the
+    device snapshot and the index keeps answering for old and new ids.  (b) BM25 documents keyed by arbitrary u32 ids
+    (bm25.rs:134-140 only requires that they fit u32) cost one slot each."""
+    from velesdb_b200 import Bm25Index, HnswIndex
+
+    x = latent_data(260, 16, seed=3)
+    ix = HnswIndex(16, DistanceMetric.Cosine)
+    for i in range(200):
+        ix.insert(1000 + i, x[i])
+    ix.save(str(tmp_path))
+    back = HnswIndex.load(str(tmp_path))
+    for i in range(200, 260):
+        back.insert(1000 + i, x[i])
+    assert back.len() == 260
+    assert back.search(x[7], 1)[0][0] == 1007 and back.search(x[250], 1)[0][0] == 1250
+    bm, ob = Bm25Index(), vo.Bm25()
+    for d, text in ((4_000_000_000, "alpha beta beta"), (7, "beta gamma"), (123_456_789, "alpha alpha gamma delta")):
+        bm.add_document(d, text)
+        ob.add_document(d, text)
+    got = bm.search("alpha beta", 3)
+    oi, os_ = ob.search("alpha beta", 3)
+    assert [g[0] for g in got] == oi.tolist() and bits_equal([g[1] for g in got], os_)

@@ -146,11 +146,17 @@ class Bm25Index:
 
     def _snapshot(self):
         if self._snap is None:
+            # External document ids (any u32; the reference keys hash maps by them, bm25.rs:62-90) are remapped to dense
+            # slots in ascending-id order, so one add_document(4_000_000_000, ..) costs one slot, not 16 GB of
+            # doc_len, and "ties by ascending id" is still "ties by ascending slot".  Results are mapped back.
+            ids = sorted(self._docs)
+            self._slot_ids = np.array(ids or [0], np.uint32)
+            slot_of = {d: i for i, d in enumerate(ids)}
             n_terms = len(self.vocab)
             lists = [[] for _ in range(n_terms)]
-            for d in sorted(self._docs):
+            for d in ids:
                 for ti, f in self._docs[d].items():
-                    lists[ti].append((d, f))
+                    lists[ti].append((slot_of[d], f))
             term_ptr = np.zeros(n_terms + 1, np.uint64)
             for t in range(n_terms):
                 term_ptr[t + 1] = term_ptr[t] + len(lists[t])
@@ -158,10 +164,11 @@ class Bm25Index:
             post_doc = np.array([p[0] for p in flat] or [0], np.uint32)
             post_tf = np.array([p[1] for p in flat] or [0], np.uint32)
             df = np.array([len(self._posting_sets.get(t, ())) for t in range(n_terms)] or [0], np.uint32)
-            slots = (max(self._docs) + 1) if self._docs else 0
+            slots = len(ids)
             doc_len = np.zeros(max(slots, 1), np.uint32)
             for d, l in self._doc_len.items():
-                doc_len[d] = l
+                if d in slot_of:
+                    doc_len[slot_of[d]] = l
             self._snap = Bm25Snapshot(term_ptr, post_doc[:len(flat)] if flat else post_doc, post_tf, df[:max(n_terms, 1)],
                                       doc_len[:max(slots, 1)], len(self._docs), self._total, self.params.k1, self.params.b)
         return self._snap
@@ -181,4 +188,5 @@ class Bm25Index:
                 terms.append(nv.INVALID_ID if ti is None else ti)
             q_ptr[i + 1] = len(terms)
         docs, sc, cnt = self._snapshot().search_batch(q_ptr, np.array(terms or [0], np.uint32)[:len(terms)], k)
-        return [[(int(docs[i, j]), float(sc[i, j])) for j in range(int(cnt[i]))] for i in range(len(queries))]
+        ext = self._slot_ids
+        return [[(int(ext[docs[i, j]]), float(sc[i, j])) for j in range(int(cnt[i]))] for i in range(len(queries))]

@@ -374,6 +374,195 @@ __global__ void __launch_bounds__(256, 5) bm25_query_kernel(Bm25View v, const ui
     }
 }
 
+// ---- one CTA per query, posting-driven (k <= kMultiK): hashed accumulation over adaptive doc-id windows -------------
+// bm25_query_kernel above pays for every doc-id range of a query -- zeroing and re-scanning a dense 7168-slot
+// accumulator ~140 times -- whatever the number of postings that fall into it (~700).  Here the work follows the
+// postings: the CTA takes as many consecutive ranges as hold at most kWindowPostings postings of the query's terms
+// (one range at least; the skip table gives the counts), accumulates them into an open-addressing table in shared
+// memory keyed by document (claim a slot with atomicCAS, then a plain add: a document occurs once per posting list, and
+// a block barrier separates the terms, so every document still receives its contributions in query-token order), and
+// scans the table -- two slots per posting instead of ten.  ~25 windows per query instead of 140 ranges.
+constexpr uint32_t kHashSlots = 8192;        // >= kRange, so a single dense range can never overflow the table
+constexpr uint32_t kWindowPostings = 4096;   // target load factor 0.5
+constexpr uint32_t kWindowLook = 16;         // ranges examined per window decision
+template <int R>
+__global__ void __launch_bounds__(256, 3) bm25_hash_kernel(Bm25View v, const uint32_t* __restrict__ q_ptr,
+                                                           const uint32_t* __restrict__ q_terms, uint32_t nq, uint32_t k,
+                                                           uint32_t* __restrict__ out_doc, float* __restrict__ out_score,
+                                                           uint32_t* __restrict__ out_cnt, uint32_t* __restrict__ work) {
+    extern __shared__ __align__(16) uint8_t bh_smem[];
+    uint32_t* hkey = reinterpret_cast<uint32_t*>(bh_smem);
+    float* hval = reinterpret_cast<float*>(bh_smem + kHashSlots * 4);
+    uint64_t* lists = reinterpret_cast<uint64_t*>(bh_smem + kHashSlots * 8);  // 8 x k keys for the final merge
+    __shared__ uint64_t s_lo[kQueryTerms], s_hi[kQueryTerms];
+    __shared__ float s_idf[kQueryTerms];
+    __shared__ uint32_t s_cnt[kWindowLook];
+    __shared__ uint32_t s_q, s_rend;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const float k1p1 = __fadd_rn(v.k1, 1.0f);
+    for (;;) {  // persistent: queries are handed out by a global counter
+        if (threadIdx.x == 0) s_q = atomicAdd(work, 1u);
+        __syncthreads();
+        const uint32_t q = s_q;
+        if (q >= nq) return;
+        const uint32_t t0 = q_ptr[q], t1 = q_ptr[q + 1];
+        const uint32_t nt = min(kQueryTerms, t1 - t0);  // host guarantees t1 - t0 <= kQueryTerms on this path
+        RegTopK<R> top;
+        top.init(k, lane);
+        uint64_t my_lo = 0;
+        const uint64_t* my_skip = nullptr;
+        if (threadIdx.x < nt) {
+            const uint32_t term = q_terms[t0 + threadIdx.x];
+            float idf = 0.0f;
+            if (term < v.n_terms) {
+                idf = v.idf[term];
+                my_skip = v.skip + (size_t)term * (v.n_ranges + 1);
+                my_lo = my_skip[0];
+            }
+            s_idf[threadIdx.x] = idf;
+        }
+        uint32_t r = 0;
+        while (r < v.n_ranges) {
+            // ---- window [r, r_end): postings of all terms in the next 1..kWindowLook ranges ----
+            if (threadIdx.x < kWindowLook) s_cnt[threadIdx.x] = 0;
+            for (uint32_t i = threadIdx.x; i < kHashSlots / 4; i += blockDim.x) {
+                reinterpret_cast<uint4*>(hkey)[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+                reinterpret_cast<float4*>(hval)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncthreads();
+            if (threadIdx.x < nt && my_skip) {
+                for (uint32_t j = 1; j <= kWindowLook && r + j <= v.n_ranges; ++j) {
+                    const uint64_t c = my_skip[r + j] - my_lo;
+                    atomicAdd(&s_cnt[j - 1], (uint32_t)min(c, (uint64_t)0x7fffffffu / kQueryTerms));
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t j = 1;
+                while (j < kWindowLook && r + j < v.n_ranges && s_cnt[j] <= kWindowPostings) ++j;  // s_cnt[j] = count of j+1 ranges
+                s_rend = r + j;
+            }
+            __syncthreads();
+            const uint32_t r_end = s_rend;
+            if (threadIdx.x < nt) {
+                s_lo[threadIdx.x] = my_lo;
+                const uint64_t hi = my_skip ? my_skip[r_end] : my_lo;
+                s_hi[threadIdx.x] = hi;
+                my_lo = hi;
+            }
+            __syncthreads();
+            // ---- (term, 256-posting chunk) walk in query order, kDepth chunks in flight ----
+            uint32_t cg = 0;
+            while (cg < nt && s_hi[cg] == s_lo[cg]) ++cg;
+            uint64_t cbase = cg < nt ? s_lo[cg] : 0;
+            uint32_t qg[kDepth], qd[kDepth], qtf[kDepth];
+            float qden[kDepth];
+            auto request = [&](int slot) {
+                qg[slot] = cg;
+                qd[slot] = VELES_INVALID_ID;
+                qtf[slot] = 0;
+                qden[slot] = 1.0f;
+                if (cg < nt) {
+                    const uint64_t p = cbase + threadIdx.x;
+                    if (p < s_hi[cg]) {
+                        qd[slot] = v.post_doc[p];
+                        qtf[slot] = v.post_tf[p];
+                        qden[slot] = v.post_den[p];
+                    }
+                    cbase += blockDim.x;
+                    if (cbase >= s_hi[cg]) {
+                        ++cg;
+                        while (cg < nt && s_hi[cg] == s_lo[cg]) ++cg;
+                        cbase = cg < nt ? s_lo[cg] : 0;
+                    }
+                }
+            };
+#pragma unroll
+            for (int i = 0; i < kDepth; ++i) request(i);
+            bool touched = false;
+            while (qg[0] < nt) {
+                if (qd[0] != VELES_INVALID_ID) {
+                    const float num = __fmul_rn((float)qtf[0], k1p1);
+                    const float contrib = __fdiv_rn(__fmul_rn(s_idf[qg[0]], num), qden[0]);
+                    uint32_t h = (qd[0] * 2654435761u) >> 19;  // 13 bits
+                    for (;;) {
+                        const uint32_t prev = atomicCAS(&hkey[h], 0xffffffffu, qd[0]);
+                        if (prev == 0xffffffffu || prev == qd[0]) break;
+                        h = (h + 1) & (kHashSlots - 1);
+                    }
+                    hval[h] = __fadd_rn(hval[h], contrib);  // this document's only posting of this term
+                }
+                touched = true;
+                if (qg[1] != qg[0]) __syncthreads();  // next term's contributions come after this term's
+#pragma unroll
+                for (int i = 0; i + 1 < kDepth; ++i) {
+                    qg[i] = qg[i + 1];
+                    qd[i] = qd[i + 1];
+                    qtf[i] = qtf[i + 1];
+                    qden[i] = qden[i + 1];
+                }
+                request(kDepth - 1);
+            }
+            __syncthreads();
+            // ---- scan: this warp's slice of the table ----
+            if (touched) {
+                const uint32_t per = kHashSlots / nwarps, i_begin = warp * per;
+                for (uint32_t i0 = i_begin; i0 < i_begin + per; i0 += 128) {
+                    const uint4 d4 = reinterpret_cast<const uint4*>(hkey)[(i0 >> 2) + lane];
+                    const float4 s4 = reinterpret_cast<const float4*>(hval)[(i0 >> 2) + lane];
+                    const float thr = top.worst == ~0ull ? 0.0f : ord_unkey(~(uint32_t)(top.worst >> 32));
+                    const bool any = (s4.x > 0.0f && s4.x >= thr) || (s4.y > 0.0f && s4.y >= thr) ||
+                                     (s4.z > 0.0f && s4.z >= thr) || (s4.w > 0.0f && s4.w >= thr);
+                    if (!__ballot_sync(FULL_MASK, any)) continue;
+                    const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+                    const uint32_t dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        uint64_t key = ~0ull;
+                        if (sv[e] > 0.0f && dv[e] != 0xffffffffu) key = ((uint64_t)(~ord_key(sv[e])) << 32) | dv[e];
+                        top.offer(key);
+                    }
+                }
+            }
+            __syncthreads();  // the table is rewritten by the next window
+            r = r_end;
+        }
+        // merge the eight per-warp lists
+        top.store(lists + (size_t)warp * k, k);
+        __syncthreads();
+        if (warp == 0) {
+            for (uint32_t w = 1; w < nwarps; ++w) {
+                const uint64_t* other = lists + (size_t)w * k;
+                for (uint32_t j0 = 0; j0 < k; j0 += 32) {
+                    const uint32_t j = j0 + lane;
+                    top.offer(j < k ? other[j] : ~0ull);
+                }
+            }
+            top.store(lists, k);
+            __syncwarp();
+            uint32_t len = 0;
+            for (uint32_t j0 = 0; j0 < k; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                if (j < k) {
+                    const uint64_t key = lists[j];
+                    uint32_t doc = VELES_INVALID_ID;
+                    float sc = __uint_as_float(0x7fc00000u);
+                    if (key != ~0ull) {
+                        doc = (uint32_t)key;
+                        sc = ord_unkey(~(uint32_t)(key >> 32));
+                        ++len;
+                    }
+                    out_doc[(size_t)q * k + j] = doc;
+                    out_score[(size_t)q * k + j] = sc;
+                }
+            }
+            len = __reduce_add_sync(FULL_MASK, len);
+            if (lane == 0) out_cnt[q] = len;
+        }
+        __syncthreads();  // `lists` and s_q are reused by the next query
+    }
+}
+
 // one warp per query: k smallest keys over its n_ranges x k partial keys
 __global__ void __launch_bounds__(32) bm25_merge_kernel(const uint64_t* __restrict__ partial, uint32_t n_ranges, uint32_t k,
                                                         uint32_t* __restrict__ out_doc, float* __restrict__ out_score,
@@ -555,9 +744,12 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
     uint32_t max_terms = 0;
     for (uint32_t i = 0; i < nq; ++i) max_terms = std::max(max_terms, q_term_ptr[i + 1] - q_term_ptr[i]);
     if (k <= kMultiK && max_terms <= kQueryTerms && std::getenv("VELES_BM25_RANGE_KERNEL") == nullptr) {
-        // one CTA per query walking its ranges (see bm25_query_kernel)
-        const size_t smem = (size_t)kRange * 4 + (size_t)8 * k * 8;
-        auto kern = k <= 32 ? bm25_query_kernel<1> : k <= 64 ? bm25_query_kernel<2> : bm25_query_kernel<4>;
+        // one CTA per query: hashed accumulation over adaptive windows (bm25_hash_kernel), or the dense per-range walk
+        // (bm25_query_kernel, VELES_BM25_DENSE=1)
+        const bool dense = std::getenv("VELES_BM25_DENSE") != nullptr;
+        const size_t smem = (dense ? (size_t)kRange * 4 : (size_t)kHashSlots * 8) + (size_t)8 * k * 8;
+        auto kern = dense ? (k <= 32 ? bm25_query_kernel<1> : k <= 64 ? bm25_query_kernel<2> : bm25_query_kernel<4>)
+                          : (k <= 32 ? bm25_hash_kernel<1> : k <= 64 ? bm25_hash_kernel<2> : bm25_hash_kernel<4>);
         VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0, dev = 0, sms = 0;
         VELES_CUDA(cudaGetDevice(&dev));

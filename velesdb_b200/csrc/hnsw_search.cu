@@ -184,7 +184,10 @@ int32_t launch_search(const veles_index* ix, const IndexView& view, SearchCtx* c
         const uint32_t per_cta_target = (uint32_t)sm_smem / want_ctas - 1024;
         if (per_cta_target > fixed + 2 * row_bytes) nslot = (per_cta_target - fixed) / row_bytes;
         nslot = std::min(std::max(nslot, 2u), kMaxSlots);
-        if (p.quad) {
+        if (p.quad == 2) {
+            // packed-bit rows: the ring holds a whole neighbour list (eval_list_bits), 64 rows = 8 KB
+            nslot = std::min(round_up(std::max(ix->stride0, 8u), 4), 64u);
+        } else if (p.quad) {
             nslot &= ~3u;
             if (nslot < 8) nslot = 8;  // at least two stages
             if (fixed + nslot * row_bytes > (uint32_t)max_smem) {

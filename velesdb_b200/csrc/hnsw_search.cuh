@@ -339,9 +339,12 @@ __device__ __forceinline__ void eval_list_single(const SearchParams& p, WarpCtx&
     }
 }
 
-// Packed-bit rows of at most 1024 bits (128 bytes): no staging ring.  8 lanes x 16 bytes read one row with
-// a single 128-bit load per lane, 16 rows (4 groups x 4) are requested back to back before the first
-// popcount, so a whole neighbour list is ~4 rounds of independent loads.  Integer sums: order free.
+// Packed-bit rows of at most 1024 bits (128 bytes).  A row is 8 lanes x 16 bytes, so one warp-wide instruction moves
+// four rows.  The whole neighbour list (up to 64 rows, 8 KB) is requested at once with per-lane 16-byte async copies
+// into the ring -- a lane copies exactly the chunk it later reads, so no barrier object and no cross-lane hand-off --
+// in two commit groups: the first half is evaluated while the second is still landing.  One DRAM round trip per
+// expansion instead of one per 16 rows (round 1: the binary config sat at 0.13 of the HBM peak, latency bound on four
+// dependent rounds of row loads).  Integer sums: order free; accepts happen in list order (consume_quad).
 template <typename M, typename F, typename T>
 __device__ __forceinline__ void eval_list_bits(const SearchParams& p, WarpCtx& c, uint32_t m, M&& maybe, F&& on_dist,
                                                T&& tick) {
@@ -349,34 +352,36 @@ __device__ __forceinline__ void eval_list_bits(const SearchParams& p, WarpCtx& c
     const uint32_t words4 = p.ix.dim >> 7;  // uint4 per row, <= 8
     const uint4* qw = reinterpret_cast<const uint4*>(c.q);
     const uint4 y = t < words4 ? qw[t] : make_uint4(0, 0, 0, 0);
-    for (uint32_t base = 0; base < m; base += 16) {
-        uint4 x[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t idx = base + 4 * u + g;
-            const uint32_t id = c.todo[idx < m ? idx : base];
-            x[u] = make_uint4(0, 0, 0, 0);
-            if (t < words4) x[u] = __ldg(reinterpret_cast<const uint4*>(p.ix.vecs + (size_t)id * p.ix.row_bytes) + t);
-        }
-        uint32_t d[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            uint32_t v = __popc(x[u].x ^ y.x) + __popc(x[u].y ^ y.y) + __popc(x[u].z ^ y.z) + __popc(x[u].w ^ y.w);
+    const uint32_t cap = p.nslot & ~3u;  // rows the ring holds (multiple of 4, >= 8)
+    for (uint32_t base = 0; base < m; base += cap) {
+        const uint32_t cnt_rows = min(cap, m - base);
+        const uint32_t nquad = (cnt_rows + 3) >> 2, half = (nquad + 1) >> 1;
+        auto issue = [&](uint32_t j) {
+            const uint32_t idx = base + 4 * j + g;
+            if (idx < m && t < words4)
+                cp_async16(c.ring + (size_t)(4 * j + g) * p.ix.row_bytes + t * 16,
+                           p.ix.vecs + (size_t)c.todo[idx] * p.ix.row_bytes + t * 16);
+        };
+        for (uint32_t j = 0; j < half; ++j) issue(j);
+        cp_async_commit();
+        for (uint32_t j = half; j < nquad; ++j) issue(j);
+        cp_async_commit();
+        for (uint32_t j = 0; j < nquad; ++j) {
+            if (j == 0) cp_async_wait<1>();
+            if (j == half) cp_async_wait<0>();
+            const uint32_t rows = min(4u, cnt_rows - 4 * j);
+            uint32_t v = 0;
+            if (g < rows && t < words4) {
+                const uint4 x = *reinterpret_cast<const uint4*>(c.ring + (size_t)(4 * j + g) * p.ix.row_bytes + t * 16);
+                v = __popc(x.x ^ y.x) + __popc(x.y ^ y.y) + __popc(x.z ^ y.z) + __popc(x.w ^ y.w);
+            }
             v += __shfl_xor_sync(FULL_MASK, v, 1);
             v += __shfl_xor_sync(FULL_MASK, v, 2);
             v += __shfl_xor_sync(FULL_MASK, v, 4);
-            d[u] = v;
+            // consume_quad indexes c.todo[4 * quad + row]: hand it the list-relative quad index
+            consume_quad(c, (base >> 2) + j, rows, (float)v, maybe, on_dist, tick);
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            for (uint32_t e = 0; e < 4; ++e) {
-                const uint32_t idx = base + 4 * u + e;
-                if (idx >= m) break;
-                const float de = (float)__shfl_sync(FULL_MASK, d[u], e * 8);
-                tick(1u);
-                if (maybe(de)) on_dist(c.todo[idx], de);
-            }
-        }
+        __syncwarp();  // every lane is done with the ring before the next chunk overwrites it
     }
 }
 
@@ -615,7 +620,7 @@ struct ResArr {
 // inserts, so the results are identical; it exists for batches too small to fill the GPU with one warp per
 // query, where a query's latency is its single warp's instruction chain.
 template <int DT, int R, int QN, bool COOP>
-__global__ void __launch_bounds__(COOP ? 256 : 32, 1) hnsw_search_kernel(const SearchParams p) {
+__global__ void __launch_bounds__(COOP ? 256 : 32, (DT == VELES_BIN1 && !COOP) ? 16 : 1) hnsw_search_kernel(const SearchParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     WarpCtx c;
     c.lane = threadIdx.x & 31;

@@ -650,9 +650,19 @@ class HnswIndex:
 
     # ---- internals
     def _materialise_staged(self):
-        """Bring host copies of a loaded snapshot's vectors back before more inserts (not supported yet)."""
+        """Before inserting into an index restored from files: bring its vectors back from the device snapshot
+        (`veles_index_get_rows`; the graph's own vectors survive a load, native/backend_adapter.rs:286-307, even though
+        ShardedVectors does not, constructors.rs:240).  The next search rebuilds the graph over old + new vectors with
+        the builder the insert path selects.  Where this differs from the reference: its NativeHnsw restarts the level
+        PRNG from the seed after file_load (backend_adapter.rs:373) and keeps the loaded adjacency; here levels follow
+        the PRNG in node-id order across the whole collection, as for an index that was never saved."""
         if self._snapshot is not None and not self._staged and self._next_idx > 0:
-            raise NotImplementedError("inserting into an index restored from files needs vacuum/rebuild support")
+            n = len(self._snapshot)
+            dt = {"f32": np.float32, "f16": np.float16}.get(self._store_dtype)
+            if dt is None:
+                raise NotImplementedError("re-staging packed-bit snapshots is not supported")
+            rows = self._snapshot.get_rows(0, n, dt).astype(np.float32)
+            self._staged = [rows[i] for i in range(n)]
 
     def _ensure_snapshot(self) -> DeviceSnapshot:
         if self._snapshot is None or self._dirty:
