@@ -251,6 +251,15 @@ int32_t veles_fuse(int32_t strategy, const uint32_t* list_ptr, uint32_t n_lists,
  * ef_construction 0 = 200.  Replaces any graph held by `idx`. */
 int32_t veles_index_build_graph(veles_index_t* idx, uint32_t M, uint32_t ef_construction, void* stream);
 
+/* HnswIndex::insert_batch_parallel on a LIVE index (index/hnsw/index/batch.rs:82-108; the reference inserts into the
+ * graph it already has): `count` more vectors become nodes n .. n+count-1 and are linked into the existing graph a
+ * block at a time, exactly as the later blocks of veles_index_build_graph are -- no rebuild, no host copy of the old
+ * vectors.  Works on built and on loaded graphs (M is the graph's; ef_construction 0 = the graph's, else 200).
+ * Levels continue the reference PRNG in node-id order (graph.rs:368-403).  The SQ8 store and the id map must be
+ * re-attached afterwards.  vectors: count*dim f32, or rows already in the store type. */
+int32_t veles_index_append(veles_index_t* idx, const void* vectors, uint64_t count, int32_t src_dtype,
+                           uint32_t ef_construction, void* stream);
+
 /* The reference's *sequential* construction, exactly: NativeHnsw::insert (native/graph.rs:158-237) for nodes
  * 0..n-1 in id order -- what HnswIndex::insert (index/hnsw/index/trait_impl.rs:10-36) builds, the one path on
  * which the reference graph is deterministic.  Same levels (graph.rs:368-403), search_layer with

@@ -245,3 +245,45 @@ def test_insert_after_load_and_sparse_bm25_ids(tmp_path):
     got = bm.search("alpha beta", 3)
     oi, os_ = ob.search("alpha beta", 3)
     assert [g[0] for g in got] == oi.tolist() and bits_equal([g[1] for g in got], os_)
+
+
+def test_append_links_new_vectors_into_the_live_graph():
+    """veles_index_append = HnswIndex::insert_batch_parallel on an index that already has a graph (batch.rs:82-108):
+    no rebuild -- old adjacency stays, new nodes are linked in, degree bounds hold, recall stays at the level of a graph
+    built at once, and the search on the grown graph still equals the oracle on the exported graph."""
+    from velesdb_b200 import HnswIndex, SearchQuality
+
+    n0, n1, dim, M = 6000, 3000, 48, 16
+    x = latent_data(n0 + n1, dim, latent=10, noise=0.3, seed=91, normalize=True)
+    snap = DeviceSnapshot.from_vectors(x[:n0], DistanceMetric.Cosine)
+    snap.build_graph(M, 100)
+    before = snap.export_graph()
+    snap.append(x[n0:], 100)
+    assert len(snap) == n0 + n1
+    layers = snap.export_graph()
+    deg = np.diff(layers[0][0].astype(np.int64))
+    assert deg.max() <= 2 * M and (deg >= 1).all()
+    lv = vo.levels(M, n0 + n1)
+    assert snap.max_layer == int(lv.max()) and snap.entry_point == int(np.argmax(lv == lv.max()))
+    # old rows only changed by reverse links: whatever left a row was replaced by a closer new node
+    rp0, c0 = before[0]
+    rp1, c1 = layers[0]
+    changed = sum(1 for i in range(0, n0, 37) if not np.array_equal(c0[rp0[i]:rp0[i + 1]], c1[rp1[i]:rp1[i + 1]]))
+    assert changed > 0
+    q = queries_near(x, 300, jitter=0.05, seed=5)
+    ids, dist, cnt, st = snap.search_batch(q, 10, 64, with_stats=True)
+    bi, _ = snap.bruteforce_batch(q, 10)
+    rec = np.mean([len(set(ids[i].tolist()) & set(bi[i].tolist())) / 10 for i in range(len(q))])
+    assert rec >= 0.95, rec
+    g = vo.Hnsw.from_arrays(vo.COSINE, x, layers, M, 2 * M, snap.entry_point, snap.max_layer)
+    oi, od, oc, ost = g.search_batch(q, 10, 64, order="canonical", threads=8)
+    keep = ost[:, 4] == 0
+    assert np.array_equal(ids[keep], oi[keep].astype(np.uint32)) and bits_equal(dist, od)
+    # the host mirror: a bulk insert into a live index goes through the append, ids stay mapped
+    ix = HnswIndex(dim, DistanceMetric.Cosine)
+    ix.insert_batch_parallel([(10_000 + i, x[i]) for i in range(n0)])
+    assert ix.search(x[5], 1)[0][0] == 10_005
+    added = ix.insert_batch_parallel([(10_000 + i, x[i]) for i in range(n0 - 50, n0 + n1)])   # 50 duplicates skipped
+    assert added == n1 and ix.len() == n0 + n1
+    res = ix.search_batch_parallel(x[[3, n0 + 7, n0 + n1 - 1]], 1, SearchQuality.Balanced)
+    assert [r[0][0] for r in res] == [10_003, 10_000 + n0 + 7, 10_000 + n0 + n1 - 1]

@@ -64,6 +64,7 @@ SYMBOLS = [
     ("veles_fuse", _i32, [_i32, _vp, _u32, _vp, _vp, _u32, _f, _f, _f, _u32, _vp, _vp, _vp, _vp]),
     ("veles_index_build_graph", _i32, [_vp, _u32, _u32, _vp]),
     ("veles_index_build_graph_exact", _i32, [_vp, _u32, _u32, _vp]),
+    ("veles_index_append", _i32, [_vp, _vp, _u64, _i32, _u32, _vp]),
     ("veles_index_attach_sq8", _i32, [_vp, _u64, _vp]),
     ("veles_index_has_sq8", _i32, [_vp]),
     ("veles_index_sq8_export", _i32, [_vp, _vp, _vp, _vp, _vp]),

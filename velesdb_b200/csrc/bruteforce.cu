@@ -615,36 +615,57 @@ __global__ void __launch_bounds__(kWarps * 32) bf_scan_kernel(IndexView ix, cons
         uint64_t* po = fuse.partial + ((size_t)q * gridDim.x + blockIdx.x) * fuse.k;
         for (uint32_t i = lane; i < fuse.k; i += 32) po[i] = i < len ? dst[i] : ~0ull;
     }
-    // ---- the last CTA merges the per-CTA lists ----
+    // ---- the last CTA merges the per-CTA lists: every warp takes a slice of them (loads batched eight deep, so the
+    // merge costs a few DRAM/L2 round trips, not one per 32 keys), then warp 0 merges the eight slices ----
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(fuse.done, 1u) == gridDim.x - 1 ? 1u : 0u;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (uint32_t q = warp; q < nq; q += kWarps) {
-        uint64_t* dst = lists + (size_t)warp * QT * fuse.k;  // reuse this warp's list space
+    for (uint32_t q = 0; q < nq; ++q) {
+        uint64_t* dst = lists + (size_t)warp * QT * fuse.k;  // this warp's list space, free again by now
         uint32_t len = 0;
         uint64_t worst = ~0ull;
         const uint64_t* in = fuse.partial + (size_t)q * gridDim.x * fuse.k;
+        // CTA lists are ascending and padded with ~0: list c of this warp's slice is c = warp, warp + kWarps, ...
         const uint32_t total = gridDim.x * fuse.k;
-        for (uint32_t j0 = 0; j0 < total; j0 += 32) {
-            const uint32_t j = j0 + lane;
-            list_offer(dst, len, worst, fuse.k, j < total ? __ldcg(in + j) : ~0ull, lane);
-        }
-        __syncwarp();
-        for (uint32_t i = lane; i < fuse.k; i += 32) {
-            uint32_t id = VELES_INVALID_ID;
-            float sc = __uint_as_float(0x7fc00000u);
-            if (i < len) {
-                id = (uint32_t)dst[i];
-                const uint32_t o = (uint32_t)(dst[i] >> 32);
-                sc = ord_unkey(fuse.desc ? ~o : o);
+        for (uint32_t j0 = warp * 32; j0 < total; j0 += kWarps * 32 * 8) {
+            uint64_t key[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t j = j0 + u * kWarps * 32 + lane;
+                key[u] = j < total ? __ldcg(in + j) : ~0ull;
             }
-            fuse.out_ids[(size_t)q * fuse.k + i] = id;
-            fuse.out_score[(size_t)q * fuse.k + i] = sc;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (__any_sync(FULL_MASK, key[u] < worst)) list_offer(dst, len, worst, fuse.k, key[u], lane);
         }
-        __syncwarp();
+        if (lane == 0) s_len[warp][0] = len;
+        __syncthreads();
+        if (warp == 0) {
+            for (uint32_t w = 1; w < kWarps; ++w) {
+                const uint64_t* src = lists + (size_t)w * QT * fuse.k;
+                const uint32_t sl = s_len[w][0];
+                for (uint32_t j0 = 0; j0 < sl; j0 += 32) {
+                    const uint32_t j = j0 + lane;
+                    list_offer(dst, len, worst, fuse.k, j < sl ? src[j] : ~0ull, lane);
+                }
+            }
+            __syncwarp();
+            for (uint32_t i = lane; i < fuse.k; i += 32) {
+                uint32_t id = VELES_INVALID_ID;
+                float sc = __uint_as_float(0x7fc00000u);
+                if (i < len) {
+                    id = (uint32_t)dst[i];
+                    const uint32_t o = (uint32_t)(dst[i] >> 32);
+                    sc = ord_unkey(fuse.desc ? ~o : o);
+                }
+                fuse.out_ids[(size_t)q * fuse.k + i] = id;
+                fuse.out_score[(size_t)q * fuse.k + i] = sc;
+            }
+        }
+        __syncthreads();
     }
     if (threadIdx.x == 0) *fuse.done = 0u;  // ready for the next launch
 }
@@ -984,7 +1005,9 @@ static int32_t launch_scores(const veles_index* ixh, const IndexView& v, const f
             int per_sm = 1;
             VELES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ks, kWarps * 32, smem_s));
             const uint64_t tiles = (ix->n + 4 * rb - 1) / (4 * rb);
-            const uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((tiles + kWarps - 1) / kWarps, (uint64_t)sms * std::max(per_sm, 1)));
+            uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((tiles + kWarps - 1) / kWarps, (uint64_t)sms * std::max(per_sm, 1)));
+            // fused selection: every CTA leaves a list for the last CTA to merge, so small collections get one CTA per SM
+            if (fz.k) gx = std::min<uint64_t>(gx, std::max<uint64_t>((uint64_t)sms, (tiles + kWarps * 4 - 1) / (kWarps * 4)));
             ks<<<(unsigned)gx, kWarps * 32, smem_s, st>>>(v, q_d, nq, sink, as_value, fz);
             count_launch();
             VELES_CUDA(cudaGetLastError());

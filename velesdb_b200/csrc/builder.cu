@@ -596,32 +596,55 @@ static uint32_t env_u32b(const char* name, uint32_t dflt) {
     return v && *v ? (uint32_t)std::strtoul(v, nullptr, 10) : dflt;
 }
 
+// distances of the existing links to their rows' owners: the side arrays of a graph that was loaded or built earlier
+// (they exist only during construction).  One warp per node: its layer-0 row, then its upper rows.
+__global__ void link_dist_kernel(IncView b, uint32_t n_old) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t gw = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t node = gw; node < n_old; node += nwarps) {
+        const uint32_t ref = b.ix.upper_ref[node];
+        const uint32_t top = ref == VELES_INVALID_ID ? 0u : (ref & 15u);
+        for (uint32_t l = 0; l <= top; ++l) {
+            const RowPtr r = link_row(b, l, (uint32_t)node);
+            if (!r.ids) continue;
+            for (uint32_t j = 0; j < r.stride; ++j) {
+                const uint32_t x = r.ids[j];
+                if (x == VELES_INVALID_ID) break;
+                const float d = node_pair_dist(b.ix, (uint32_t)node, x, lane);
+                if (lane == 0) r.dist[j] = d;
+            }
+        }
+    }
+}
+
 }  // namespace veles
 
 using namespace veles;
 
-extern "C" int32_t veles_index_build_graph(veles_index_t* ix, uint32_t M, uint32_t ef_construction, void* stream) {
-    NvtxRange nvtx_range("veles::build_graph (NativeHnsw::insert, block insertion)");
-    VELES_REQUIRE(ix != nullptr, "index is NULL");
-    VELES_REQUIRE(M >= 2 && M <= 128, "M must be in 2..128, got %u", M);
-    if (ef_construction == 0) ef_construction = env_u32b("VELES_BUILD_EF", 200);
-    VELES_REQUIRE(ef_construction >= 1 && ef_construction <= 4096, "ef_construction must be in 1..4096, got %u", ef_construction);
-    cudaStream_t st = (cudaStream_t)stream;
-    std::lock_guard<std::mutex> g(ix->mu);
+// Inserts nodes [first, ix->n) into the graph, a block at a time (file header).  first == 0: a fresh build (M, levels,
+// rows planned from scratch; the first block is seeded all-pairs).  first > 0: the vectors of the new nodes are already
+// in ix->vecs and the graph over nodes < first is live: its arrays are grown, the link distances of its rows are
+// recomputed once, and the new nodes are linked in exactly as the later blocks of a fresh build are.  ix->mu is held.
+static int32_t insert_blocks(veles_index* ix, uint64_t first, uint32_t M, uint32_t ef_construction, cudaStream_t st) {
     const uint64_t n = ix->n;
+    const bool append = first > 0;
     const uint32_t M0 = 2 * M;
     const uint32_t ef_c = ef_construction;
-    ix->M = M;
-    ix->M0 = M0;
-    ix->stride0 = round_up(M0, 32);
-    ix->strideU = round_up(M, 32);
+    const uint64_t old_rows = append ? ix->upper_rows : 0;
+    if (!append) {
+        ix->M = M;
+        ix->M0 = M0;
+        ix->stride0 = round_up(M0, 32);
+        ix->strideU = round_up(M, 32);
+        ix->has_graph = true;
+        ix->has_entry = false;
+        ix->entry = 0;
+        ix->max_layer = 0;
+        ix->num_layers = 1;
+        ix->upper_rows = 0;
+    }
     ix->ef_construction = ef_c;
-    ix->has_graph = true;
-    ix->has_entry = false;
-    ix->entry = 0;
-    ix->max_layer = 0;
-    ix->num_layers = 1;
-    ix->upper_rows = 0;
     if (n == 0) {
         VELES_TRY(ix->adj0.alloc(16));
         VELES_TRY(ix->upper_ref.alloc(16));
@@ -629,35 +652,36 @@ extern "C" int32_t veles_index_build_graph(veles_index_t* ix, uint32_t M, uint32
         return VELES_OK;
     }
     const auto t_start = std::chrono::steady_clock::now();
-    // levels and upper rows (graph.rs:168-178)
+    // levels and upper rows (graph.rs:168-178).  Levels follow the reference PRNG in node-id order over the whole
+    // collection; an append plans rows only for the new nodes, after the rows the live graph already owns.
     std::vector<uint8_t> level;
     reference_levels(n, M, level);
-    std::vector<uint32_t> h_ref(n, VELES_INVALID_ID);
-    uint64_t rows = 0;
-    for (uint64_t i = 0; i < n; ++i)
+    std::vector<uint32_t> h_ref(n - first, VELES_INVALID_ID);
+    uint64_t rows = old_rows;
+    for (uint64_t i = first; i < n; ++i)
         if (level[i] > 0) {
             VELES_REQUIRE(rows < (1ull << 28), "too many upper-layer rows");
-            h_ref[i] = (uint32_t)(rows << 4) | level[i];
+            h_ref[i - first] = (uint32_t)(rows << 4) | level[i];
             rows += level[i];
         }
     ix->upper_rows = rows;
 
     // ---- block plan: seed block, then blocks of at most 1/growth of the graph, cut after a node that raises the
     // top layer (it becomes the entry point, graph.rs:230-233, and the next block must see it) ----
-    const uint32_t n_seed = (uint32_t)std::min<uint64_t>(n, std::max(2u, env_u32b("VELES_BUILD_SEED", 256)));
+    const uint32_t n_seed = append ? 0u : (uint32_t)std::min<uint64_t>(n, std::max(2u, env_u32b("VELES_BUILD_SEED", 256)));
     const uint32_t growth = std::max(1u, env_u32b("VELES_BUILD_GROWTH", 4));
     const uint32_t cap_auto = (uint32_t)std::min<uint64_t>(65536, std::max<uint64_t>(1024, n / 64));
     const uint32_t cap = std::max(32u, env_u32b("VELES_BUILD_BLOCK_CAP", cap_auto));
     std::vector<BlockPlan> plan;
     std::vector<uint32_t> job_node, job_task0, task_node;
     std::vector<uint8_t> job_top, task_layer;
-    uint32_t cur_max = 0, entry = 0;
+    uint32_t cur_max = append ? ix->max_layer : 0u, entry = append ? (uint32_t)ix->entry : 0u;
     for (uint32_t i = 0; i < n_seed; ++i)
         if (level[i] > cur_max) {
             cur_max = level[i];
             entry = i;
         }
-    {
+    if (!append) {
         BlockPlan bp{0, n_seed, cur_max, entry, 0, 0, 0, 0};
         for (uint32_t i = 0; i < n_seed; ++i)
             for (uint32_t l = level[i]; l >= 1; --l) {
@@ -667,8 +691,8 @@ extern "C" int32_t veles_index_build_graph(veles_index_t* ix, uint32_t M, uint32
         bp.n_tasks = (uint32_t)task_node.size();
         plan.push_back(bp);
     }
-    uint32_t max_block = n_seed, max_jobs = 0, max_tasks = plan[0].n_tasks;
-    for (uint64_t done = n_seed; done < n;) {
+    uint32_t max_block = std::max(n_seed, 1u), max_jobs = 0, max_tasks = append ? 0u : plan[0].n_tasks;
+    for (uint64_t done = append ? first : n_seed; done < n;) {
         const uint64_t want = std::min<uint64_t>(cap, std::max<uint64_t>(32, done / growth));
         uint64_t end = std::min<uint64_t>(n, done + want);
         uint32_t new_top = VELES_INVALID_ID;
@@ -706,19 +730,29 @@ extern "C" int32_t veles_index_build_graph(veles_index_t* ix, uint32_t M, uint32
     // ---- device state ----
     DevBuf adj0_d, lock0, upper_d, lockU, level_d, jobs_node_d, jobs_top_d, jobs_task0_d, task_node_d, task_layer_d;
     DevBuf qbuf, c0_ids, c0_dist, c0_cnt, cu_ids, cu_dist, cu_cnt, uvis, ulog, utie, uerr;
-    VELES_TRY(ix->adj0.alloc((size_t)n * ix->stride0 * 4));
-    VELES_TRY(ix->upper_ref.alloc((size_t)n * 4));
-    VELES_TRY(ix->upper_adj.alloc(std::max<size_t>((size_t)rows * ix->strideU * 4, 16)));
+    // graph arrays for n nodes / `rows` upper rows: fresh, or grown with the live graph's content in front
+    auto grow = [&](DevBuf& buf, size_t old_bytes, size_t new_bytes) -> int32_t {
+        DevBuf nb;
+        VELES_TRY(nb.alloc(std::max<size_t>(new_bytes, 16)));
+        if (old_bytes) VELES_CUDA(cudaMemcpyAsync(nb.p, buf.p, old_bytes, cudaMemcpyDeviceToDevice, st));
+        if (new_bytes > old_bytes)
+            VELES_CUDA(cudaMemsetAsync(static_cast<uint8_t*>(nb.p) + old_bytes, 0xff, new_bytes - old_bytes, st));
+        VELES_CUDA(cudaStreamSynchronize(st));  // the old buffer is freed when `nb` goes out of scope
+        std::swap(buf.p, nb.p);
+        std::swap(buf.bytes, nb.bytes);
+        return VELES_OK;
+    };
+    VELES_TRY(grow(ix->adj0, (size_t)first * ix->stride0 * 4, (size_t)n * ix->stride0 * 4));
+    VELES_TRY(grow(ix->upper_ref, (size_t)first * 4, (size_t)n * 4));
+    VELES_TRY(grow(ix->upper_adj, (size_t)old_rows * ix->strideU * 4, (size_t)rows * ix->strideU * 4));
     VELES_TRY(adj0_d.alloc((size_t)n * ix->stride0 * 4));
     VELES_TRY(lock0.alloc((size_t)n * 4));
     VELES_TRY(upper_d.alloc(std::max<size_t>((size_t)rows * ix->strideU * 4, 16)));
     VELES_TRY(lockU.alloc(std::max<size_t>((size_t)rows * 4, 16)));
     VELES_TRY(level_d.alloc((size_t)n));
-    VELES_CUDA(cudaMemsetAsync(ix->adj0.p, 0xff, ix->adj0.bytes, st));
-    VELES_CUDA(cudaMemsetAsync(ix->upper_adj.p, 0xff, ix->upper_adj.bytes, st));
     VELES_CUDA(cudaMemsetAsync(lock0.p, 0, lock0.bytes, st));
     VELES_CUDA(cudaMemsetAsync(lockU.p, 0, lockU.bytes, st));
-    VELES_CUDA(cudaMemcpyAsync(ix->upper_ref.p, h_ref.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    VELES_CUDA(cudaMemcpyAsync(ix->upper_ref.as<uint32_t>() + first, h_ref.data(), (size_t)(n - first) * 4, cudaMemcpyHostToDevice, st));
     VELES_CUDA(cudaMemcpyAsync(level_d.p, level.data(), (size_t)n, cudaMemcpyHostToDevice, st));
     auto upload = [&](DevBuf& d, const void* src, size_t bytes) -> int32_t {
         VELES_TRY(d.alloc(std::max<size_t>(bytes, 16)));
@@ -739,7 +773,7 @@ extern "C" int32_t veles_index_build_graph(veles_index_t* ix, uint32_t M, uint32
     VELES_TRY(cu_dist.alloc(std::max<size_t>((size_t)max_tasks * cstride * 4, 16)));
     VELES_TRY(cu_cnt.alloc(std::max<size_t>((size_t)max_tasks * 4, 16)));
     const int sms = device_sm_count();
-    const uint32_t up_slots = std::max(1u, std::min<uint32_t>(max_jobs, (uint32_t)sms * 8));
+    const uint32_t up_slots = std::max(1u, std::min<uint32_t>(std::max(max_jobs, 1u), (uint32_t)sms * 8));
     const uint32_t up_words = (uint32_t)((rows + 31) / 32 + 1);
     VELES_TRY(uvis.alloc((size_t)up_slots * up_words * 4));
     VELES_TRY(ulog.alloc((size_t)up_slots * kBuildLogCap * 4));
@@ -776,6 +810,14 @@ extern "C" int32_t veles_index_build_graph(veles_index_t* ix, uint32_t M, uint32
         return VELES_OK;
     };
     const bool verbose = env_u32b("VELES_BUILD_VERBOSE", 0) != 0;
+    if (append) {
+        b.ix = ix->view();
+        b.cur_max_layer = ix->max_layer;
+        b.entry = (uint32_t)ix->entry;
+        link_dist_kernel<<<sms * 8, 256, 0, st>>>(b, (uint32_t)first);
+        count_launch();
+        VELES_CUDA(cudaGetLastError());
+    }
     SearchCtx* sctx = nullptr;
     VELES_TRY(acquire_ctx(ix, st, true, &sctx));  // one context for every block's search (same stream, overflow flag sticky)
     struct CtxGuard {
@@ -796,7 +838,7 @@ extern "C" int32_t veles_index_build_graph(veles_index_t* ix, uint32_t M, uint32
         TaskList t0{nullptr, nullptr, (uint32_t)bp.begin, count, c0_ids.as<uint32_t>(), c0_dist.as<float>(), c0_cnt.as<uint32_t>(), cstride};
         TaskList tu{task_node_d.as<uint32_t>() + bp.task0, task_layer_d.as<uint8_t>() + bp.task0, 0, bp.n_tasks,
                     cu_ids.as<uint32_t>(), cu_dist.as<float>(), cu_cnt.as<uint32_t>(), cstride};
-        if (bi == 0) {
+        if (bi == 0 && !append) {
             inc_seed_kernel<<<std::min<uint32_t>(count, (uint32_t)sms * 16), 32, res_smem, st>>>(b, t0, n_seed);
             count_launch();
             if (tu.n_tasks) {
@@ -848,4 +890,61 @@ extern "C" int32_t veles_index_build_graph(veles_index_t* ix, uint32_t M, uint32
         return VELES_ERR_OVERFLOW;
     }
     return VELES_OK;
+}
+
+extern "C" int32_t veles_index_build_graph(veles_index_t* ix, uint32_t M, uint32_t ef_construction, void* stream) {
+    NvtxRange nvtx_range("veles::build_graph (NativeHnsw::insert, block insertion)");
+    VELES_REQUIRE(ix != nullptr, "index is NULL");
+    VELES_REQUIRE(M >= 2 && M <= 128, "M must be in 2..128, got %u", M);
+    if (ef_construction == 0) ef_construction = env_u32b("VELES_BUILD_EF", 200);
+    VELES_REQUIRE(ef_construction >= 1 && ef_construction <= 4096, "ef_construction must be in 1..4096, got %u", ef_construction);
+    std::lock_guard<std::mutex> g(ix->mu);
+    return insert_blocks(ix, 0, M, ef_construction, (cudaStream_t)stream);
+}
+
+// HnswIndex::insert_batch_parallel on a live index (index/hnsw/index/batch.rs:82-108): `count` more vectors become
+// nodes n .. n + count - 1 and are inserted into the existing graph, a block at a time, exactly as the later blocks of
+// veles_index_build_graph are -- no rebuild.  Works on built and on loaded graphs (M is the graph's).
+extern "C" int32_t veles_index_append(veles_index_t* ix, const void* vectors, uint64_t count, int32_t src_dtype,
+                                      uint32_t ef_construction, void* stream) {
+    NvtxRange nvtx_range("veles::append (HnswIndex::insert_batch_parallel on a live graph)");
+    VELES_REQUIRE(ix != nullptr, "index is NULL");
+    VELES_REQUIRE(count == 0 || vectors != nullptr, "vectors is NULL");
+    VELES_REQUIRE(src_dtype == VELES_F32 || src_dtype == ix->dtype, "unsupported conversion: src dtype %d -> store dtype %d", src_dtype,
+                  ix->dtype);
+    VELES_REQUIRE(ef_construction <= 4096, "ef_construction must be <= 4096, got %u", ef_construction);
+    if (count == 0) return VELES_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint64_t first = 0;
+    {
+        std::lock_guard<std::mutex> g(ix->mu);
+        VELES_REQUIRE(ix->n == 0 || (ix->has_graph && ix->M >= 2), "snapshot has no graph to append to; build or load one first");
+        VELES_REQUIRE(ix->n + count < (1ull << 31), "at most 2^31-1 nodes per snapshot");
+        first = ix->n;
+        // grow the row store, old rows in front
+        DevBuf nv;
+        VELES_TRY(nv.alloc((size_t)(first + count) * ix->row_bytes));
+        if (first) VELES_CUDA(cudaMemcpyAsync(nv.p, ix->vecs.p, (size_t)first * ix->row_bytes, cudaMemcpyDeviceToDevice, st));
+        VELES_CUDA(cudaMemsetAsync(static_cast<uint8_t*>(nv.p) + (size_t)first * ix->row_bytes, 0, (size_t)count * ix->row_bytes, st));
+        VELES_CUDA(cudaStreamSynchronize(st));
+        std::swap(ix->vecs.p, nv.p);
+        std::swap(ix->vecs.bytes, nv.bytes);
+        ix->n = first + count;
+        ix->x16.release();  // derived copies no longer cover the collection
+        ix->x16_dpad = 0;
+        ix->has_sq8 = false;
+    }
+    {
+        // the new rows: staged on the device in the caller's type, then the conversion of veles_index_set_rows_d
+        const size_t width = src_dtype == VELES_BIN1 ? (size_t)(ix->dim / 64) * 8 : (size_t)ix->dim * (src_dtype == VELES_F32 ? 4 : 2);
+        DevBuf stage;
+        VELES_TRY(stage.alloc(count * width));
+        VELES_CUDA(cudaMemcpyAsync(stage.p, vectors, count * width, cudaMemcpyHostToDevice, st));
+        VELES_TRY(veles_index_set_rows_d(ix, first, count, stage.p, src_dtype, stream));
+        VELES_CUDA(cudaStreamSynchronize(st));
+    }
+    std::lock_guard<std::mutex> g(ix->mu);
+    const uint32_t efc = ef_construction ? ef_construction : (ix->ef_construction ? std::min(ix->ef_construction, 4096u) : 200u);
+    if (first == 0) return insert_blocks(ix, 0, ix->M >= 2 ? ix->M : 16, efc, st);
+    return insert_blocks(ix, first, ix->M, efc, st);
 }

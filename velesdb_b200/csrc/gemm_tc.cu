@@ -524,14 +524,16 @@ int32_t bruteforce_relaxed_d(const veles_index* ix, const float* q_d, uint32_t n
     const uint32_t s_rows = s_tiles * kTcBlockM;
     const uint32_t cand_cap = (uint32_t)std::min<uint64_t>(n, std::max<uint64_t>(4096, (uint64_t)kp * (n / s_rows + 1) * 4));
     const uint32_t chunk = std::min<uint32_t>(nq, 1024);
-    DevBuf q16, tiles_d, sample, thr, cnt, cand, err;
-    VELES_TRY(q16.alloc((size_t)round_up(chunk, 256) * dpad * 2));
-    VELES_TRY(tiles_d.alloc((size_t)s_tiles * 4));
-    VELES_TRY(sample.alloc((size_t)chunk * s_rows * 4));
-    VELES_TRY(thr.alloc((size_t)chunk * 4));
-    VELES_TRY(cnt.alloc((size_t)chunk * 4));
-    VELES_TRY(cand.alloc((size_t)chunk * cand_cap * 8));
-    VELES_TRY(err.alloc(16));
+    // work buffers live with the snapshot (cudaMalloc / cudaFree per call cost more than the GEMM)
+    DevBuf &q16 = ix->tc_q16, &tiles_d = ix->tc_tiles, &sample = ix->tc_sample, &thr = ix->tc_thr, &cnt = ix->tc_cnt,
+           &cand = ix->tc_cand, &err = ix->tc_err;
+    VELES_TRY(q16.ensure((size_t)round_up(chunk, 256) * dpad * 2));
+    VELES_TRY(tiles_d.ensure((size_t)s_tiles * 4));
+    VELES_TRY(sample.ensure((size_t)chunk * s_rows * 4));
+    VELES_TRY(thr.ensure((size_t)chunk * 4));
+    VELES_TRY(cnt.ensure((size_t)chunk * 4));
+    VELES_TRY(cand.ensure((size_t)chunk * cand_cap * 8));
+    VELES_TRY(err.ensure(16));
     VELES_CUDA(cudaMemsetAsync(err.p, 0, 16, st));
     {
         std::vector<uint32_t> tl(s_tiles);
@@ -551,7 +553,7 @@ int32_t bruteforce_relaxed_d(const veles_index* ix, const float* q_d, uint32_t n
     for (uint32_t q0 = 0; q0 < nq; q0 += chunk) {
         const uint32_t nn = std::min(chunk, nq - q0);
         const uint32_t bn = nn > 128 ? 256 : 128;
-        VELES_CUDA(cudaMemsetAsync(q16.p, 0, q16.bytes, st));
+        VELES_CUDA(cudaMemsetAsync(q16.p, 0, (size_t)round_up(chunk, 256) * dpad * 2, st));
         to_f16_operand_kernel<<<std::min<uint32_t>((nn + 7) / 8, (uint32_t)sms * 8), 256, 0, st>>>(
             reinterpret_cast<const uint8_t*>(q_d + (size_t)q0 * ix->dim), (uint64_t)ix->dim * 4, 0, 0xffffffffu,
             ix->metric == VELES_COSINE ? 1 : 0, nn, ix->dim, dpad, q16.as<__half>(), nullptr);

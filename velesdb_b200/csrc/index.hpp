@@ -66,6 +66,7 @@ struct veles_index {
     // x16_dpad halves (dim padded to 64), cosine rows pre-normalised; x16_bias = |row16|^2 (L2)
     mutable veles::DevBuf x16, x16_bias;
     mutable uint32_t x16_dpad = 0;
+    mutable veles::DevBuf tc_q16, tc_tiles, tc_sample, tc_thr, tc_cnt, tc_cand, tc_err;  // work buffers of that path
 
     // node index -> external id, live (not tombstoned) bitmap: ShardedMappings on the device (postfilter.cu)
     veles::DevBuf id_map_d, live_d;

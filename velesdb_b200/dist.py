@@ -90,8 +90,18 @@ class PeerGather:
         every = torch.empty(world * nb, dtype=torch.uint8, device=device)
         dist.all_gather_into_tensor(every, mine)
         self._blobs = every.cpu().numpy()
-        nv.check(lib.veles_comm_connect(self.h, nv.ptr(self._blobs)))
-        dist.barrier()
+        # every rank must know whether EVERY rank mapped its peers, or a later collective would hang on the ones that
+        # did not: agree on the outcome before anyone raises
+        err = None
+        try:
+            nv.check(lib.veles_comm_connect(self.h, nv.ptr(self._blobs)))
+        except Exception as e:  # noqa: BLE001
+            err = e
+        ok = torch.tensor([0 if err else 1], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            self.close()
+            raise RuntimeError(f"peer windows could not be mapped on every rank ({err or 'another rank failed'})")
 
     def search_gather(self, q_t, ef, stream=None, mid_event=None):
         from . import _native as nv

@@ -254,6 +254,11 @@ class DeviceSnapshot:
     def search_wait(self, ticket):
         nv.check(nv.lib().veles_search_wait(self.h, ticket))
 
+    def append(self, vectors, ef_construction=0, src_dtype="f32", stream=None):
+        """veles_index_append: more vectors linked into the live graph (insert_batch_parallel on an existing index)."""
+        vectors = np.ascontiguousarray(vectors)
+        nv.check(nv.lib().veles_index_append(self.h, nv.ptr(vectors), vectors.shape[0], _DT[src_dtype], ef_construction, stream))
+
     def build_graph_exact(self, M, ef_construction, stream=None):
         """NativeHnsw::insert for nodes 0..n-1 in order (graph.rs:158-237): the reference's deterministic graph."""
         nv.check(nv.lib().veles_index_build_graph_exact(self.h, M, ef_construction, stream))
@@ -468,10 +473,36 @@ class HnswIndex:
 
     def insert_batch_parallel(self, vectors) -> int:
         """index/hnsw/index/batch.rs:82-108: (id, vector) pairs; returns how many were new.  Batches of fewer
-        than 100 vectors are inserted sequentially by the reference too (backend_adapter.rs:110-118)."""
+        than 100 vectors are inserted sequentially by the reference too (backend_adapter.rs:110-118).  A batch of
+        >= 100 vectors into an index whose snapshot is live goes straight into that graph on the device
+        (veles_index_append), as the reference inserts into the graph it has; otherwise the vectors are staged and the
+        next search builds the snapshot."""
         vectors = list(vectors)
         if len(vectors) >= 100:
             self._bulk = True
+        live = self._snapshot is not None and not self._dirty and len(vectors) >= 100 and self._next_idx > 0
+        if live and self._store_dtype != "bin1":
+            self._materialise_staged()
+            fresh, seen = [], set()
+            for id, v in vectors:
+                if id in self._id_to_idx or id in seen:
+                    continue  # duplicate ids are skipped silently (trait_impl.rs:12-25)
+                v = np.ascontiguousarray(v, dtype=np.float32).reshape(-1)
+                if v.shape[0] != self._dimension:
+                    raise DimensionMismatch(f"Vector dimension mismatch: expected {self._dimension}, got {v.shape[0]}")
+                seen.add(id)
+                fresh.append((id, v))
+            if not fresh:
+                return 0
+            self._snapshot.append(np.stack([v for _, v in fresh]), min(self._params.ef_construction, 4096))
+            for id, v in fresh:
+                idx = self._next_idx
+                self._next_idx += 1
+                self._id_to_idx[id] = idx
+                self._idx_to_id[idx] = id
+                self._staged.append(v.copy())
+            self._map_dirty = True
+            return len(fresh)
         count = 0
         for id, v in vectors:
             before = len(self._id_to_idx)
