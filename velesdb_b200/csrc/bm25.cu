@@ -374,6 +374,170 @@ __global__ void __launch_bounds__(256, 5) bm25_query_kernel(Bm25View v, const ui
     }
 }
 
+// ---- one CTA per query, whole range in flight (k <= kMultiK) -------------------------------------------------------
+// bm25_query_kernel above is latency bound: within a range it requests one 256-posting chunk of one term at a time, so
+// a range of five terms costs five dependent DRAM round trips (ncu, round 1: IPC 2.4 but 37 % of the samples waiting
+// on the posting loads; 2.3 ms per 1024 queries = 0.08 of the HBM peak).  Here ALL postings of a range -- every term's
+// slice, flattened term-major -- are loaded at once, kPre per thread, before anything is applied: one round trip per
+// range.  They are then applied term by term (a block barrier when the term changes), so every document still receives
+// its contributions in query-token order and the f32 sums keep the reference's bits.
+constexpr int kPre = 4;  // postings per thread per round: 1024 per CTA round (a range holds ~700 on the bench corpus)
+template <int R>
+__global__ void __launch_bounds__(256, 5) bm25_prefetch_kernel(Bm25View v, const uint32_t* __restrict__ q_ptr,
+                                                               const uint32_t* __restrict__ q_terms, uint32_t nq, uint32_t k,
+                                                               uint32_t* __restrict__ out_doc, float* __restrict__ out_score,
+                                                               uint32_t* __restrict__ out_cnt, uint32_t* __restrict__ work) {
+    extern __shared__ __align__(16) uint8_t bq_smem[];
+    float* acc = reinterpret_cast<float*>(bq_smem);
+    uint64_t* lists = reinterpret_cast<uint64_t*>(bq_smem + kRange * 4);  // 8 x k keys for the final merge
+    __shared__ uint64_t s_lo[kQueryTerms];
+    __shared__ uint32_t s_off[kQueryTerms + 1];  // flattened start of each term's slice within the range
+    __shared__ float s_idf[kQueryTerms];
+    __shared__ uint32_t s_q;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const float k1p1 = __fadd_rn(v.k1, 1.0f);
+    const float4* acc4 = reinterpret_cast<const float4*>(acc);
+    for (;;) {  // persistent: queries are handed out by a global counter
+        if (threadIdx.x == 0) s_q = atomicAdd(work, 1u);
+        __syncthreads();
+        const uint32_t q = s_q;
+        if (q >= nq) return;
+        const uint32_t t0 = q_ptr[q], t1 = q_ptr[q + 1];
+        const uint32_t nt = min(kQueryTerms, t1 - t0);  // host guarantees t1 - t0 <= kQueryTerms on this path
+        RegTopK<R> top;
+        top.init(k, lane);
+        uint64_t my_lo = 0, my_next = 0;
+        const uint64_t* my_skip = nullptr;
+        if (threadIdx.x < nt) {
+            const uint32_t term = q_terms[t0 + threadIdx.x];
+            float idf = 0.0f;
+            if (term < v.n_terms) {
+                idf = v.idf[term];
+                my_skip = v.skip + (size_t)term * (v.n_ranges + 1);
+                my_lo = my_skip[0];
+                my_next = my_skip[1];
+            }
+            s_idf[threadIdx.x] = idf;
+        }
+        for (uint32_t r = 0; r < v.n_ranges; ++r) {
+            const uint32_t base_doc = r * kRange;
+            // warp 0: slice boundaries of every term in this range and their flattened offsets (exclusive scan)
+            if (warp == 0) {
+                uint32_t cnt = 0;
+                if (lane < nt) {
+                    s_lo[lane] = my_lo;
+                    cnt = (uint32_t)min(my_next - my_lo, (uint64_t)0x03ffffffu);
+                    my_lo = my_next;
+                    if (my_skip && r + 2 <= v.n_ranges) my_next = my_skip[r + 2];  // boundary after the next range
+                }
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(FULL_MASK, incl, o);
+                    if ((int)lane >= o) incl += up;
+                }
+                if (lane < nt) s_off[lane] = incl - cnt;
+                if (lane == 31) s_off[nt] = incl;  // lanes >= nt carry cnt = 0: lane 31 holds the total
+            }
+            for (uint32_t i = threadIdx.x; i < kRange / 4; i += blockDim.x)
+                reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncthreads();
+            const uint32_t total = s_off[nt];
+            for (uint32_t round = 0; round < total; round += kPre * 256) {
+                // ---- request: up to kPre postings per thread, all loads issued before anything is used ----
+                uint32_t pt[kPre], pd[kPre], ptf[kPre];
+                float pden[kPre];
+#pragma unroll
+                for (int j = 0; j < kPre; ++j) {
+                    const uint32_t pos = round + j * 256 + threadIdx.x;
+                    pt[j] = 0xffffffffu;
+                    pd[j] = 0;
+                    ptf[j] = 0;
+                    pden[j] = 1.0f;
+                    if (pos < total) {
+                        uint32_t t = 0;
+                        while (t + 1 < nt && s_off[t + 1] <= pos) ++t;
+                        const uint64_t p = s_lo[t] + (pos - s_off[t]);
+                        pt[j] = t;
+                        pd[j] = v.post_doc[p];
+                        ptf[j] = v.post_tf[p];
+                        pden[j] = v.post_den[p];
+                    }
+                }
+                // ---- apply term by term; positions are term-major, so round order = query-token order ----
+                const uint32_t last_pos = min(total, round + kPre * 256) - 1;
+                uint32_t t_first = 0, t_last = 0;
+                while (t_first + 1 < nt && s_off[t_first + 1] <= round) ++t_first;
+                t_last = t_first;
+                while (t_last + 1 < nt && s_off[t_last + 1] <= last_pos) ++t_last;
+                for (uint32_t t = t_first; t <= t_last; ++t) {
+#pragma unroll
+                    for (int j = 0; j < kPre; ++j) {
+                        if (pt[j] == t) {
+                            const float num = __fmul_rn((float)ptf[j], k1p1);
+                            const float contrib = __fdiv_rn(__fmul_rn(s_idf[t], num), pden[j]);
+                            acc[pd[j] - base_doc] = __fadd_rn(acc[pd[j] - base_doc], contrib);
+                        }
+                    }
+                    __syncthreads();  // the next term's (or round's) contributions come after this term's
+                }
+            }
+            // scan: this warp's slice of the range
+            if (total > 0) {
+                const uint32_t per = kRange / nwarps, i_begin = warp * per;
+                for (uint32_t i0 = i_begin; i0 < i_begin + per; i0 += 128) {
+                    const float4 s4 = acc4[(i0 >> 2) + lane];
+                    const float thr = top.worst == ~0ull ? 0.0f : ord_unkey(~(uint32_t)(top.worst >> 32));
+                    const bool any = (s4.x > 0.0f && s4.x >= thr) || (s4.y > 0.0f && s4.y >= thr) ||
+                                     (s4.z > 0.0f && s4.z >= thr) || (s4.w > 0.0f && s4.w >= thr);
+                    if (!__ballot_sync(FULL_MASK, any)) continue;
+                    const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        uint64_t key = ~0ull;
+                        if (sv[e] > 0.0f) key = ((uint64_t)(~ord_key(sv[e])) << 32) | (base_doc + i0 + lane * 4 + e);
+                        top.offer(key);
+                    }
+                }
+            }
+            __syncthreads();  // the accumulator and s_off are rewritten by the next range
+        }
+        // merge the eight per-warp lists
+        top.store(lists + (size_t)warp * k, k);
+        __syncthreads();
+        if (warp == 0) {
+            for (uint32_t w = 1; w < nwarps; ++w) {
+                const uint64_t* other = lists + (size_t)w * k;
+                for (uint32_t j0 = 0; j0 < k; j0 += 32) {
+                    const uint32_t j = j0 + lane;
+                    top.offer(j < k ? other[j] : ~0ull);
+                }
+            }
+            top.store(lists, k);
+            __syncwarp();
+            uint32_t len = 0;
+            for (uint32_t j0 = 0; j0 < k; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                if (j < k) {
+                    const uint64_t key = lists[j];
+                    uint32_t doc = VELES_INVALID_ID;
+                    float sc = __uint_as_float(0x7fc00000u);
+                    if (key != ~0ull) {
+                        doc = (uint32_t)key;
+                        sc = ord_unkey(~(uint32_t)(key >> 32));
+                        ++len;
+                    }
+                    out_doc[(size_t)q * k + j] = doc;
+                    out_score[(size_t)q * k + j] = sc;
+                }
+            }
+            len = __reduce_add_sync(FULL_MASK, len);
+            if (lane == 0) out_cnt[q] = len;
+        }
+        __syncthreads();  // `lists` and s_q are reused by the next query
+    }
+}
+
 // ---- one CTA per query, posting-driven (k <= kMultiK): hashed accumulation over adaptive doc-id windows -------------
 // bm25_query_kernel above pays for every doc-id range of a query -- zeroing and re-scanning a dense 7168-slot
 // accumulator ~140 times -- whatever the number of postings that fall into it (~700).  Here the work follows the
@@ -744,12 +908,16 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
     uint32_t max_terms = 0;
     for (uint32_t i = 0; i < nq; ++i) max_terms = std::max(max_terms, q_term_ptr[i + 1] - q_term_ptr[i]);
     if (k <= kMultiK && max_terms <= kQueryTerms && std::getenv("VELES_BM25_RANGE_KERNEL") == nullptr) {
-        // one CTA per query: hashed accumulation over adaptive windows (bm25_hash_kernel), or the dense per-range walk
-        // (bm25_query_kernel, VELES_BM25_DENSE=1)
-        const bool dense = std::getenv("VELES_BM25_DENSE") != nullptr;
-        const size_t smem = (dense ? (size_t)kRange * 4 : (size_t)kHashSlots * 8) + (size_t)8 * k * 8;
-        auto kern = dense ? (k <= 32 ? bm25_query_kernel<1> : k <= 64 ? bm25_query_kernel<2> : bm25_query_kernel<4>)
-                          : (k <= 32 ? bm25_hash_kernel<1> : k <= 64 ? bm25_hash_kernel<2> : bm25_hash_kernel<4>);
+        // one CTA per query walking its doc-id ranges
+        // default: bm25_prefetch_kernel (whole range in flight); VELES_BM25_WALK=1: the chunk-at-a-time walk of round 1
+        // (bm25_query_kernel); VELES_BM25_HASH=1: hashed accumulation over adaptive windows (bm25_hash_kernel; measured
+        // slower on B200: 4.1 ms against 2.3 ms per 1024 queries -- three CTAs per SM and a CAS per posting)
+        const bool walk = std::getenv("VELES_BM25_WALK") != nullptr;
+        const bool hash = !walk && std::getenv("VELES_BM25_HASH") != nullptr;
+        const size_t smem = (hash ? (size_t)kHashSlots * 8 : (size_t)kRange * 4) + (size_t)8 * k * 8;
+        auto kern = hash   ? (k <= 32 ? bm25_hash_kernel<1> : k <= 64 ? bm25_hash_kernel<2> : bm25_hash_kernel<4>)
+                    : walk ? (k <= 32 ? bm25_query_kernel<1> : k <= 64 ? bm25_query_kernel<2> : bm25_query_kernel<4>)
+                           : (k <= 32 ? bm25_prefetch_kernel<1> : k <= 64 ? bm25_prefetch_kernel<2> : bm25_prefetch_kernel<4>);
         VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0, dev = 0, sms = 0;
         VELES_CUDA(cudaGetDevice(&dev));

@@ -45,9 +45,9 @@ struct TcParams {
     float* out;                 // STORE: out[q * ld_out + tile_pos * 128 + r]
     uint32_t ld_out;
     const float* thr;           // FILTER: per query threshold
-    uint32_t* cand_cnt;         // FILTER: per query count
-    uint64_t* cand;             // FILTER: nq x cand_cap entries (score bits << 32 | row)
-    uint32_t cand_cap;
+    uint32_t* cand_cnt;         // FILTER: gridDim.x x nq counts -- every CTA owns a segment of every query's list,
+    uint64_t* cand;             // FILTER: gridDim.x x nq x cand_cap entries (score bits << 32 | row)
+    uint32_t cand_cap;          //         so appends are shared-memory atomics + a store, never a global round trip
     const float* row_bias;      // null, or per row: score = scale * acc - row_bias[row]
     float scale;
     uint32_t* err;              // [0] pipeline timeout, [1] candidate overflow
@@ -134,7 +134,9 @@ struct TcCfg {
     static constexpr uint32_t kBBytes = BN * 128;
     static constexpr uint32_t kStageBytes = kABytes + kBBytes;
     static constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator stages: 256 or 512 columns (powers of two)
-    static constexpr uint32_t kSmemBytes = 1024 /* alignment slack */ + kStages * kStageBytes + 256 /* barriers */ + 2 * BN * 4;
+    static constexpr uint32_t kMaxQ = 1024;  // queries per launch (per-CTA candidate counters live in shared memory)
+    static constexpr uint32_t kSmemBytes =
+        1024 /* alignment slack */ + kStages * kStageBytes + 256 /* barriers */ + 2 * BN * 4 + kMaxQ * 4;
 };
 
 template <int BN>
@@ -149,6 +151,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* thr_s = reinterpret_cast<float*>(tiles + C::kStages * C::kStageBytes + 256);  // 2 x BN
+    uint32_t* cnt_s = reinterpret_cast<uint32_t*>(thr_s + 2 * BN);                       // kMaxQ: this CTA's candidates per query
+    for (uint32_t i = threadIdx.x; i < C::kMaxQ; i += blockDim.x) cnt_s[i] = 0;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -262,9 +266,9 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
                         const float s = p.scale * __uint_as_float(v[j]) - bias;
                         if (s >= thr[c0 + j]) {
                             const uint32_t q = nb * BN + c0 + j;
-                            const uint32_t slot = atomicAdd(&p.cand_cnt[q], 1u);
+                            const uint32_t slot = atomicAdd(&cnt_s[q], 1u);  // shared memory: no DRAM round trip
                             if (slot < p.cand_cap)
-                                p.cand[(size_t)q * p.cand_cap + slot] = ((uint64_t)__float_as_uint(s) << 32) | row;
+                                p.cand[((size_t)blockIdx.x * p.nq + q) * p.cand_cap + slot] = ((uint64_t)__float_as_uint(s) << 32) | row;
                             else
                                 atomicExch(p.err + 1, 1u);
                         }
@@ -280,6 +284,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
+    if (p.mode == 1)
+        for (uint32_t q = threadIdx.x; q < p.nq; q += blockDim.x) p.cand_cnt[(size_t)blockIdx.x * p.nq + q] = min(cnt_s[q], p.cand_cap);
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols) : "memory");
@@ -369,7 +375,7 @@ constexpr int kFinWarps = 8;
 __global__ void __launch_bounds__(kFinWarps * 32) relaxed_finish_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq,
                                                                       const uint64_t* __restrict__ cand,
                                                                       const uint32_t* __restrict__ cand_cnt, uint32_t cand_cap,
-                                                                      uint32_t k, uint32_t* __restrict__ out_ids,
+                                                                      uint32_t n_seg, uint32_t k, uint32_t* __restrict__ out_ids,
                                                                       float* __restrict__ out_score) {
     extern __shared__ __align__(16) uint8_t fin_smem[];
     float* qs = reinterpret_cast<float*>(fin_smem);                                       // dim
@@ -381,11 +387,16 @@ __global__ void __launch_bounds__(kFinWarps * 32) relaxed_finish_kernel(IndexVie
     const bool desc = ix.metric == VELES_COSINE || ix.metric == VELES_DOT || ix.metric == VELES_JACCARD;
     float na = 0.0f;
     if (ix.metric == VELES_COSINE) na = __fsqrt_rn(warp_tree_reduce<0>(qs, qs, ix.dim, lane));
-    const uint32_t m = min(cand_cnt[q], cand_cap);
     uint64_t* mine = lists + (size_t)warp * k;
     uint32_t len = 0;
-    for (uint32_t c = warp; c < m; c += kFinWarps) {
-        const uint32_t row = (uint32_t)cand[(size_t)q * cand_cap + c];
+    // the query's candidates: one segment per GEMM CTA; this warp takes every kFinWarps-th candidate of the flattened list
+    uint32_t flat = 0;
+    for (uint32_t seg = 0; seg < n_seg; ++seg) {
+      const uint32_t m = min(cand_cnt[(size_t)seg * nq + q], cand_cap);
+      const uint64_t* base = cand + ((size_t)seg * nq + q) * cand_cap;
+      for (uint32_t c = 0; c < m; ++c, ++flat) {
+        if (flat % kFinWarps != warp) continue;
+        const uint32_t row = (uint32_t)base[c];
         const uint8_t* rp = ix.vecs + (size_t)row * ix.row_bytes;
         const float nb = ix.metric == VELES_COSINE ? *reinterpret_cast<const float*>(rp + ix.norm_off) : 0.0f;
         const float v = ix.dtype == VELES_F32 ? warp_metric(ix.metric, true, qs, reinterpret_cast<const float*>(rp), ix.dim, na, nb, lane)
@@ -402,6 +413,7 @@ __global__ void __launch_bounds__(kFinWarps * 32) relaxed_finish_kernel(IndexVie
             }
         }
         __syncwarp();
+      }
     }
     __shared__ uint32_t s_len[kFinWarps];
     if (lane == 0) s_len[warp] = len;
@@ -519,10 +531,16 @@ int32_t bruteforce_relaxed_d(const veles_index* ix, const float* q_d, uint32_t n
     // Gamma(j)-distributed around j * n / sample_rows, and small j would make the 4x candidate capacity overflow
     const uint32_t kp = (uint32_t)std::min<uint64_t>(std::max<uint64_t>((uint64_t)k * oversample, 16), n);
     const uint32_t n_mtiles = (uint32_t)((n + kTcBlockM - 1) / kTcBlockM);
-    // sample: enough row tiles that the expected candidates per query (kp * n / sample_rows) stay near 64 * kp
-    const uint32_t s_tiles = std::min<uint32_t>(n_mtiles, std::max<uint32_t>(std::max<uint32_t>(kTcSampleTiles, n_mtiles / 64), kp / kTcBlockM + 2));
+    // sample: one row tile in 16 -- the expected candidates per query are kp * n / sample_rows ~ 16 * kp, spread over the
+    // GEMM CTAs' segments of the query's list
+    const uint32_t s_tiles = std::min<uint32_t>(n_mtiles, std::max<uint32_t>(std::max<uint32_t>(kTcSampleTiles, n_mtiles / 16), kp / kTcBlockM + 2));
     const uint32_t s_rows = s_tiles * kTcBlockM;
-    const uint32_t cand_cap = (uint32_t)std::min<uint64_t>(n, std::max<uint64_t>(4096, (uint64_t)kp * (n / s_rows + 1) * 4));
+    const uint32_t n_seg = (uint32_t)std::min<uint64_t>((uint64_t)n_mtiles * ((std::min<uint32_t>(nq, 1024) + 255) / 256 + 1), (uint64_t)sms);
+    const uint64_t expect = (uint64_t)kp * (n / s_rows + 1);  // per query, all segments
+    // tiny collections can have fewer than kp sampled rows (threshold = -inf: every row is a candidate): a segment must
+    // then hold every row of its CTA's tiles
+    const uint64_t all_rows = n <= 8192 ? (uint64_t)kTcBlockM * ((n_mtiles + n_seg - 1) / std::max(n_seg, 1u)) : 0;
+    const uint32_t cand_cap = (uint32_t)std::min<uint64_t>(n, std::max<uint64_t>(std::max<uint64_t>(64, all_rows), 4 * expect / std::max(n_seg, 1u) + 32));
     const uint32_t chunk = std::min<uint32_t>(nq, 1024);
     // work buffers live with the snapshot (cudaMalloc / cudaFree per call cost more than the GEMM)
     DevBuf &q16 = ix->tc_q16, &tiles_d = ix->tc_tiles, &sample = ix->tc_sample, &thr = ix->tc_thr, &cnt = ix->tc_cnt,
@@ -531,8 +549,8 @@ int32_t bruteforce_relaxed_d(const veles_index* ix, const float* q_d, uint32_t n
     VELES_TRY(tiles_d.ensure((size_t)s_tiles * 4));
     VELES_TRY(sample.ensure((size_t)chunk * s_rows * 4));
     VELES_TRY(thr.ensure((size_t)chunk * 4));
-    VELES_TRY(cnt.ensure((size_t)chunk * 4));
-    VELES_TRY(cand.ensure((size_t)chunk * cand_cap * 8));
+    VELES_TRY(cnt.ensure((size_t)sms * chunk * 4));
+    VELES_TRY(cand.ensure((size_t)sms * chunk * cand_cap * 8));
     VELES_TRY(err.ensure(16));
     VELES_CUDA(cudaMemsetAsync(err.p, 0, 16, st));
     {
@@ -581,7 +599,7 @@ int32_t bruteforce_relaxed_d(const veles_index* ix, const float* q_d, uint32_t n
         count_launch();
         VELES_CUDA(cudaGetLastError());
         // 3. filter pass over every tile
-        VELES_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)nn * 4, st));
+        VELES_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)sms * nn * 4, st));  // CTAs that never launch leave empty segments
         p.mode = 1;
         p.n_mtiles = n_mtiles;
         p.tile_list = nullptr;
@@ -597,7 +615,7 @@ int32_t bruteforce_relaxed_d(const veles_index* ix, const float* q_d, uint32_t n
         const size_t fsm = ((ix->dim * 4 + 15) & ~15u) + (size_t)kFinWarps * k * 8;
         VELES_CUDA(cudaFuncSetAttribute(relaxed_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
         relaxed_finish_kernel<<<nn, kFinWarps * 32, fsm, st>>>(v, q_d + (size_t)q0 * ix->dim, nn, cand.as<uint64_t>(), cnt.as<uint32_t>(),
-                                                            cand_cap, k, ids_d + (size_t)q0 * k, score_d + (size_t)q0 * k);
+                                                            cand_cap, (uint32_t)sms, k, ids_d + (size_t)q0 * k, score_d + (size_t)q0 * k);
         count_launch();
         VELES_CUDA(cudaGetLastError());
         if (gemm_ms) {
