@@ -76,6 +76,40 @@ def test_committed_bench_lines_follow_the_contract():
         assert not set(j["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
 
 
+def test_round2_bench_lines_follow_the_contract():
+    # every config's line printed on the B200 in round 2 (profiles/r2*_bench_*.json)
+    import glob
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lines = sorted(glob.glob(os.path.join(root, "profiles", "r2*_bench_*.json")))
+    assert len(lines) >= 10
+    seen_ref = False
+    for path in lines:
+        j = json.loads([l for l in open(path).read().splitlines() if l.startswith("{")][-1])
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                    "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches"):
+            assert key in j, (path, key)
+        assert j["higher_is_better"] is True and j["vs_baseline"] is None and "workload" in j["config"]
+        assert "build_s" not in j["config"] and "datagen_s" not in j["config"]   # keep timings out of `config`
+        assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(j["e2e"])
+        if j.get("impl") == "reference":
+            seen_ref = True
+            assert j["gpu_launches"] == 0 and j["cpu_baseline"]["kind"] == "port" and j["steps"] >= 20
+            assert all(len(v) == 64 for v in j["frozen_files"]["sha256"].values())
+            continue
+        assert j["warmup"] >= 3 and j["gpu_launches"] >= j["steps"]
+        r = j["roofline"]
+        assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0 < r["frac"] <= 1.0
+        assert r["kernel_ms"] <= j["ms_per_step"] * 1.001
+        assert r["traffic"] is None or r["traffic"] >= r["algorithmic_bytes_per_launch"] * 0.98
+        assert not set(j["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if "cpu_baseline" in j:
+            assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["ids_match_gpu"] is True
+        if "parity" in j:
+            assert j["parity"]["ids_and_distance_bits_equal_oracle"] is True and j["parity"]["queries"] >= 256
+    assert seen_ref
+
+
 def test_integration_md_ffi_block_matches_the_header():
     # every `pub fn veles_*` INTEGRATION.md shows a maintainer exists in include/veles_b200.h with the same arity
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

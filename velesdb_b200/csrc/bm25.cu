@@ -909,15 +909,17 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
     for (uint32_t i = 0; i < nq; ++i) max_terms = std::max(max_terms, q_term_ptr[i + 1] - q_term_ptr[i]);
     if (k <= kMultiK && max_terms <= kQueryTerms && std::getenv("VELES_BM25_RANGE_KERNEL") == nullptr) {
         // one CTA per query walking its doc-id ranges
-        // default: bm25_prefetch_kernel (whole range in flight); VELES_BM25_WALK=1: the chunk-at-a-time walk of round 1
-        // (bm25_query_kernel); VELES_BM25_HASH=1: hashed accumulation over adaptive windows (bm25_hash_kernel; measured
-        // slower on B200: 4.1 ms against 2.3 ms per 1024 queries -- three CTAs per SM and a CAS per posting)
-        const bool walk = std::getenv("VELES_BM25_WALK") != nullptr;
-        const bool hash = !walk && std::getenv("VELES_BM25_HASH") != nullptr;
+        // default: bm25_query_kernel (chunk-at-a-time walk).  Two round-2 experiments stay selectable and are measured
+        // slower on B200 for 1024 queries of 3-6 terms over 1M documents (profiles/README.md): VELES_BM25_PREFETCH=1
+        // (bm25_prefetch_kernel, whole range in flight: 2.85 ms against 2.70 ms -- the loads were not the bound, the
+        // ~1000 instructions per warp and range are) and VELES_BM25_HASH=1 (bm25_hash_kernel: 4.2 ms -- three CTAs per
+        // SM and a CAS per posting).
+        const bool pre = std::getenv("VELES_BM25_PREFETCH") != nullptr;
+        const bool hash = !pre && std::getenv("VELES_BM25_HASH") != nullptr;
         const size_t smem = (hash ? (size_t)kHashSlots * 8 : (size_t)kRange * 4) + (size_t)8 * k * 8;
-        auto kern = hash   ? (k <= 32 ? bm25_hash_kernel<1> : k <= 64 ? bm25_hash_kernel<2> : bm25_hash_kernel<4>)
-                    : walk ? (k <= 32 ? bm25_query_kernel<1> : k <= 64 ? bm25_query_kernel<2> : bm25_query_kernel<4>)
-                           : (k <= 32 ? bm25_prefetch_kernel<1> : k <= 64 ? bm25_prefetch_kernel<2> : bm25_prefetch_kernel<4>);
+        auto kern = hash  ? (k <= 32 ? bm25_hash_kernel<1> : k <= 64 ? bm25_hash_kernel<2> : bm25_hash_kernel<4>)
+                    : pre ? (k <= 32 ? bm25_prefetch_kernel<1> : k <= 64 ? bm25_prefetch_kernel<2> : bm25_prefetch_kernel<4>)
+                          : (k <= 32 ? bm25_query_kernel<1> : k <= 64 ? bm25_query_kernel<2> : bm25_query_kernel<4>);
         VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0, dev = 0, sms = 0;
         VELES_CUDA(cudaGetDevice(&dev));

@@ -1001,9 +1001,8 @@ static int32_t launch_scores(const veles_index* ixh, const IndexView& v, const f
 #undef VELES_SCAN
             const ScanFuse fz = fuse ? *fuse : ScanFuse();
             const size_t smem_s = ((((size_t)qt * ix->dim + qt) + 3) & ~(size_t)3) * 4 + (size_t)kWarps * qt * fz.k * 8;
-            VELES_CUDA(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-            int per_sm = 1;
-            VELES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ks, kWarps * 32, smem_s));
+            const int per_sm = cached_blocks_per_sm(reinterpret_cast<const void*>(ks), kWarps * 32, smem_s);
+            if (per_sm < 1) return VELES_ERR_CUDA;
             const uint64_t tiles = (ix->n + 4 * rb - 1) / (4 * rb);
             uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((tiles + kWarps - 1) / kWarps, (uint64_t)sms * std::max(per_sm, 1)));
             // fused selection: every CTA leaves a list for the last CTA to merge, so small collections get one CTA per SM

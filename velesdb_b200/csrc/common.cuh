@@ -25,6 +25,11 @@ void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
 inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Resident CTAs per SM of `kernel` at (threads, dynamic shared memory), with the kernel's dynamic shared-memory limit
+// raised to `smem`; queried once per distinct triple (the two runtime calls cost ~10 us, which is most of a
+// single-query brute-force scan over a small collection).  < 1 on error (message set).
+int cached_blocks_per_sm(const void* kernel, int threads, size_t smem);
+
 // NVTX range around each kernel group, named after the reference function it stands for: the tracing counterpart of
 // the reference's spans (core/metrics.rs:977-1058).  Header-only NVTX 3: a no-op unless a profiler is attached.
 struct NvtxRange {

@@ -143,8 +143,10 @@ template <int BN>
 __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                                                          const TcParams p) {
     using C = TcCfg<BN>;
-    extern __shared__ uint8_t tc_smem_raw[];
-    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment (128-byte swizzle atoms) is requested from the declaration, not by rounding a pointer: the
+    // compiler then still knows these are shared-memory addresses (LDS/STS instead of generic loads in the epilogue)
+    extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
+    uint8_t* tiles = tc_smem_raw;
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + C::kStages * C::kStageBytes);
     uint64_t* empty = full + C::kStages;
     uint64_t* tfull = empty + C::kStages;
@@ -154,6 +156,10 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     uint32_t* cnt_s = reinterpret_cast<uint32_t*>(thr_s + 2 * BN);                       // kMaxQ: this CTA's candidates per query
     for (uint32_t i = threadIdx.x; i < C::kMaxQ; i += blockDim.x) cnt_s[i] = 0;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if ((smem_u32(tiles) & 1023u) != 0) {  // the swizzled tiles need the alignment the declaration asks for
+        if (threadIdx.x == 0) atomicExch(p.err, 2u);
+        return;
+    }
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
@@ -250,28 +256,49 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             const uint32_t row = mt * kTcBlockM + r_in_tile;
             const bool row_ok = row < p.n_rows;
             const float bias = (p.row_bias && row_ok) ? p.row_bias[row] : 0.0f;
+            const bool affine = p.row_bias != nullptr || p.scale != 1.0f;
             for (uint32_t c0 = 0; c0 < (uint32_t)BN; c0 += 32) {
                 uint32_t v[32];
                 tc_ld32(tmem_base + acc * BN + c0 + ((ew * 32u) << 16), v);
+                if (p.mode == 1) {
+                    // FILTER: one compare per column, no branches -- a single warp per scheduler cannot hide the latency
+                    // of a branchy per-column chain (ncu, first version: the epilogue paced the whole kernel).  The pass
+                    // mask is almost always zero; the rare set bits are appended afterwards.
+                    if (affine) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(p.scale * __uint_as_float(v[j]) - bias);
+                    }
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(thr + c0 + 4 * j4);
+                        mask |= (__uint_as_float(v[4 * j4 + 0]) >= t4.x ? 1u : 0u) << (4 * j4 + 0);
+                        mask |= (__uint_as_float(v[4 * j4 + 1]) >= t4.y ? 1u : 0u) << (4 * j4 + 1);
+                        mask |= (__uint_as_float(v[4 * j4 + 2]) >= t4.z ? 1u : 0u) << (4 * j4 + 2);
+                        mask |= (__uint_as_float(v[4 * j4 + 3]) >= t4.w ? 1u : 0u) << (4 * j4 + 3);
+                    }
+                    if (!row_ok) mask = 0;
+                    while (mask) {
+                        const int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        uint32_t sv = 0;
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) sv = u == j ? v[u] : sv;  // select, not an indexed access: v[] stays in registers
+                        const uint32_t q = nb * BN + c0 + j;
+                        const uint32_t slot = atomicAdd(&cnt_s[q], 1u);  // shared memory: no DRAM round trip
+                        if (slot < p.cand_cap)
+                            p.cand[((size_t)blockIdx.x * p.nq + q) * p.cand_cap + slot] = ((uint64_t)sv << 32) | row;
+                        else
+                            atomicExch(p.err + 1, 1u);
+                    }
+                    continue;
+                }
                 if (p.mode == 0) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const uint32_t q = nb * BN + c0 + j;
                         if (q < p.nq) p.out[(size_t)q * p.ld_out + (size_t)mpos * kTcBlockM + r_in_tile] =
                             row_ok ? p.scale * __uint_as_float(v[j]) - bias : __int_as_float(0xff800000);
-                    }
-                } else if (row_ok) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float s = p.scale * __uint_as_float(v[j]) - bias;
-                        if (s >= thr[c0 + j]) {
-                            const uint32_t q = nb * BN + c0 + j;
-                            const uint32_t slot = atomicAdd(&cnt_s[q], 1u);  // shared memory: no DRAM round trip
-                            if (slot < p.cand_cap)
-                                p.cand[((size_t)blockIdx.x * p.nq + q) * p.cand_cap + slot] = ((uint64_t)__float_as_uint(s) << 32) | row;
-                            else
-                                atomicExch(p.err + 1, 1u);
-                        }
                     }
                 }
             }
@@ -631,7 +658,7 @@ int32_t bruteforce_relaxed_d(const veles_index* ix, const float* q_d, uint32_t n
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     if (h[0]) {
-        set_error("tensor-core GEMM: pipeline wait timed out");
+        set_error(h[0] == 2 ? "tensor-core GEMM: shared memory is not 1024-byte aligned" : "tensor-core GEMM: pipeline wait timed out");
         return VELES_ERR_CUDA;
     }
     if (h[1]) {

@@ -121,12 +121,17 @@ int32_t launch_search(const veles_index* ix, const IndexView& view, SearchCtx* c
         p.off_ring = round_up(p.off_q + q_bytes, 128);
     };
     carve(false);
-    int dev = 0, max_smem = 0, sms = 0;
+    // device limits: looked up once per device (the attribute queries cost microseconds a single-query search notices)
+    static thread_local int cached_dev = -1, c_max_smem = 0, c_sms = 0, c_sm_smem = 0;
+    int dev = 0;
     VELES_CUDA(cudaGetDevice(&dev));
-    VELES_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    VELES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int sm_smem = 0;
-    VELES_CUDA(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    if (dev != cached_dev) {
+        VELES_CUDA(cudaDeviceGetAttribute(&c_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        VELES_CUDA(cudaDeviceGetAttribute(&c_sms, cudaDevAttrMultiProcessorCount, dev));
+        VELES_CUDA(cudaDeviceGetAttribute(&c_sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+        cached_dev = dev;
+    }
+    const int max_smem = c_max_smem, sms = c_sms, sm_smem = c_sm_smem;
     // Quad path: four candidates per step (8 lanes each); f32 / f16 rows from 16 dimensions up (the reference's
     // wide16 regime: 32-element blocks, then its 8-wide and scalar tails).
     const bool can_quad = (dtype == VELES_BIN1 && ix->dim % 128 == 0) || dtype == VELES_SQ8 ||
@@ -208,9 +213,8 @@ int32_t launch_search(const veles_index* ix, const IndexView& view, SearchCtx* c
                         : dtype == VELES_F16 ? search_kernel_f16(reg_mode, coop)
                         : dtype == VELES_SQ8 ? search_kernel_sq8(reg_mode, sq_qn, coop)
                                              : search_kernel_bin1(reg_mode);
-    VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    int ctas_per_sm = 0;
-    VELES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, (int)(32 * warps), smem_bytes));
+    const int ctas_per_sm = cached_blocks_per_sm(reinterpret_cast<const void*>(kern), (int)(32 * warps), smem_bytes);
+    if (ctas_per_sm < 0) return VELES_ERR_CUDA;
     VELES_REQUIRE(ctas_per_sm >= 1, "search kernel does not fit on an SM");
     const uint32_t max_slots = (uint32_t)(ctas_per_sm * sms);
     const uint32_t grid = std::min(nq, max_slots);

@@ -1,6 +1,10 @@
 // runtime.cu -- process-level state of libveles_b200: device selection, errors, counters.
 #include "common.cuh"
 
+#include <map>
+#include <mutex>
+#include <tuple>
+
 namespace veles {
 
 static thread_local char g_err[1024] = "";
@@ -11,6 +15,29 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+int cached_blocks_per_sm(const void* kernel, int threads, size_t smem) {
+    static std::mutex mu;
+    static std::map<std::tuple<const void*, int, size_t, int>, int> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const auto key = std::make_tuple(kernel, threads, smem, dev);
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) return it->second;
+    }
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+    if (e != cudaSuccess) {
+        set_error("kernel configuration failed: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    std::lock_guard<std::mutex> g(mu);
+    cache[key] = per_sm;
+    return per_sm;
 }
 
 }  // namespace veles
