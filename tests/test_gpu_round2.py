@@ -287,3 +287,41 @@ def test_append_links_new_vectors_into_the_live_graph():
     assert added == n1 and ix.len() == n0 + n1
     res = ix.search_batch_parallel(x[[3, n0 + 7, n0 + n1 - 1]], 1, SearchQuality.Balanced)
     assert [r[0][0] for r in res] == [10_003, 10_000 + n0 + 7, 10_000 + n0 + n1 - 1]
+
+
+def test_gather_window_of_a_single_rank_equals_the_plain_search():
+    """veles_search_batch_gather_d with world = 1 (the degenerate box): the search writes straight into the gather
+    window, two epochs alternate between its two buffers, and the window equals veles_search_batch_d's outputs."""
+    import ctypes as C
+
+    import torch
+
+    x = latent_data(4000, 32, seed=8)
+    g = build_oracle(vo.COSINE, x, M=16, ef_c=100)
+    snap = DeviceSnapshot.from_arrays(x, DistanceMetric.Cosine, g.export_graph(), g.M, g.M0, g.entry_point, g.max_layer)
+    lib = nv.lib()
+    nq, k, ef = 200, 10, 64
+    blob = np.zeros(lib.veles_comm_handle_bytes(), np.uint8)
+    h = C.c_void_p()
+    nv.check(lib.veles_comm_create(0, 1, nq, k, C.byref(h), nv.ptr(blob)))
+    dev = torch.device("cuda", 0)
+    try:
+        for seed in (1, 2, 3):
+            q = queries_near(x, nq, seed=seed)
+            want = snap.search_batch(q, k, ef)
+            q_d = torch.from_numpy(q).to(dev)
+            nv.check(lib.veles_search_batch_gather_d(snap.h, h, nv.ptr(q_d), nq, k, ef, None, None))
+            nv.check(lib.veles_comm_status(h, None))
+            pi, pd, pc = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            nv.check(lib.veles_comm_window(h, C.byref(pi), C.byref(pd), C.byref(pc)))
+            from velesdb_b200.dist import _device_view
+
+            ids = _device_view(pi.value, (nq, k), torch.int32, dev).cpu().numpy().astype(np.uint32)
+            dd = _device_view(pd.value, (nq, k), torch.float32, dev).cpu().numpy()
+            cnt = _device_view(pc.value, (nq,), torch.int32, dev).cpu().numpy().astype(np.uint32)
+            assert np.array_equal(ids, want[0]) and bits_equal(dd, want[1]) and np.array_equal(cnt, want[2])
+        with pytest.raises(nv.VelesError):
+            lib_call = lib.veles_search_batch_gather_d(snap.h, h, nv.ptr(q_d), nq - 1, k, ef, None, None)
+            nv.check(lib_call)   # the window was created for nq queries
+    finally:
+        lib.veles_comm_destroy(h)

@@ -474,9 +474,11 @@ __device__ __forceinline__ void scan_rows(const IndexView& ix, const float* qs, 
 // in shared memory (a ballot per tile decides whether anything can enter -- after the first tiles almost nothing
 // does), the CTA merges its warps' lists, writes one list per (query, CTA) and the last CTA to finish merges those
 // and writes the result: the scan and the top-k are ONE launch and no score matrix exists.
+constexpr uint32_t kFuseFastK = 32;  // up to this k the fused scan selects by counting (bf_scan_kernel's tail)
 struct ScanFuse {
     uint32_t k = 0;             // 0 = not fused (scores go to the sink)
     uint32_t desc = 0;
+    uint32_t fast = 0;            // 1: k <= kFuseFastK and the shared memory holds gridDim.x * k staged keys (counting tail)
     uint64_t* partial = nullptr;  // nq x gridDim.x x k keys
     uint32_t* done = nullptr;     // CTA counter (self-resetting)
     uint32_t* out_ids = nullptr;
@@ -593,9 +595,103 @@ __global__ void __launch_bounds__(kWarps * 32) bf_scan_kernel(IndexView ix, cons
         }
     }
     if (fuse.k == 0) return;
-    // ---- CTA merge: warp q % kWarps merges query q's kWarps lists into warp 0's list of that query ----
     __shared__ uint32_t s_len[kWarps][QT];
     __shared__ uint32_t s_last;
+    if (fuse.fast) {
+        // ---- k <= 32: selection by counting, no serial list insertion anywhere on the critical path ----
+        // (1) CTA merge: the <= 8 * k keys of a query rank themselves (a key's rank = how many keys are smaller; keys are
+        //     unique), the first k land in this CTA's slot of `partial`
+        __shared__ uint32_t s_red[kWarps];
+        if (lane == 0)
+            for (int q = 0; q < QT; ++q) s_len[warp][q] = flen[q];
+        __syncthreads();
+        for (uint32_t q = 0; q < (uint32_t)QT && q < nq; ++q) {
+            const uint32_t T = kWarps * fuse.k;
+            uint64_t* po = fuse.partial + ((size_t)q * gridDim.x + blockIdx.x) * fuse.k;
+            for (uint32_t i = threadIdx.x; i < fuse.k; i += blockDim.x) po[i] = ~0ull;
+            __syncthreads();
+            for (uint32_t j = threadIdx.x; j < T; j += blockDim.x) {
+                const uint32_t w = j / fuse.k, i = j - w * fuse.k;
+                if (i >= s_len[w][q]) continue;
+                const uint64_t key = lists[((size_t)w * QT + q) * fuse.k + i];
+                uint32_t rank = 0;
+                for (uint32_t w2 = 0; w2 < kWarps; ++w2) {
+                    const uint64_t* l2 = lists + ((size_t)w2 * QT + q) * fuse.k;
+                    const uint32_t n2 = s_len[w2][q];
+                    for (uint32_t i2 = 0; i2 < n2; ++i2) rank += l2[i2] < key ? 1u : 0u;
+                }
+                if (rank < fuse.k) po[rank] = key;
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(fuse.done, 1u) == gridDim.x - 1 ? 1u : 0u;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        // (2) the last CTA: per query, stage the gridDim.x * k keys in shared memory and find the k-th smallest by a
+        //     bitwise descent (64 counting steps over the staged keys), then rank the keys at or below it
+        uint64_t* stage = lists + (size_t)kWarps * QT * fuse.k;  // gridDim.x * k keys (host sized the shared memory)
+        const uint32_t T = gridDim.x * fuse.k;
+        for (uint32_t q = 0; q < nq; ++q) {
+            const uint64_t* in = fuse.partial + (size_t)q * T;
+            uint32_t local = 0;
+            for (uint32_t j = threadIdx.x; j < T; j += blockDim.x) {
+                const uint64_t key = __ldcg(in + j);
+                stage[j] = key;
+                local += key != ~0ull ? 1u : 0u;
+            }
+            local = __reduce_add_sync(FULL_MASK, local);
+            if (lane == 0) s_red[warp] = local;
+            __syncthreads();
+            uint32_t valid = 0;
+            for (uint32_t w = 0; w < kWarps; ++w) valid += s_red[w];
+            __syncthreads();
+            const uint32_t kk = min(fuse.k, valid);
+            uint64_t prefix = 0;
+            uint32_t need = kk;
+            if (kk > 0) {
+                for (int b = 63; b >= 0; --b) {
+                    const uint64_t hi = b == 63 ? 0ull : ~((1ull << (b + 1)) - 1ull);
+                    uint32_t c = 0;
+                    for (uint32_t j = threadIdx.x; j < T; j += blockDim.x) {
+                        const uint64_t key = stage[j];
+                        c += ((key & hi) == (prefix & hi) && ((key >> b) & 1ull) == 0ull) ? 1u : 0u;
+                    }
+                    c = __reduce_add_sync(FULL_MASK, c);
+                    if (lane == 0) s_red[warp] = c;
+                    __syncthreads();
+                    uint32_t c0 = 0;
+                    for (uint32_t w = 0; w < kWarps; ++w) c0 += s_red[w];
+                    __syncthreads();
+                    if (need > c0) {
+                        need -= c0;
+                        prefix |= 1ull << b;
+                    }
+                }
+            }
+            // prefix = the kk-th smallest key; every key <= prefix writes itself at its rank
+            for (uint32_t i = threadIdx.x; i < fuse.k; i += blockDim.x) {
+                if (i >= kk) {
+                    fuse.out_ids[(size_t)q * fuse.k + i] = VELES_INVALID_ID;
+                    fuse.out_score[(size_t)q * fuse.k + i] = __uint_as_float(0x7fc00000u);
+                }
+            }
+            for (uint32_t j = threadIdx.x; j < T; j += blockDim.x) {
+                const uint64_t key = stage[j];
+                if (kk == 0 || key > prefix) continue;
+                uint32_t rank = 0;
+                for (uint32_t i = 0; i < T; ++i) rank += stage[i] < key ? 1u : 0u;
+                const uint32_t o = (uint32_t)(key >> 32);
+                fuse.out_ids[(size_t)q * fuse.k + rank] = (uint32_t)key;
+                fuse.out_score[(size_t)q * fuse.k + rank] = ord_unkey(fuse.desc ? ~o : o);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) *fuse.done = 0u;  // ready for the next launch
+        return;
+    }
+    // ---- k > 32: CTA merge: warp q % kWarps merges query q's kWarps lists into warp 0's list of that query ----
     if (lane == 0)
         for (int q = 0; q < QT; ++q) s_len[warp][q] = flen[q];
     __syncthreads();
@@ -999,14 +1095,28 @@ static int32_t launch_scores(const veles_index* ixh, const IndexView& v, const f
             else
                 ks = VELES_SCAN(__half);
 #undef VELES_SCAN
-            const ScanFuse fz = fuse ? *fuse : ScanFuse();
-            const size_t smem_s = ((((size_t)qt * ix->dim + qt) + 3) & ~(size_t)3) * 4 + (size_t)kWarps * qt * fz.k * 8;
-            const int per_sm = cached_blocks_per_sm(reinterpret_cast<const void*>(ks), kWarps * 32, smem_s);
-            if (per_sm < 1) return VELES_ERR_CUDA;
+            ScanFuse fz = fuse ? *fuse : ScanFuse();
             const uint64_t tiles = (ix->n + 4 * rb - 1) / (4 * rb);
-            uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((tiles + kWarps - 1) / kWarps, (uint64_t)sms * std::max(per_sm, 1)));
-            // fused selection: every CTA leaves a list for the last CTA to merge, so small collections get one CTA per SM
-            if (fz.k) gx = std::min<uint64_t>(gx, std::max<uint64_t>((uint64_t)sms, (tiles + kWarps * 4 - 1) / (kWarps * 4)));
+            const size_t smem_base = ((((size_t)qt * ix->dim + qt) + 3) & ~(size_t)3) * 4 + (size_t)kWarps * qt * fz.k * 8;
+            int per_sm = cached_blocks_per_sm(reinterpret_cast<const void*>(ks), kWarps * 32, smem_base);
+            if (per_sm < 1) return VELES_ERR_CUDA;
+            uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((tiles + kWarps - 1) / kWarps, (uint64_t)sms * per_sm));
+            size_t smem_s = smem_base;
+            if (fz.k) {
+                // fused selection: every CTA leaves a list for the last CTA to merge, so small collections get one CTA per
+                // SM; with k <= 32 the last CTA stages all of them in shared memory and selects by counting
+                gx = std::min<uint64_t>(gx, std::max<uint64_t>((uint64_t)sms, (tiles + kWarps * 4 - 1) / (kWarps * 4)));
+                const size_t stage = (size_t)gx * fz.k * 8;
+                // (only in the one-CTA-per-SM regime of small collections: there the tail IS the kernel; for large ones the
+                // staging memory would cost resident CTAs, i.e. bandwidth, and the tail is noise)
+                if (fz.k <= kFuseFastK && stage <= 64 * 1024 && gx <= (uint64_t)sms) {
+                    fz.fast = 1;
+                    smem_s = smem_base + stage;
+                    per_sm = cached_blocks_per_sm(reinterpret_cast<const void*>(ks), kWarps * 32, smem_s);
+                    if (per_sm < 1) return VELES_ERR_CUDA;
+                    gx = std::min<uint64_t>(gx, (uint64_t)sms * per_sm);
+                }
+            }
             ks<<<(unsigned)gx, kWarps * 32, smem_s, st>>>(v, q_d, nq, sink, as_value, fz);
             count_launch();
             VELES_CUDA(cudaGetLastError());

@@ -183,14 +183,19 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t total = p.n_mtiles * p.n_nblocks;
+    // this CTA's row tiles: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const uint32_t my_tiles = p.n_mtiles > blockIdx.x ? (p.n_mtiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+    const uint32_t total = my_tiles * p.n_nblocks;
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer =====
             uint32_t stage = 0, phase = 0;
             bool ok = true;
-            for (uint32_t w = blockIdx.x; w < total && ok; w += gridDim.x) {
-                const uint32_t mpos = w / p.n_nblocks, nb = w - mpos * p.n_nblocks;
+            // work items: every row tile of this CTA (blockIdx.x, + gridDim.x, ...) against every query block, query
+            // blocks innermost -- the A tile is re-read from L2 by the same SM, and every CTA sees every query, so the
+            // candidates of a query spread evenly over the CTAs' segments
+            for (uint32_t w = 0; w < total && ok; ++w) {
+                const uint32_t mpos = blockIdx.x + (w / p.n_nblocks) * gridDim.x, nb = w % p.n_nblocks;
                 const uint32_t mt = p.tile_list ? p.tile_list[mpos] : mpos;
                 for (uint32_t kb = 0; kb < p.k_blocks && ok; ++kb) {
                     ok = mbar_wait_bounded(&empty[stage], phase ^ 1u, p.err);
@@ -211,7 +216,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((kTcBlockM >> 4) << 24);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             bool ok = true;
-            for (uint32_t w = blockIdx.x; w < total && ok; w += gridDim.x) {
+            for (uint32_t w = 0; w < total && ok; ++w) {
                 ok = mbar_wait_bounded(&tempty[acc], acc_phase ^ 1u, p.err);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -239,8 +244,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
         const uint32_t et = threadIdx.x - 128;
         uint32_t acc = 0, acc_phase = 0;
         bool ok = true;
-        for (uint32_t w = blockIdx.x; w < total; w += gridDim.x) {
-            const uint32_t mpos = w / p.n_nblocks, nb = w - mpos * p.n_nblocks;
+        for (uint32_t w = 0; w < total; ++w) {
+            const uint32_t mpos = blockIdx.x + (w / p.n_nblocks) * gridDim.x, nb = w % p.n_nblocks;
             const uint32_t mt = p.tile_list ? p.tile_list[mpos] : mpos;
             float* thr = thr_s + acc * BN;
             if (p.mode == 1) {
@@ -507,9 +512,8 @@ static int32_t make_tensor_map(CUtensorMap* tm, const void* base, uint64_t rows,
 
 static int32_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, uint32_t bn, cudaStream_t st) {
     const int sms = device_sm_count();
-    const uint32_t total = p.n_mtiles * p.n_nblocks;
-    if (total == 0) return VELES_OK;
-    const uint32_t grid = std::min<uint32_t>(total, (uint32_t)sms);
+    if (p.n_mtiles == 0 || p.n_nblocks == 0) return VELES_OK;
+    const uint32_t grid = std::min<uint32_t>(p.n_mtiles, (uint32_t)sms);
     if (bn == 256) {
         VELES_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<256>::kSmemBytes));
         gemm_tc_kernel<256><<<grid, 256, TcCfg<256>::kSmemBytes, st>>>(ta, tb, p);
@@ -562,7 +566,7 @@ int32_t bruteforce_relaxed_d(const veles_index* ix, const float* q_d, uint32_t n
     // GEMM CTAs' segments of the query's list
     const uint32_t s_tiles = std::min<uint32_t>(n_mtiles, std::max<uint32_t>(std::max<uint32_t>(kTcSampleTiles, n_mtiles / 16), kp / kTcBlockM + 2));
     const uint32_t s_rows = s_tiles * kTcBlockM;
-    const uint32_t n_seg = (uint32_t)std::min<uint64_t>((uint64_t)n_mtiles * ((std::min<uint32_t>(nq, 1024) + 255) / 256 + 1), (uint64_t)sms);
+    const uint32_t n_seg = std::min<uint32_t>(n_mtiles, (uint32_t)sms);  // = the filter pass's grid: one segment per CTA
     const uint64_t expect = (uint64_t)kp * (n / s_rows + 1);  // per query, all segments
     // tiny collections can have fewer than kp sampled rows (threshold = -inf: every row is a candidate): a segment must
     // then hold every row of its CTA's tiles

@@ -20,22 +20,25 @@ void set_error(const char* fmt, ...) {
 int cached_blocks_per_sm(const void* kernel, int threads, size_t smem) {
     static std::mutex mu;
     static std::map<std::tuple<const void*, int, size_t, int>, int> cache;
+    static std::map<std::pair<const void*, int>, size_t> limit;  // the dynamic shared-memory limit set per kernel: only ever raised
     int dev = 0;
     cudaGetDevice(&dev);
     const auto key = std::make_tuple(kernel, threads, smem, dev);
-    {
-        std::lock_guard<std::mutex> g(mu);
-        auto it = cache.find(key);
-        if (it != cache.end()) return it->second;
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    cudaError_t e = cudaSuccess;
+    size_t& lim = limit[std::make_pair(kernel, dev)];
+    if (smem > lim) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) lim = smem;
     }
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
     if (e != cudaSuccess) {
         set_error("kernel configuration failed: %s", cudaGetErrorString(e));
         return -1;
     }
-    std::lock_guard<std::mutex> g(mu);
     cache[key] = per_sm;
     return per_sm;
 }
