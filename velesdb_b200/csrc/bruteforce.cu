@@ -602,6 +602,9 @@ __global__ void __launch_bounds__(kWarps * 32) bf_scan_kernel(IndexView ix, cons
         // (1) CTA merge: the <= 8 * k keys of a query rank themselves (a key's rank = how many keys are smaller; keys are
         //     unique), the first k land in this CTA's slot of `partial`
         __shared__ uint32_t s_red[kWarps];
+        __shared__ uint32_t s_hist[256];
+        __shared__ uint32_t s_sel[4];
+        __shared__ uint64_t s_win[kFuseFastK];
         if (lane == 0)
             for (int q = 0; q < QT; ++q) s_len[warp][q] = flen[q];
         __syncthreads();
@@ -648,40 +651,68 @@ __global__ void __launch_bounds__(kWarps * 32) bf_scan_kernel(IndexView ix, cons
             for (uint32_t w = 0; w < kWarps; ++w) valid += s_red[w];
             __syncthreads();
             const uint32_t kk = min(fuse.k, valid);
+            // radix select, eight bits per step: histogram of the next byte among the keys that match the prefix so far,
+            // then the bucket that holds the kk-th smallest (eight steps of three barriers instead of 64 x 2)
             uint64_t prefix = 0;
             uint32_t need = kk;
             if (kk > 0) {
-                for (int b = 63; b >= 0; --b) {
-                    const uint64_t hi = b == 63 ? 0ull : ~((1ull << (b + 1)) - 1ull);
-                    uint32_t c = 0;
+                for (int shift = 56; shift >= 0; shift -= 8) {
+                    s_hist[threadIdx.x] = 0;  // blockDim.x == 256 bins
+                    __syncthreads();
+                    const uint64_t hi = shift == 56 ? 0ull : ~((1ull << (shift + 8)) - 1ull);
                     for (uint32_t j = threadIdx.x; j < T; j += blockDim.x) {
                         const uint64_t key = stage[j];
-                        c += ((key & hi) == (prefix & hi) && ((key >> b) & 1ull) == 0ull) ? 1u : 0u;
+                        if ((key & hi) == (prefix & hi)) atomicAdd(&s_hist[(uint32_t)(key >> shift) & 255u], 1u);
                     }
-                    c = __reduce_add_sync(FULL_MASK, c);
-                    if (lane == 0) s_red[warp] = c;
                     __syncthreads();
-                    uint32_t c0 = 0;
-                    for (uint32_t w = 0; w < kWarps; ++w) c0 += s_red[w];
-                    __syncthreads();
-                    if (need > c0) {
-                        need -= c0;
-                        prefix |= 1ull << b;
+                    if (warp == 0) {
+                        // lane l owns bins 8l .. 8l+7: inclusive scan of the lane totals, then a walk inside the lane's bins
+                        uint32_t c[8], tot = 0;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            c[e] = s_hist[lane * 8 + e];
+                            tot += c[e];
+                        }
+                        uint32_t incl = tot;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t up = __shfl_up_sync(FULL_MASK, incl, o);
+                            if ((int)lane >= o) incl += up;
+                        }
+                        const uint32_t before = incl - tot;
+                        if (need > before && need <= incl) {  // exactly one lane
+                            uint32_t acc = before;
+                            int e = 0;
+                            while (acc + c[e] < need) acc += c[e++];
+                            s_sel[0] = lane * 8 + e;   // the byte
+                            s_sel[1] = need - acc;     // rank inside that bucket
+                        }
                     }
+                    __syncthreads();
+                    prefix |= (uint64_t)s_sel[0] << shift;
+                    need = s_sel[1];
+                    __syncthreads();
                 }
             }
-            // prefix = the kk-th smallest key; every key <= prefix writes itself at its rank
+            // prefix = the kk-th smallest key.  The keys at or below it are exactly the kk smallest: collect them, then
+            // each ranks itself among them (kk <= 32 comparisons)
+            if (threadIdx.x == 0) s_sel[2] = 0;
             for (uint32_t i = threadIdx.x; i < fuse.k; i += blockDim.x) {
                 if (i >= kk) {
                     fuse.out_ids[(size_t)q * fuse.k + i] = VELES_INVALID_ID;
                     fuse.out_score[(size_t)q * fuse.k + i] = __uint_as_float(0x7fc00000u);
                 }
             }
+            __syncthreads();
             for (uint32_t j = threadIdx.x; j < T; j += blockDim.x) {
                 const uint64_t key = stage[j];
-                if (kk == 0 || key > prefix) continue;
+                if (kk != 0 && key <= prefix) s_win[atomicAdd(&s_sel[2], 1u) & (kFuseFastK - 1)] = key;
+            }
+            __syncthreads();
+            if (threadIdx.x < kk) {
+                const uint64_t key = s_win[threadIdx.x];
                 uint32_t rank = 0;
-                for (uint32_t i = 0; i < T; ++i) rank += stage[i] < key ? 1u : 0u;
+                for (uint32_t i = 0; i < kk; ++i) rank += s_win[i] < key ? 1u : 0u;
                 const uint32_t o = (uint32_t)(key >> 32);
                 fuse.out_ids[(size_t)q * fuse.k + rank] = (uint32_t)key;
                 fuse.out_score[(size_t)q * fuse.k + rank] = ord_unkey(fuse.desc ? ~o : o);
