@@ -1301,7 +1301,9 @@ static int32_t bruteforce_fused(const veles_index* ix, const float* q_d, uint32_
     const bool fast_metric = ix->dtype != VELES_BIN1 && ix->dim >= 16 &&
                              (ix->metric == VELES_COSINE || ix->metric == VELES_EUCLIDEAN || ix->metric == VELES_DOT);
     if (std::getenv("VELES_BF_NO_FUSE")) return VELES_OK;
-    if (fast_metric && ix->dim % 32 == 0 && nq <= 8 && k <= 128) {
+    // (small collections with more than two queries: the per-query selection tail outweighs the one launch it saves --
+    // measured 10K x 768, 8 queries: 152 us fused against 79 us through the L2-resident score matrix)
+    if (fast_metric && ix->dim % 32 == 0 && nq <= 8 && k <= 128 && (nq <= 2 || ix->n >= 65536)) {
         const uint32_t qt = nq <= 1 ? 1 : nq <= 2 ? 2 : nq <= 4 ? 4 : 8;
         if ((size_t)kWarps * qt * k * 8 > 96 * 1024) return VELES_OK;
         const size_t max_ctas = (size_t)sms * 16;
