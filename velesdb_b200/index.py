@@ -703,7 +703,7 @@ class HnswIndex:
                 # sequential inserts: the reference's deterministic graph (graph.rs:158-237), id for id
                 snap.build_graph_exact(self._params.max_connections, self._params.ef_construction)
             else:
-                snap.build_graph(self._params.max_connections)
+                snap.build_graph(self._params.max_connections, min(self._params.ef_construction, 4096))
             self._snapshot, self._dirty = snap, False
             self._map_dirty = True
         return self._snapshot
