@@ -41,7 +41,7 @@ struct veles_bm25 {
     uint32_t n_terms = 0, n_doc_slots = 0, n_ranges = 0;
     uint64_t doc_count = 0, total_len = 0, n_postings = 0;
     float k1 = 1.2f, b = 0.75f, avgdl = 0.0f;
-    veles::DevBuf term_ptr, post_doc, post_tf, post_den, doc_len, idf, skip;
+    veles::DevBuf term_ptr, post_doc, post_tf, post_den, post_dc, doc_len, idf, skip;
     mutable std::mutex mu;
     mutable veles::DevBuf q_ptr_d, q_terms_d, partial_d, out_doc_d, out_score_d, out_cnt_d;
 };
@@ -52,6 +52,7 @@ struct Bm25View {
     const uint32_t* post_doc;
     const uint32_t* post_tf;
     const float* post_den;  // tf + k1 * (1 - b + b * doc_len / avgdl), the denominator of bm25.rs:371-372 per posting
+    const uint2* post_dc;   // (doc, contribution bits): idf * (tf * (k1 + 1)) / den, a constant of the snapshot per posting
     const uint32_t* doc_len;
     const float* idf;
     const uint64_t* skip;  // n_terms x (n_ranges + 1)
@@ -337,6 +338,152 @@ __global__ void __launch_bounds__(256, 5) bm25_query_kernel(Bm25View v, const ui
                 }
             }
             __syncthreads();  // the accumulator is rewritten by the next range
+        }
+        // merge the eight per-warp lists
+        top.store(lists + (size_t)warp * k, k);
+        __syncthreads();
+        if (warp == 0) {
+            for (uint32_t w = 1; w < nwarps; ++w) {
+                const uint64_t* other = lists + (size_t)w * k;
+                for (uint32_t j0 = 0; j0 < k; j0 += 32) {
+                    const uint32_t j = j0 + lane;
+                    top.offer(j < k ? other[j] : ~0ull);
+                }
+            }
+            top.store(lists, k);
+            __syncwarp();
+            uint32_t len = 0;
+            for (uint32_t j0 = 0; j0 < k; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                if (j < k) {
+                    const uint64_t key = lists[j];
+                    uint32_t doc = VELES_INVALID_ID;
+                    float sc = __uint_as_float(0x7fc00000u);
+                    if (key != ~0ull) {
+                        doc = (uint32_t)key;
+                        sc = ord_unkey(~(uint32_t)(key >> 32));
+                        ++len;
+                    }
+                    out_doc[(size_t)q * k + j] = doc;
+                    out_score[(size_t)q * k + j] = sc;
+                }
+            }
+            len = __reduce_add_sync(FULL_MASK, len);
+            if (lane == 0) out_cnt[q] = len;
+        }
+        __syncthreads();  // `lists` and s_q are reused by the next query
+    }
+}
+
+// ---- one CTA per query, warp-sliced (k <= kMultiK): no barrier between terms ---------------------------------------------
+// The walk above spends ~1300 instructions per warp and range on ~90 postings per warp: the terms of a range are applied
+// one after another with a block barrier each, because all eight warps share the range's accumulator.  Here every warp
+// OWNS a 896-document slice of the range instead: it reads every posting of the range (8 bytes: doc + the precomputed
+// contribution) and adds the ones that fall into its slice.  A warp applies the terms in program order, so query-token
+// order is kept by construction and the only synchronisation inside a range is a warp barrier per term; the eight warps
+// meet once per range (so that they read the same posting lines while those are in L1).  The next term's postings are
+// requested before the current term's are applied.
+constexpr uint32_t kSliceU = 8;  // postings per lane per request: 256 per warp, covers a typical (term, range) slice in one go
+template <int R>
+__global__ void __launch_bounds__(256, 5) bm25_slice_kernel(Bm25View v, const uint32_t* __restrict__ q_ptr,
+                                                            const uint32_t* __restrict__ q_terms, uint32_t nq, uint32_t k,
+                                                            uint32_t* __restrict__ out_doc, float* __restrict__ out_score,
+                                                            uint32_t* __restrict__ out_cnt, uint32_t* __restrict__ work) {
+    extern __shared__ __align__(16) uint8_t bq_smem[];
+    float* acc = reinterpret_cast<float*>(bq_smem);
+    uint64_t* lists = reinterpret_cast<uint64_t*>(bq_smem + kRange * 4);  // 8 x k keys for the final merge
+    __shared__ uint32_t s_q;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    constexpr uint32_t kSub = kRange / 8;  // documents per warp slice (blockDim.x == 256)
+    float* mine = acc + warp * kSub;
+    for (;;) {  // persistent: queries are handed out by a global counter
+        if (threadIdx.x == 0) s_q = atomicAdd(work, 1u);
+        __syncthreads();
+        const uint32_t q = s_q;
+        if (q >= nq) return;
+        const uint32_t t0 = q_ptr[q], t1 = q_ptr[q + 1];
+        const uint32_t nt = min(kQueryTerms, t1 - t0);  // host guarantees t1 - t0 <= kQueryTerms on this path
+        RegTopK<R> top;
+        top.init(k, lane);
+        // lane t < nt of EVERY warp tracks term t: its skip row and the posting range of the current doc range
+        uint64_t my_lo = 0, my_next = 0;
+        const uint64_t* my_skip = nullptr;
+        if (lane < nt) {
+            const uint32_t term = q_terms[t0 + lane];
+            if (term < v.n_terms) {
+                my_skip = v.skip + (size_t)term * (v.n_ranges + 1);
+                my_lo = my_skip[0];
+                my_next = my_skip[1];
+            }
+        }
+        for (uint32_t r = 0; r < v.n_ranges; ++r) {
+            const uint32_t slice_lo = r * kRange + warp * kSub;  // first document of this warp's slice
+            const uint64_t lo = my_lo, hi = my_next;
+            my_lo = my_next;
+            if (my_skip && r + 2 <= v.n_ranges) my_next = my_skip[r + 2];  // boundary after the next range
+            const uint32_t any = __ballot_sync(FULL_MASK, hi > lo);
+#pragma unroll
+            for (uint32_t i = 0; i < kSub / 128; ++i) reinterpret_cast<float4*>(mine)[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            if (any) {
+                // requests run one batch ahead of the applies: (term, offset) cursor over the non-empty slices
+                uint2 cur[kSliceU], nxt[kSliceU];
+                uint32_t ct = __ffs(any) - 1;  // current term
+                uint64_t cbeg = __shfl_sync(FULL_MASK, lo, ct), cend = __shfl_sync(FULL_MASK, hi, ct);
+                auto request = [&](uint2 (&dst)[kSliceU], uint64_t beg, uint64_t end) {
+#pragma unroll
+                    for (uint32_t u = 0; u < kSliceU; ++u) {
+                        const uint64_t p = beg + u * 32 + lane;
+                        dst[u] = p < end ? v.post_dc[p] : make_uint2(0xffffffffu, 0u);
+                    }
+                };
+                request(cur, cbeg, cend);
+                for (;;) {
+                    // the batch after this one: same term if it has more postings, else the next non-empty term
+                    uint32_t nt_term = ct;
+                    uint64_t nbeg = cbeg + kSliceU * 32, nend = cend;
+                    bool more = nbeg < cend;
+                    if (!more) {
+                        const uint32_t rest = any & ~((2u << ct) - 1u);
+                        if (rest) {
+                            nt_term = __ffs(rest) - 1;
+                            nbeg = __shfl_sync(FULL_MASK, lo, nt_term);
+                            nend = __shfl_sync(FULL_MASK, hi, nt_term);
+                            more = true;
+                        }
+                    }
+                    if (more) request(nxt, nbeg, nend);
+#pragma unroll
+                    for (uint32_t u = 0; u < kSliceU; ++u) {
+                        const uint32_t off = cur[u].x - slice_lo;  // unsigned: documents below the slice wrap to huge values
+                        if (off < kSub) mine[off] = __fadd_rn(mine[off], __uint_as_float(cur[u].y));
+                    }
+                    if (!more) break;
+                    if (nt_term != ct) __syncwarp();  // the next term's adds come after this term's (different lanes, same slot)
+#pragma unroll
+                    for (uint32_t u = 0; u < kSliceU; ++u) cur[u] = nxt[u];
+                    ct = nt_term;
+                    cbeg = nbeg;
+                    cend = nend;
+                }
+                __syncwarp();
+                // scan this warp's slice
+                for (uint32_t i0 = 0; i0 < kSub; i0 += 128) {
+                    const float4 s4 = reinterpret_cast<const float4*>(mine)[(i0 >> 2) + lane];
+                    const float thr = top.worst == ~0ull ? 0.0f : ord_unkey(~(uint32_t)(top.worst >> 32));
+                    const bool hit = (s4.x > 0.0f && s4.x >= thr) || (s4.y > 0.0f && s4.y >= thr) ||
+                                     (s4.z > 0.0f && s4.z >= thr) || (s4.w > 0.0f && s4.w >= thr);
+                    if (!__ballot_sync(FULL_MASK, hit)) continue;
+                    const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        uint64_t key = ~0ull;
+                        if (sv[e] > 0.0f) key = ((uint64_t)(~ord_key(sv[e])) << 32) | (slice_lo + i0 + lane * 4 + e);
+                        top.offer(key);
+                    }
+                }
+            }
+            __syncthreads();  // keeps the eight warps on the same posting lines (L1), nothing else depends on it
         }
         // merge the eight per-warp lists
         top.store(lists + (size_t)warp * k, k);
@@ -842,6 +989,27 @@ int32_t veles_bm25_from_csr(uint32_t n_terms, const uint64_t* term_ptr, const ui
             den[p] = (float)post_tf[p] + kl;
         }
     }
+    // The whole contribution of a posting, idf * (tf * (k1 + 1.0)) / (tf + k1 * len_norm) (bm25.rs:360-375), depends only
+    // on the snapshot: idf on the term, the rest on the posting.  Precomputed with the reference's operation order, packed
+    // next to the doc id: the slice kernel reads 8 bytes per posting and does one add.
+    std::vector<uint2> dc(std::max<uint64_t>(np, 1));
+    {
+        const volatile float k1p1 = k1 + 1.0f;
+        for (uint32_t t = 0; t < n_terms; ++t) {
+            const float idf_t = idf[t];
+            for (uint64_t p = term_ptr[t]; p < term_ptr[t + 1]; ++p) {
+                const volatile float num = (float)post_tf[p] * k1p1;
+                const volatile float top = idf_t * num;
+                const volatile float c = top / den[p];
+                const float cf = c;
+                uint32_t bits;
+                std::memcpy(&bits, &cf, 4);
+                dc[p] = make_uint2(post_doc[p], bits);
+            }
+        }
+    }
+    VELES_TRY(ix->post_dc.alloc(std::max<size_t>(np * 8, 16)));
+    if (np) VELES_CUDA(cudaMemcpy(ix->post_dc.p, dc.data(), np * 8, cudaMemcpyHostToDevice));
     VELES_TRY(ix->term_ptr.alloc(((size_t)n_terms + 1) * 8));
     VELES_TRY(ix->post_doc.alloc(std::max<size_t>(np * 4, 16)));
     VELES_TRY(ix->post_tf.alloc(std::max<size_t>(np * 4, 16)));
@@ -896,6 +1064,7 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
     v.post_doc = ix->post_doc.as<uint32_t>();
     v.post_tf = ix->post_tf.as<uint32_t>();
     v.post_den = ix->post_den.as<float>();
+    v.post_dc = ix->post_dc.as<uint2>();
     v.doc_len = ix->doc_len.as<uint32_t>();
     v.idf = ix->idf.as<float>();
     v.skip = ix->skip.as<uint64_t>();
@@ -909,17 +1078,17 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
     for (uint32_t i = 0; i < nq; ++i) max_terms = std::max(max_terms, q_term_ptr[i + 1] - q_term_ptr[i]);
     if (k <= kMultiK && max_terms <= kQueryTerms && std::getenv("VELES_BM25_RANGE_KERNEL") == nullptr) {
         // one CTA per query walking its doc-id ranges
-        // default: bm25_query_kernel (chunk-at-a-time walk).  Two round-2 experiments stay selectable and are measured
-        // slower on B200 for 1024 queries of 3-6 terms over 1M documents (profiles/README.md): VELES_BM25_PREFETCH=1
-        // (bm25_prefetch_kernel, whole range in flight: 2.85 ms against 2.70 ms -- the loads were not the bound, the
-        // ~1000 instructions per warp and range are) and VELES_BM25_HASH=1 (bm25_hash_kernel: 4.2 ms -- three CTAs per
-        // SM and a CAS per posting).
-        const bool pre = std::getenv("VELES_BM25_PREFETCH") != nullptr;
-        const bool hash = !pre && std::getenv("VELES_BM25_HASH") != nullptr;
+        // default: bm25_slice_kernel (warp-sliced ranges, precomputed contributions).  Earlier kernels stay selectable
+        // for comparison (profiles/README.md): VELES_BM25_WALK=1 (bm25_query_kernel, round 1), VELES_BM25_PREFETCH=1,
+        // VELES_BM25_HASH=1.
+        const bool walk = std::getenv("VELES_BM25_WALK") != nullptr;
+        const bool pre = !walk && std::getenv("VELES_BM25_PREFETCH") != nullptr;
+        const bool hash = !walk && !pre && std::getenv("VELES_BM25_HASH") != nullptr;
         const size_t smem = (hash ? (size_t)kHashSlots * 8 : (size_t)kRange * 4) + (size_t)8 * k * 8;
-        auto kern = hash  ? (k <= 32 ? bm25_hash_kernel<1> : k <= 64 ? bm25_hash_kernel<2> : bm25_hash_kernel<4>)
-                    : pre ? (k <= 32 ? bm25_prefetch_kernel<1> : k <= 64 ? bm25_prefetch_kernel<2> : bm25_prefetch_kernel<4>)
-                          : (k <= 32 ? bm25_query_kernel<1> : k <= 64 ? bm25_query_kernel<2> : bm25_query_kernel<4>);
+        auto kern = hash   ? (k <= 32 ? bm25_hash_kernel<1> : k <= 64 ? bm25_hash_kernel<2> : bm25_hash_kernel<4>)
+                    : pre  ? (k <= 32 ? bm25_prefetch_kernel<1> : k <= 64 ? bm25_prefetch_kernel<2> : bm25_prefetch_kernel<4>)
+                    : walk ? (k <= 32 ? bm25_query_kernel<1> : k <= 64 ? bm25_query_kernel<2> : bm25_query_kernel<4>)
+                           : (k <= 32 ? bm25_slice_kernel<1> : k <= 64 ? bm25_slice_kernel<2> : bm25_slice_kernel<4>);
         VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0, dev = 0, sms = 0;
         VELES_CUDA(cudaGetDevice(&dev));
