@@ -19,9 +19,9 @@ bm = Bm25Snapshot(corp["term_ptr"], corp["post_doc"], corp["tf"], corp["df"], co
 alg = int(corp["df"][corp["q_terms"]].astype(np.int64).sum() * 12 + nq * k * 8)
 peak, _ = measured_peak()
 ref = None
-for name, env in (("slice (default)", {}), ("walk (round 1)", {"VELES_BM25_WALK": "1"}), ("prefetch", {"VELES_BM25_PREFETCH": "1"}),
+for name, env in (("walk, precomputed postings (default)", {}), ("slice", {"VELES_BM25_SLICE": "1"}), ("prefetch", {"VELES_BM25_PREFETCH": "1"}),
                   ("hash", {"VELES_BM25_HASH": "1"})):
-    for key in ("VELES_BM25_WALK", "VELES_BM25_PREFETCH", "VELES_BM25_HASH"):
+    for key in ("VELES_BM25_SLICE", "VELES_BM25_PREFETCH", "VELES_BM25_HASH"):
         os.environ.pop(key, None)
     os.environ.update(env)
     for _ in range(3):

@@ -275,19 +275,18 @@ __global__ void __launch_bounds__(256, 5) bm25_query_kernel(Bm25View v, const ui
             uint32_t cg = 0;  // cursor: next chunk to request
             while (cg < nt && s_hi[cg] == s_lo[cg]) ++cg;
             uint64_t cbase = cg < nt ? s_lo[cg] : 0;
-            uint32_t qg[kDepth], qd[kDepth], qtf[kDepth];
-            float qden[kDepth];
+            uint32_t qg[kDepth], qd[kDepth];
+            float qc[kDepth];  // the posting's whole contribution, precomputed per snapshot (Bm25View::post_dc)
             auto request = [&](int slot) {
                 qg[slot] = cg;
                 qd[slot] = VELES_INVALID_ID;
-                qtf[slot] = 0;
-                qden[slot] = 1.0f;
+                qc[slot] = 0.0f;
                 if (cg < nt) {
                     const uint64_t p = cbase + threadIdx.x;
                     if (p < s_hi[cg]) {
-                        qd[slot] = v.post_doc[p];
-                        qtf[slot] = v.post_tf[p];
-                        qden[slot] = v.post_den[p];
+                        const uint2 dc = v.post_dc[p];
+                        qd[slot] = dc.x;
+                        qc[slot] = __uint_as_float(dc.y);
                     }
                     cbase += blockDim.x;
                     if (cbase >= s_hi[cg]) {
@@ -301,19 +300,14 @@ __global__ void __launch_bounds__(256, 5) bm25_query_kernel(Bm25View v, const ui
             for (int i = 0; i < kDepth; ++i) request(i);
             bool touched = false;
             while (qg[0] < nt) {
-                if (qd[0] != VELES_INVALID_ID) {
-                    const float num = __fmul_rn((float)qtf[0], k1p1);
-                    const float contrib = __fdiv_rn(__fmul_rn(s_idf[qg[0]], num), qden[0]);
-                    acc[qd[0] - base_doc] = __fadd_rn(acc[qd[0] - base_doc], contrib);
-                }
+                if (qd[0] != VELES_INVALID_ID) acc[qd[0] - base_doc] = __fadd_rn(acc[qd[0] - base_doc], qc[0]);
                 touched = true;
                 if (qg[1] != qg[0]) __syncthreads();  // next term's contributions come after this term's
 #pragma unroll
                 for (int i = 0; i + 1 < kDepth; ++i) {
                     qg[i] = qg[i + 1];
                     qd[i] = qd[i + 1];
-                    qtf[i] = qtf[i + 1];
-                    qden[i] = qden[i + 1];
+                    qc[i] = qc[i + 1];
                 }
                 request(kDepth - 1);
             }
@@ -1078,17 +1072,18 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
     for (uint32_t i = 0; i < nq; ++i) max_terms = std::max(max_terms, q_term_ptr[i + 1] - q_term_ptr[i]);
     if (k <= kMultiK && max_terms <= kQueryTerms && std::getenv("VELES_BM25_RANGE_KERNEL") == nullptr) {
         // one CTA per query walking its doc-id ranges
-        // default: bm25_slice_kernel (warp-sliced ranges, precomputed contributions).  Earlier kernels stay selectable
-        // for comparison (profiles/README.md): VELES_BM25_WALK=1 (bm25_query_kernel, round 1), VELES_BM25_PREFETCH=1,
-        // VELES_BM25_HASH=1.
-        const bool walk = std::getenv("VELES_BM25_WALK") != nullptr;
-        const bool pre = !walk && std::getenv("VELES_BM25_PREFETCH") != nullptr;
-        const bool hash = !walk && !pre && std::getenv("VELES_BM25_HASH") != nullptr;
+        // default: bm25_query_kernel (chunk-at-a-time walk; since round 2 it reads the precomputed 8-byte postings).
+        // Three round-2 restructurings stay selectable and are all measured slower on B200 (profiles/README.md, DESIGN.md
+        // section 4.4): VELES_BM25_SLICE=1 (warp-sliced ranges), VELES_BM25_PREFETCH=1 (whole range in flight),
+        // VELES_BM25_HASH=1 (hashed windows).
+        const bool slice = std::getenv("VELES_BM25_SLICE") != nullptr;
+        const bool pre = !slice && std::getenv("VELES_BM25_PREFETCH") != nullptr;
+        const bool hash = !slice && !pre && std::getenv("VELES_BM25_HASH") != nullptr;
         const size_t smem = (hash ? (size_t)kHashSlots * 8 : (size_t)kRange * 4) + (size_t)8 * k * 8;
-        auto kern = hash   ? (k <= 32 ? bm25_hash_kernel<1> : k <= 64 ? bm25_hash_kernel<2> : bm25_hash_kernel<4>)
-                    : pre  ? (k <= 32 ? bm25_prefetch_kernel<1> : k <= 64 ? bm25_prefetch_kernel<2> : bm25_prefetch_kernel<4>)
-                    : walk ? (k <= 32 ? bm25_query_kernel<1> : k <= 64 ? bm25_query_kernel<2> : bm25_query_kernel<4>)
-                           : (k <= 32 ? bm25_slice_kernel<1> : k <= 64 ? bm25_slice_kernel<2> : bm25_slice_kernel<4>);
+        auto kern = hash    ? (k <= 32 ? bm25_hash_kernel<1> : k <= 64 ? bm25_hash_kernel<2> : bm25_hash_kernel<4>)
+                    : pre   ? (k <= 32 ? bm25_prefetch_kernel<1> : k <= 64 ? bm25_prefetch_kernel<2> : bm25_prefetch_kernel<4>)
+                    : slice ? (k <= 32 ? bm25_slice_kernel<1> : k <= 64 ? bm25_slice_kernel<2> : bm25_slice_kernel<4>)
+                            : (k <= 32 ? bm25_query_kernel<1> : k <= 64 ? bm25_query_kernel<2> : bm25_query_kernel<4>);
         VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0, dev = 0, sms = 0;
         VELES_CUDA(cudaGetDevice(&dev));
