@@ -216,3 +216,32 @@ def test_multi_query_search_and_search_with_filter_end_to_end():
     cand = [h for h in hx.search(qs[0], max(4 * k, k + 10)) if even(h[0])][:k]
     assert got == sorted(cand, key=lambda h: -h[1]) and len(got) == k and all(even(h[0]) for h in got)
     assert search_with_filter(hx, qs[0], k, lambda i: False) == []
+
+
+@pytest.mark.parametrize("k", [20, 50, 100])
+def test_bm25_work_items_split_and_merge_bit_exact(k, monkeypatch):
+    """bm25_flat_kernel cuts a query into (query, part of the doc-id ranges) work items and the last one to finish
+    merges the parts: any split -- one item per query, two, one per range (what a single query gets) -- and round 1's
+    walk kernel return the oracle's documents and score bits.  30000 docs = 5 ranges; the frequent terms need
+    several 1024-posting rounds per range."""
+    docs, p = zipf_corpus(30000, 3000, seed=5)
+    o, snap = build_both(docs)
+    rng = np.random.default_rng(2)
+    for nq in (1, 5):
+        q_ptr, q_terms = [0], []
+        for _ in range(nq):
+            q_terms += rng.choice(3000, size=int(rng.integers(1, 7)), p=p).astype(np.uint32).tolist()
+            q_ptr.append(len(q_terms))
+        oi, os_, oc = o.search_batch_terms(q_ptr, q_terms, k, threads=4)
+        for env in ({}, {"VELES_BM25_PARTS": "1"}, {"VELES_BM25_PARTS": "2"}, {"VELES_BM25_FLAT_OCC": "5"}, {"VELES_BM25_WALK": "1"}):
+            for key in ("VELES_BM25_PARTS", "VELES_BM25_FLAT_OCC", "VELES_BM25_WALK"):
+                monkeypatch.delenv(key, raising=False)
+            for key, val in env.items():
+                monkeypatch.setenv(key, val)
+            for rep in range(2):  # the per-query tickets must be back at zero for the second call
+                docs_g, sc_g, cnt_g = snap.search_batch(q_ptr, q_terms, k)
+                assert np.array_equal(cnt_g, oc), (env, rep)
+                for i in range(nq):
+                    c = int(cnt_g[i])
+                    assert np.array_equal(docs_g[i, :c], oi[i, :c].astype(np.uint32)), (env, rep, i)
+                    assert bits_equal(sc_g[i, :c], os_[i, :c]), (env, rep, i)

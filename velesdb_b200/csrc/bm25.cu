@@ -679,6 +679,284 @@ __global__ void __launch_bounds__(256, 5) bm25_prefetch_kernel(Bm25View v, const
     }
 }
 
+// ---- (query, part of the doc-id space) work items, warp-step mapping, rounds pipelined (k <= kMultiK) ---------------
+// What the three kernels above have in common is ~1000+ issued instructions per warp and range for ~90 postings per
+// warp: cursor bookkeeping per 256-posting chunk of ONE term (chunks 55 % full on the bench corpus), one DRAM round
+// trip per chunk, a separate zeroing pass, and 1024 queries over 740 resident CTAs (a second wave 38 % full).  Here
+//   * the postings of a range are cut into WARP-STEPS (32 consecutive postings of one term).  The steps of all terms,
+//     term-major, are dealt round-robin to the eight warps, kFlatH per warp per ROUND (1024 postings); which term a
+//     step belongs to is one ballot against the per-lane step prefix, uniform across the warp -- no per-thread search,
+//     no per-term chunk loop.  A typical range is one round;
+//   * the NEXT round's postings (next range included) are requested before the current round is applied, so the DRAM
+//     round trip overlaps the apply + scan of the round in hand;
+//   * a round is applied term by term, present terms only, with a block barrier after each (all eight warps share the
+//     range's accumulator): every document still receives its contributions in query-token order, so the f32 sums
+//     keep the reference's bits;
+//   * the scan re-zeroes what it reads, so there is no zeroing pass;
+//   * a work item is (query, 1/P of the ranges) with P chosen so that the batch is >= 6 waves of CTAs; the last item
+//     of a query to finish (a ticket per query) merges the P sorted lists.  A single query therefore runs on up to
+//     n_ranges CTAs instead of one.
+constexpr int kFlatH = 4;                      // warp-steps a warp holds per round
+constexpr uint32_t kFlatRound = 8 * kFlatH;    // warp-steps per round (8 warps)
+struct __align__(16) FlatEnt {
+    uint64_t at;    // address of the first (doc, contribution) pair of the term's slice of the range
+    uint32_t len;   // postings in the slice
+    uint32_t cum;   // warp-steps of the terms before this one
+};
+struct FlatHold {
+    uint32_t d[kFlatH];  // document of this lane's posting of step h
+    uint32_t c[kFlatH];  // bits of its contribution
+    uint32_t tags;       // byte h: query-token index of step h, 0xff = no posting for this lane
+    uint32_t mask;       // query tokens with steps in this round (uniform)
+};
+template <int R, int OCC>
+__global__ void __launch_bounds__(256, OCC) bm25_flat_kernel(Bm25View v, const uint32_t* __restrict__ q_ptr,
+                                                           const uint32_t* __restrict__ q_terms, uint32_t nq, uint32_t k,
+                                                           uint32_t parts, uint64_t* __restrict__ partial,
+                                                           uint32_t* __restrict__ tickets, uint32_t* __restrict__ qthr,
+                                                           uint32_t* __restrict__ out_doc,
+                                                           float* __restrict__ out_score, uint32_t* __restrict__ out_cnt,
+                                                           uint32_t* __restrict__ work) {
+    extern __shared__ __align__(16) uint8_t bq_smem[];
+    float* acc = reinterpret_cast<float*>(bq_smem);
+    uint64_t* lists = reinterpret_cast<uint64_t*>(bq_smem + kRange * 4);  // 8 x k keys for the merge
+    __shared__ FlatEnt s_ent[4][kQueryTerms];  // ring over ranges: r, r+1 (being prefetched), r+2 (being written)
+    __shared__ uint32_t s_total[4];            // warp-steps of the range
+    __shared__ uint64_t s_bound[2][kQueryTerms];  // per token: the two boundaries of the next range to set up (warp 0's state)
+    __shared__ uint32_t s_term[kQueryTerms];
+    __shared__ uint32_t s_item;
+    // bits of the best k-th score any full list of this query is known to hold (this CTA's warps, and through qthr[q]
+    // the query's other work items): k documents score at least this much, so anything below it is dropped unseen
+    __shared__ uint32_t s_thr;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* acc4 = reinterpret_cast<float4*>(acc);
+    for (uint32_t i = threadIdx.x; i < kRange / 4; i += 256) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (;;) {  // persistent: work items are handed out by a global counter
+        if (threadIdx.x == 0) s_item = atomicAdd(work, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= nq * parts) return;
+        // part-major: by the time a query's later parts start, its earlier ones have published their k-th score (qthr)
+        const uint32_t part = item / nq, q = item - part * nq;
+        const uint32_t r_begin = (uint32_t)((uint64_t)part * v.n_ranges / parts);
+        const uint32_t r_end = (uint32_t)((uint64_t)(part + 1) * v.n_ranges / parts);
+        const uint32_t t0 = q_ptr[q], t1 = q_ptr[q + 1];
+        const uint32_t nt = min(kQueryTerms, t1 - t0);  // host guarantees t1 - t0 <= kQueryTerms on this path
+        RegTopK<R> top;
+        top.init(k, lane);
+        uint32_t thr_seen = 0;  // warp 0, lane 0: qthr[q] as last read (requested a range ahead)
+        // warp 0, lane g < nt: the skip row of query token g and the two boundaries of the next range to set up; kept in
+        // shared memory between set-ups (once per range) rather than in six registers of every thread
+        if (warp == 0) {
+            if (lane == 0) {
+                thr_seen = *reinterpret_cast<volatile uint32_t*>(qthr + q);
+                s_thr = 0;
+            }
+            uint32_t term = 0xffffffffu;
+            uint64_t lo = 0, hi = 0;
+            if (lane < nt) term = q_terms[t0 + lane];
+            if (term < v.n_terms) {  // unknown term: df = 0, contributes nothing
+                const uint64_t* row = v.skip + (size_t)term * (v.n_ranges + 1);
+                lo = row[r_begin];
+                hi = row[r_begin + 1];
+            }
+            s_term[lane] = term;
+            s_bound[0][lane] = lo;
+            s_bound[1][lane] = hi;
+        }
+        auto setup = [&](uint32_t r) {  // warp 0, all lanes: entries of range r into the ring
+            const uint64_t my_lo = s_bound[0][lane], my_hi = s_bound[1][lane];
+            const uint32_t len = (uint32_t)(my_hi - my_lo);  // <= kRange
+            const uint32_t steps = (len + 31) >> 5;
+            uint32_t incl = steps;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(FULL_MASK, incl, o);
+                if ((int)lane >= o) incl += up;
+            }
+            if (lane < nt) {
+                FlatEnt e;
+                e.at = reinterpret_cast<uint64_t>(v.post_dc + my_lo);
+                e.len = len;
+                e.cum = incl - steps;
+                s_ent[r & 3][lane] = e;
+            }
+            if (lane == 31) s_total[r & 3] = incl;  // lanes >= nt carry 0 steps
+            const uint32_t term = s_term[lane];
+            s_bound[0][lane] = my_hi;
+            if (term < v.n_terms && r + 2 <= v.n_ranges) s_bound[1][lane] = v.skip[(size_t)term * (v.n_ranges + 1) + r + 2];
+        };
+        if (warp == 0) {
+            setup(r_begin);
+            if (r_begin + 1 < r_end) setup(r_begin + 1);
+        }
+        __syncthreads();
+        // requests the postings of round (r, j0) into h
+        auto load_round = [&](FlatHold& h, uint32_t r, uint32_t j0) {
+            const FlatEnt* ent = s_ent[r & 3];
+            uint32_t my_cum = 0xffffffffu, my_end = 0;
+            if (lane < nt) {
+                const uint4 e = *reinterpret_cast<const uint4*>(ent + lane);
+                my_cum = e.w;
+                my_end = e.w + ((e.z + 31) >> 5);
+            }
+            h.mask = __ballot_sync(FULL_MASK, my_cum < j0 + kFlatRound && my_end > j0 && my_end > my_cum);
+            h.tags = 0xffffffffu;
+#pragma unroll
+            for (int i = 0; i < kFlatH; ++i) {
+                h.d[i] = 0;
+                h.c[i] = 0;
+            }
+            if (h.mask == 0) return;
+#pragma unroll
+            for (int i = 0; i < kFlatH; ++i) {
+                const uint32_t j = j0 + i * 8 + warp;
+                const uint32_t g = __popc(__ballot_sync(FULL_MASK, my_cum <= j)) - 1;  // mask != 0: token 0 has cum 0 <= j
+                const uint4 e = *reinterpret_cast<const uint4*>(ent + g);
+                const uint32_t off = ((j - e.w) << 5) + lane;
+                const bool ok = off < e.z;  // also false for j past the last step
+                const uint64_t src = (((uint64_t)e.y << 32) | e.x) + (uint64_t)off * 8;
+                if (ok) h.tags ^= (g ^ 0xffu) << (8 * i);
+                // the load lands in the hold registers themselves and is first looked at when the round is applied
+                // (a C++ "if (ok) d = load" made the compiler wait for the data right here to select it)
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.global.nc.v2.u32 {%0, %1}, [%2];\n\t}"
+                    : "+r"(h.d[i]), "+r"(h.c[i])
+                    : "l"(src), "r"((uint32_t)ok));
+            }
+        };
+        bool touched = false;
+        uint32_t r = r_begin, j0 = 0;
+        // one round: request the next one into `nxt`, apply `cur`, finish the range if this was its last round
+        auto round = [&](FlatHold& cur, FlatHold& nxt) {
+            const uint32_t total = s_total[r & 3];
+            uint32_t nr = r, nj0 = j0 + kFlatRound;
+            const bool last = nj0 >= total;
+            if (last) {
+                nr = r + 1;
+                nj0 = 0;
+            }
+            const uint32_t base_doc = r * kRange;
+            // ptxas gives the two register sets' loads the SAME hardware scoreboard, so the first use of `cur` waits for
+            // every load outstanding on it: look at `cur` (its accumulator slots) BEFORE requesting `nxt`, or each round
+            // would wait for its own prefetch (ncu, first version: 13 % of the samples on exactly that).
+            static_assert(kFlatH == 4, "the pin below names four slots");
+            uint32_t slot[kFlatH];
+#pragma unroll
+            for (int i = 0; i < kFlatH; ++i) slot[i] = cur.d[i] - base_doc;
+            asm volatile("" ::"r"(slot[0]), "r"(slot[1]), "r"(slot[2]), "r"(slot[3]) : "memory");
+            if (nr < r_end) load_round(nxt, nr, nj0);
+            for (uint32_t m = cur.mask; m; m &= m - 1) {
+                const uint32_t g = __ffs(m) - 1;
+                const uint32_t diff = cur.tags ^ (g * 0x01010101u);  // byte h is zero where step h belongs to token g
+#pragma unroll
+                for (int i = 0; i < kFlatH; ++i)
+                    if ((diff & (0xffu << (8 * i))) == 0) acc[slot[i]] = __fadd_rn(acc[slot[i]], __uint_as_float(cur.c[i]));
+                __syncthreads();  // the next token's (or round's) contributions come after this token's, per document
+            }
+            touched |= cur.mask != 0;
+            if (last) {
+                if (warp == 0 && r + 2 < r_end) setup(r + 2);
+                if (touched) {  // scan this warp's 896 documents; what is read is zeroed for the next range
+                    // own list: a warp meets its documents in ascending order, so an equal score never displaces a kept
+                    // one (strictly greater); shared bound: ties with another list's k-th score may still win on the id
+                    float thr_own = top.worst == ~0ull ? 0.0f : ord_unkey(~(uint32_t)(top.worst >> 32));
+                    float thr_sh = __uint_as_float(*reinterpret_cast<volatile uint32_t*>(&s_thr));
+                    const uint32_t i_begin = warp * (kRange / 8);
+#pragma unroll 1
+                    for (uint32_t i0 = i_begin; i0 < i_begin + kRange / 8; i0 += 128) {
+                        const float4 s4 = acc4[(i0 >> 2) + lane];
+                        acc4[(i0 >> 2) + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float mx = fmaxf(fmaxf(s4.x, s4.y), fmaxf(s4.z, s4.w));
+                        if (!__ballot_sync(FULL_MASK, mx > thr_own && mx >= thr_sh)) continue;
+                        const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            uint64_t key = ~0ull;
+                            if (sv[e] > 0.0f && sv[e] >= thr_sh)
+                                key = ((uint64_t)(~ord_key(sv[e])) << 32) | (base_doc + i0 + lane * 4 + e);
+                            top.offer(key);
+                        }
+                        if (top.worst != ~0ull) {
+                            thr_own = ord_unkey(~(uint32_t)(top.worst >> 32));
+                            if (lane == 0 && thr_own > thr_sh) atomicMax(&s_thr, __float_as_uint(thr_own));  // positive floats order as their bits
+                        }
+                        thr_sh = __uint_as_float(*reinterpret_cast<volatile uint32_t*>(&s_thr));
+                    }
+                    touched = false;
+                }
+                if (threadIdx.x == 0 && parts > 1) {  // exchange the bound with the query's other work items
+                    const uint32_t mine = *reinterpret_cast<volatile uint32_t*>(&s_thr);
+                    if (thr_seen > mine) atomicMax(&s_thr, thr_seen);
+                    if (mine > thr_seen) atomicMax(qthr + q, mine);  // no return value used: fire and forget
+                    thr_seen = *reinterpret_cast<volatile uint32_t*>(qthr + q);  // consumed at the end of the next range
+                }
+                __syncthreads();  // accumulator clean and ring entry r + 2 written before anyone goes on
+            }
+            r = nr;
+            j0 = nj0;
+        };
+        FlatHold ha, hb;
+        if (r < r_end) load_round(ha, r, 0);
+        while (r < r_end) {
+            round(ha, hb);
+            if (r >= r_end) break;
+            round(hb, ha);
+        }
+        // merge the eight per-warp lists; publish the item's list; the query's last item merges the parts
+        top.store(lists + (size_t)warp * k, k);
+        __syncthreads();
+        if (warp == 0) {
+            for (uint32_t w = 1; w < 8; ++w) {
+                const uint64_t* other = lists + (size_t)w * k;
+                for (uint32_t jj = 0; jj < k; jj += 32) top.offer(jj + lane < k ? other[jj + lane] : ~0ull);
+            }
+            bool finisher = true;
+            if (parts > 1) {
+                top.store(partial + ((size_t)q * parts + part) * k, k);
+                __threadfence();
+                __syncwarp();
+                uint32_t t = 0;
+                if (lane == 0) t = atomicAdd(tickets + q, 1u);
+                t = __shfl_sync(FULL_MASK, t, 0);
+                if (t == parts - 1) {
+                    __threadfence();
+                    for (uint32_t pp = 0; pp < parts; ++pp) {
+                        if (pp == part) continue;
+                        const volatile uint64_t* other = partial + ((size_t)q * parts + pp) * k;
+                        for (uint32_t jj = 0; jj < k; jj += 32) top.offer(jj + lane < k ? other[jj + lane] : ~0ull);
+                    }
+                    if (lane == 0) tickets[q] = 0;  // ready for the next call
+                }
+                finisher = t == parts - 1;
+            }
+            if (finisher) {
+                top.store(lists, k);
+                __syncwarp();
+                uint32_t len = 0;
+                for (uint32_t jj = 0; jj < k; jj += 32) {
+                    const uint32_t j = jj + lane;
+                    if (j < k) {
+                        const uint64_t key = lists[j];
+                        uint32_t doc = VELES_INVALID_ID;
+                        float sc = __uint_as_float(0x7fc00000u);
+                        if (key != ~0ull) {
+                            doc = (uint32_t)key;
+                            sc = ord_unkey(~(uint32_t)(key >> 32));
+                            ++len;
+                        }
+                        out_doc[(size_t)q * k + j] = doc;
+                        out_score[(size_t)q * k + j] = sc;
+                    }
+                }
+                len = __reduce_add_sync(FULL_MASK, len);
+                if (lane == 0) out_cnt[q] = len;
+            }
+        }
+        __syncthreads();  // `lists` and s_item are reused by the next item
+    }
+}
+
 // ---- one CTA per query, posting-driven (k <= kMultiK): hashed accumulation over adaptive doc-id windows -------------
 // bm25_query_kernel above pays for every doc-id range of a query -- zeroing and re-scanning a dense 7168-slot
 // accumulator ~140 times -- whatever the number of postings that fall into it (~700).  Here the work follows the
@@ -1072,30 +1350,57 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
     for (uint32_t i = 0; i < nq; ++i) max_terms = std::max(max_terms, q_term_ptr[i + 1] - q_term_ptr[i]);
     if (k <= kMultiK && max_terms <= kQueryTerms && std::getenv("VELES_BM25_RANGE_KERNEL") == nullptr) {
         // one CTA per query walking its doc-id ranges
-        // default: bm25_query_kernel (chunk-at-a-time walk; since round 2 it reads the precomputed 8-byte postings).
-        // Three round-2 restructurings stay selectable and are all measured slower on B200 (profiles/README.md, DESIGN.md
-        // section 4.4): VELES_BM25_SLICE=1 (warp-sliced ranges), VELES_BM25_PREFETCH=1 (whole range in flight),
-        // VELES_BM25_HASH=1 (hashed windows).
-        const bool slice = std::getenv("VELES_BM25_SLICE") != nullptr;
-        const bool pre = !slice && std::getenv("VELES_BM25_PREFETCH") != nullptr;
-        const bool hash = !slice && !pre && std::getenv("VELES_BM25_HASH") != nullptr;
+        // default: bm25_flat_kernel ((query, part) items, warp-step mapping, rounds pipelined).  VELES_BM25_WALK=1 selects
+        // round 1's bm25_query_kernel; three other round-2 restructurings stay selectable and are measured slower on B200
+        // (profiles/README.md): VELES_BM25_SLICE=1, VELES_BM25_PREFETCH=1, VELES_BM25_HASH=1.
+        const bool walk = std::getenv("VELES_BM25_WALK") != nullptr;
+        const bool slice = !walk && std::getenv("VELES_BM25_SLICE") != nullptr;
+        const bool pre = !walk && !slice && std::getenv("VELES_BM25_PREFETCH") != nullptr;
+        const bool hash = !walk && !slice && !pre && std::getenv("VELES_BM25_HASH") != nullptr;
+        const bool flat = !walk && !slice && !pre && !hash;
         const size_t smem = (hash ? (size_t)kHashSlots * 8 : (size_t)kRange * 4) + (size_t)8 * k * 8;
-        auto kern = hash    ? (k <= 32 ? bm25_hash_kernel<1> : k <= 64 ? bm25_hash_kernel<2> : bm25_hash_kernel<4>)
-                    : pre   ? (k <= 32 ? bm25_prefetch_kernel<1> : k <= 64 ? bm25_prefetch_kernel<2> : bm25_prefetch_kernel<4>)
-                    : slice ? (k <= 32 ? bm25_slice_kernel<1> : k <= 64 ? bm25_slice_kernel<2> : bm25_slice_kernel<4>)
-                            : (k <= 32 ? bm25_query_kernel<1> : k <= 64 ? bm25_query_kernel<2> : bm25_query_kernel<4>);
-        VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0, dev = 0, sms = 0;
         VELES_CUDA(cudaGetDevice(&dev));
         VELES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        VELES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
-        VELES_REQUIRE(per_sm >= 1, "bm25 query kernel does not fit on an SM");
-        VELES_TRY(ix->partial_d.ensure(64));
-        VELES_CUDA(cudaMemsetAsync(ix->partial_d.p, 0, 4, st));
-        const uint32_t grid = std::min<uint32_t>(nq, (uint32_t)(per_sm * sms));
-        kern<<<grid, 256, smem, st>>>(v, ix->q_ptr_d.as<uint32_t>(), ix->q_terms_d.as<uint32_t>(), nq, k,
-                                      ix->out_doc_d.as<uint32_t>(), ix->out_score_d.as<float>(), ix->out_cnt_d.as<uint32_t>(),
-                                      ix->partial_d.as<uint32_t>());
+        if (flat) {
+            // 4 CTAs per SM: 64 registers, no spills; VELES_BM25_FLAT_OCC=5 selects the 48-register build (experiments)
+            const bool occ5 = std::getenv("VELES_BM25_FLAT_OCC") != nullptr && std::atoi(std::getenv("VELES_BM25_FLAT_OCC")) == 5;
+            auto kern = occ5 ? (k <= 32 ? bm25_flat_kernel<1, 5> : k <= 64 ? bm25_flat_kernel<2, 5> : bm25_flat_kernel<4, 5>)
+                             : (k <= 32 ? bm25_flat_kernel<1, 4> : k <= 64 ? bm25_flat_kernel<2, 4> : bm25_flat_kernel<4, 4>);
+            VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            VELES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+            VELES_REQUIRE(per_sm >= 1, "bm25 query kernel does not fit on an SM");
+            const uint32_t resident = (uint32_t)(per_sm * sms);
+            // parts per query: at least ~6 waves of work items, so that the last wave costs little and a small batch
+            // still fills the GPU (env override for experiments)
+            uint32_t parts = std::max<uint32_t>(1, std::min<uint32_t>(ix->n_ranges, (6 * resident + nq - 1) / nq));
+            if (const char* e = std::getenv("VELES_BM25_PARTS")) parts = std::max(1, std::min<int>((int)ix->n_ranges, std::atoi(e)));
+            const size_t tickets_off = 256, thr_off = (tickets_off + (size_t)nq * 4 + 255) / 256 * 256;
+            const size_t lists_off = (thr_off + (size_t)nq * 4 + 255) / 256 * 256;
+            VELES_TRY(ix->partial_d.ensure(lists_off + (size_t)nq * parts * k * 8));
+            VELES_CUDA(cudaMemsetAsync(ix->partial_d.p, 0, lists_off, st));
+            uint8_t* pb = ix->partial_d.as<uint8_t>();
+            const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)nq * parts, resident);
+            kern<<<grid, 256, smem, st>>>(v, ix->q_ptr_d.as<uint32_t>(), ix->q_terms_d.as<uint32_t>(), nq, k, parts,
+                                          reinterpret_cast<uint64_t*>(pb + lists_off), reinterpret_cast<uint32_t*>(pb + tickets_off),
+                                          reinterpret_cast<uint32_t*>(pb + thr_off),
+                                          ix->out_doc_d.as<uint32_t>(), ix->out_score_d.as<float>(), ix->out_cnt_d.as<uint32_t>(),
+                                          reinterpret_cast<uint32_t*>(pb));
+        } else {
+            auto kern = hash    ? (k <= 32 ? bm25_hash_kernel<1> : k <= 64 ? bm25_hash_kernel<2> : bm25_hash_kernel<4>)
+                        : pre   ? (k <= 32 ? bm25_prefetch_kernel<1> : k <= 64 ? bm25_prefetch_kernel<2> : bm25_prefetch_kernel<4>)
+                        : slice ? (k <= 32 ? bm25_slice_kernel<1> : k <= 64 ? bm25_slice_kernel<2> : bm25_slice_kernel<4>)
+                                : (k <= 32 ? bm25_query_kernel<1> : k <= 64 ? bm25_query_kernel<2> : bm25_query_kernel<4>);
+            VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            VELES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+            VELES_REQUIRE(per_sm >= 1, "bm25 query kernel does not fit on an SM");
+            VELES_TRY(ix->partial_d.ensure(64));
+            VELES_CUDA(cudaMemsetAsync(ix->partial_d.p, 0, 4, st));
+            const uint32_t grid = std::min<uint32_t>(nq, (uint32_t)(per_sm * sms));
+            kern<<<grid, 256, smem, st>>>(v, ix->q_ptr_d.as<uint32_t>(), ix->q_terms_d.as<uint32_t>(), nq, k,
+                                          ix->out_doc_d.as<uint32_t>(), ix->out_score_d.as<float>(), ix->out_cnt_d.as<uint32_t>(),
+                                          ix->partial_d.as<uint32_t>());
+        }
         count_launch();
         VELES_CUDA(cudaGetLastError());
     } else {
