@@ -719,10 +719,13 @@ __global__ void __launch_bounds__(256, OCC) bm25_flat_kernel(Bm25View v, const u
                                                            uint32_t* __restrict__ work) {
     extern __shared__ __align__(16) uint8_t bq_smem[];
     float* acc = reinterpret_cast<float*>(bq_smem);
-    uint64_t* lists = reinterpret_cast<uint64_t*>(bq_smem + kRange * 4);  // 8 x k keys for the merge
+    uint64_t* lists = reinterpret_cast<uint64_t*>(bq_smem + kRange * 4);  // 8 x k keys + k merged
     __shared__ FlatEnt s_ent[4][kQueryTerms];  // ring over ranges: r, r+1 (being prefetched), r+2 (being written)
     __shared__ uint32_t s_total[4];            // warp-steps of the range
-    __shared__ uint64_t s_bound[2][kQueryTerms];  // per token: the two boundaries of the next range to set up (warp 0's state)
+    // per token: skip[term][r] for a ring of four ranges.  Warp 0's set-up of range r reads entries r and r + 1 and
+    // requests entry r + 3 with cp.async, so no thread ever waits for a skip entry (a plain load stored to shared
+    // memory made warp 0 -- and with it the whole CTA at the next barrier -- wait a DRAM round trip per range)
+    __shared__ uint64_t s_skip[4][kQueryTerms];
     __shared__ uint32_t s_term[kQueryTerms];
     __shared__ uint32_t s_item;
     // bits of the best k-th score any full list of this query is known to hold (this CTA's warps, and through qthr[q]
@@ -745,8 +748,7 @@ __global__ void __launch_bounds__(256, OCC) bm25_flat_kernel(Bm25View v, const u
         RegTopK<R> top;
         top.init(k, lane);
         uint32_t thr_seen = 0;  // warp 0, lane 0: qthr[q] as last read (requested a range ahead)
-        // warp 0, lane g < nt: the skip row of query token g and the two boundaries of the next range to set up; kept in
-        // shared memory between set-ups (once per range) rather than in six registers of every thread
+        // warp 0, lane g < nt: the skip entries of query token g for the first two ranges; the third is on its way
         if (warp == 0) {
             if (lane == 0) {
                 thr_seen = *reinterpret_cast<volatile uint32_t*>(qthr + q);
@@ -761,11 +763,19 @@ __global__ void __launch_bounds__(256, OCC) bm25_flat_kernel(Bm25View v, const u
                 hi = row[r_begin + 1];
             }
             s_term[lane] = term;
-            s_bound[0][lane] = lo;
-            s_bound[1][lane] = hi;
+            if (!(term < v.n_terms)) s_skip[(r_begin + 2) & 3][lane] = s_skip[(r_begin + 3) & 3][lane] = 0;  // never requested
+            s_skip[r_begin & 3][lane] = lo;
+            s_skip[(r_begin + 1) & 3][lane] = hi;
+            if (term < v.n_terms && r_begin + 2 <= v.n_ranges)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&s_skip[(r_begin + 2) & 3][lane])),
+                             "l"(v.skip + (size_t)term * (v.n_ranges + 1) + r_begin + 2)
+                             : "memory");
+            cp_async_commit();
         }
         auto setup = [&](uint32_t r) {  // warp 0, all lanes: entries of range r into the ring
-            const uint64_t my_lo = s_bound[0][lane], my_hi = s_bound[1][lane];
+            cp_async_wait<0>();  // entry r + 1 was requested a whole range ago
+            __syncwarp();
+            const uint64_t my_lo = s_skip[r & 3][lane], my_hi = s_skip[(r + 1) & 3][lane];
             const uint32_t len = (uint32_t)(my_hi - my_lo);  // <= kRange
             const uint32_t steps = (len + 31) >> 5;
             uint32_t incl = steps;
@@ -783,8 +793,11 @@ __global__ void __launch_bounds__(256, OCC) bm25_flat_kernel(Bm25View v, const u
             }
             if (lane == 31) s_total[r & 3] = incl;  // lanes >= nt carry 0 steps
             const uint32_t term = s_term[lane];
-            s_bound[0][lane] = my_hi;
-            if (term < v.n_terms && r + 2 <= v.n_ranges) s_bound[1][lane] = v.skip[(size_t)term * (v.n_ranges + 1) + r + 2];
+            if (term < v.n_terms && r + 3 <= v.n_ranges)  // slot (r + 3) & 3 held entry r - 1: free
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&s_skip[(r + 3) & 3][lane])),
+                             "l"(v.skip + (size_t)term * (v.n_ranges + 1) + r + 3)
+                             : "memory");
+            cp_async_commit();
         };
         if (warp == 0) {
             setup(r_begin);
@@ -792,7 +805,7 @@ __global__ void __launch_bounds__(256, OCC) bm25_flat_kernel(Bm25View v, const u
         }
         __syncthreads();
         // requests the postings of round (r, j0) into h
-        auto load_round = [&](FlatHold& h, uint32_t r, uint32_t j0) {
+        auto load_round = [&](FlatHold& h, uint32_t r, uint32_t j0, uint32_t total) {
             const FlatEnt* ent = s_ent[r & 3];
             uint32_t my_cum = 0xffffffffu, my_end = 0;
             if (lane < nt) {
@@ -810,6 +823,7 @@ __global__ void __launch_bounds__(256, OCC) bm25_flat_kernel(Bm25View v, const u
             if (h.mask == 0) return;
 #pragma unroll
             for (int i = 0; i < kFlatH; ++i) {
+                if (j0 + i * 8 >= total) break;  // uniform: a half-empty round costs half
                 const uint32_t j = j0 + i * 8 + warp;
                 const uint32_t g = __popc(__ballot_sync(FULL_MASK, my_cum <= j)) - 1;  // mask != 0: token 0 has cum 0 <= j
                 const uint4 e = *reinterpret_cast<const uint4*>(ent + g);
@@ -845,7 +859,7 @@ __global__ void __launch_bounds__(256, OCC) bm25_flat_kernel(Bm25View v, const u
 #pragma unroll
             for (int i = 0; i < kFlatH; ++i) slot[i] = cur.d[i] - base_doc;
             asm volatile("" ::"r"(slot[0]), "r"(slot[1]), "r"(slot[2]), "r"(slot[3]) : "memory");
-            if (nr < r_end) load_round(nxt, nr, nj0);
+            if (nr < r_end) load_round(nxt, nr, nj0, last ? s_total[nr & 3] : total);
             for (uint32_t m = cur.mask; m; m &= m - 1) {
                 const uint32_t g = __ffs(m) - 1;
                 const uint32_t diff = cur.tags ^ (g * 0x01010101u);  // byte h is zero where step h belongs to token g
@@ -860,29 +874,40 @@ __global__ void __launch_bounds__(256, OCC) bm25_flat_kernel(Bm25View v, const u
                 if (touched) {  // scan this warp's 896 documents; what is read is zeroed for the next range
                     // own list: a warp meets its documents in ascending order, so an equal score never displaces a kept
                     // one (strictly greater); shared bound: ties with another list's k-th score may still win on the id
+                    constexpr int kBlocks = kRange / 8 / 128;  // 128-document blocks per warp
+                    float4* mine4 = acc4 + warp * (kRange / 8 / 4) + lane;
                     float thr_own = top.worst == ~0ull ? 0.0f : ord_unkey(~(uint32_t)(top.worst >> 32));
                     float thr_sh = __uint_as_float(*reinterpret_cast<volatile uint32_t*>(&s_thr));
-                    const uint32_t i_begin = warp * (kRange / 8);
-#pragma unroll 1
-                    for (uint32_t i0 = i_begin; i0 < i_begin + kRange / 8; i0 += 128) {
-                        const float4 s4 = acc4[(i0 >> 2) + lane];
-                        acc4[(i0 >> 2) + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float mx = fmaxf(fmaxf(s4.x, s4.y), fmaxf(s4.z, s4.w));
-                        if (!__ballot_sync(FULL_MASK, mx > thr_own && mx >= thr_sh)) continue;
-                        const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+                    // pass 1: the largest score of the warp's slice; nearly always it does not reach the bounds
+                    float top_s = 0.0f;
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            uint64_t key = ~0ull;
-                            if (sv[e] > 0.0f && sv[e] >= thr_sh)
-                                key = ((uint64_t)(~ord_key(sv[e])) << 32) | (base_doc + i0 + lane * 4 + e);
-                            top.offer(key);
-                        }
-                        if (top.worst != ~0ull) {
-                            thr_own = ord_unkey(~(uint32_t)(top.worst >> 32));
-                            if (lane == 0 && thr_own > thr_sh) atomicMax(&s_thr, __float_as_uint(thr_own));  // positive floats order as their bits
-                        }
-                        thr_sh = __uint_as_float(*reinterpret_cast<volatile uint32_t*>(&s_thr));
+                    for (int bI = 0; bI < kBlocks; ++bI) {
+                        const float4 s4 = mine4[bI * 32];
+                        top_s = fmaxf(top_s, fmaxf(fmaxf(s4.x, s4.y), fmaxf(s4.z, s4.w)));
                     }
+                    if (__ballot_sync(FULL_MASK, top_s > thr_own && top_s >= thr_sh)) {
+#pragma unroll 1
+                        for (int bI = 0; bI < kBlocks; ++bI) {
+                            const float4 s4 = mine4[bI * 32];
+                            const float mx = fmaxf(fmaxf(s4.x, s4.y), fmaxf(s4.z, s4.w));
+                            if (!__ballot_sync(FULL_MASK, mx > thr_own && mx >= thr_sh)) continue;
+                            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+                            const uint32_t doc0 = base_doc + warp * (kRange / 8) + bI * 128 + lane * 4;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                uint64_t key = ~0ull;
+                                if (sv[e] > 0.0f && sv[e] >= thr_sh) key = ((uint64_t)(~ord_key(sv[e])) << 32) | (doc0 + e);
+                                top.offer(key);
+                            }
+                            if (top.worst != ~0ull) {
+                                thr_own = ord_unkey(~(uint32_t)(top.worst >> 32));
+                                if (lane == 0 && thr_own > thr_sh) atomicMax(&s_thr, __float_as_uint(thr_own));  // positive floats order as their bits
+                            }
+                            thr_sh = __uint_as_float(*reinterpret_cast<volatile uint32_t*>(&s_thr));
+                        }
+                    }
+#pragma unroll
+                    for (int bI = 0; bI < kBlocks; ++bI) mine4[bI * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
                     touched = false;
                 }
                 if (threadIdx.x == 0 && parts > 1) {  // exchange the bound with the query's other work items
@@ -897,47 +922,69 @@ __global__ void __launch_bounds__(256, OCC) bm25_flat_kernel(Bm25View v, const u
             j0 = nj0;
         };
         FlatHold ha, hb;
-        if (r < r_end) load_round(ha, r, 0);
+        if (r < r_end) load_round(ha, r, 0, s_total[r & 3]);
         while (r < r_end) {
             round(ha, hb);
             if (r >= r_end) break;
             round(hb, ha);
         }
-        // merge the eight per-warp lists; publish the item's list; the query's last item merges the parts
+        // merge the eight per-warp lists by RANK, all threads at once: the lists are sorted and their keys distinct, so a
+        // key's place in the merged order is the sum of its lower bounds in the eight lists (a serial merge in one warp
+        // held the other seven at the barrier for ~5 us per item).  Then publish; the query's last item merges the parts.
         top.store(lists + (size_t)warp * k, k);
+        uint64_t* merged = lists + (size_t)8 * k;
+        for (uint32_t i = threadIdx.x; i < k; i += 256) merged[i] = ~0ull;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < 8 * k; i += 256) {
+            const uint64_t key = lists[i];
+            if (key == ~0ull) continue;
+            uint32_t rank = 0;
+#pragma unroll 1
+            for (uint32_t w = 0; w < 8; ++w) {
+                const uint64_t* l = lists + (size_t)w * k;
+                uint32_t lo = 0, hi = k;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (l[mid] < key) lo = mid + 1; else hi = mid;
+                }
+                rank += lo;
+            }
+            if (rank < k) merged[rank] = key;
+        }
         __syncthreads();
         if (warp == 0) {
-            for (uint32_t w = 1; w < 8; ++w) {
-                const uint64_t* other = lists + (size_t)w * k;
-                for (uint32_t jj = 0; jj < k; jj += 32) top.offer(jj + lane < k ? other[jj + lane] : ~0ull);
-            }
             bool finisher = true;
             if (parts > 1) {
-                top.store(partial + ((size_t)q * parts + part) * k, k);
+                uint64_t* mine = partial + ((size_t)q * parts + part) * k;
+                for (uint32_t j = lane; j < k; j += 32) mine[j] = merged[j];
                 __threadfence();
                 __syncwarp();
                 uint32_t t = 0;
                 if (lane == 0) t = atomicAdd(tickets + q, 1u);
                 t = __shfl_sync(FULL_MASK, t, 0);
-                if (t == parts - 1) {
+                finisher = t == parts - 1;
+                if (finisher) {
                     __threadfence();
+#pragma unroll
+                    for (int sI = 0; sI < R; ++sI) top.k[sI] = 32u * sI + lane < k ? merged[32u * sI + lane] : ~0ull;
+                    top.worst = merged[k - 1];  // ~0 unless the list is full
                     for (uint32_t pp = 0; pp < parts; ++pp) {
                         if (pp == part) continue;
                         const volatile uint64_t* other = partial + ((size_t)q * parts + pp) * k;
                         for (uint32_t jj = 0; jj < k; jj += 32) top.offer(jj + lane < k ? other[jj + lane] : ~0ull);
                     }
                     if (lane == 0) tickets[q] = 0;  // ready for the next call
+                    __syncwarp();
+                    top.store(merged, k);
+                    __syncwarp();
                 }
-                finisher = t == parts - 1;
             }
             if (finisher) {
-                top.store(lists, k);
-                __syncwarp();
                 uint32_t len = 0;
                 for (uint32_t jj = 0; jj < k; jj += 32) {
                     const uint32_t j = jj + lane;
                     if (j < k) {
-                        const uint64_t key = lists[j];
+                        const uint64_t key = merged[j];
                         uint32_t doc = VELES_INVALID_ID;
                         float sc = __uint_as_float(0x7fc00000u);
                         if (key != ~0ull) {
@@ -1365,6 +1412,7 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
         if (flat) {
             // 4 CTAs per SM: 64 registers, no spills; VELES_BM25_FLAT_OCC=5 selects the 48-register build (experiments)
             const bool occ5 = std::getenv("VELES_BM25_FLAT_OCC") != nullptr && std::atoi(std::getenv("VELES_BM25_FLAT_OCC")) == 5;
+            const size_t smem = (size_t)kRange * 4 + (size_t)9 * k * 8;  // accumulator, eight lists, the merged list
             auto kern = occ5 ? (k <= 32 ? bm25_flat_kernel<1, 5> : k <= 64 ? bm25_flat_kernel<2, 5> : bm25_flat_kernel<4, 5>)
                              : (k <= 32 ? bm25_flat_kernel<1, 4> : k <= 64 ? bm25_flat_kernel<2, 4> : bm25_flat_kernel<4, 4>);
             VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
