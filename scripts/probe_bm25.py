@@ -19,10 +19,11 @@ bm = Bm25Snapshot(corp["term_ptr"], corp["post_doc"], corp["tf"], corp["df"], co
 alg = int(corp["df"][corp["q_terms"]].astype(np.int64).sum() * 12 + nq * k * 8)
 peak, _ = measured_peak()
 ref = None
-KEYS = ("VELES_BM25_WALK", "VELES_BM25_SLICE", "VELES_BM25_PREFETCH", "VELES_BM25_HASH", "VELES_BM25_PARTS", "VELES_BM25_FLAT_OCC")
-VARIANTS = (("flat (default)", {}), ("flat, 5 CTAs per SM", {"VELES_BM25_FLAT_OCC": "5"}), ("flat, 1 part", {"VELES_BM25_PARTS": "1"}),
-            ("flat, 2 parts", {"VELES_BM25_PARTS": "2"}), ("flat, 3 parts", {"VELES_BM25_PARTS": "3"}), ("flat, 4 parts", {"VELES_BM25_PARTS": "4"}), ("flat, 10 parts", {"VELES_BM25_PARTS": "10"}),
-            ("walk (round 1, precomputed postings)", {"VELES_BM25_WALK": "1"}))
+KEYS = ("VELES_BM25_WALK", "VELES_BM25_SLICE", "VELES_BM25_PREFETCH", "VELES_BM25_HASH", "VELES_BM25_PARTS", "VELES_BM25_FLAT_OCC",
+        "VELES_BM25_FLAT")
+VARIANTS = (("sub (default)", {}), ("sub, 4 parts", {"VELES_BM25_PARTS": "4"}), ("sub, 7 parts", {"VELES_BM25_PARTS": "7"}),
+            ("sub, 28 parts", {"VELES_BM25_PARTS": "28"}), ("sub, 56 parts", {"VELES_BM25_PARTS": "56"}),
+            ("flat", {"VELES_BM25_FLAT": "1"}), ("walk (round 1, precomputed postings)", {"VELES_BM25_WALK": "1"}))
 if len(sys.argv) > 1 and sys.argv[1] == "all":
     VARIANTS += (("slice", {"VELES_BM25_SLICE": "1"}), ("prefetch", {"VELES_BM25_PREFETCH": "1"}), ("hash", {"VELES_BM25_HASH": "1"}))
 if len(sys.argv) > 1 and sys.argv[1] == "default":

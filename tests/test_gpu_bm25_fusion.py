@@ -220,10 +220,10 @@ def test_multi_query_search_and_search_with_filter_end_to_end():
 
 @pytest.mark.parametrize("k", [20, 50, 100])
 def test_bm25_work_items_split_and_merge_bit_exact(k, monkeypatch):
-    """bm25_flat_kernel cuts a query into (query, part of the doc-id ranges) work items and the last one to finish
-    merges the parts: any split -- one item per query, two, one per range (what a single query gets) -- and round 1's
-    walk kernel return the oracle's documents and score bits.  30000 docs = 5 ranges; the frequent terms need
-    several 1024-posting rounds per range."""
+    """bm25_sub_kernel (one warp per item) and bm25_flat_kernel (one CTA per item) cut a query into (query, part of the
+    doc-id space) work items and the last one to finish merges the parts: any split -- one item per query, two, one per
+    sub-range (what a single query gets) -- and round 1's walk kernel return the oracle's documents and score bits.
+    30000 docs = 30 sub-ranges = 5 ranges; the frequent terms need several passes per sub-range / rounds per range."""
     docs, p = zipf_corpus(30000, 3000, seed=5)
     o, snap = build_both(docs)
     rng = np.random.default_rng(2)
@@ -233,8 +233,10 @@ def test_bm25_work_items_split_and_merge_bit_exact(k, monkeypatch):
             q_terms += rng.choice(3000, size=int(rng.integers(1, 7)), p=p).astype(np.uint32).tolist()
             q_ptr.append(len(q_terms))
         oi, os_, oc = o.search_batch_terms(q_ptr, q_terms, k, threads=4)
-        for env in ({}, {"VELES_BM25_PARTS": "1"}, {"VELES_BM25_PARTS": "2"}, {"VELES_BM25_FLAT_OCC": "5"}, {"VELES_BM25_WALK": "1"}):
-            for key in ("VELES_BM25_PARTS", "VELES_BM25_FLAT_OCC", "VELES_BM25_WALK"):
+        for env in ({}, {"VELES_BM25_PARTS": "1"}, {"VELES_BM25_PARTS": "2"}, {"VELES_BM25_PARTS": "30"}, {"VELES_BM25_FLAT": "1"},
+                    {"VELES_BM25_FLAT": "1", "VELES_BM25_PARTS": "1"}, {"VELES_BM25_FLAT": "1", "VELES_BM25_PARTS": "2"},
+                    {"VELES_BM25_FLAT": "1", "VELES_BM25_FLAT_OCC": "5"}, {"VELES_BM25_WALK": "1"}):
+            for key in ("VELES_BM25_PARTS", "VELES_BM25_FLAT", "VELES_BM25_FLAT_OCC", "VELES_BM25_WALK"):
                 monkeypatch.delenv(key, raising=False)
             for key, val in env.items():
                 monkeypatch.setenv(key, val)

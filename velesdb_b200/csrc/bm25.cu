@@ -35,13 +35,15 @@ namespace veles {
 constexpr uint32_t kRange = 7168;  // docs per range: 28 KB of f32 accumulators -> 7 query CTAs per SM (1036 >= 1024 resident)
 constexpr uint32_t kTermChunk = 32; // query tokens whose metadata is staged at once
 constexpr uint32_t kMultiK = 128;   // up to this k every warp of the CTA keeps its own top-k list
+constexpr uint32_t kFine = 1024;    // docs per sub-range of the fine skip table: 4 KB of f32 accumulators per WARP (bm25_sub_kernel)
 }
 
 struct veles_bm25 {
     uint32_t n_terms = 0, n_doc_slots = 0, n_ranges = 0;
     uint64_t doc_count = 0, total_len = 0, n_postings = 0;
     float k1 = 1.2f, b = 0.75f, avgdl = 0.0f;
-    veles::DevBuf term_ptr, post_doc, post_tf, post_den, post_dc, doc_len, idf, skip;
+    uint32_t n_fine = 0;  // sub-ranges of kFine documents; 0 = no fine table (it would not fit: see veles_bm25_from_csr)
+    veles::DevBuf term_ptr, post_doc, post_tf, post_den, post_dc, doc_len, idf, skip, skipf;
     mutable std::mutex mu;
     mutable veles::DevBuf q_ptr_d, q_terms_d, partial_d, out_doc_d, out_score_d, out_cnt_d;
 };
@@ -56,6 +58,9 @@ struct Bm25View {
     const uint32_t* doc_len;
     const float* idf;
     const uint64_t* skip;  // n_terms x (n_ranges + 1)
+    const uint64_t* term_ptr;  // n_terms + 1
+    const uint32_t* skipf;     // n_terms x (n_fine + 1): first posting of the term, relative to term_ptr, with doc >= s * kFine
+    uint32_t n_fine;
     uint32_t n_terms, n_ranges, n_doc_slots;
     float k1, b, avgdl;
 };
@@ -1004,6 +1009,212 @@ __global__ void __launch_bounds__(256, OCC) bm25_flat_kernel(Bm25View v, const u
     }
 }
 
+// ---- one WARP per (query, span of sub-ranges): owner computes, no block barriers (k <= kMultiK) -------------------------
+// Every kernel above shares one accumulator among the eight warps of a CTA, so the terms of a range must be separated by
+// block barriers (a document may occur in two terms, held by two warps), and the ncu profiles of all of them end the
+// same way: a third of the samples at barriers, half the issue slots empty, and any warp that meets a candidate for
+// the top-k makes the other seven wait.  The cure is a finer skip table: skipf[term][s] = first posting of the term
+// with doc >= s * 1024, so ONE warp can find, with no search, every posting of every query token that falls into
+// "its" 1024 documents.  A warp then owns a span of sub-ranges of one query outright:
+//   per sub-range: lane g holds token g's slice boundaries (the next ones are requested two sub-ranges ahead); the
+//   slices are read 32 postings at a time in token order (typically one step per token), up to kSubH steps in flight;
+//   they are added into the warp's private 4 KB accumulator in the same order with a __syncwarp between tokens -- the
+//   reference's f32 order per document; the warp scans its accumulator (zeroing it) against its own register-resident
+//   top-k and the best k-th score published for the query (qthr).
+// No block barrier anywhere, 40+ independent warps per SM.  Work items are (query, part) with parts ~ 2 x resident
+// warps / queries, part-major; the last part of a query to finish merges the parts' lists (ticket per query).
+// Cost: the fine table, 4 bytes x terms x (docs / 1024); it is built when it fits the budget in veles_bm25_from_csr.
+constexpr int kSubWarps = 4;  // warps per CTA (they share nothing but the launch)
+constexpr int kSubH = 6;      // 32-posting steps in flight per pass
+template <int R>
+__global__ void __launch_bounds__(kSubWarps * 32, 10) bm25_sub_kernel(Bm25View v, const uint32_t* __restrict__ q_ptr,
+                                                                     const uint32_t* __restrict__ q_terms, uint32_t nq, uint32_t k,
+                                                                     uint32_t parts, uint64_t* __restrict__ partial,
+                                                                     uint32_t* __restrict__ tickets, uint32_t* __restrict__ qthr,
+                                                                     uint32_t* __restrict__ out_doc, float* __restrict__ out_score,
+                                                                     uint32_t* __restrict__ out_cnt, uint32_t* __restrict__ work) {
+    extern __shared__ __align__(16) uint8_t bs_smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* acc = reinterpret_cast<float*>(bs_smem) + warp * kFine;
+    float4* acc4 = reinterpret_cast<float4*>(acc) + lane;
+    uint64_t* stage = reinterpret_cast<uint64_t*>(bs_smem + (size_t)kSubWarps * kFine * 4) + (size_t)warp * k;  // k keys
+#pragma unroll
+    for (int bI = 0; bI < (int)(kFine / 128); ++bI) acc4[bI * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    for (;;) {  // persistent: work items are handed out to warps by a global counter
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(work, 1u);
+        item = __shfl_sync(FULL_MASK, item, 0);
+        if (item >= nq * parts) return;
+        // part-major: a query's later parts start with the k-th score its earlier parts have published (qthr)
+        const uint32_t part = item / nq, q = item - part * nq;
+        const uint32_t s_begin = (uint32_t)((uint64_t)part * v.n_fine / parts);
+        const uint32_t s_end = (uint32_t)((uint64_t)(part + 1) * v.n_fine / parts);
+        const uint32_t t0 = q_ptr[q], t1 = q_ptr[q + 1];
+        const uint32_t nt = min(kQueryTerms, t1 - t0);  // host guarantees t1 - t0 <= kQueryTerms on this path
+        // lane g < nt: query token g -- its fine skip row, its posting list, the boundaries of the next three sub-ranges
+        const uint32_t* row = nullptr;
+        const uint2* plist = nullptr;
+        uint32_t b0 = 0, b1 = 0, b2 = 0;
+        if (lane < nt) {
+            const uint32_t term = q_terms[t0 + lane];
+            if (term < v.n_terms) {  // unknown term: df = 0, contributes nothing
+                row = v.skipf + (size_t)term * (v.n_fine + 1);
+                plist = v.post_dc + v.term_ptr[term];
+                b0 = row[s_begin];
+                b1 = row[s_begin + 1];
+                b2 = row[min(s_begin + 2, v.n_fine)];
+            }
+        }
+        RegTopK<R> top;
+        top.init(k, lane);
+        uint32_t thr_bits = 0;
+        if (lane == 0) thr_bits = *reinterpret_cast<volatile uint32_t*>(qthr + q);
+        float thr_sh = __uint_as_float(__shfl_sync(FULL_MASK, thr_bits, 0));
+        uint32_t thr_next = 0;  // lane 0: qthr[q], re-read every 8 sub-ranges, consumed one sub-range later
+        for (uint32_t sr = s_begin; sr < s_end; ++sr) {
+            uint32_t b3 = b2;
+            if (row && sr + 3 <= v.n_fine) b3 = row[sr + 3];  // needed three sub-ranges from now
+            if (((sr - s_begin) & 7u) == 7u) {
+                if (lane == 0) thr_next = *reinterpret_cast<volatile uint32_t*>(qthr + q);
+            } else if (((sr - s_begin) & 7u) == 0u && sr != s_begin) {
+                thr_sh = fmaxf(thr_sh, __uint_as_float(__shfl_sync(FULL_MASK, thr_next, 0)));
+            }
+            const uint32_t len = b1 - b0;  // <= kFine
+            uint32_t m = __ballot_sync(FULL_MASK, len != 0);
+            if (m) {
+                const uint32_t base_doc = sr * kFine;
+                const uint2* my_first = plist + b0;
+                uint32_t off = 0;
+                while (m) {
+                    // ---- request up to kSubH steps, token order ----
+                    uint32_t d[kSubH], c[kSubH];
+                    uint32_t fresh = 0;  // bit h: step h is the first of its token (a __syncwarp goes before it)
+                    int issued = 0;
+#pragma unroll
+                    for (int h = 0; h < kSubH; ++h) {
+                        d[h] = 0xffffffffu;
+                        c[h] = 0;
+                        if (m) {  // uniform
+                            const uint32_t g = __ffs(m) - 1;
+                            const uint32_t lg = __shfl_sync(FULL_MASK, len, g);
+                            const uint64_t first = __shfl_sync(FULL_MASK, reinterpret_cast<uint64_t>(my_first), g);
+                            const uint32_t o = off + lane;
+                            const uint32_t ok = o < lg;
+                            const uint64_t src = first + (uint64_t)(ok ? o : 0) * 8;
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.global.nc.v2.u32 {%0, %1}, [%2];\n\t}"
+                                : "+r"(d[h]), "+r"(c[h])
+                                : "l"(src), "r"(ok));
+                            if (off == 0) fresh |= 1u << h;
+                            off += 32;
+                            if (off >= lg) {
+                                m &= m - 1;
+                                off = 0;
+                            }
+                            issued = h + 1;
+                        }
+                    }
+                    // ---- apply in the same order: per document, contributions arrive in query-token order ----
+#pragma unroll
+                    for (int h = 0; h < kSubH; ++h) {
+                        if (h < issued) {  // uniform
+                            if ((fresh >> h) & 1u) __syncwarp();
+                            if (d[h] != 0xffffffffu) acc[d[h] - base_doc] = __fadd_rn(acc[d[h] - base_doc], __uint_as_float(c[h]));
+                        }
+                    }
+                    __syncwarp();
+                }
+                // ---- scan the warp's 1024 accumulators; what is read is zeroed for the next sub-range ----
+                // own list: documents arrive in ascending order, so an equal score never displaces a kept one (strictly
+                // greater); published bound: ties with another part's k-th score may still win on the document id
+                float thr_own = top.worst == ~0ull ? 0.0f : ord_unkey(~(uint32_t)(top.worst >> 32));
+                constexpr int kBlocks = kFine / 128;
+                float top_s = 0.0f;
+#pragma unroll
+                for (int bI = 0; bI < kBlocks; ++bI) {
+                    const float4 s4 = acc4[bI * 32];
+                    top_s = fmaxf(top_s, fmaxf(fmaxf(s4.x, s4.y), fmaxf(s4.z, s4.w)));
+                }
+                if (__ballot_sync(FULL_MASK, top_s > thr_own && top_s >= thr_sh)) {
+                    bool grew = false;
+#pragma unroll 1
+                    for (int bI = 0; bI < kBlocks; ++bI) {
+                        const float4 s4 = acc4[bI * 32];
+                        const float mx = fmaxf(fmaxf(s4.x, s4.y), fmaxf(s4.z, s4.w));
+                        if (!__ballot_sync(FULL_MASK, mx > thr_own && mx >= thr_sh)) continue;
+                        const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+                        const uint32_t doc0 = base_doc + bI * 128 + lane * 4;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            uint64_t key = ~0ull;
+                            if (sv[e] > 0.0f && sv[e] >= thr_sh) key = ((uint64_t)(~ord_key(sv[e])) << 32) | (doc0 + e);
+                            top.offer(key);
+                        }
+                        if (top.worst != ~0ull) {
+                            thr_own = ord_unkey(~(uint32_t)(top.worst >> 32));
+                            grew = true;
+                        }
+                    }
+                    if (grew && thr_own > thr_sh) {  // publish: k documents of this query score at least thr_own
+                        thr_sh = thr_own;
+                        if (lane == 0 && parts > 1) atomicMax(qthr + q, __float_as_uint(thr_own));  // positive floats order as their bits
+                    }
+                }
+#pragma unroll
+                for (int bI = 0; bI < kBlocks; ++bI) acc4[bI * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncwarp();
+            }
+            b0 = b1;
+            b1 = b2;
+            b2 = b3;
+        }
+        // publish the item's list; the query's last item to finish merges the parts and writes the result
+        bool finisher = true;
+        if (parts > 1) {
+            top.store(partial + ((size_t)q * parts + part) * k, k);
+            __threadfence();
+            __syncwarp();
+            uint32_t t = 0;
+            if (lane == 0) t = atomicAdd(tickets + q, 1u);
+            t = __shfl_sync(FULL_MASK, t, 0);
+            finisher = t == parts - 1;
+            if (finisher) {
+                __threadfence();
+                for (uint32_t pp = 0; pp < parts; ++pp) {
+                    if (pp == part) continue;
+                    const volatile uint64_t* other = partial + ((size_t)q * parts + pp) * k;
+                    for (uint32_t jj = 0; jj < k; jj += 32) top.offer(jj + lane < k ? other[jj + lane] : ~0ull);
+                }
+                if (lane == 0) tickets[q] = 0;  // ready for the next call
+            }
+        }
+        if (finisher) {
+            top.store(stage, k);
+            __syncwarp();
+            uint32_t len = 0;
+            for (uint32_t jj = 0; jj < k; jj += 32) {
+                const uint32_t j = jj + lane;
+                if (j < k) {
+                    const uint64_t key = stage[j];
+                    uint32_t doc = VELES_INVALID_ID;
+                    float sc = __uint_as_float(0x7fc00000u);
+                    if (key != ~0ull) {
+                        doc = (uint32_t)key;
+                        sc = ord_unkey(~(uint32_t)(key >> 32));
+                        ++len;
+                    }
+                    out_doc[(size_t)q * k + j] = doc;
+                    out_score[(size_t)q * k + j] = sc;
+                }
+            }
+            len = __reduce_add_sync(FULL_MASK, len);
+            if (lane == 0) out_cnt[q] = len;
+            __syncwarp();
+        }
+    }
+}
+
 // ---- one CTA per query, posting-driven (k <= kMultiK): hashed accumulation over adaptive doc-id windows -------------
 // bm25_query_kernel above pays for every doc-id range of a query -- zeroing and re-scanning a dense 7168-slot
 // accumulator ~140 times -- whatever the number of postings that fall into it (~700).  Here the work follows the
@@ -1294,6 +1505,31 @@ int32_t veles_bm25_from_csr(uint32_t n_terms, const uint64_t* term_ptr, const ui
         }
         while (r < nr) row[++r] = e;
     }
+    // fine skip table for bm25_sub_kernel: u32 offsets relative to term_ptr, one row per term.  Built when it stays within
+    // 2 GiB and 4x the postings themselves (a large vocabulary over few documents would be all table): otherwise the
+    // query path uses bm25_flat_kernel, which needs only the coarse table.
+    std::vector<uint32_t> skipf;
+    {
+        const uint32_t nf = std::max(1u, (n_doc_slots + kFine - 1) / kFine);
+        const uint64_t bytes = (uint64_t)std::max(n_terms, 1u) * (nf + 1) * 4;
+        bool fits = bytes <= ((uint64_t)2 << 30) && bytes <= std::max<uint64_t>(np * 8 * 4, (uint64_t)64 << 20);
+        for (uint32_t t = 0; fits && t < n_terms; ++t) fits = term_ptr[t + 1] - term_ptr[t] <= 0xffffffffull;
+        if (std::getenv("VELES_BM25_NO_FINE_TABLE")) fits = false;
+        if (fits) {
+            ix->n_fine = nf;
+            skipf.assign((size_t)std::max(n_terms, 1u) * (nf + 1), 0);
+            for (uint32_t t = 0; t < n_terms; ++t) {
+                const uint64_t p0 = term_ptr[t], e = term_ptr[t + 1];
+                uint32_t* row = skipf.data() + (size_t)t * (nf + 1);
+                uint32_t r = 0;
+                for (uint64_t p = p0; p < e; ++p) {
+                    const uint32_t sub = post_doc[p] / kFine;
+                    while (r < sub) row[++r] = (uint32_t)(p - p0);
+                }
+                while (r < nf) row[++r] = (uint32_t)(e - p0);
+            }
+        }
+    }
     // per-posting denominator, with the reference's f32 operation order (bm25.rs:357-358, 371-372); the host
     // compiler targets baseline x86-64, so nothing here is contracted into an FMA
     std::vector<float> den(std::max<uint64_t>(np, 1));
@@ -1330,12 +1566,17 @@ int32_t veles_bm25_from_csr(uint32_t n_terms, const uint64_t* term_ptr, const ui
     VELES_TRY(ix->post_dc.alloc(std::max<size_t>(np * 8, 16)));
     if (np) VELES_CUDA(cudaMemcpy(ix->post_dc.p, dc.data(), np * 8, cudaMemcpyHostToDevice));
     VELES_TRY(ix->term_ptr.alloc(((size_t)n_terms + 1) * 8));
+    if (n_terms) VELES_CUDA(cudaMemcpy(ix->term_ptr.p, term_ptr, ((size_t)n_terms + 1) * 8, cudaMemcpyHostToDevice));
     VELES_TRY(ix->post_doc.alloc(std::max<size_t>(np * 4, 16)));
     VELES_TRY(ix->post_tf.alloc(std::max<size_t>(np * 4, 16)));
     VELES_TRY(ix->post_den.alloc(std::max<size_t>(np * 4, 16)));
     VELES_TRY(ix->doc_len.alloc(std::max<size_t>((size_t)n_doc_slots * 4, 16)));
     VELES_TRY(ix->idf.alloc(idf.size() * 4));
     VELES_TRY(ix->skip.alloc(skip.size() * 8));
+    if (ix->n_fine) {
+        VELES_TRY(ix->skipf.alloc(skipf.size() * 4));
+        VELES_CUDA(cudaMemcpy(ix->skipf.p, skipf.data(), skipf.size() * 4, cudaMemcpyHostToDevice));
+    }
     if (np) {
         VELES_CUDA(cudaMemcpy(ix->post_doc.p, post_doc, np * 4, cudaMemcpyHostToDevice));
         VELES_CUDA(cudaMemcpy(ix->post_tf.p, post_tf, np * 4, cudaMemcpyHostToDevice));
@@ -1387,6 +1628,9 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
     v.doc_len = ix->doc_len.as<uint32_t>();
     v.idf = ix->idf.as<float>();
     v.skip = ix->skip.as<uint64_t>();
+    v.term_ptr = ix->term_ptr.as<uint64_t>();
+    v.skipf = ix->skipf.as<uint32_t>();
+    v.n_fine = ix->n_fine;
     v.n_terms = ix->n_terms;
     v.n_ranges = ix->n_ranges;
     v.n_doc_slots = ix->n_doc_slots;
@@ -1397,19 +1641,46 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
     for (uint32_t i = 0; i < nq; ++i) max_terms = std::max(max_terms, q_term_ptr[i + 1] - q_term_ptr[i]);
     if (k <= kMultiK && max_terms <= kQueryTerms && std::getenv("VELES_BM25_RANGE_KERNEL") == nullptr) {
         // one CTA per query walking its doc-id ranges
-        // default: bm25_flat_kernel ((query, part) items, warp-step mapping, rounds pipelined).  VELES_BM25_WALK=1 selects
-        // round 1's bm25_query_kernel; three other round-2 restructurings stay selectable and are measured slower on B200
-        // (profiles/README.md): VELES_BM25_SLICE=1, VELES_BM25_PREFETCH=1, VELES_BM25_HASH=1.
+        // default: bm25_sub_kernel (one warp per (query, span of 1024-document sub-ranges), no block barriers) when the
+        // snapshot has the fine skip table, else bm25_flat_kernel ((query, part) items per CTA, warp-step mapping, rounds
+        // pipelined; VELES_BM25_FLAT=1 forces it).  VELES_BM25_WALK=1 selects round 1's bm25_query_kernel; three other
+        // round-2 restructurings stay selectable and are measured slower on B200 (profiles/README.md, DESIGN.md section
+        // 4.4): VELES_BM25_SLICE=1, VELES_BM25_PREFETCH=1, VELES_BM25_HASH=1.
         const bool walk = std::getenv("VELES_BM25_WALK") != nullptr;
         const bool slice = !walk && std::getenv("VELES_BM25_SLICE") != nullptr;
         const bool pre = !walk && !slice && std::getenv("VELES_BM25_PREFETCH") != nullptr;
         const bool hash = !walk && !slice && !pre && std::getenv("VELES_BM25_HASH") != nullptr;
-        const bool flat = !walk && !slice && !pre && !hash;
+        const bool other = walk || slice || pre || hash;
+        const bool sub = !other && ix->n_fine > 0 && std::getenv("VELES_BM25_FLAT") == nullptr;
+        const bool flat = !other && !sub;
         const size_t smem = (hash ? (size_t)kHashSlots * 8 : (size_t)kRange * 4) + (size_t)8 * k * 8;
         int per_sm = 0, dev = 0, sms = 0;
         VELES_CUDA(cudaGetDevice(&dev));
         VELES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        if (flat) {
+        if (sub) {
+            auto kern = k <= 32 ? bm25_sub_kernel<1> : k <= 64 ? bm25_sub_kernel<2> : bm25_sub_kernel<4>;
+            const size_t smem_s = (size_t)kSubWarps * kFine * 4 + (size_t)kSubWarps * k * 8;  // accumulators + output staging
+            VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+            VELES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSubWarps * 32, smem_s));
+            VELES_REQUIRE(per_sm >= 1, "bm25 query kernel does not fit on an SM");
+            const uint32_t resident_warps = (uint32_t)(per_sm * sms) * kSubWarps;
+            // parts per query: ~2 work items per resident warp, so that the heavy queries do not set the finish time and
+            // a small batch still fills the GPU; at most 64 (the last part of a query merges them serially)
+            uint32_t parts = std::max<uint32_t>(1, std::min<uint32_t>(std::min<uint32_t>(ix->n_fine, 64), (2 * resident_warps + nq - 1) / nq));
+            if (const char* e = std::getenv("VELES_BM25_PARTS")) parts = std::max(1, std::min<int>((int)ix->n_fine, std::atoi(e)));
+            const size_t tickets_off = 256, thr_off = (tickets_off + (size_t)nq * 4 + 255) / 256 * 256;
+            const size_t lists_off = (thr_off + (size_t)nq * 4 + 255) / 256 * 256;
+            VELES_TRY(ix->partial_d.ensure(lists_off + (size_t)nq * parts * k * 8));
+            VELES_CUDA(cudaMemsetAsync(ix->partial_d.p, 0, lists_off, st));
+            uint8_t* pb = ix->partial_d.as<uint8_t>();
+            const uint64_t items = (uint64_t)nq * parts;
+            const uint32_t grid = (uint32_t)std::min<uint64_t>((items + kSubWarps - 1) / kSubWarps, (uint64_t)per_sm * sms);
+            kern<<<grid, kSubWarps * 32, smem_s, st>>>(v, ix->q_ptr_d.as<uint32_t>(), ix->q_terms_d.as<uint32_t>(), nq, k, parts,
+                                                       reinterpret_cast<uint64_t*>(pb + lists_off), reinterpret_cast<uint32_t*>(pb + tickets_off),
+                                                       reinterpret_cast<uint32_t*>(pb + thr_off), ix->out_doc_d.as<uint32_t>(),
+                                                       ix->out_score_d.as<float>(), ix->out_cnt_d.as<uint32_t>(),
+                                                       reinterpret_cast<uint32_t*>(pb));
+        } else if (flat) {
             // 4 CTAs per SM: 64 registers, no spills; VELES_BM25_FLAT_OCC=5 selects the 48-register build (experiments)
             const bool occ5 = std::getenv("VELES_BM25_FLAT_OCC") != nullptr && std::atoi(std::getenv("VELES_BM25_FLAT_OCC")) == 5;
             const size_t smem = (size_t)kRange * 4 + (size_t)9 * k * 8;  // accumulator, eight lists, the merged list
