@@ -20,9 +20,10 @@ alg = int(corp["df"][corp["q_terms"]].astype(np.int64).sum() * 12 + nq * k * 8)
 peak, _ = measured_peak()
 ref = None
 KEYS = ("VELES_BM25_WALK", "VELES_BM25_SLICE", "VELES_BM25_PREFETCH", "VELES_BM25_HASH", "VELES_BM25_PARTS", "VELES_BM25_FLAT_OCC",
-        "VELES_BM25_FLAT")
-VARIANTS = (("sub (default)", {}), ("sub, 4 parts", {"VELES_BM25_PARTS": "4"}), ("sub, 7 parts", {"VELES_BM25_PARTS": "7"}),
-            ("sub, 28 parts", {"VELES_BM25_PARTS": "28"}), ("sub, 56 parts", {"VELES_BM25_PARTS": "56"}),
+        "VELES_BM25_FLAT", "VELES_BM25_SUB_OCC")
+VARIANTS = (("sub (default)", {}), ("sub, 8 CTAs per SM", {"VELES_BM25_SUB_OCC": "8"}),
+            ("sub, 8 CTAs per SM, 16 parts", {"VELES_BM25_SUB_OCC": "8", "VELES_BM25_PARTS": "16"}),
+            ("sub, 12 parts", {"VELES_BM25_PARTS": "12"}), ("sub, 40 parts", {"VELES_BM25_PARTS": "40"}),
             ("flat", {"VELES_BM25_FLAT": "1"}), ("walk (round 1, precomputed postings)", {"VELES_BM25_WALK": "1"}))
 if len(sys.argv) > 1 and sys.argv[1] == "all":
     VARIANTS += (("slice", {"VELES_BM25_SLICE": "1"}), ("prefetch", {"VELES_BM25_PREFETCH": "1"}), ("hash", {"VELES_BM25_HASH": "1"}))

@@ -1026,8 +1026,8 @@ __global__ void __launch_bounds__(256, OCC) bm25_flat_kernel(Bm25View v, const u
 // Cost: the fine table, 4 bytes x terms x (docs / 1024); it is built when it fits the budget in veles_bm25_from_csr.
 constexpr int kSubWarps = 4;  // warps per CTA (they share nothing but the launch)
 constexpr int kSubH = 6;      // 32-posting steps in flight per pass
-template <int R>
-__global__ void __launch_bounds__(kSubWarps * 32, 10) bm25_sub_kernel(Bm25View v, const uint32_t* __restrict__ q_ptr,
+template <int R, int OCC>
+__global__ void __launch_bounds__(kSubWarps * 32, OCC) bm25_sub_kernel(Bm25View v, const uint32_t* __restrict__ q_ptr,
                                                                      const uint32_t* __restrict__ q_terms, uint32_t nq, uint32_t k,
                                                                      uint32_t parts, uint64_t* __restrict__ partial,
                                                                      uint32_t* __restrict__ tickets, uint32_t* __restrict__ qthr,
@@ -1071,14 +1071,13 @@ __global__ void __launch_bounds__(kSubWarps * 32, 10) bm25_sub_kernel(Bm25View v
         uint32_t thr_bits = 0;
         if (lane == 0) thr_bits = *reinterpret_cast<volatile uint32_t*>(qthr + q);
         float thr_sh = __uint_as_float(__shfl_sync(FULL_MASK, thr_bits, 0));
-        uint32_t thr_next = 0;  // lane 0: qthr[q], re-read every 8 sub-ranges, consumed one sub-range later
+        uint32_t thr_next = thr_bits;  // lane 0: qthr[q], re-read every sub-range, consumed one sub-range later
         for (uint32_t sr = s_begin; sr < s_end; ++sr) {
             uint32_t b3 = b2;
             if (row && sr + 3 <= v.n_fine) b3 = row[sr + 3];  // needed three sub-ranges from now
-            if (((sr - s_begin) & 7u) == 7u) {
-                if (lane == 0) thr_next = *reinterpret_cast<volatile uint32_t*>(qthr + q);
-            } else if (((sr - s_begin) & 7u) == 0u && sr != s_begin) {
+            if (parts > 1) {
                 thr_sh = fmaxf(thr_sh, __uint_as_float(__shfl_sync(FULL_MASK, thr_next, 0)));
+                if (lane == 0) thr_next = *reinterpret_cast<volatile uint32_t*>(qthr + q);
             }
             const uint32_t len = b1 - b0;  // <= kFine
             uint32_t m = __ballot_sync(FULL_MASK, len != 0);
@@ -1658,15 +1657,21 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
         VELES_CUDA(cudaGetDevice(&dev));
         VELES_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         if (sub) {
-            auto kern = k <= 32 ? bm25_sub_kernel<1> : k <= 64 ? bm25_sub_kernel<2> : bm25_sub_kernel<4>;
+            // 10 CTAs (40 warps) per SM at 48 registers.  Measured on B200, 1024 queries: 12 CTAs per SM at 40 registers
+            // 0.89 ms against 0.77 ms (VELES_BM25_SUB_OCC=12 / 8 select the other builds, for experiments)
+            const int occ = std::getenv("VELES_BM25_SUB_OCC") ? std::atoi(std::getenv("VELES_BM25_SUB_OCC")) : 10;
+            auto kern = occ == 12  ? (k <= 32 ? bm25_sub_kernel<1, 12> : k <= 64 ? bm25_sub_kernel<2, 12> : bm25_sub_kernel<4, 12>)
+                        : occ == 8 ? (k <= 32 ? bm25_sub_kernel<1, 8> : k <= 64 ? bm25_sub_kernel<2, 8> : bm25_sub_kernel<4, 8>)
+                                   : (k <= 32 ? bm25_sub_kernel<1, 10> : k <= 64 ? bm25_sub_kernel<2, 10> : bm25_sub_kernel<4, 10>);
             const size_t smem_s = (size_t)kSubWarps * kFine * 4 + (size_t)kSubWarps * k * 8;  // accumulators + output staging
             VELES_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
             VELES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSubWarps * 32, smem_s));
             VELES_REQUIRE(per_sm >= 1, "bm25 query kernel does not fit on an SM");
             const uint32_t resident_warps = (uint32_t)(per_sm * sms) * kSubWarps;
-            // parts per query: ~2 work items per resident warp, so that the heavy queries do not set the finish time and
-            // a small batch still fills the GPU; at most 64 (the last part of a query merges them serially)
-            uint32_t parts = std::max<uint32_t>(1, std::min<uint32_t>(std::min<uint32_t>(ix->n_fine, 64), (2 * resident_warps + nq - 1) / nq));
+            // parts per query: ~4 work items per resident warp, so that the heavy queries do not set the finish time and
+            // a small batch still fills the GPU (measured on B200, 1024 queries: 12 parts 0.84 ms, 24 parts 0.77 ms, 56 parts
+            // 0.79 ms); at most 64 (the last part of a query merges them serially)
+            uint32_t parts = std::max<uint32_t>(1, std::min<uint32_t>(std::min<uint32_t>(ix->n_fine, 64), (4 * resident_warps + nq - 1) / nq));
             if (const char* e = std::getenv("VELES_BM25_PARTS")) parts = std::max(1, std::min<int>((int)ix->n_fine, std::atoi(e)));
             const size_t tickets_off = 256, thr_off = (tickets_off + (size_t)nq * 4 + 255) / 256 * 256;
             const size_t lists_off = (thr_off + (size_t)nq * 4 + 255) / 256 * 256;
