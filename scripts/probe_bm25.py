@@ -21,8 +21,7 @@ peak, _ = measured_peak()
 ref = None
 KEYS = ("VELES_BM25_WALK", "VELES_BM25_SLICE", "VELES_BM25_PREFETCH", "VELES_BM25_HASH", "VELES_BM25_PARTS", "VELES_BM25_FLAT_OCC",
         "VELES_BM25_FLAT", "VELES_BM25_SUB_OCC")
-VARIANTS = (("sub (default)", {}), ("sub, 8 CTAs per SM", {"VELES_BM25_SUB_OCC": "8"}),
-            ("sub, 8 CTAs per SM, 16 parts", {"VELES_BM25_SUB_OCC": "8", "VELES_BM25_PARTS": "16"}),
+VARIANTS = (("sub (default)", {}), ("sub, 8 CTAs per SM", {"VELES_BM25_SUB_OCC": "8"}), ("sub, 12 CTAs per SM", {"VELES_BM25_SUB_OCC": "12"}),
             ("sub, 12 parts", {"VELES_BM25_PARTS": "12"}), ("sub, 40 parts", {"VELES_BM25_PARTS": "40"}),
             ("flat", {"VELES_BM25_FLAT": "1"}), ("walk (round 1, precomputed postings)", {"VELES_BM25_WALK": "1"}))
 if len(sys.argv) > 1 and sys.argv[1] == "all":

@@ -10,19 +10,23 @@
 //   keep score > 0; order by score descending (total order), ties by doc id ascending (the reference's
 //   tie order is hash/roaring iteration + select_nth_unstable, i.e. unspecified -- SURVEY 8a a19).
 //
-// Layout in HBM: postings CSR by term, doc ids ascending within a term, (doc u32, tf u32, den f32) in
-// three arrays, den = tf + k1 * len_norm precomputed per posting (the snapshot is immutable); idf[term];
-// and a skip table skip[term][r] = first posting of `term` whose doc id is >= r * kRange, so the doc-id
-// range r of one query reads exactly its slice of every posting list, coalesced, with no search.
+// Layout in HBM: postings CSR by term, doc ids ascending within a term.  post_dc = (doc u32, contribution f32), the
+// whole per-posting term of the sum precomputed per snapshot with the reference's operation order (the snapshot is
+// immutable: avgdl and idf are constants of it); (doc, tf, den) in three arrays for the fallback; two skip tables:
+// skip[term][r] = first posting with doc >= r * kRange (u64) and skipf[term][s] = first posting with doc >= s * kFine,
+// relative to the term's list (u32, built when it fits), so a worker reads exactly its slice of every posting list,
+// coalesced, with no search.
 //
-// bm25_query_kernel (k <= kMultiK, <= kQueryTerms tokens): one persistent CTA per query walks the
-// ranges in order.  A dense f32 accumulator for the range lives in shared memory; the query's terms
-// are applied one after another with a block barrier when the term changes, so every document
-// receives its term contributions in query order (a document occurs at most once per posting list:
-// no intra-term conflicts, no atomics).  Every warp keeps a register-resident top-k over its slice of
-// all ranges; the eight lists are merged once per query.
-// Fallback (larger k / longer queries): bm25_range_kernel, one CTA per (doc range, query), writes
-// per-range lists and bm25_merge_kernel merges them.
+// Query path, k <= kMultiK and <= kQueryTerms tokens:
+//   bm25_sub_kernel   (default) one WARP per (query, span of kFine-document sub-ranges), private 4 KB accumulator, no
+//                     block barriers; (query, part) work items, the last part of a query merges the parts.
+//   bm25_flat_kernel  (no fine table) one CTA per (query, part of the kRange-document ranges), warp-step mapping,
+//                     pipelined rounds, a block barrier per token.
+//   bm25_query_kernel (round 1) one CTA per query, chunk-at-a-time walk; and three measured experiments.
+// Every document receives its token contributions in query order in all of them (a document occurs at most once per
+// posting list: no intra-token conflicts, no atomics), so the f32 sums keep the reference's bits.
+// Fallback (larger k / longer queries): bm25_range_kernel, one CTA per (doc range, query), writes per-range lists and
+// bm25_merge_kernel merges them.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
