@@ -437,11 +437,10 @@ __device__ __forceinline__ void scan_fma(const float4& x, const float4& y, float
     }
 }
 
+// U row loads per lane in flight, while at least U steps of 32 elements remain
 template <typename TB, int QT, int RB, int U, bool L2>
-__device__ __forceinline__ void scan_rows(const IndexView& ix, const float* qs, const TB* const (&r)[RB], uint32_t t,
-                                          float (&acc)[RB][QT][4]) {
-    const uint32_t dim = ix.dim;
-    uint32_t i = t * 4;
+__device__ __forceinline__ void scan_rows_chunks(uint32_t dim, const float* qs, const TB* const (&r)[RB], uint32_t& i,
+                                                 float (&acc)[RB][QT][4]) {
     for (; i + 32 * (U - 1) < dim; i += 32 * U) {
         float4 x[U][RB];
 #pragma unroll
@@ -457,17 +456,15 @@ __device__ __forceinline__ void scan_rows(const IndexView& ix, const float* qs, 
                 for (int b = 0; b < RB; ++b) scan_fma<L2>(x[u][b], y, acc[b][q]);
             }
     }
-    for (; i < dim; i += 32) {
-        float4 x[RB];
-#pragma unroll
-        for (int b = 0; b < RB; ++b) x[b] = load4(r[b] + i);
-#pragma unroll
-        for (int q = 0; q < QT; ++q) {
-            const float4 y = *reinterpret_cast<const float4*>(qs + (size_t)q * dim + i);
-#pragma unroll
-            for (int b = 0; b < RB; ++b) scan_fma<L2>(x[b], y, acc[b][q]);
-        }
-    }
+}
+
+template <typename TB, int QT, int RB, int U, bool L2>
+__device__ __forceinline__ void scan_rows(const IndexView& ix, const float* qs, const TB* const (&r)[RB], uint32_t t,
+                                          float (&acc)[RB][QT][4]) {
+    const uint32_t dim = ix.dim;
+    uint32_t i = t * 4;
+    scan_rows_chunks<TB, QT, RB, U, L2>(dim, qs, r, i, acc);
+    scan_rows_chunks<TB, QT, RB, 1, L2>(dim, qs, r, i, acc);
 }
 
 // Fused selection for the scan kernel (fuse.k != 0): every warp keeps, per query, a sorted list of its k best keys
@@ -478,12 +475,21 @@ constexpr uint32_t kFuseFastK = 32;  // up to this k the fused scan selects by c
 struct ScanFuse {
     uint32_t k = 0;             // 0 = not fused (scores go to the sink)
     uint32_t desc = 0;
-    uint32_t fast = 0;            // 1: k <= kFuseFastK and the shared memory holds gridDim.x * k staged keys (counting tail)
+    uint32_t fast = 0;            // 1: k <= kFuseFastK: register-resident lists + rank merges in the tail
     uint64_t* partial = nullptr;  // nq x gridDim.x x k keys
     uint32_t* done = nullptr;     // CTA counter (self-resetting)
     uint32_t* out_ids = nullptr;
     float* out_score = nullptr;
+    unsigned long long* dbg = nullptr;  // VELES_BF_DEBUG_TIMING=1: 8 globaltimer stamps per CTA (thread 0)
 };
+
+__device__ __forceinline__ void fuse_stamp(const ScanFuse& f, int slot) {
+    if (f.dbg != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        f.dbg[(size_t)blockIdx.x * 8 + slot] = t;
+    }
+}
 
 // all lanes of the warp call it; inserts `key` into the ascending list res[0..len) capped at k
 __device__ __forceinline__ void list_offer(uint64_t* res, uint32_t& len, uint64_t& worst, uint32_t k, uint64_t key, uint32_t lane) {
@@ -507,30 +513,32 @@ __device__ __forceinline__ void list_offer(uint64_t* res, uint32_t& len, uint64_
 template <typename TB, int QT, int RB>
 __global__ void __launch_bounds__(kWarps * 32) bf_scan_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq,
                                                               ScoreSink out, bool as_value, ScanFuse fuse) {
-    extern __shared__ __align__(16) float qs[];  // QT x dim, then QT norms, then (fused) kWarps x QT lists of k keys
+    extern __shared__ __align__(16) float qs[];  // QT x dim, then QT norms, then (fused) kWarps x QT lists of k keys (+ staging for tail (2a))
+    fuse_stamp(fuse, 0);
     constexpr int U = RB >= 4 ? 2 : (RB == 2 ? 4 : 8);  // 8 row loads in flight per lane
     const uint32_t dim = ix.dim;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* qnorm = qs + (size_t)QT * dim;
-    for (uint32_t i = threadIdx.x; i < QT * dim; i += blockDim.x) {
-        const uint32_t t = i / dim;
-        qs[i] = t < nq ? queries[(size_t)t * dim + (i - t * dim)] : 0.0f;
-    }
-    __syncthreads();
-    if (ix.metric == VELES_COSINE) {
-        for (uint32_t t = warp; t < QT; t += kWarps) {
-            const float* q = qs + (size_t)t * dim;
-            const float s = warp_tree_reduce<0>(q, q, dim, lane);
-            if (lane == 0) qnorm[t] = __fsqrt_rn(s);
-        }
-    }
-    __syncthreads();
     const bool l2 = ix.metric == VELES_EUCLIDEAN;
     const uint64_t n = ix.n;
     const uint32_t g = lane >> 3, t = lane & 7;
     const uint64_t tiles = (n + 4 * RB - 1) / (4 * RB);
     // fused selection state: list q of this warp at lists + (warp * QT + q) * k
     uint64_t* lists = reinterpret_cast<uint64_t*>(qs + (((size_t)QT * dim + QT + 3) & ~(size_t)3));
+    float* qnorm = qs + (size_t)QT * dim;
+    for (uint32_t i = threadIdx.x; i < QT * dim; i += blockDim.x) {
+        const uint32_t tq = i / dim;
+        qs[i] = tq < nq ? queries[(size_t)tq * dim + (i - tq * dim)] : 0.0f;
+    }
+    __syncthreads();
+    if (ix.metric == VELES_COSINE) {
+        for (uint32_t tq = warp; tq < QT; tq += kWarps) {
+            const float* q = qs + (size_t)tq * dim;
+            const float s = warp_tree_reduce<0>(q, q, dim, lane);
+            if (lane == 0) qnorm[tq] = __fsqrt_rn(s);
+        }
+    }
+    __syncthreads();
+    fuse_stamp(fuse, 1);
     uint32_t flen[QT];
     uint64_t fworst[QT];
 #pragma unroll
@@ -552,14 +560,19 @@ __global__ void __launch_bounds__(kWarps * 32) bf_scan_kernel(IndexView ix, cons
         for (int b = 0; b < RB; ++b)
 #pragma unroll
             for (int q = 0; q < QT; ++q) acc[b][q][0] = acc[b][q][1] = acc[b][q][2] = acc[b][q][3] = 0.0f;
+        float nbs[RB];
+#pragma unroll
+        for (int b = 0; b < RB; ++b) {
+            nbs[b] = 0.0f;
+            if (ix.metric == VELES_COSINE) nbs[b] = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(r[b]) + ix.norm_off);
+        }
         if (l2)
             scan_rows<TB, QT, RB, U, true>(ix, qs, r, t, acc);
         else
             scan_rows<TB, QT, RB, U, false>(ix, qs, r, t, acc);
 #pragma unroll
         for (int b = 0; b < RB; ++b) {
-            float nb = 0.0f;
-            if (ix.metric == VELES_COSINE) nb = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(r[b]) + ix.norm_off);
+            const float nb = nbs[b];
             float mine = 0.0f;  // lane t of the group keeps query t's value
 #pragma unroll
             for (int q = 0; q < QT; ++q) {
@@ -595,16 +608,13 @@ __global__ void __launch_bounds__(kWarps * 32) bf_scan_kernel(IndexView ix, cons
         }
     }
     if (fuse.k == 0) return;
+    fuse_stamp(fuse, 2);
     __shared__ uint32_t s_len[kWarps][QT];
     __shared__ uint32_t s_last;
     if (fuse.fast) {
         // ---- k <= 32: selection by counting, no serial list insertion anywhere on the critical path ----
         // (1) CTA merge: the <= 8 * k keys of a query rank themselves (a key's rank = how many keys are smaller; keys are
         //     unique), the first k land in this CTA's slot of `partial`
-        __shared__ uint32_t s_red[kWarps];
-        __shared__ uint32_t s_hist[256];
-        __shared__ uint32_t s_sel[4];
-        __shared__ uint64_t s_win[kFuseFastK];
         if (lane == 0)
             for (int q = 0; q < QT; ++q) s_len[warp][q] = flen[q];
         __syncthreads();
@@ -626,99 +636,164 @@ __global__ void __launch_bounds__(kWarps * 32) bf_scan_kernel(IndexView ix, cons
                 if (rank < fuse.k) po[rank] = key;
             }
         }
+        fuse_stamp(fuse, 3);
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) s_last = atomicAdd(fuse.done, 1u) == gridDim.x - 1 ? 1u : 0u;
         __syncthreads();
+        fuse_stamp(fuse, 4);
         if (!s_last) return;
         __threadfence();
-        // (2) the last CTA: per query, stage the gridDim.x * k keys in shared memory and find the k-th smallest by a
-        //     bitwise descent (64 counting steps over the staged keys), then rank the keys at or below it
-        uint64_t* stage = lists + (size_t)kWarps * QT * fuse.k;  // gridDim.x * k keys (host sized the shared memory)
-        const uint32_t T = gridDim.x * fuse.k;
-        for (uint32_t q = 0; q < nq; ++q) {
-            const uint64_t* in = fuse.partial + (size_t)q * T;
-            uint32_t local = 0;
-            for (uint32_t j = threadIdx.x; j < T; j += blockDim.x) {
-                const uint64_t key = __ldcg(in + j);
-                stage[j] = key;
-                local += key != ~0ull ? 1u : 0u;
-            }
-            local = __reduce_add_sync(FULL_MASK, local);
-            if (lane == 0) s_red[warp] = local;
-            __syncthreads();
-            uint32_t valid = 0;
-            for (uint32_t w = 0; w < kWarps; ++w) valid += s_red[w];
-            __syncthreads();
-            const uint32_t kk = min(fuse.k, valid);
-            // radix select, eight bits per step: histogram of the next byte among the keys that match the prefix so far,
-            // then the bucket that holds the kk-th smallest (eight steps of three barriers instead of 64 x 2)
-            uint64_t prefix = 0;
-            uint32_t need = kk;
-            if (kk > 0) {
-                for (int shift = 56; shift >= 0; shift -= 8) {
-                    s_hist[threadIdx.x] = 0;  // blockDim.x == 256 bins
-                    __syncthreads();
-                    const uint64_t hi = shift == 56 ? 0ull : ~((1ull << (shift + 8)) - 1ull);
-                    for (uint32_t j = threadIdx.x; j < T; j += blockDim.x) {
-                        const uint64_t key = stage[j];
-                        if ((key & hi) == (prefix & hi)) atomicAdd(&s_hist[(uint32_t)(key >> shift) & 255u], 1u);
-                    }
-                    __syncthreads();
-                    if (warp == 0) {
-                        // lane l owns bins 8l .. 8l+7: inclusive scan of the lane totals, then a walk inside the lane's bins
-                        uint32_t c[8], tot = 0;
+        if (fuse.fast == 2) {
+            // (2a) small grids (the collection is small, so this tail IS the kernel): per query, all gridDim.x * k keys are
+            //      staged in shared memory; the k-th smallest of the CTA lists' HEADS bounds the answer from above (k distinct
+            //      keys lie at or below it), each head ranks itself among the heads (one pass, all threads); only keys at or
+            //      below the bound -- at most k * k, typically a few dozen -- are candidates, and they rank themselves among
+            //      each other.  No serial insertion anywhere.
+            uint64_t* stage = lists + (size_t)kWarps * QT * fuse.k;  // gridDim.x * k keys (host sized all of this)
+            const uint32_t G = gridDim.x, T = G * fuse.k;
+            uint64_t* heads = stage + T;                                  // gridDim.x heads, dense
+            uint64_t* cand = heads + G;                                   // k * k candidates
+            uint32_t* hrank = reinterpret_cast<uint32_t*>(cand + (size_t)fuse.k * fuse.k);  // gridDim.x ranks
+            __shared__ uint64_t s_bound;
+            __shared__ uint32_t s_ncand;
+            for (uint32_t q = 0; q < nq; ++q) {
+                const uint64_t* in = fuse.partial + (size_t)q * T;
+                // every key of the query in ONE round trip: up to 16 loads per thread in flight (grids of <= 2 CTAs per SM)
+                for (uint32_t j0 = threadIdx.x; j0 < T; j0 += blockDim.x * 16) {
+                    uint64_t key[16];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            c[e] = s_hist[lane * 8 + e];
-                            tot += c[e];
-                        }
-                        uint32_t incl = tot;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const uint32_t up = __shfl_up_sync(FULL_MASK, incl, o);
-                            if ((int)lane >= o) incl += up;
-                        }
-                        const uint32_t before = incl - tot;
-                        if (need > before && need <= incl) {  // exactly one lane
-                            uint32_t acc = before;
-                            int e = 0;
-                            while (acc + c[e] < need) acc += c[e++];
-                            s_sel[0] = lane * 8 + e;   // the byte
-                            s_sel[1] = need - acc;     // rank inside that bucket
-                        }
+                    for (int u = 0; u < 16; ++u) {
+                        const uint32_t j = j0 + u * blockDim.x;
+                        key[u] = j < T ? __ldcg(in + j) : ~0ull;
                     }
-                    __syncthreads();
-                    prefix |= (uint64_t)s_sel[0] << shift;
-                    need = s_sel[1];
-                    __syncthreads();
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const uint32_t j = j0 + u * blockDim.x;
+                        if (j < T) stage[j] = key[u];
+                    }
                 }
-            }
-            // prefix = the kk-th smallest key.  The keys at or below it are exactly the kk smallest: collect them, then
-            // each ranks itself among them (kk <= 32 comparisons)
-            if (threadIdx.x == 0) s_sel[2] = 0;
-            for (uint32_t i = threadIdx.x; i < fuse.k; i += blockDim.x) {
-                if (i >= kk) {
+                for (uint32_t c = threadIdx.x; c < G; c += blockDim.x) hrank[c] = 0;
+                if (threadIdx.x == 0) {
+                    s_bound = ~0ull;  // fewer than k lists with a row: everything found is a candidate
+                    s_ncand = 0;
+                }
+                __syncthreads();
+                for (uint32_t c = threadIdx.x; c < G; c += blockDim.x) heads[c] = stage[(size_t)c * fuse.k];
+                __syncthreads();
+                // a head's rank among the heads, the work split in two halves per head so that all threads are busy
+                for (uint32_t w = threadIdx.x; w < 2 * G; w += blockDim.x) {
+                    const uint32_t c = w >> 1, half = w & 1;
+                    const uint64_t head = heads[c];
+                    const uint32_t lo = half ? G / 2 : 0, hi = half ? G : G / 2;
+                    uint32_t rank = 0;
+#pragma unroll 8
+                    for (uint32_t c2 = lo; c2 < hi; ++c2) rank += heads[c2] < head ? 1u : 0u;
+                    if (rank) atomicAdd(&hrank[c], rank);
+                }
+                __syncthreads();
+                for (uint32_t c = threadIdx.x; c < G; c += blockDim.x)
+                    if (hrank[c] == fuse.k - 1 && heads[c] != ~0ull) s_bound = heads[c];
+                __syncthreads();
+                const uint64_t bound = s_bound;
+                for (uint32_t j = threadIdx.x; j < T; j += blockDim.x) {
+                    const uint64_t key = stage[j];
+                    if (key != ~0ull && key <= bound) {
+                        const uint32_t slot = atomicAdd(&s_ncand, 1u);
+                        if (slot < fuse.k * fuse.k) cand[slot] = key;
+                    }
+                }
+                __syncthreads();
+                const uint32_t nc = min(s_ncand, fuse.k * fuse.k);
+                for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
+                    const uint64_t key = cand[i];
+                    uint32_t rank = 0;
+                    for (uint32_t i2 = 0; i2 < nc; ++i2) rank += cand[i2] < key ? 1u : 0u;
+                    if (rank < fuse.k) {
+                        const uint32_t o = (uint32_t)(key >> 32);
+                        fuse.out_ids[(size_t)q * fuse.k + rank] = (uint32_t)key;
+                        fuse.out_score[(size_t)q * fuse.k + rank] = ord_unkey(fuse.desc ? ~o : o);
+                    }
+                }
+                for (uint32_t i = nc + threadIdx.x; i < fuse.k; i += blockDim.x) {  // fewer rows than k
                     fuse.out_ids[(size_t)q * fuse.k + i] = VELES_INVALID_ID;
                     fuse.out_score[(size_t)q * fuse.k + i] = __uint_as_float(0x7fc00000u);
                 }
+                __syncthreads();
             }
-            __syncthreads();
-            for (uint32_t j = threadIdx.x; j < T; j += blockDim.x) {
-                const uint64_t key = stage[j];
-                if (kk != 0 && key <= prefix) s_win[atomicAdd(&s_sel[2], 1u) & (kFuseFastK - 1)] = key;
+            fuse_stamp(fuse, 6);
+            if (threadIdx.x == 0) *fuse.done = 0u;  // ready for the next launch
+            return;
+        }
+        // (2) the last CTA: its warps are shared out among the queries (kWarps / QT each).  A warp reads its share of a
+        //     query's gridDim.x * k keys, eight loads in flight, into a register-resident top-k; the lists of a query's
+        //     warps are then merged by rank (sorted lists of distinct keys: a key's place is the sum of its lower bounds),
+        //     all threads at once.  (The first version selected by an eight-pass radix descent over keys staged in shared
+        //     memory: ~8 us of barriers per query, and the queries one after another.)
+        constexpr int WPQ = kWarps / QT;
+        const uint32_t T = gridDim.x * fuse.k;
+        {
+            const uint32_t myq = warp / WPQ, sub = warp % WPQ;
+            RegTopK<1> top;
+            top.init(fuse.k, lane);
+            if (myq < nq) {
+                const uint64_t* in = fuse.partial + (size_t)myq * T;
+                for (uint32_t j0 = sub * 32; j0 < T; j0 += WPQ * 32 * 8) {
+                    uint64_t key[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t j = j0 + u * WPQ * 32 + lane;
+                        key[u] = j < T ? __ldcg(in + j) : ~0ull;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) top.offer(key[u]);
+                }
             }
-            __syncthreads();
-            if (threadIdx.x < kk) {
-                const uint64_t key = s_win[threadIdx.x];
-                uint32_t rank = 0;
-                for (uint32_t i = 0; i < kk; ++i) rank += s_win[i] < key ? 1u : 0u;
+            top.store(lists + (size_t)warp * fuse.k, fuse.k);  // the warps' lists of part (1) are no longer needed
+        }
+        __syncthreads();
+        fuse_stamp(fuse, 5);
+        for (uint32_t idx = threadIdx.x; idx < kWarps * fuse.k; idx += blockDim.x) {
+            const uint32_t w = idx / fuse.k, q = w / WPQ;
+            if (q >= nq) continue;
+            const uint64_t key = lists[idx];
+            if (key == ~0ull) continue;
+            uint32_t rank = 0;
+            for (uint32_t w2 = q * WPQ; w2 < (q + 1) * WPQ; ++w2) {
+                const uint64_t* l = lists + (size_t)w2 * fuse.k;
+                uint32_t lo = 0, hi = fuse.k;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (l[mid] < key) lo = mid + 1; else hi = mid;
+                }
+                rank += lo;
+            }
+            if (rank < fuse.k) {
                 const uint32_t o = (uint32_t)(key >> 32);
                 fuse.out_ids[(size_t)q * fuse.k + rank] = (uint32_t)key;
                 fuse.out_score[(size_t)q * fuse.k + rank] = ord_unkey(fuse.desc ? ~o : o);
             }
-            __syncthreads();
         }
+        // positions past the number of rows found (collections smaller than k)
+        for (uint32_t idx = threadIdx.x; idx < nq * fuse.k; idx += blockDim.x) {
+            const uint32_t q = idx / fuse.k, pos = idx - q * fuse.k;
+            uint32_t have = 0;
+            for (uint32_t w2 = q * WPQ; w2 < (q + 1) * WPQ && have <= pos; ++w2) {
+                const uint64_t* l = lists + (size_t)w2 * fuse.k;
+                uint32_t lo = 0, hi = fuse.k;  // the list is sorted and padded with ~0
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (l[mid] != ~0ull) lo = mid + 1; else hi = mid;
+                }
+                have += lo;
+            }
+            if (pos >= have) {
+                fuse.out_ids[idx] = VELES_INVALID_ID;
+                fuse.out_score[idx] = __uint_as_float(0x7fc00000u);
+            }
+        }
+        __syncthreads();
+        fuse_stamp(fuse, 6);
         if (threadIdx.x == 0) *fuse.done = 0u;  // ready for the next launch
         return;
     }
@@ -1134,23 +1209,49 @@ static int32_t launch_scores(const veles_index* ixh, const IndexView& v, const f
             uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((tiles + kWarps - 1) / kWarps, (uint64_t)sms * per_sm));
             size_t smem_s = smem_base;
             if (fz.k) {
-                // fused selection: every CTA leaves a list for the last CTA to merge, so small collections get one CTA per
-                // SM; with k <= 32 the last CTA stages all of them in shared memory and selects by counting
-                gx = std::min<uint64_t>(gx, std::max<uint64_t>((uint64_t)sms, (tiles + kWarps * 4 - 1) / (kWarps * 4)));
-                const size_t stage = (size_t)gx * fz.k * 8;
-                // (only in the one-CTA-per-SM regime of small collections: there the tail IS the kernel; for large ones the
-                // staging memory would cost resident CTAs, i.e. bandwidth, and the tail is noise)
-                if (fz.k <= kFuseFastK && stage <= 64 * 1024 && gx <= (uint64_t)sms) {
-                    fz.fast = 1;
-                    smem_s = smem_base + stage;
-                    per_sm = cached_blocks_per_sm(reinterpret_cast<const void*>(ks), kWarps * 32, smem_s);
-                    if (per_sm < 1) return VELES_ERR_CUDA;
-                    gx = std::min<uint64_t>(gx, (uint64_t)sms * per_sm);
+                // fused selection: every CTA leaves a list for the last CTA to merge, so small collections get at most two
+                // CTAs per SM (one tile per warp where that is enough); k <= 32 selects with register lists and rank merges
+                gx = std::min<uint64_t>(gx, std::max<uint64_t>((uint64_t)sms * std::min(per_sm, 2), (tiles + kWarps * 4 - 1) / (kWarps * 4)));
+                fz.fast = fz.k <= kFuseFastK ? 1u : 0u;
+                // small grids (the collection is small, so the tail IS the kernel): the last CTA stages every CTA's list in
+                // shared memory and selects by ranks (tail (2a)) when that costs no resident CTA
+                const size_t stage = ((size_t)gx * fz.k + (size_t)gx + (size_t)fz.k * fz.k) * 8 + (size_t)gx * 4;
+                if (fz.fast && gx <= (uint64_t)2 * sms && stage <= 64 * 1024 && std::getenv("VELES_BF_NO_STAGED_TAIL") == nullptr) {
+                    const int per_sm2 = cached_blocks_per_sm(reinterpret_cast<const void*>(ks), kWarps * 32, smem_base + stage);
+                    if (per_sm2 >= 1 && per_sm2 * (uint64_t)sms >= gx) {
+                        fz.fast = 2;
+                        smem_s += stage;
+                    }
                 }
+            }
+            static const bool dbg_timing = std::getenv("VELES_BF_DEBUG_TIMING") != nullptr;
+            unsigned long long* dbg_d = nullptr;
+            if (dbg_timing && fz.k) {  // diagnostics only: phase stamps per CTA, printed after a synchronize
+                VELES_CUDA(cudaMalloc(&dbg_d, (size_t)gx * 64));
+                VELES_CUDA(cudaMemsetAsync(dbg_d, 0, (size_t)gx * 64, st));
+                fz.dbg = dbg_d;
             }
             ks<<<(unsigned)gx, kWarps * 32, smem_s, st>>>(v, q_d, nq, sink, as_value, fz);
             count_launch();
             VELES_CUDA(cudaGetLastError());
+            if (dbg_d) {
+                std::vector<unsigned long long> h((size_t)gx * 8);
+                VELES_CUDA(cudaStreamSynchronize(st));
+                VELES_CUDA(cudaMemcpy(h.data(), dbg_d, h.size() * 8, cudaMemcpyDeviceToHost));
+                cudaFree(dbg_d);
+                unsigned long long t0 = ~0ull;
+                for (uint64_t c = 0; c < gx; ++c) t0 = std::min(t0, h[c * 8]);
+                static const char* names[7] = {"entry", "query staged", "scan done", "cta merged", "ticket", "lists read", "done"};
+                for (int sl = 0; sl < 7; ++sl) {
+                    unsigned long long lo = ~0ull, hi = 0;
+                    for (uint64_t c = 0; c < gx; ++c)
+                        if (h[c * 8 + sl]) {
+                            lo = std::min(lo, h[c * 8 + sl] - t0);
+                            hi = std::max(hi, h[c * 8 + sl] - t0);
+                        }
+                    if (hi) std::fprintf(stderr, "[bf timing] %-13s first %6.2f us  last %6.2f us (grid %llu, tail %u)\n", names[sl], lo / 1e3, hi / 1e3, (unsigned long long)gx, fz.fast);
+                }
+            }
             return VELES_OK;
         }
         if (ix->dim % kTsK == 0 && nq >= 16 && std::getenv("VELES_BF_NO_SMEM_TILE") == nullptr) {
