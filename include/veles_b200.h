@@ -211,7 +211,12 @@ int32_t veles_distance_pairs(int32_t metric, const float* a, const float* b, uin
  * within a term, with the term frequency beside each doc (the reference keeps tf in per-document
  * maps, bm25.rs:62-67).  doc_len is indexed by doc id (0 = absent).  df[t] is the posting-list
  * length the reference would report (PostingList::len), which can exceed the live postings after
- * a document was replaced (bm25.rs:188-196 keeps stale postings). */
+ * a document was replaced (bm25.rs:188-196 keeps stale postings).
+ * Device memory: 8 bytes per posting for the query path ((doc, contribution) with the contribution
+ * precomputed in the reference's f32 operation order), 12 more for the long-query fallback, a
+ * coarse skip table (8 bytes x terms x docs/7168) and, when it stays below 2 GiB and 4x the
+ * postings, a fine one (4 bytes x terms x docs/1024) that the default query kernel needs; without
+ * it queries go through the coarse-table kernel (same results, ~1.6x slower on the bench corpus). */
 int32_t veles_bm25_from_csr(uint32_t n_terms, const uint64_t* term_ptr, const uint32_t* post_doc,
                             const uint32_t* post_tf, const uint32_t* df, uint32_t n_doc_slots, const uint32_t* doc_len,
                             uint64_t doc_count, uint64_t total_len, float k1, float b, veles_bm25_t** out);

@@ -247,3 +247,27 @@ def test_bm25_work_items_split_and_merge_bit_exact(k, monkeypatch):
                     c = int(cnt_g[i])
                     assert np.array_equal(docs_g[i, :c], oi[i, :c].astype(np.uint32)), (env, rep, i)
                     assert bits_equal(sc_g[i, :c], os_[i, :c]), (env, rep, i)
+
+
+def test_bm25_snapshot_without_the_fine_skip_table(monkeypatch):
+    """A snapshot built without the fine skip table (what a vocabulary too large for it gets) answers through
+    bm25_flat_kernel by default: same documents and score bits as the oracle and as the snapshot with the table."""
+    docs, p = zipf_corpus(20000, 1500, seed=9)
+    monkeypatch.setenv("VELES_BM25_NO_FINE_TABLE", "1")
+    o, snap_coarse = build_both(docs)
+    monkeypatch.delenv("VELES_BM25_NO_FINE_TABLE")
+    _, snap_fine = build_both(docs)
+    rng = np.random.default_rng(3)
+    nq, k = 33, 10
+    q_ptr, q_terms = [0], []
+    for _ in range(nq):
+        q_terms += rng.choice(1500, size=int(rng.integers(1, 7)), p=p).astype(np.uint32).tolist()
+        q_ptr.append(len(q_terms))
+    oi, os_, oc = o.search_batch_terms(q_ptr, q_terms, k, threads=4)
+    for snap in (snap_coarse, snap_fine):
+        docs_g, sc_g, cnt_g = snap.search_batch(q_ptr, q_terms, k)
+        assert np.array_equal(cnt_g, oc)
+        for i in range(nq):
+            c = int(cnt_g[i])
+            assert np.array_equal(docs_g[i, :c], oi[i, :c].astype(np.uint32)), i
+            assert bits_equal(sc_g[i, :c], os_[i, :c]), i
