@@ -355,6 +355,7 @@ __device__ __forceinline__ uint32_t lower_bound_warp(const uint64_t* res, uint32
 // Inserts `key` at position pos, shifting res[pos..new_len-1) up by one (the old last element
 // falls off when the array is full).  Chunks move from the top so nothing unread is overwritten.
 __device__ __forceinline__ void insert_at(uint64_t* res, uint32_t pos, uint32_t new_len, uint64_t key, uint32_t lane) {
+    __syncwarp();  // the lanes' reads of the search that found `pos` come before any write below
     int32_t top = (int32_t)new_len - 1;  // exclusive end of the source range
     while (top > (int32_t)pos) {
         const int32_t i = top - 1 - (int32_t)lane;
