@@ -325,3 +325,31 @@ def test_gather_window_of_a_single_rank_equals_the_plain_search():
             nv.check(lib_call)   # the window was created for nq queries
     finally:
         lib.veles_comm_destroy(h)
+
+
+@pytest.mark.parametrize("n,nq,k", [(5000, 1, 10), (5000, 2, 7), (9, 1, 10), (3000, 1, 32)])
+def test_fused_brute_force_small_collection_tail_and_tied_scores(n, nq, k, monkeypatch):
+    """Small collections select in the scan kernel's last CTA from staged keys under a bound taken from the CTA lists'
+    heads (tail 2a).  (a) random rows: ids and score bits equal the oracle's and the general tail's; (b) a collection of
+    identical rows -- every score ties, the candidates overflow the k * k table -- falls back to the general tail and
+    still returns the k smallest ids."""
+    rng = np.random.default_rng(n + k)
+    x = latent_data(n, 64, latent=8, noise=0.3, seed=n)
+    q = queries_near(x, nq, jitter=0.2, seed=3)
+    for metric in (vo.COSINE, vo.EUCLIDEAN):
+        snap = DeviceSnapshot.from_vectors(x, metric)
+        fi, fs = snap.bruteforce_batch(q, k)
+        oi, os_ = vo.bruteforce_batch(metric, x, q, k, threads=4)
+        kk = min(k, n)
+        assert np.array_equal(fi[:, :kk], oi.astype(np.uint32)[:, :kk]) and bits_equal(fs[:, :kk], os_[:, :kk])
+        assert (fi[:, kk:] == 0xFFFFFFFF).all()
+        monkeypatch.setenv("VELES_BF_NO_STAGED_TAIL", "1")
+        gi, gs = snap.bruteforce_batch(q, k)
+        monkeypatch.delenv("VELES_BF_NO_STAGED_TAIL")
+        assert np.array_equal(fi, gi) and bits_equal(fs[:, :kk], gs[:, :kk])
+    same = np.tile(rng.normal(size=(1, 64)).astype(np.float32), (n, 1))
+    snap = DeviceSnapshot.from_vectors(same, vo.EUCLIDEAN)
+    ti, ts = snap.bruteforce_batch(same[:nq] + 0.5, k)
+    kk = min(k, n)
+    assert np.array_equal(ti[:, :kk], np.tile(np.arange(kk, dtype=np.uint32), (nq, 1)))
+    assert (ts[:, :kk].view(np.uint32) == ts[0, 0].view(np.uint32)).all()

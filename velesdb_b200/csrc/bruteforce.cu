@@ -646,17 +646,18 @@ __global__ void __launch_bounds__(kWarps * 32) bf_scan_kernel(IndexView ix, cons
         __threadfence();
         if (fuse.fast == 2) {
             // (2a) small grids (the collection is small, so this tail IS the kernel): per query, all gridDim.x * k keys are
-            //      staged in shared memory; the k-th smallest of the CTA lists' HEADS bounds the answer from above (k distinct
-            //      keys lie at or below it), each head ranks itself among the heads (one pass, all threads); only keys at or
-            //      below the bound -- at most k * k, typically a few dozen -- are candidates, and they rank themselves among
-            //      each other.  No serial insertion anywhere.
+            //      staged in shared memory in one round trip.  The k-th smallest SCORE among the CTA lists' heads bounds
+            //      the answer from above (k distinct keys lie at or below it): every head counts the heads with a smaller
+            //      score (32-bit compares, four per shared-memory load), the largest score among the heads with fewer
+            //      than k smaller ones is that bound.  Only keys at or below it -- at most k * k unless scores tie
+            //      heavily -- are candidates; they rank themselves among each other.  No serial insertion anywhere; if the
+            //      candidates overflow (ties), the general tail (2) below redoes the batch.
             uint64_t* stage = lists + (size_t)kWarps * QT * fuse.k;  // gridDim.x * k keys (host sized all of this)
-            const uint32_t G = gridDim.x, T = G * fuse.k;
-            uint64_t* heads = stage + T;                                  // gridDim.x heads, dense
-            uint64_t* cand = heads + G;                                   // k * k candidates
-            uint32_t* hrank = reinterpret_cast<uint32_t*>(cand + (size_t)fuse.k * fuse.k);  // gridDim.x ranks
-            __shared__ uint64_t s_bound;
-            __shared__ uint32_t s_ncand;
+            const uint32_t G = gridDim.x, T = G * fuse.k, G4 = (G + 3) & ~3u;
+            uint64_t* cand = stage + T;                                                      // k * k candidates
+            uint32_t* hhi = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(cand + (size_t)fuse.k * fuse.k) + 15) & ~(uintptr_t)15);  // gridDim.x head scores (+ pad)
+            __shared__ uint32_t s_bound_hi, s_ncand, s_overflow;
+            if (threadIdx.x == 0) s_overflow = 0;
             for (uint32_t q = 0; q < nq; ++q) {
                 const uint64_t* in = fuse.partial + (size_t)q * T;
                 // every key of the query in ONE round trip: up to 16 loads per thread in flight (grids of <= 2 CTAs per SM)
@@ -673,29 +674,28 @@ __global__ void __launch_bounds__(kWarps * 32) bf_scan_kernel(IndexView ix, cons
                         if (j < T) stage[j] = key[u];
                     }
                 }
-                for (uint32_t c = threadIdx.x; c < G; c += blockDim.x) hrank[c] = 0;
                 if (threadIdx.x == 0) {
-                    s_bound = ~0ull;  // fewer than k lists with a row: everything found is a candidate
+                    s_bound_hi = G < fuse.k ? 0xffffffffu : 0u;  // fewer than k lists: no bound, all G * k < k * k keys are candidates
                     s_ncand = 0;
                 }
                 __syncthreads();
-                for (uint32_t c = threadIdx.x; c < G; c += blockDim.x) heads[c] = stage[(size_t)c * fuse.k];
+                fuse_stamp(fuse, 5);
+                for (uint32_t c = threadIdx.x; c < G4; c += blockDim.x) hhi[c] = c < G ? (uint32_t)(stage[(size_t)c * fuse.k] >> 32) : 0xffffffffu;
                 __syncthreads();
-                // a head's rank among the heads, the work split in two halves per head so that all threads are busy
-                for (uint32_t w = threadIdx.x; w < 2 * G; w += blockDim.x) {
-                    const uint32_t c = w >> 1, half = w & 1;
-                    const uint64_t head = heads[c];
-                    const uint32_t lo = half ? G / 2 : 0, hi = half ? G : G / 2;
-                    uint32_t rank = 0;
-#pragma unroll 8
-                    for (uint32_t c2 = lo; c2 < hi; ++c2) rank += heads[c2] < head ? 1u : 0u;
-                    if (rank) atomicAdd(&hrank[c], rank);
+                for (uint32_t c = threadIdx.x; c < G; c += blockDim.x) {
+                    const uint32_t mine = hhi[c];
+                    uint32_t smaller = 0;
+                    const uint4* h4 = reinterpret_cast<const uint4*>(hhi);
+#pragma unroll 4
+                    for (uint32_t c4 = 0; c4 < G4 / 4; ++c4) {
+                        const uint4 h = h4[c4];
+                        smaller += (h.x < mine ? 1u : 0u) + (h.y < mine ? 1u : 0u) + (h.z < mine ? 1u : 0u) + (h.w < mine ? 1u : 0u);
+                    }
+                    if (smaller < fuse.k) atomicMax(&s_bound_hi, mine);  // empty lists (score bits ~0) qualify when fewer than k have a row
                 }
                 __syncthreads();
-                for (uint32_t c = threadIdx.x; c < G; c += blockDim.x)
-                    if (hrank[c] == fuse.k - 1 && heads[c] != ~0ull) s_bound = heads[c];
-                __syncthreads();
-                const uint64_t bound = s_bound;
+                fuse_stamp(fuse, 7);
+                const uint64_t bound = ((uint64_t)s_bound_hi << 32) | 0xffffffffull;
                 for (uint32_t j = threadIdx.x; j < T; j += blockDim.x) {
                     const uint64_t key = stage[j];
                     if (key != ~0ull && key <= bound) {
@@ -704,7 +704,12 @@ __global__ void __launch_bounds__(kWarps * 32) bf_scan_kernel(IndexView ix, cons
                     }
                 }
                 __syncthreads();
-                const uint32_t nc = min(s_ncand, fuse.k * fuse.k);
+                if (s_ncand > fuse.k * fuse.k) {  // uniform: heavily tied scores
+                    if (threadIdx.x == 0) s_overflow = 1;
+                    __syncthreads();
+                    continue;
+                }
+                const uint32_t nc = s_ncand;
                 for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
                     const uint64_t key = cand[i];
                     uint32_t rank = 0;
@@ -721,9 +726,12 @@ __global__ void __launch_bounds__(kWarps * 32) bf_scan_kernel(IndexView ix, cons
                 }
                 __syncthreads();
             }
-            fuse_stamp(fuse, 6);
-            if (threadIdx.x == 0) *fuse.done = 0u;  // ready for the next launch
-            return;
+            if (!s_overflow) {
+                fuse_stamp(fuse, 6);
+                if (threadIdx.x == 0) *fuse.done = 0u;  // ready for the next launch
+                return;
+            }
+            __syncthreads();
         }
         // (2) the last CTA: its warps are shared out among the queries (kWarps / QT each).  A warp reads its share of a
         //     query's gridDim.x * k keys, eight loads in flight, into a register-resident top-k; the lists of a query's
@@ -1215,7 +1223,7 @@ static int32_t launch_scores(const veles_index* ixh, const IndexView& v, const f
                 fz.fast = fz.k <= kFuseFastK ? 1u : 0u;
                 // small grids (the collection is small, so the tail IS the kernel): the last CTA stages every CTA's list in
                 // shared memory and selects by ranks (tail (2a)) when that costs no resident CTA
-                const size_t stage = ((size_t)gx * fz.k + (size_t)gx + (size_t)fz.k * fz.k) * 8 + (size_t)gx * 4;
+                const size_t stage = ((size_t)gx * fz.k + (size_t)fz.k * fz.k) * 8 + 16 + ((size_t)gx + 4) * 4;
                 if (fz.fast && gx <= (uint64_t)2 * sms && stage <= 64 * 1024 && std::getenv("VELES_BF_NO_STAGED_TAIL") == nullptr) {
                     const int per_sm2 = cached_blocks_per_sm(reinterpret_cast<const void*>(ks), kWarps * 32, smem_base + stage);
                     if (per_sm2 >= 1 && per_sm2 * (uint64_t)sms >= gx) {
@@ -1241,8 +1249,8 @@ static int32_t launch_scores(const veles_index* ixh, const IndexView& v, const f
                 cudaFree(dbg_d);
                 unsigned long long t0 = ~0ull;
                 for (uint64_t c = 0; c < gx; ++c) t0 = std::min(t0, h[c * 8]);
-                static const char* names[7] = {"entry", "query staged", "scan done", "cta merged", "ticket", "lists read", "done"};
-                for (int sl = 0; sl < 7; ++sl) {
+                static const char* names[8] = {"entry", "query staged", "scan done", "cta merged", "ticket", "keys staged", "done", "bound found"};
+                for (int sl = 0; sl < 8; ++sl) {
                     unsigned long long lo = ~0ull, hi = 0;
                     for (uint64_t c = 0; c < gx; ++c)
                         if (h[c * 8 + sl]) {
