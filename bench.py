@@ -72,6 +72,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strong", action="store_true", help="N > 1: split ONE batch of nq queries over the GPUs (strong scaling)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N > 1: the library's peer-store gather, or torch NCCL")
+    ap.add_argument("--hybrid-three-calls", action="store_true",
+                    help="c5: time search, BM25 and RRF as three host-API calls (round 2's first form) instead of veles_hybrid_search_batch")
     ap.add_argument("--cache", default=os.environ.get("VELES_BENCH_CACHE", "/tmp/veles_bench_cache"))
     a = ap.parse_args()
     cfg = dict(CONFIGS[a.config])
@@ -482,7 +484,7 @@ def main():
 
     bm = corp = None
     if kind == "hybrid":
-        from velesdb_b200 import Bm25Snapshot, rrf_hybrid_batch
+        from velesdb_b200 import Bm25Snapshot, hybrid_search_batch, rrf_hybrid_batch
 
         corp = bm25_corpus(cfg, nq, 11 + rank)
         bm = Bm25Snapshot(corp["term_ptr"], corp["post_doc"], corp["tf"], corp["df"], corp["lens"], corp["n_docs"], corp["total"])
@@ -559,7 +561,30 @@ def main():
         if kind == "hybrid":
             torch.cuda.current_stream().synchronize()
             td, ts, tc = bm.search_batch(corp["q_ptr"], corp["q_terms"], k_vec)
-            rrf_hybrid_batch(ids_t.cpu().numpy().astype(np.uint32), cnt_t.cpu().numpy().astype(np.uint32), td, tc, k, 0.5)
+            return rrf_hybrid_batch(ids_t.cpu().numpy().astype(np.uint32), cnt_t.cpu().numpy().astype(np.uint32), td, tc, k, 0.5)
+
+    # hybrid: the product call is veles_hybrid_search_batch -- host buffers in, fused top-k out, both legs concurrent on
+    # the device.  --hybrid-three-calls times round 2's first form (search, BM25 and RRF as three host-API calls).
+    hybrid_one = kind == "hybrid" and not a.hybrid_three_calls
+    qn_host = q_h.numpy()
+
+    def step_hybrid():
+        return hybrid_search_batch(snap, bm, qn_host, corp["q_ptr"], corp["q_terms"], k, ef, 0.5, stream)
+
+    three_ms = None
+    if hybrid_one:
+        three = step_device()
+        one = step_hybrid()
+        for _ in range(3):
+            step_device()
+        t3 = time.perf_counter()
+        for _ in range(a.steps):
+            step_device()
+        three_ms = (time.perf_counter() - t3) * 1e3 / a.steps  # the three-call form on the same batch, for the record
+        assert all(np.array_equal(x, y) for x, y in zip((three[0], three[1].view(np.uint32), three[2]),
+                                                        (one[0], one[1].view(np.uint32), one[2]))), \
+            "veles_hybrid_search_batch differs from the three separate calls"
+        step_device = step_hybrid  # noqa: F811
 
     for _ in range(max(a.warmup, 3)):
         step_device()
@@ -578,6 +603,11 @@ def main():
     t_wall = time.perf_counter()
     e0.record()
     for i in range(a.steps):
+        if hybrid_one:
+            kev[i][0].record()
+            step_hybrid()
+            kev[i][1].record()
+            continue
         if flush is not None:
             flush.zero_()
         kev[i][0].record()
@@ -667,6 +697,13 @@ def main():
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
     kname = {"brute": "bf_tile_smem_kernel + topk", "hybrid": "hnsw_search_kernel<f32>"}.get(kind, f"hnsw_search_kernel<{'sq8' if sq8 else cfg['store']}>")
+    if hybrid_one:
+        # both legs run concurrently inside one call, so the events bracket the call: charge it with both legs' bytes
+        # (text leg: 12 bytes per posting of every query token + its 2k results)
+        df_q = corp["df"][corp["q_terms"][corp["q_terms"] < len(corp["df"])]].astype(np.int64)
+        alg_bytes += int(df_q.sum() * 12 + nq * k_vec * 8)
+        achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
+        kname = "veles_hybrid_search_batch: hnsw_search_kernel<f32> || bm25_sub_kernel, then rrf_hybrid_kernel (host copies included)"
     line = {"metric": metric_name(cfg), "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms_dev / a.steps, "higher_is_better": True,
             "scaling": "strong" if (a.strong and use_dist) else "weak", "vs_baseline": None,
@@ -689,10 +726,19 @@ def main():
                        "sync_value": total_q / (e2e[1] / 1e3), "sync_api": "veles_search_batch, one call at a time"}
     else:
         # these configs' public call is the host API already timed above (hybrid) or the device-pointer call
-        line["e2e"] = {"value": value, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4 if kind == "hybrid" else 0,
-                       "d2h_bytes_per_step": nq * k_vec * 8 if kind == "hybrid" else 0,
-                       "note": "hybrid steps already run BM25 + fusion through the host API" if kind == "hybrid"
-                               else "device-resident call only for this config"}
+        line["e2e"] = {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                       "note": "device-resident call only for this config"}
+        if hybrid_one:
+            line["e2e"].update({"h2d_bytes_per_step": int(nq * dim * 4 + corp["q_ptr"].nbytes + corp["q_terms"].nbytes),
+                                "d2h_bytes_per_step": nq * k * 8 + nq * 4 + 8,
+                                "api": "veles_hybrid_search_batch: pinned host queries + term ids in, fused top-k out, one call per step",
+                                "note": "the timed step IS the host-API call; results equal the three separate calls bit for bit",
+                                "three_calls_ms_per_step": three_ms})
+        elif kind == "hybrid":
+            line["e2e"].update({"h2d_bytes_per_step": int(nq * k_vec * 8 + nq * 8 + corp["q_ptr"].nbytes + corp["q_terms"].nbytes),
+                                "d2h_bytes_per_step": nq * k_vec * 12 + nq * 8 + nq * k * 8 + nq * 4,
+                                "api": "veles_search_batch_d + veles_bm25_search_batch + veles_rrf_hybrid (--hybrid-three-calls)",
+                                "note": "hybrid steps already run BM25 + fusion through the host API"})
 
     # ---------------- CPU baseline: the oracle on the same graph and queries ----------------
     if rank == 0 and not a.no_cpu_baseline and not (a.strong and use_dist):

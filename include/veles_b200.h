@@ -237,6 +237,18 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
 int32_t veles_rrf_hybrid(const uint32_t* vec_ids, const uint32_t* vec_cnt, const uint32_t* txt_ids,
                          const uint32_t* txt_cnt, uint32_t nq, uint32_t in_k, float vector_weight, uint32_t k,
                          uint32_t* out_ids, float* out_score, uint32_t* out_counts, void* stream);
+/* Collection::hybrid_search (collection/search/text.rs:113-203, minus the storage fetch of lines 183-203) for a
+ * batch, in ONE call: `self.index.search(vector_query, 2k)` (NativeHnsw::search with the caller's ef; the reference
+ * passes ef_search(Balanced, 2k)) on `stream`, `self.text_index.search(text_query, 2k)` concurrently on a stream
+ * owned by `bm`, then the RRF of lines 133-180 over the two device-resident lists and one copy back.  Same kernels,
+ * hence the same bits, as veles_search_batch + veles_bm25_search_batch + veles_rrf_hybrid called in sequence, without
+ * their host round trips.  Node ids of `idx` are the document ids of `bm`.  queries nq*dim f32; q_term_ptr / q_terms
+ * as veles_bm25_search_batch; out_ids / out_score nq*k, out_counts nq (as veles_rrf_hybrid).  Host pointers;
+ * returns when the results are in the output buffers.  VELES_ERR_OVERFLOW as veles_search_batch. */
+int32_t veles_hybrid_search_batch(const veles_index_t* idx, const veles_bm25_t* bm, const float* queries,
+                                  const uint32_t* q_term_ptr, const uint32_t* q_terms, uint32_t nq, uint32_t k, uint32_t ef,
+                                  float vector_weight, uint32_t* out_ids, float* out_score, uint32_t* out_counts,
+                                  void* stream);
 /* FusionStrategy::fuse (fusion/strategy.rs:138-300) for one multi-query request: n_lists ranked
  * (id, score) lists.  strategy 0 Average, 1 Maximum, 2 RRF{k}, 3 Weighted{avg,max,hit}.  Output
  * sorted score-descending, ties by ascending id; at most `cap` entries. */

@@ -6,7 +6,8 @@ import pytest
 
 from oracle import oracle as vo
 from tests.gpu_util import bits_equal
-from velesdb_b200 import Bm25Index, Bm25Snapshot, FusionStrategy, hybrid_search, rrf_hybrid_batch
+from velesdb_b200 import (Bm25Index, Bm25Snapshot, DeviceSnapshot, DimensionMismatch, DistanceMetric, FusionStrategy, hybrid_search,
+                          hybrid_search_batch, rrf_hybrid_batch)
 
 pytestmark = pytest.mark.gpu
 
@@ -271,3 +272,57 @@ def test_bm25_snapshot_without_the_fine_skip_table(monkeypatch):
             c = int(cnt_g[i])
             assert np.array_equal(docs_g[i, :c], oi[i, :c].astype(np.uint32)), i
             assert bits_equal(sc_g[i, :c], os_[i, :c]), i
+
+
+def test_hybrid_search_batch_one_call_equals_the_three_calls_and_the_oracle():
+    """veles_hybrid_search_batch = Collection::hybrid_search (text.rs:113-203) for a batch: vector leg and text leg
+    concurrently on the device, RRF over the device-resident lists.  Must equal, bit for bit, veles_search_batch +
+    veles_bm25_search_batch + veles_rrf_hybrid called in sequence, and the oracle's search / Bm25 / rrf_hybrid."""
+    rng = np.random.default_rng(21)
+    n, dim, vocab = 3000, 64, 400
+    z = rng.normal(size=(n, 8)).astype(np.float32) @ rng.normal(size=(8, dim)).astype(np.float32)
+    x = (z + 0.3 * rng.normal(size=(n, dim))).astype(np.float32)
+    g = vo.Hnsw(vo.COSINE, dim, M=16, ef_construction=100)
+    g.insert_many(x)
+    snap = DeviceSnapshot.from_arrays(x, DistanceMetric.Cosine, g.export_graph(), g.M, g.M0, g.entry_point, g.max_layer)
+    docs, p = zipf_corpus(n, vocab, seed=3)                      # document d describes vector d
+    o, bm = build_both(docs)
+    for nq, k, ef in ((1, 5, 32), (37, 10, 64), (300, 10, 128), (64, 40, 200)):
+        q = (x[rng.integers(0, n, nq)] + 0.2 * rng.normal(size=(nq, dim))).astype(np.float32)
+        q_ptr, q_terms = [0], []
+        for i in range(nq):
+            t = rng.choice(vocab, size=int(rng.integers(1, 7)), p=p).astype(np.uint32)
+            if i % 5 == 0:
+                t = np.array([0xFFFFFFFF], np.uint32)            # no known term: the text leg returns nothing
+            if i % 9 == 0:
+                t = np.concatenate([t, t[:1]])
+            q_terms += t.tolist()
+            q_ptr.append(len(q_terms))
+        q_ptr, q_terms = np.array(q_ptr, np.uint32), np.array(q_terms, np.uint32)
+        vi, vd, vc = snap.search_batch(q, 2 * k, ef)
+        td, ts, tc = bm.search_batch(q_ptr, q_terms, 2 * k)
+        for w in (None, 0.3, 1.0, 0.0):
+            ids, sc, cnt = hybrid_search_batch(snap, bm, q, q_ptr, q_terms, k, ef, w)
+            ri, rs, rc = rrf_hybrid_batch(vi, vc, td, tc, k, 0.5 if w is None else w)
+            assert np.array_equal(cnt, rc), (nq, k, w)
+            for i in range(nq):
+                assert np.array_equal(ids[i, :cnt[i]], ri[i, :rc[i]]), (nq, k, w, i)
+                assert bits_equal(sc[i, :cnt[i]], rs[i, :rc[i]])
+        # against the oracle, end to end (canonical tie order on both sides)
+        oi, od, oc, _ = g.search_batch(q, 2 * k, ef, order="canonical")
+        ids, sc, cnt = hybrid_search_batch(snap, bm, q, q_ptr, q_terms, k, ef, 0.5)
+        bi, _, bc = o.search_batch_terms(q_ptr, q_terms, 2 * k, threads=8)
+        for i in range(nq):
+            fi, fs = vo.rrf_hybrid(oi[i, :oc[i]].astype(np.uint32), bi[i, :bc[i]].astype(np.uint32), k, 0.5)
+            assert cnt[i] == len(fi) and np.array_equal(ids[i, :cnt[i]], fi.astype(np.uint32)), (nq, k, i)
+            assert bits_equal(sc[i, :cnt[i]], fs)
+    with pytest.raises(DimensionMismatch):
+        hybrid_search_batch(snap, bm, np.zeros((2, dim + 1), np.float32), np.zeros(3, np.uint32), np.zeros(0, np.uint32), 5, 32)
+    # an empty text index: the fusion sees the vector list only (bm25.rs:275-278)
+    empty = Bm25Snapshot(np.zeros(2, np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(1, np.uint32),
+                         np.zeros(1, np.uint32), 0, 0)
+    q = x[:4].copy()
+    ids, sc, cnt = hybrid_search_batch(snap, empty, q, np.array([0, 1, 2, 3, 4], np.uint32), np.zeros(4, np.uint32), 5, 64, 0.5)
+    vi, vd, vc = snap.search_batch(q, 10, 64)
+    ri, rs, rc = rrf_hybrid_batch(vi, vc, np.full((4, 10), 0xFFFFFFFF, np.uint32), np.zeros(4, np.uint32), 5, 0.5)
+    assert np.array_equal(cnt, rc) and np.array_equal(ids, ri) and bits_equal(sc, rs)

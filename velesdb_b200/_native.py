@@ -61,6 +61,7 @@ SYMBOLS = [
     ("veles_bm25_free", _i32, [_vp]),
     ("veles_bm25_search_batch", _i32, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp]),
     ("veles_rrf_hybrid", _i32, [_vp, _vp, _vp, _vp, _u32, _u32, _f, _u32, _vp, _vp, _vp, _vp]),
+    ("veles_hybrid_search_batch", _i32, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _f, _vp, _vp, _vp, _vp]),
     ("veles_fuse", _i32, [_i32, _vp, _u32, _vp, _vp, _u32, _f, _f, _f, _u32, _vp, _vp, _vp, _vp]),
     ("veles_index_build_graph", _i32, [_vp, _u32, _u32, _vp]),
     ("veles_index_build_graph_exact", _i32, [_vp, _u32, _u32, _vp]),

@@ -33,7 +33,7 @@
 #include <memory>
 #include <mutex>
 
-#include "common.cuh"
+#include "index.hpp"
 
 namespace veles {
 constexpr uint32_t kRange = 7168;  // docs per range: 28 KB of f32 accumulators -> 7 query CTAs per SM (1036 >= 1024 resident)
@@ -50,6 +50,17 @@ struct veles_bm25 {
     veles::DevBuf term_ptr, post_doc, post_tf, post_den, post_dc, doc_len, idf, skip, skipf;
     mutable std::mutex mu;
     mutable veles::DevBuf q_ptr_d, q_terms_d, partial_d, out_doc_d, out_score_d, out_cnt_d;
+    // veles_hybrid_search_batch: the text leg runs on `side` next to the vector leg on the caller's stream
+    mutable cudaStream_t side = nullptr;
+    mutable cudaEvent_t side_done = nullptr;
+    mutable veles::DevBuf hy_ids_d, hy_score_d, hy_cnt_d;
+    veles_bm25() = default;
+    veles_bm25(const veles_bm25&) = delete;
+    veles_bm25& operator=(const veles_bm25&) = delete;
+    ~veles_bm25() {
+        if (side_done) cudaEventDestroy(side_done);
+        if (side) cudaStreamDestroy(side);
+    }
 };
 
 namespace veles {
@@ -1597,32 +1608,10 @@ int32_t veles_bm25_free(veles_bm25_t* ix) {
     return VELES_OK;
 }
 
-int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_ptr, const uint32_t* q_terms, uint32_t nq,
-                                uint32_t k, uint32_t* out_doc, float* out_score, uint32_t* out_counts, void* stream) {
-    VELES_REQUIRE(ix != nullptr, "index is NULL");
-    VELES_REQUIRE(nq == 0 || (q_term_ptr && out_doc && out_score && out_counts), "NULL buffer");
-    VELES_REQUIRE(k >= 1 && k <= 4096, "k must be in 1..4096, got %u", k);
-    if (nq == 0) return VELES_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    std::lock_guard<std::mutex> g(ix->mu);
-    const uint32_t n_qterms = q_term_ptr[nq];
-    VELES_REQUIRE(n_qterms == 0 || q_terms, "q_terms is NULL");
-    // Bm25Index::search returns nothing for an empty index (bm25.rs:275-278)
-    if (ix->doc_count == 0 || ix->n_postings == 0) {
-        for (uint32_t i = 0; i < nq; ++i) out_counts[i] = 0;
-        for (size_t i = 0; i < (size_t)nq * k; ++i) {
-            out_doc[i] = VELES_INVALID_ID;
-            out_score[i] = std::nanf("");
-        }
-        return VELES_OK;
-    }
-    VELES_TRY(ix->q_ptr_d.ensure(((size_t)nq + 1) * 4));
-    VELES_TRY(ix->q_terms_d.ensure(std::max<size_t>((size_t)n_qterms * 4, 16)));
-    VELES_TRY(ix->out_doc_d.ensure((size_t)nq * k * 4));
-    VELES_TRY(ix->out_score_d.ensure((size_t)nq * k * 4));
-    VELES_TRY(ix->out_cnt_d.ensure((size_t)nq * 4));
-    VELES_CUDA(cudaMemcpyAsync(ix->q_ptr_d.p, q_term_ptr, ((size_t)nq + 1) * 4, cudaMemcpyHostToDevice, st));
-    if (n_qterms) VELES_CUDA(cudaMemcpyAsync(ix->q_terms_d.p, q_terms, (size_t)n_qterms * 4, cudaMemcpyHostToDevice, st));
+// The query kernels over a batch whose term lists are already in ix->q_ptr_d / ix->q_terms_d; results go to
+// ix->out_{doc,score,cnt}_d.  Only enqueues on `st`; the caller holds ix->mu.  max_terms = longest query of the batch.
+static int32_t bm25_enqueue(const veles_bm25* ix, uint32_t nq, uint32_t k, uint32_t max_terms, cudaStream_t st) {
+    NvtxRange nvtx_range("veles::bm25 query kernels (Bm25Index::search)");
     Bm25View v;
     v.post_doc = ix->post_doc.as<uint32_t>();
     v.post_tf = ix->post_tf.as<uint32_t>();
@@ -1640,8 +1629,6 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
     v.k1 = ix->k1;
     v.b = ix->b;
     v.avgdl = ix->avgdl;
-    uint32_t max_terms = 0;
-    for (uint32_t i = 0; i < nq; ++i) max_terms = std::max(max_terms, q_term_ptr[i + 1] - q_term_ptr[i]);
     if (k <= kMultiK && max_terms <= kQueryTerms && std::getenv("VELES_BM25_RANGE_KERNEL") == nullptr) {
         // one CTA per query walking its doc-id ranges
         // default: bm25_sub_kernel (one warp per (query, span of 1024-document sub-ranges), no block barriers) when the
@@ -1752,11 +1739,115 @@ int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_p
             VELES_CUDA(cudaGetLastError());
         }
     }
+    return VELES_OK;
+}
+
+// upload of a batch's term lists + bm25_enqueue; the caller holds ix->mu and has checked the arguments
+static int32_t bm25_stage_and_enqueue(const veles_bm25* ix, const uint32_t* q_term_ptr, const uint32_t* q_terms, uint32_t nq,
+                                      uint32_t k, cudaStream_t st) {
+    const uint32_t n_qterms = q_term_ptr[nq];
+    VELES_TRY(ix->q_ptr_d.ensure(((size_t)nq + 1) * 4));
+    VELES_TRY(ix->q_terms_d.ensure(std::max<size_t>((size_t)n_qterms * 4, 16)));
+    VELES_TRY(ix->out_doc_d.ensure((size_t)nq * k * 4));
+    VELES_TRY(ix->out_score_d.ensure((size_t)nq * k * 4));
+    VELES_TRY(ix->out_cnt_d.ensure((size_t)nq * 4));
+    VELES_CUDA(cudaMemcpyAsync(ix->q_ptr_d.p, q_term_ptr, ((size_t)nq + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (n_qterms) VELES_CUDA(cudaMemcpyAsync(ix->q_terms_d.p, q_terms, (size_t)n_qterms * 4, cudaMemcpyHostToDevice, st));
+    uint32_t max_terms = 0;
+    for (uint32_t i = 0; i < nq; ++i) max_terms = std::max(max_terms, q_term_ptr[i + 1] - q_term_ptr[i]);
+    return bm25_enqueue(ix, nq, k, max_terms, st);
+}
+
+int32_t veles_bm25_search_batch(const veles_bm25_t* ix, const uint32_t* q_term_ptr, const uint32_t* q_terms, uint32_t nq,
+                                uint32_t k, uint32_t* out_doc, float* out_score, uint32_t* out_counts, void* stream) {
+    VELES_REQUIRE(ix != nullptr, "index is NULL");
+    VELES_REQUIRE(nq == 0 || (q_term_ptr && out_doc && out_score && out_counts), "NULL buffer");
+    VELES_REQUIRE(k >= 1 && k <= 4096, "k must be in 1..4096, got %u", k);
+    if (nq == 0) return VELES_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> g(ix->mu);
+    const uint32_t n_qterms = q_term_ptr[nq];
+    VELES_REQUIRE(n_qterms == 0 || q_terms, "q_terms is NULL");
+    // Bm25Index::search returns nothing for an empty index (bm25.rs:275-278)
+    if (ix->doc_count == 0 || ix->n_postings == 0) {
+        for (uint32_t i = 0; i < nq; ++i) out_counts[i] = 0;
+        for (size_t i = 0; i < (size_t)nq * k; ++i) {
+            out_doc[i] = VELES_INVALID_ID;
+            out_score[i] = std::nanf("");
+        }
+        return VELES_OK;
+    }
+    VELES_TRY(bm25_stage_and_enqueue(ix, q_term_ptr, q_terms, nq, k, st));
     VELES_CUDA(cudaMemcpyAsync(out_doc, ix->out_doc_d.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
     VELES_CUDA(cudaMemcpyAsync(out_score, ix->out_score_d.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
     VELES_CUDA(cudaMemcpyAsync(out_counts, ix->out_cnt_d.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     VELES_CUDA(cudaStreamSynchronize(st));
     return VELES_OK;
+}
+
+
+// Collection::hybrid_search (collection/search/text.rs:113-203) for a batch, in one call: the vector leg
+// (self.index.search(query, 2k): NativeHnsw::search with the caller's ef) on `stream`, the text leg
+// (self.text_index.search(text, 2k)) concurrently on a stream of the BM25 snapshot -- the traversal is HBM-bound on
+// one warp per query, the posting scan issue-bound, so the text leg runs in the vector leg's shadow -- then the RRF
+// (text.rs:133-180) over the two device-resident lists and ONE copy back.  Same kernels as veles_search_batch,
+// veles_bm25_search_batch and veles_rrf_hybrid called one after the other, hence the same bits, without their three
+// host round trips.  Ids: node ids of `idx` are the document ids of `bm` (the storage fetch, text.rs:183-203, stays
+// with the host).
+int32_t veles_hybrid_search_batch(const veles_index_t* idx, const veles_bm25_t* bm, const float* queries, const uint32_t* q_term_ptr,
+                                  const uint32_t* q_terms, uint32_t nq, uint32_t k, uint32_t ef, float vector_weight,
+                                  uint32_t* out_ids, float* out_score, uint32_t* out_counts, void* stream) {
+    VELES_REQUIRE(idx != nullptr && bm != nullptr, "index is NULL");
+    VELES_REQUIRE(nq == 0 || (queries && q_term_ptr && out_ids && out_score && out_counts), "NULL buffer");
+    VELES_REQUIRE(k >= 1 && k <= 2048, "k must be in 1..2048 (both legs fetch 2k), got %u", k);
+    if (nq == 0) return VELES_OK;
+    VELES_REQUIRE(q_term_ptr[nq] == 0 || q_terms, "q_terms is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t in_k = 2 * k;  // text.rs:137-140
+    std::lock_guard<std::mutex> g(bm->mu);
+    if (!bm->side) {
+        VELES_CUDA(cudaStreamCreateWithFlags(&bm->side, cudaStreamNonBlocking));
+        VELES_CUDA(cudaEventCreateWithFlags(&bm->side_done, cudaEventDisableTiming));
+    }
+    SearchCtx* ctx = nullptr;
+    {
+        std::lock_guard<std::mutex> gi(idx->mu);
+        VELES_TRY(acquire_ctx(idx, st, true, &ctx));
+    }
+    auto body = [&]() -> int32_t {
+        // vector leg first: its grid (one CTA per query, every query resident) takes the SMs, the text leg fills in
+        const size_t qb = (size_t)nq * idx->dim * 4, lb = (size_t)nq * in_k * 4, ob = (size_t)nq * k * 4;
+        VELES_TRY(ctx->q_d.ensure(qb));
+        VELES_TRY(ctx->ids_d.ensure(lb));
+        VELES_TRY(ctx->val_d.ensure(lb));
+        VELES_TRY(ctx->cnt_d.ensure((size_t)nq * 4));
+        VELES_TRY(bm->hy_ids_d.ensure(ob));
+        VELES_TRY(bm->hy_score_d.ensure(ob));
+        VELES_TRY(bm->hy_cnt_d.ensure((size_t)nq * 4));
+        VELES_CUDA(cudaMemcpyAsync(ctx->q_d.p, queries, qb, cudaMemcpyHostToDevice, st));
+        VELES_TRY(launch_search(idx, idx->view(), ctx, ctx->q_d.as<float>(), nq, in_k, ef, ctx->ids_d.as<uint32_t>(),
+                                ctx->val_d.as<float>(), ctx->cnt_d.as<uint32_t>(), nullptr, st));
+        // text leg; Bm25Index::search returns nothing for an empty index (bm25.rs:275-278)
+        VELES_TRY(bm->out_doc_d.ensure(lb));
+        VELES_TRY(bm->out_cnt_d.ensure((size_t)nq * 4));
+        if (bm->doc_count == 0 || bm->n_postings == 0)
+            VELES_CUDA(cudaMemsetAsync(bm->out_cnt_d.p, 0, (size_t)nq * 4, bm->side));
+        else
+            VELES_TRY(bm25_stage_and_enqueue(bm, q_term_ptr, q_terms, nq, in_k, bm->side));
+        VELES_CUDA(cudaEventRecord(bm->side_done, bm->side));
+        VELES_CUDA(cudaStreamWaitEvent(st, bm->side_done, 0));
+        VELES_TRY(rrf_hybrid_enqueue_d(ctx->ids_d.as<uint32_t>(), ctx->cnt_d.as<uint32_t>(), bm->out_doc_d.as<uint32_t>(),
+                                       bm->out_cnt_d.as<uint32_t>(), nq, in_k, vector_weight, k, bm->hy_ids_d.as<uint32_t>(),
+                                       bm->hy_score_d.as<float>(), bm->hy_cnt_d.as<uint32_t>(), st));
+        VELES_CUDA(cudaMemcpyAsync(out_ids, bm->hy_ids_d.p, ob, cudaMemcpyDeviceToHost, st));
+        VELES_CUDA(cudaMemcpyAsync(out_score, bm->hy_score_d.p, ob, cudaMemcpyDeviceToHost, st));
+        VELES_CUDA(cudaMemcpyAsync(out_counts, bm->hy_cnt_d.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+        return check_search_error_flag(ctx, st);  // synchronises `st` (and with it the joined text leg)
+    };
+    const int32_t rc = body();
+    if (rc != VELES_OK) cudaStreamSynchronize(bm->side);  // nothing of this call may still run when the lock is dropped
+    release_ctx(idx, ctx);
+    return rc;
 }
 
 }  // extern "C"

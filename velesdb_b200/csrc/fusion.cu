@@ -6,7 +6,7 @@
 #include <algorithm>
 #include <cmath>
 
-#include "common.cuh"
+#include "index.hpp"
 
 namespace veles {
 
@@ -232,6 +232,25 @@ __global__ void __launch_bounds__(256) fuse_kernel(int strategy, const uint32_t*
 
 using namespace veles;
 
+namespace veles {
+// rrf_hybrid_kernel over lists that already live on the device (both legs of veles_hybrid_search_batch leave theirs
+// there); only enqueues.  `vector_weight` is clamped as text.rs:133 does.
+int32_t rrf_hybrid_enqueue_d(const uint32_t* vec_ids_d, const uint32_t* vec_cnt_d, const uint32_t* txt_ids_d,
+                             const uint32_t* txt_cnt_d, uint32_t nq, uint32_t in_k, float vector_weight, uint32_t k,
+                             uint32_t* out_ids_d, float* out_score_d, uint32_t* out_counts_d, cudaStream_t st) {
+    float w = vector_weight;  // f32::clamp(0.0, 1.0), text.rs:133
+    if (w < 0.0f) w = 0.0f;
+    if (w > 1.0f) w = 1.0f;
+    const size_t smem = (size_t)4 * in_k * 4 + (size_t)k * 8;
+    VELES_CUDA(cudaFuncSetAttribute(rrf_hybrid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rrf_hybrid_kernel<<<nq, 32, smem, st>>>(vec_ids_d, vec_cnt_d, txt_ids_d, txt_cnt_d, in_k, w, k, out_ids_d, out_score_d,
+                                            out_counts_d);
+    count_launch();
+    VELES_CUDA(cudaGetLastError());
+    return VELES_OK;
+}
+}  // namespace veles
+
 extern "C" {
 
 int32_t veles_rrf_hybrid(const uint32_t* vec_ids, const uint32_t* vec_cnt, const uint32_t* txt_ids, const uint32_t* txt_cnt,
@@ -242,9 +261,6 @@ int32_t veles_rrf_hybrid(const uint32_t* vec_ids, const uint32_t* vec_cnt, const
     VELES_REQUIRE(in_k >= 1 && in_k <= 4096, "in_k must be in 1..4096, got %u", in_k);
     if (nq == 0) return VELES_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    float w = vector_weight;  // f32::clamp(0.0, 1.0), text.rs:133
-    if (w < 0.0f) w = 0.0f;
-    if (w > 1.0f) w = 1.0f;
     DevBuf dv, dvc, dt, dtc, oi, os, oc;
     const size_t lb = (size_t)nq * in_k * 4, ob = (size_t)nq * k * 4;
     VELES_TRY(dv.alloc(lb));
@@ -258,12 +274,8 @@ int32_t veles_rrf_hybrid(const uint32_t* vec_ids, const uint32_t* vec_cnt, const
     VELES_CUDA(cudaMemcpyAsync(dt.p, txt_ids, lb, cudaMemcpyHostToDevice, st));
     VELES_CUDA(cudaMemcpyAsync(dvc.p, vec_cnt, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
     VELES_CUDA(cudaMemcpyAsync(dtc.p, txt_cnt, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
-    const size_t smem = (size_t)4 * in_k * 4 + (size_t)k * 8;
-    VELES_CUDA(cudaFuncSetAttribute(rrf_hybrid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rrf_hybrid_kernel<<<nq, 32, smem, st>>>(dv.as<uint32_t>(), dvc.as<uint32_t>(), dt.as<uint32_t>(), dtc.as<uint32_t>(), in_k, w,
-                                            k, oi.as<uint32_t>(), os.as<float>(), oc.as<uint32_t>());
-    count_launch();
-    VELES_CUDA(cudaGetLastError());
+    VELES_TRY(rrf_hybrid_enqueue_d(dv.as<uint32_t>(), dvc.as<uint32_t>(), dt.as<uint32_t>(), dtc.as<uint32_t>(), nq, in_k,
+                                   vector_weight, k, oi.as<uint32_t>(), os.as<float>(), oc.as<uint32_t>(), st));
     VELES_CUDA(cudaMemcpyAsync(out_ids, oi.p, ob, cudaMemcpyDeviceToHost, st));
     VELES_CUDA(cudaMemcpyAsync(out_score, os.p, ob, cudaMemcpyDeviceToHost, st));
     VELES_CUDA(cudaMemcpyAsync(out_counts, oc.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));

@@ -147,4 +147,8 @@ int32_t launch_search(const veles_index* ix, const IndexView& view, SearchCtx* c
                       const uint32_t* extra_entries_d = nullptr, const PeerOut* peers = nullptr);
 // synchronises `st`, reads and clears the context's overflow flag
 int32_t check_search_error_flag(SearchCtx* ctx, cudaStream_t st);
+// hybrid RRF over device-resident lists (fusion.cu); only enqueues
+int32_t rrf_hybrid_enqueue_d(const uint32_t* vec_ids_d, const uint32_t* vec_cnt_d, const uint32_t* txt_ids_d,
+                             const uint32_t* txt_cnt_d, uint32_t nq, uint32_t in_k, float vector_weight, uint32_t k,
+                             uint32_t* out_ids_d, float* out_score_d, uint32_t* out_counts_d, cudaStream_t st);
 }  // namespace veles

@@ -87,6 +87,30 @@ def rrf_hybrid_batch(vec_ids, vec_cnt, txt_ids, txt_cnt, k, vector_weight=0.5):
     return oi, os_, oc
 
 
+def hybrid_search_batch(snapshot, text_snapshot, queries, q_ptr, q_terms, k, ef, vector_weight=None, stream=None):
+    """``Collection::hybrid_search`` (text.rs:113-203, minus the storage fetch) for a batch in ONE device call
+    (``veles_hybrid_search_batch``): vector top-2k on ``snapshot`` (a ``DeviceSnapshot``; ``ef`` as the caller's
+    quality dictates, the reference uses ``ef_search(Balanced, 2k)``) and BM25 top-2k on ``text_snapshot`` (a
+    ``Bm25Snapshot``) run concurrently, the RRF reads both lists on the device, one copy back.  ``q_ptr`` /
+    ``q_terms``: per-query term-id lists as ``Bm25Snapshot.search_batch``.  Node ids are document ids.
+    Returns ``(ids [nq, k] u32, scores [nq, k] f32, counts [nq] u32)``; identical to the three separate calls."""
+    nv.init()
+    w = 0.5 if vector_weight is None else vector_weight
+    from .index import _as_f32_2d
+    queries = _as_f32_2d(queries, snapshot.dim, "Query")                  # DimensionMismatch, text.rs:124-130
+    q_ptr = np.ascontiguousarray(q_ptr, np.uint32)
+    q_terms = np.ascontiguousarray(q_terms, np.uint32)
+    nq = queries.shape[0]
+    assert q_ptr.size == nq + 1
+    qt = q_terms if q_terms.size else np.zeros(1, np.uint32)
+    oi = np.empty((nq, k), np.uint32)
+    os_ = np.empty((nq, k), np.float32)
+    oc = np.zeros(nq, np.uint32)
+    nv.check(nv.lib().veles_hybrid_search_batch(snapshot.h, text_snapshot.h, nv.ptr(queries), nv.ptr(q_ptr), nv.ptr(qt), nq, k,
+                                                ef, float(w), nv.ptr(oi), nv.ptr(os_), nv.ptr(oc), stream))
+    return oi, os_, oc
+
+
 def hybrid_search(index, text_index, vector_query, text_query, k, vector_weight=None):
     """``Collection::hybrid_search`` (text.rs:113-203) minus the storage fetch: vector top-2k (Balanced) and
     BM25 top-2k, fused by RRF on the device.  Ids are the external ids of ``index`` (must fit u32)."""
