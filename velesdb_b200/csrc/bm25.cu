@@ -52,13 +52,14 @@ struct veles_bm25 {
     mutable veles::DevBuf q_ptr_d, q_terms_d, partial_d, out_doc_d, out_score_d, out_cnt_d;
     // veles_hybrid_search_batch: the text leg runs on `side` next to the vector leg on the caller's stream
     mutable cudaStream_t side = nullptr;
-    mutable cudaEvent_t side_done = nullptr;
+    mutable cudaEvent_t side_done = nullptr, side_fork = nullptr;
     mutable veles::DevBuf hy_ids_d, hy_score_d, hy_cnt_d;
     veles_bm25() = default;
     veles_bm25(const veles_bm25&) = delete;
     veles_bm25& operator=(const veles_bm25&) = delete;
     ~veles_bm25() {
         if (side_done) cudaEventDestroy(side_done);
+        if (side_fork) cudaEventDestroy(side_fork);
         if (side) cudaStreamDestroy(side);
     }
 };
@@ -1808,6 +1809,7 @@ int32_t veles_hybrid_search_batch(const veles_index_t* idx, const veles_bm25_t* 
     if (!bm->side) {
         VELES_CUDA(cudaStreamCreateWithFlags(&bm->side, cudaStreamNonBlocking));
         VELES_CUDA(cudaEventCreateWithFlags(&bm->side_done, cudaEventDisableTiming));
+        VELES_CUDA(cudaEventCreateWithFlags(&bm->side_fork, cudaEventDisableTiming));
     }
     SearchCtx* ctx = nullptr;
     {
@@ -1825,6 +1827,10 @@ int32_t veles_hybrid_search_batch(const veles_index_t* idx, const veles_bm25_t* 
         VELES_TRY(bm->hy_score_d.ensure(ob));
         VELES_TRY(bm->hy_cnt_d.ensure((size_t)nq * 4));
         VELES_CUDA(cudaMemcpyAsync(ctx->q_d.p, queries, qb, cudaMemcpyHostToDevice, st));
+        // the text leg may start once the queries are on the device, i.e. together with the traversal behind the copy
+        // (not during the copy: its CTAs would take the SMs first and the traversal would start thin)
+        VELES_CUDA(cudaEventRecord(bm->side_fork, st));
+        VELES_CUDA(cudaStreamWaitEvent(bm->side, bm->side_fork, 0));
         VELES_TRY(launch_search(idx, idx->view(), ctx, ctx->q_d.as<float>(), nq, in_k, ef, ctx->ids_d.as<uint32_t>(),
                                 ctx->val_d.as<float>(), ctx->cnt_d.as<uint32_t>(), nullptr, st));
         // text leg; Bm25Index::search returns nothing for an empty index (bm25.rs:275-278)
