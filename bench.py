@@ -72,6 +72,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strong", action="store_true", help="N > 1: split ONE batch of nq queries over the GPUs (strong scaling)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N > 1: the library's peer-store gather, or torch NCCL")
+    ap.add_argument("--pipe-depth", type=int, default=2, help="e2e: batches in flight through veles_search_submit / _wait")
     ap.add_argument("--hybrid-three-calls", action="store_true",
                     help="c5: time search, BM25 and RRF as three host-API calls (round 2's first form) instead of veles_hybrid_search_batch")
     ap.add_argument("--cache", default=os.environ.get("VELES_BENCH_CACHE", "/tmp/veles_bench_cache"))
@@ -639,7 +640,8 @@ def main():
     e2e = None
     if kind == "hnsw" and not sq8:
         bufs = []
-        for _ in range(2):
+        depth = max(1, min(a.pipe_depth, 8))
+        for _ in range(depth):
             bufs.append((torch.empty((nq, k), dtype=torch.int32).pin_memory(), torch.empty((nq, k), dtype=torch.float32).pin_memory(),
                          torch.empty(nq, dtype=torch.int32).pin_memory()))
         qn = q_h.numpy()
@@ -651,8 +653,8 @@ def main():
         def run_pipelined(steps):
             tickets = []
             for i in range(steps):
-                o = bufs[i % 2]
-                if len(tickets) == 2:
+                o = bufs[i % depth]
+                if len(tickets) == depth:
                     snap.search_wait(tickets.pop(0))
                 tickets.append(snap.search_submit(q_h, k, ef, o[0], o[1], o[2]))
             for t in tickets:
@@ -722,7 +724,7 @@ def main():
     if e2e:
         line["e2e"] = {"value": total_q / (e2e[0] / 1e3), "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
                        "d2h_bytes_per_step": nq * k * 8 + nq * 4 + 8, "ms_per_step": e2e[0] / a.steps,
-                       "api": "veles_search_submit / veles_search_wait, two batches in flight, pinned host buffers",
+                       "api": f"veles_search_submit / veles_search_wait, {depth} batches in flight, pinned host buffers",
                        "sync_value": total_q / (e2e[1] / 1e3), "sync_api": "veles_search_batch, one call at a time"}
     else:
         # these configs' public call is the host API already timed above (hybrid) or the device-pointer call

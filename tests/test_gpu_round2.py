@@ -200,7 +200,9 @@ def test_tensor_core_relaxed_brute_force(metric, store, n, dim, nq, k):
 
 
 @pytest.mark.parametrize("metric,dim,nq,k", [(vo.COSINE, 64, 40, 10), (vo.EUCLIDEAN, 96, 9, 5), (vo.DOT, 128, 33, 20),
-                                            (vo.HAMMING, 64, 12, 10), (vo.COSINE, 64, 3, 10), (vo.EUCLIDEAN, 64, 8, 100)])
+                                            (vo.HAMMING, 64, 12, 10), (vo.COSINE, 64, 3, 10), (vo.EUCLIDEAN, 64, 8, 100),
+                                            # rows beyond 64 MB, dim % 128 == 0: the tile kernel's dynamic chunk-major items
+                                            (vo.COSINE, 256, 70, 10), (vo.EUCLIDEAN, 256, 33, 5)])
 def test_fused_brute_force_equals_the_matrix_path_and_the_oracle(metric, dim, nq, k, monkeypatch):
     """The exact scan without the [nq, n] score matrix: <= 8 queries select inside the scan kernel, larger batches go
     sample -> bound -> filtered scan -> select.  Both must return exactly what the matrix path and the oracle do."""
@@ -218,8 +220,14 @@ def test_fused_brute_force_equals_the_matrix_path_and_the_oracle(metric, dim, nq
     mi, ms = snap.bruteforce_batch(q, k)
     monkeypatch.delenv("VELES_BF_NO_FUSE")
     assert np.array_equal(fi, mi) and bits_equal(fs, ms)
-    oi, os_ = vo.bruteforce_batch(metric, x, q[:6], k, threads=8)
-    assert np.array_equal(fi[:6], oi.astype(np.uint32)) and bits_equal(fs[:6], os_)
+    if dim % 128 == 0:
+        monkeypatch.setenv("VELES_BF_STATIC_TILES", "1")   # the static (tile, query group) mapping of the same kernel
+        si, ss = snap.bruteforce_batch(q, k)
+        monkeypatch.delenv("VELES_BF_STATIC_TILES")
+        assert np.array_equal(fi, si) and bits_equal(fs, ss)
+    pick = np.unique(np.linspace(0, nq - 1, 6).astype(int))  # queries of every 32-query group
+    oi, os_ = vo.bruteforce_batch(metric, x, q[pick], k, threads=8)
+    assert np.array_equal(fi[pick], oi.astype(np.uint32)) and bits_equal(fs[pick], os_)
 
 
 def test_insert_after_load_and_sparse_bm25_ids(tmp_path):

@@ -299,35 +299,49 @@ __global__ void __launch_bounds__(kWarps * 32, 2) bf_tile8_kernel(IndexView ix, 
 // (bf_tile8_kernel waits on L2 for its rows: 19 TFLOP/s), and a row element is fetched from L2 once per 32
 // queries instead of once per 8.  Arithmetic, summation order and results are unchanged.
 constexpr int kTsQ = 32, kTsR = 16, kTsK = 128;
+// Work mapping.  Static (`work` == nullptr; collections that fit the L2): grid (x, query group), CTA x takes tiles x,
+// x + gridDim.x, ...  Dynamic (large collections): a 1-D grid pulls (chunk of `chunk_tiles` row tiles, query group)
+// items from a global counter, chunk-major, so at any moment all CTAs work within a window of a few chunks and every
+// query group's pass over a chunk finds the rows the first one brought into the L2: the collection leaves DRAM once
+// per batch (ncu, 1M x 768 x 1024 queries: 8.3 GB read with the static mapping, whose query groups drift apart,
+// against 3.1 GB of rows).  A CTA restages its 32 queries when its next item belongs to another group (96 KB from the
+// L2 per 3 MB of rows).
 template <typename TB>
 __global__ void __launch_bounds__(kWarps * 32, 2) bf_tile_smem_kernel(IndexView ix, const float* __restrict__ queries,
-                                                                   uint32_t nq, ScoreSink out, bool as_value) {
+                                                                   uint32_t nq, ScoreSink out, bool as_value,
+                                                                   uint32_t* __restrict__ work, uint32_t chunk_tiles,
+                                                                   uint32_t ngroups) {
     extern __shared__ __align__(16) uint8_t ts_smem[];
+    __shared__ uint32_t s_item;
     const uint32_t dim = ix.dim;
     float* qs_all = reinterpret_cast<float*>(ts_smem);               // kTsQ x dim
     float* qnorm_all = qs_all + (size_t)kTsQ * dim;                  // kTsQ
     TB* slab = reinterpret_cast<TB*>(qnorm_all + kTsQ);              // 2 x kTsR x kTsK
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t cta_q0 = blockIdx.y * kTsQ;
-    const uint32_t cta_nq = min((uint32_t)kTsQ, nq - cta_q0);
-    for (uint32_t i = threadIdx.x; i < kTsQ * dim; i += blockDim.x) {
-        const uint32_t t = i / dim;
-        qs_all[i] = t < cta_nq ? queries[(size_t)(cta_q0 + t) * dim + (i - t * dim)] : 0.0f;
-    }
-    __syncthreads();
-    if (ix.metric == VELES_COSINE) {
-        for (uint32_t t = warp; t < kTsQ; t += kWarps) {
-            const float* q = qs_all + (size_t)t * dim;
-            const float s = warp_tree_reduce<0>(q, q, dim, lane);
-            if (lane == 0) qnorm_all[t] = __fsqrt_rn(s);
-        }
-    }
-    __syncthreads();
     const uint32_t qg = warp & 3, rg = warp >> 2;
     const float* qs = qs_all + (size_t)qg * kQT * dim;
     const float* qnorm = qnorm_all + qg * kQT;
-    const uint32_t qbase = cta_q0 + qg * kQT;
-    const uint32_t nqt = qbase < nq ? min((uint32_t)kQT, nq - qbase) : 0u;
+    uint32_t qbase = 0, nqt = 0;
+    // the CTA's 32 queries (and their norms) into shared memory; every thread calls it
+    auto stage = [&](uint32_t group) {
+        const uint32_t cta_q0 = group * kTsQ;
+        const uint32_t cta_nq = min((uint32_t)kTsQ, nq - cta_q0);
+        for (uint32_t i = threadIdx.x; i < kTsQ * dim; i += blockDim.x) {
+            const uint32_t t = i / dim;
+            qs_all[i] = t < cta_nq ? queries[(size_t)(cta_q0 + t) * dim + (i - t * dim)] : 0.0f;
+        }
+        __syncthreads();
+        if (ix.metric == VELES_COSINE) {
+            for (uint32_t t = warp; t < kTsQ; t += kWarps) {
+                const float* q = qs_all + (size_t)t * dim;
+                const float s = warp_tree_reduce<0>(q, q, dim, lane);
+                if (lane == 0) qnorm_all[t] = __fsqrt_rn(s);
+            }
+        }
+        __syncthreads();
+        qbase = cta_q0 + qg * kQT;
+        nqt = qbase < nq ? min((uint32_t)kQT, nq - qbase) : 0u;
+    };
     const bool l2 = ix.metric == VELES_EUCLIDEAN;
     const uint64_t n = ix.n;
     const uint64_t tiles = (n + kTsR - 1) / kTsR;
@@ -336,7 +350,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) bf_tile_smem_kernel(IndexView 
     constexpr uint32_t kChunks = kTsR * kChunksPerRow;               // per slab: 512 (f32) or 256 (f16)
     const uint32_t a = (lane & 1) | (lane & 2) | (lane & 4) | ((lane & 16) >> 1) | ((lane & 8) << 1);
     const uint32_t my_r = a >> 3, my_t = a & 7;
-    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    auto do_tile = [&](uint64_t tile) {
         const uint64_t r0 = tile * kTsR;
         // a thread copies the same (row, 16-byte column) chunks of every slab: addresses are set up once per tile
         constexpr uint32_t kPerThread = (kChunks + kWarps * 32 - 1) / (kWarps * 32);  // 2 (f32) or 1 (f16)
@@ -410,6 +424,28 @@ __global__ void __launch_bounds__(kWarps * 32, 2) bf_tile_smem_kernel(IndexView 
                 out.emit(qbase + my_t, row, v);
             }
         }
+    };
+    if (work == nullptr) {
+        stage(blockIdx.y);
+        for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) do_tile(tile);
+        return;
+    }
+    const uint64_t nchunks = (tiles + chunk_tiles - 1) / chunk_tiles;
+    const uint64_t items = nchunks * ngroups;
+    uint32_t staged = 0xffffffffu;
+    for (;;) {
+        __syncthreads();  // the previous item's epilogue (norms in shared memory) and its read of s_item are done
+        if (threadIdx.x == 0) s_item = atomicAdd(work, 1u);
+        __syncthreads();
+        const uint32_t w = s_item;
+        if (w >= items) break;
+        const uint32_t chunk = w / ngroups, group = w - chunk * ngroups;
+        if (group != staged) {
+            stage(group);
+            staged = group;
+        }
+        const uint64_t t0 = (uint64_t)chunk * chunk_tiles, t1 = min(tiles, t0 + chunk_tiles);
+        for (uint64_t tile = t0; tile < t1; ++tile) do_tile(tile);
     }
 }
 
@@ -1277,12 +1313,29 @@ static int32_t launch_scores(const veles_index* ixh, const IndexView& v, const f
                 const uint32_t qgroups = (nq + kTsQ - 1) / kTsQ;
                 const uint64_t tiles = (ix->n + kTsR - 1) / kTsR;
                 const uint64_t slots = (uint64_t)sms * std::max(per_sm, 1);
+                // rows that do not fit the L2 and several query groups: dynamic chunk-major items (see the kernel), 64
+                // tiles (1024 rows) per item, or fewer when that would leave less than ~8 items per CTA
+                const uint64_t touched = v.n * (uint64_t)ix->dim * tb;
+                if (touched > ((uint64_t)64 << 20) && qgroups > 1 && qgroups <= 32768 && tiles * qgroups < 0xffffff00ull &&
+                    std::getenv("VELES_BF_STATIC_TILES") == nullptr) {
+                    uint64_t chunk_tiles = 64;
+                    while (chunk_tiles > 8 && (tiles / chunk_tiles) * qgroups < 8 * slots) chunk_tiles >>= 1;
+                    if (!ixh->bf_work.p) VELES_TRY(ixh->bf_work.alloc(64));
+                    VELES_CUDA(cudaMemsetAsync(ixh->bf_work.p, 0, 4, st));
+                    const uint64_t items = (tiles + chunk_tiles - 1) / chunk_tiles * qgroups;
+                    kt<<<(unsigned)std::min<uint64_t>(slots, items), kWarps * 32, smem_t, st>>>(
+                        v, q_d, nq, sink, as_value, ixh->bf_work.as<uint32_t>(), (uint32_t)chunk_tiles, qgroups);
+                    count_launch();
+                    VELES_CUDA(cudaGetLastError());
+                    return VELES_OK;
+                }
                 for (uint32_t g0 = 0; g0 < qgroups; g0 += 32768) {
                     const uint32_t ng = std::min(32768u, qgroups - g0);
                     const uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>(tiles, std::max<uint64_t>(1, slots / ng)));
                     dim3 grid((unsigned)gx, ng);
                     const uint32_t qoff = g0 * kTsQ;
-                    kt<<<grid, kWarps * 32, smem_t, st>>>(v, q_d + (size_t)qoff * ix->dim, nq - qoff, sink.at(qoff), as_value);
+                    kt<<<grid, kWarps * 32, smem_t, st>>>(v, q_d + (size_t)qoff * ix->dim, nq - qoff, sink.at(qoff), as_value, nullptr, 0u,
+                                                          ng);
                     count_launch();
                 }
                 VELES_CUDA(cudaGetLastError());

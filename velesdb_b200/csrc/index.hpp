@@ -76,7 +76,7 @@ struct veles_index {
     mutable std::mutex mu;
     mutable std::vector<std::unique_ptr<veles::SearchCtx>> ctxs;
     mutable std::vector<cudaStream_t> overflowed;  // streams whose overflow flag was harvested when a context moved on
-    mutable veles::DevBuf q_d, out_ids_d, out_val_d, out_cnt_d, out_stats_d, scores_d, topk_d, bf_aux, bf_done;
+    mutable veles::DevBuf q_d, out_ids_d, out_val_d, out_cnt_d, out_stats_d, scores_d, topk_d, bf_aux, bf_done, bf_work;
 
     veles::IndexView view() const {
         veles::IndexView v;
