@@ -72,7 +72,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strong", action="store_true", help="N > 1: split ONE batch of nq queries over the GPUs (strong scaling)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N > 1: the library's peer-store gather, or torch NCCL")
-    ap.add_argument("--pipe-depth", type=int, default=2, help="e2e: batches in flight through veles_search_submit / _wait")
+    ap.add_argument("--pipe-depth", type=int, default=3, help="e2e: batches in flight through veles_search_submit / _wait")
     ap.add_argument("--hybrid-three-calls", action="store_true",
                     help="c5: time search, BM25 and RRF as three host-API calls (round 2's first form) instead of veles_hybrid_search_batch")
     ap.add_argument("--cache", default=os.environ.get("VELES_BENCH_CACHE", "/tmp/veles_bench_cache"))

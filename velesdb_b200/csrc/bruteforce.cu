@@ -306,13 +306,12 @@ constexpr int kTsQ = 32, kTsR = 16, kTsK = 128;
 // per batch (ncu, 1M x 768 x 1024 queries: 8.3 GB read with the static mapping, whose query groups drift apart,
 // against 3.1 GB of rows).  A CTA restages its 32 queries when its next item belongs to another group (96 KB from the
 // L2 per 3 MB of rows).
-template <typename TB>
+template <typename TB, bool DYN>
 __global__ void __launch_bounds__(kWarps * 32, 2) bf_tile_smem_kernel(IndexView ix, const float* __restrict__ queries,
                                                                    uint32_t nq, ScoreSink out, bool as_value,
                                                                    uint32_t* __restrict__ work, uint32_t chunk_tiles,
                                                                    uint32_t ngroups) {
     extern __shared__ __align__(16) uint8_t ts_smem[];
-    __shared__ uint32_t s_item;
     const uint32_t dim = ix.dim;
     float* qs_all = reinterpret_cast<float*>(ts_smem);               // kTsQ x dim
     float* qnorm_all = qs_all + (size_t)kTsQ * dim;                  // kTsQ
@@ -425,27 +424,28 @@ __global__ void __launch_bounds__(kWarps * 32, 2) bf_tile_smem_kernel(IndexView 
             }
         }
     };
-    if (work == nullptr) {
+    if (!DYN) {
         stage(blockIdx.y);
         for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) do_tile(tile);
-        return;
-    }
-    const uint64_t nchunks = (tiles + chunk_tiles - 1) / chunk_tiles;
-    const uint64_t items = nchunks * ngroups;
-    uint32_t staged = 0xffffffffu;
-    for (;;) {
-        __syncthreads();  // the previous item's epilogue (norms in shared memory) and its read of s_item are done
-        if (threadIdx.x == 0) s_item = atomicAdd(work, 1u);
-        __syncthreads();
-        const uint32_t w = s_item;
-        if (w >= items) break;
-        const uint32_t chunk = w / ngroups, group = w - chunk * ngroups;
-        if (group != staged) {
-            stage(group);
-            staged = group;
+    } else {
+        __shared__ uint32_t s_item;
+        const uint64_t nchunks = (tiles + chunk_tiles - 1) / chunk_tiles;
+        const uint64_t items = nchunks * ngroups;
+        uint32_t staged = 0xffffffffu;
+        for (;;) {
+            __syncthreads();  // the previous item's epilogue (norms in shared memory) and its read of s_item are done
+            if (threadIdx.x == 0) s_item = atomicAdd(work, 1u);
+            __syncthreads();
+            const uint32_t w = s_item;
+            if (w >= items) break;
+            const uint32_t chunk = w / ngroups, group = w - chunk * ngroups;
+            if (group != staged) {
+                stage(group);
+                staged = group;
+            }
+            const uint64_t t0 = (uint64_t)chunk * chunk_tiles, t1 = min(tiles, t0 + chunk_tiles);
+            for (uint64_t tile = t0; tile < t1; ++tile) do_tile(tile);
         }
-        const uint64_t t0 = (uint64_t)chunk * chunk_tiles, t1 = min(tiles, t0 + chunk_tiles);
-        for (uint64_t tile = t0; tile < t1; ++tile) do_tile(tile);
     }
 }
 
@@ -1306,8 +1306,10 @@ static int32_t launch_scores(const veles_index* ixh, const IndexView& v, const f
             VELES_CUDA(cudaGetDevice(&dev_id));
             VELES_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev_id));
             if (smem_t <= (size_t)max_optin) {
-                auto kt = ix->dtype == VELES_F32 ? bf_tile_smem_kernel<float> : bf_tile_smem_kernel<__half>;
+                auto kt = ix->dtype == VELES_F32 ? bf_tile_smem_kernel<float, false> : bf_tile_smem_kernel<__half, false>;
+                auto ktd = ix->dtype == VELES_F32 ? bf_tile_smem_kernel<float, true> : bf_tile_smem_kernel<__half, true>;
                 VELES_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+                VELES_CUDA(cudaFuncSetAttribute(ktd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
                 int per_sm = 1;
                 VELES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kt, kWarps * 32, smem_t));
                 const uint32_t qgroups = (nq + kTsQ - 1) / kTsQ;
@@ -1323,7 +1325,7 @@ static int32_t launch_scores(const veles_index* ixh, const IndexView& v, const f
                     if (!ixh->bf_work.p) VELES_TRY(ixh->bf_work.alloc(64));
                     VELES_CUDA(cudaMemsetAsync(ixh->bf_work.p, 0, 4, st));
                     const uint64_t items = (tiles + chunk_tiles - 1) / chunk_tiles * qgroups;
-                    kt<<<(unsigned)std::min<uint64_t>(slots, items), kWarps * 32, smem_t, st>>>(
+                    ktd<<<(unsigned)std::min<uint64_t>(slots, items), kWarps * 32, smem_t, st>>>(
                         v, q_d, nq, sink, as_value, ixh->bf_work.as<uint32_t>(), (uint32_t)chunk_tiles, qgroups);
                     count_launch();
                     VELES_CUDA(cudaGetLastError());
