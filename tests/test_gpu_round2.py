@@ -179,8 +179,9 @@ def test_index_directory_round_trip_in_the_reference_layout(tmp_path):
 
 
 @pytest.mark.parametrize("metric,store,n,dim,nq,k", [(vo.COSINE, "f32", 20000, 768, 300, 10), (vo.EUCLIDEAN, "f32", 5000, 100, 130, 5),
-                                                    (vo.DOT, "f16", 9000, 64, 64, 20), (vo.COSINE, "f32", 300, 48, 7, 10)])
-def test_tensor_core_relaxed_brute_force(metric, store, n, dim, nq, k):
+                                                    (vo.DOT, "f16", 9000, 64, 64, 20), (vo.COSINE, "f32", 300, 48, 7, 10),
+                                                    (vo.COSINE, "f32", 6000, 64, 40, 40)])
+def test_tensor_core_relaxed_brute_force(metric, store, n, dim, nq, k, monkeypatch):
     """veles_bruteforce_batch_relaxed: candidates from the tcgen05 fp16 GEMM, exact re-rank.  Recall-gated against the
     exact path (fp16 rounding may only move rows near rank k * oversample); every returned score must be the exact
     metric value of its row, bit for bit, and the order must be the exact path's order."""
@@ -197,6 +198,12 @@ def test_tensor_core_relaxed_brute_force(metric, store, n, dim, nq, k):
     assert bits_equal(exact_of, rs)
     sign = -1.0 if metric in (vo.COSINE, vo.DOT) else 1.0
     assert (np.diff(sign * rs.astype(np.float64), axis=1) >= 0).all()
+    # the CTA-per-query bound kernel and the flattened finish kernel against the first versions: same bound, same
+    # candidates, same keys -> identical output
+    monkeypatch.setenv("VELES_TC_OLD_TAIL", "1")
+    oi, os_ = snap.bruteforce_batch_relaxed(q, k, oversample=4)
+    monkeypatch.delenv("VELES_TC_OLD_TAIL")
+    assert np.array_equal(ri, oi) and bits_equal(rs, os_)
 
 
 @pytest.mark.parametrize("metric,dim,nq,k", [(vo.COSINE, 64, 40, 10), (vo.EUCLIDEAN, 96, 9, 5), (vo.DOT, 128, 33, 20),

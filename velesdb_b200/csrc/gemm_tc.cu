@@ -401,6 +401,45 @@ __global__ void tc_threshold_kernel(const float* __restrict__ scores, uint32_t l
     if (lane == 0) thr[q] = len == kp ? ord_unkey(~(uint32_t)(res[kp - 1] >> 32)) : __int_as_float(0xff800000);
 }
 
+// The same bound with a CTA per query (kp <= 32 * R): the eight warps scan interleaved 256-score blocks with eight
+// independent coalesced loads in flight per lane, each keeping a register-resident sorted list (RegTopK); warp 0 merges
+// the lists.  The one-warp kernel above walks its row one dependent 128-byte load at a time: 1.1 ms for 1024 queries x
+// 62 K sampled scores -- as long as the filter GEMM itself.
+template <int R>
+__global__ void __launch_bounds__(256) tc_threshold_cta_kernel(const float* __restrict__ scores, uint32_t ld, uint32_t m, uint32_t kp,
+                                                               float* __restrict__ thr) {
+    __shared__ uint64_t s_keys[8][32 * R];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = blockIdx.x;
+    const float* row = scores + (size_t)q * ld;
+    const float ninf = __int_as_float(0xff800000);
+    RegTopK<R> top;
+    top.init(kp, lane);
+    constexpr uint32_t U = 8;
+    for (uint32_t base = warp * 32 * U; base < m; base += 8 * 32 * U) {
+        float v[U];
+#pragma unroll
+        for (uint32_t u = 0; u < U; ++u) {
+            const uint32_t i = base + u * 32 + lane;
+            v[u] = i < m ? row[i] : ninf;
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < U; ++u) {
+            const uint32_t i = base + u * 32 + lane;
+            top.offer(v[u] > ninf ? (((uint64_t)(~ord_key(v[u])) << 32) | i) : ~0ull);
+        }
+    }
+    top.store(s_keys[warp], 32 * R);
+    __syncthreads();
+    if (warp != 0) return;
+    for (uint32_t w = 1; w < 8; ++w)
+        for (uint32_t j = 0; j < kp; j += 32) {
+            const uint64_t key = j + lane < kp ? s_keys[w][j + lane] : ~0ull;
+            if (__shfl_sync(FULL_MASK, key, 0) >= top.worst) break;  // the list is ascending: nothing further can enter
+            top.offer(key);
+        }
+    if (lane == 0) thr[q] = top.worst != ~0ull ? ord_unkey(~(uint32_t)(top.worst >> 32)) : ninf;
+}
+
 // One CTA per query: exact metric value of every candidate (compute_distance, index/hnsw/index/search.rs:30-38, with the
 // reference's accumulation tree), top-k in DistanceMetric::sort_results order (core/distance.rs:95-103), ties by row id.
 constexpr int kFinWarps = 8;
@@ -448,6 +487,117 @@ __global__ void __launch_bounds__(kFinWarps * 32) relaxed_finish_kernel(IndexVie
       }
     }
     __shared__ uint32_t s_len[kFinWarps];
+    if (lane == 0) s_len[warp] = len;
+    __syncthreads();
+    if (warp != 0) return;
+    for (uint32_t w = 1; w < kFinWarps; ++w) {
+        const uint64_t* other = lists + (size_t)w * k;
+        for (uint32_t j = 0; j < s_len[w]; ++j) {
+            const uint64_t key = other[j];
+            if (len == k && key >= mine[k - 1]) break;
+            const uint32_t pos = lower_bound_warp(mine, len, key, lane);
+            if (len < k) {
+                insert_at(mine, pos, len + 1, key, lane);
+                ++len;
+            } else {
+                insert_at(mine, pos, len, key, lane);
+            }
+            __syncwarp();
+        }
+    }
+    for (uint32_t j = lane; j < k; j += 32) {
+        uint32_t id = VELES_INVALID_ID;
+        float sc = __uint_as_float(0x7fc00000u);
+        if (j < len) {
+            id = (uint32_t)mine[j];
+            const uint32_t kb = (uint32_t)(mine[j] >> 32);
+            sc = ord_unkey(desc ? ~kb : kb);
+        }
+        out_ids[(size_t)q * k + j] = id;
+        out_score[(size_t)q * k + j] = sc;
+    }
+}
+
+// relaxed_finish_kernel with the candidate walk flattened: the per-segment counts are read by all threads at once and
+// prefix-summed (the loop above reads 148 counts one dependent load after the other, per warp), a warp's candidate f is
+// located by a search in that prefix table, the next candidate's row id is fetched and its row prefetched into the L2
+// while the current one is evaluated.  Same arithmetic, same keys, same merge: same results.
+constexpr int kFinMaxSeg = 256;
+__global__ void __launch_bounds__(kFinWarps * 32) relaxed_finish_flat_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq,
+                                                                           const uint64_t* __restrict__ cand,
+                                                                           const uint32_t* __restrict__ cand_cnt, uint32_t cand_cap,
+                                                                           uint32_t n_seg, uint32_t k, uint32_t* __restrict__ out_ids,
+                                                                           float* __restrict__ out_score) {
+    extern __shared__ __align__(16) uint8_t fin_smem[];
+    __shared__ uint32_t s_off[kFinMaxSeg + 1];
+    __shared__ uint32_t s_len[kFinWarps];
+    float* qs = reinterpret_cast<float*>(fin_smem);                                       // dim
+    uint64_t* lists = reinterpret_cast<uint64_t*>(fin_smem + ((ix.dim * 4 + 15) & ~15u));  // kFinWarps x k
+    const uint32_t q = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* qg = queries + (size_t)q * ix.dim;
+    for (uint32_t i = threadIdx.x; i < ix.dim; i += blockDim.x) qs[i] = qg[i];
+    // exclusive prefix sum of the segment counts (n_seg <= 256 = one count per thread)
+    {
+        const uint32_t c = threadIdx.x < n_seg ? min(cand_cnt[(size_t)threadIdx.x * nq + q], cand_cap) : 0u;
+        uint32_t x = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL_MASK, x, o);
+            if ((int)lane >= o) x += y;
+        }
+        if (lane == 31) s_len[warp] = x;
+        __syncthreads();
+        uint32_t before = 0;
+        for (uint32_t w = 0; w < warp; ++w) before += s_len[w];
+        s_off[threadIdx.x + 1] = before + x;
+        if (threadIdx.x == 0) s_off[0] = 0;
+        __syncthreads();
+    }
+    const uint32_t total = s_off[kFinWarps * 32];
+    const bool desc = ix.metric == VELES_COSINE || ix.metric == VELES_DOT || ix.metric == VELES_JACCARD;
+    float na = 0.0f;
+    if (ix.metric == VELES_COSINE) na = __fsqrt_rn(warp_tree_reduce<0>(qs, qs, ix.dim, lane));
+    uint64_t* mine = lists + (size_t)warp * k;
+    uint32_t len = 0;
+    // row id of flattened candidate f: the segment is the last one whose offset is <= f
+    auto row_of = [&](uint32_t f) -> uint32_t {
+        uint32_t lo = 0, hi = kFinWarps * 32;  // s_off[lo] <= f < s_off[hi]
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_off[mid] <= f)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        return (uint32_t)cand[((size_t)lo * nq + q) * cand_cap + (f - s_off[lo])];
+    };
+    uint32_t row = warp < total ? row_of(warp) : 0u;
+    for (uint32_t f = warp; f < total; f += kFinWarps) {
+        const uint32_t fn = f + kFinWarps;
+        uint32_t next_row = 0;
+        if (fn < total) {
+            next_row = row_of(fn);
+            const uint8_t* np_ = ix.vecs + (size_t)next_row * ix.row_bytes;
+            if (lane * 128u < ix.row_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + lane * 128u));
+        }
+        const uint8_t* rp = ix.vecs + (size_t)row * ix.row_bytes;
+        const float nb = ix.metric == VELES_COSINE ? *reinterpret_cast<const float*>(rp + ix.norm_off) : 0.0f;
+        const float v = ix.dtype == VELES_F32 ? warp_metric(ix.metric, true, qs, reinterpret_cast<const float*>(rp), ix.dim, na, nb, lane)
+                                              : warp_metric(ix.metric, true, qs, reinterpret_cast<const __half*>(rp), ix.dim, na, nb, lane);
+        const uint32_t ok = ord_key(v);
+        const uint64_t key = ((uint64_t)(desc ? ~ok : ok) << 32) | row;
+        if (len < k || key < mine[k - 1]) {
+            const uint32_t pos = lower_bound_warp(mine, len, key, lane);
+            if (len < k) {
+                insert_at(mine, pos, len + 1, key, lane);
+                ++len;
+            } else {
+                insert_at(mine, pos, len, key, lane);
+            }
+        }
+        __syncwarp();
+        row = next_row;
+    }
+    __syncthreads();  // s_len is reused below: every warp is past the prefix sum (trivially) and done with its list
     if (lane == 0) s_len[warp] = len;
     __syncthreads();
     if (warp != 0) return;
@@ -624,9 +774,18 @@ int32_t bruteforce_relaxed_d(const veles_index* ix, const float* q_d, uint32_t n
         p.ld_out = s_rows;
         if (gemm_ms) VELES_CUDA(cudaEventRecord(e0, st));
         VELES_TRY(launch_gemm(ta, tb, p, bn, st));
-        const uint32_t tw = kp <= 256 ? 8 : (kp <= 1024 ? 2 : 1);
-        tc_threshold_kernel<<<(nn + tw - 1) / tw, tw * 32, (size_t)tw * kp * 8, st>>>(sample.as<float>(), s_rows, s_rows, nn, kp,
-                                                                                  thr.as<float>());
+        // VELES_TC_OLD_TAIL=1: round 2's first threshold / finish kernels (one warp per query; serial segment walk), for A/B
+        const bool old_tail = std::getenv("VELES_TC_OLD_TAIL") != nullptr;
+        if (kp <= 128 && !old_tail) {
+            if (kp <= 64)
+                tc_threshold_cta_kernel<2><<<nn, 256, 0, st>>>(sample.as<float>(), s_rows, s_rows, kp, thr.as<float>());
+            else
+                tc_threshold_cta_kernel<4><<<nn, 256, 0, st>>>(sample.as<float>(), s_rows, s_rows, kp, thr.as<float>());
+        } else {
+            const uint32_t tw = kp <= 256 ? 8 : (kp <= 1024 ? 2 : 1);
+            tc_threshold_kernel<<<(nn + tw - 1) / tw, tw * 32, (size_t)tw * kp * 8, st>>>(sample.as<float>(), s_rows, s_rows, nn, kp,
+                                                                                      thr.as<float>());
+        }
         count_launch();
         VELES_CUDA(cudaGetLastError());
         // 3. filter pass over every tile
@@ -644,9 +803,10 @@ int32_t bruteforce_relaxed_d(const veles_index* ix, const float* q_d, uint32_t n
         }
         // 4. exact re-rank of the candidates, top-k
         const size_t fsm = ((ix->dim * 4 + 15) & ~15u) + (size_t)kFinWarps * k * 8;
-        VELES_CUDA(cudaFuncSetAttribute(relaxed_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-        relaxed_finish_kernel<<<nn, kFinWarps * 32, fsm, st>>>(v, q_d + (size_t)q0 * ix->dim, nn, cand.as<uint64_t>(), cnt.as<uint32_t>(),
-                                                            cand_cap, (uint32_t)sms, k, ids_d + (size_t)q0 * k, score_d + (size_t)q0 * k);
+        auto fin = (sms <= kFinMaxSeg && !old_tail) ? relaxed_finish_flat_kernel : relaxed_finish_kernel;
+        VELES_CUDA(cudaFuncSetAttribute(fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+        fin<<<nn, kFinWarps * 32, fsm, st>>>(v, q_d + (size_t)q0 * ix->dim, nn, cand.as<uint64_t>(), cnt.as<uint32_t>(), cand_cap,
+                                          (uint32_t)sms, k, ids_d + (size_t)q0 * k, score_d + (size_t)q0 * k);
         count_launch();
         VELES_CUDA(cudaGetLastError());
         if (gemm_ms) {
