@@ -198,12 +198,19 @@ def test_tensor_core_relaxed_brute_force(metric, store, n, dim, nq, k, monkeypat
     assert bits_equal(exact_of, rs)
     sign = -1.0 if metric in (vo.COSINE, vo.DOT) else 1.0
     assert (np.diff(sign * rs.astype(np.float64), axis=1) >= 0).all()
-    # the CTA-per-query bound kernel and the flattened finish kernel against the first versions: same bound, same
-    # candidates, same keys -> identical output
+    # re-ranking EVERY candidate that passed the bound (VELES_TC_RERANK_ALL: CTA-per-query bound kernel + flattened
+    # finish kernel) against the first versions of those two kernels: same bound, same candidates, same keys ->
+    # identical output; and it can only agree with the exact path at least as often as the default, which re-ranks the
+    # 2 * k * oversample best candidates by GEMM score
+    monkeypatch.setenv("VELES_TC_RERANK_ALL", "1")
+    ai, as_ = snap.bruteforce_batch_relaxed(q, k, oversample=4)
+    monkeypatch.delenv("VELES_TC_RERANK_ALL")
     monkeypatch.setenv("VELES_TC_OLD_TAIL", "1")
     oi, os_ = snap.bruteforce_batch_relaxed(q, k, oversample=4)
     monkeypatch.delenv("VELES_TC_OLD_TAIL")
-    assert np.array_equal(ri, oi) and bits_equal(rs, os_)
+    assert np.array_equal(ai, oi) and bits_equal(as_, os_)
+    rec_all = np.mean([len(set(ei[i].tolist()) & set(ai[i].tolist())) / k for i in range(nq)])
+    assert rec_all >= rec - 1e-9, (rec_all, rec)
 
 
 @pytest.mark.parametrize("metric,dim,nq,k", [(vo.COSINE, 64, 40, 10), (vo.EUCLIDEAN, 96, 9, 5), (vo.DOT, 128, 33, 20),

@@ -629,6 +629,148 @@ __global__ void __launch_bounds__(kFinWarps * 32) relaxed_finish_flat_kernel(Ind
     }
 }
 
+// The finish most calls take (kp <= 128).  A candidate carries its fp16-GEMM score, so the exact re-rank does not have
+// to touch every row that passed the (loose, sampled) bound: phase A keeps the `kr` best candidates by GEMM score -- 8
+// bytes per candidate, one candidate per lane, register-resident lists merged by warp 0 -- and phase B computes the exact
+// metric value of those kr rows only (kr = 2 * kp clamped to 64..128: the k * oversample the caller asked for, doubled
+// as a margin for fp16 rank noise).  That is the reference's own shape (search_with_rerank re-ranks rerank_k candidates,
+// index/hnsw/index/search.rs:118-160), and it decouples the re-rank traffic (kr rows of dim * 4 bytes per query) from
+// the sample size: the sample can be 4x smaller and the candidate lists 4x longer for the same finish cost.
+__global__ void __launch_bounds__(kFinWarps * 32) relaxed_finish_select_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq,
+                                                                             const uint64_t* __restrict__ cand,
+                                                                             const uint32_t* __restrict__ cand_cnt, uint32_t cand_cap,
+                                                                             uint32_t n_seg, uint32_t k, uint32_t kr,
+                                                                             uint32_t* __restrict__ out_ids, float* __restrict__ out_score) {
+    constexpr int R = 4;
+    extern __shared__ __align__(16) uint8_t fin_smem[];
+    __shared__ uint32_t s_off[kFinMaxSeg + 1];
+    __shared__ uint32_t s_len[kFinWarps];
+    __shared__ uint64_t s_keys[kFinWarps][32 * R];
+    __shared__ uint32_t s_pick;
+    float* qs = reinterpret_cast<float*>(fin_smem);                                       // dim
+    uint64_t* lists = reinterpret_cast<uint64_t*>(fin_smem + ((ix.dim * 4 + 15) & ~15u));  // kFinWarps x k
+    const uint32_t q = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* qg = queries + (size_t)q * ix.dim;
+    for (uint32_t i = threadIdx.x; i < ix.dim; i += blockDim.x) qs[i] = qg[i];
+    {
+        const uint32_t c = threadIdx.x < n_seg ? min(cand_cnt[(size_t)threadIdx.x * nq + q], cand_cap) : 0u;
+        uint32_t x = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL_MASK, x, o);
+            if ((int)lane >= o) x += y;
+        }
+        if (lane == 31) s_len[warp] = x;
+        __syncthreads();
+        uint32_t before = 0;
+        for (uint32_t w = 0; w < warp; ++w) before += s_len[w];
+        s_off[threadIdx.x + 1] = before + x;
+        if (threadIdx.x == 0) s_off[0] = 0;
+        __syncthreads();
+    }
+    const uint32_t total = s_off[kFinWarps * 32];
+    // ---- phase A: the kr best candidates by GEMM score (descending score = ascending key; ties by row id) ----
+    RegTopK<R> top;
+    top.init(kr, lane);
+    constexpr uint32_t U = 4;
+    for (uint32_t base = warp * 32 * U; base < total; base += kFinWarps * 32 * U) {
+        uint64_t key[U];
+#pragma unroll
+        for (uint32_t u = 0; u < U; ++u) {
+            const uint32_t f = base + u * 32 + lane;
+            key[u] = ~0ull;
+            if (f < total) {
+                uint32_t lo = 0, hi = kFinWarps * 32;  // s_off[lo] <= f < s_off[hi]
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (s_off[mid] <= f)
+                        lo = mid;
+                    else
+                        hi = mid;
+                }
+                const uint64_t e = cand[((size_t)lo * nq + q) * cand_cap + (f - s_off[lo])];
+                key[u] = ((uint64_t)(~ord_key(__uint_as_float((uint32_t)(e >> 32)))) << 32) | (uint32_t)e;
+            }
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < U; ++u) top.offer(key[u]);
+    }
+    top.store(s_keys[warp], 32 * R);
+    __syncthreads();
+    if (warp == 0) {
+        for (uint32_t w = 1; w < kFinWarps; ++w)
+            for (uint32_t j = 0; j < kr; j += 32) {
+                const uint64_t key = j + lane < kr ? s_keys[w][j + lane] : ~0ull;
+                if (__shfl_sync(FULL_MASK, key, 0) >= top.worst) break;  // ascending list: nothing further can enter
+                top.offer(key);
+            }
+        const uint32_t cnt = top.size();
+        __syncwarp();
+        top.store(s_keys[0], 32 * R);
+        if (lane == 0) s_pick = cnt;
+    }
+    __syncthreads();
+    const uint32_t npick = s_pick;
+    // ---- phase B: exact metric value of the picked rows, top-k in sort_results order ----
+    const bool desc = ix.metric == VELES_COSINE || ix.metric == VELES_DOT || ix.metric == VELES_JACCARD;
+    float na = 0.0f;
+    if (ix.metric == VELES_COSINE) na = __fsqrt_rn(warp_tree_reduce<0>(qs, qs, ix.dim, lane));
+    uint64_t* mine = lists + (size_t)warp * k;
+    uint32_t len = 0;
+    for (uint32_t c = warp; c < npick; c += kFinWarps) {
+        const uint32_t row = (uint32_t)s_keys[0][c];
+        if (c + kFinWarps < npick) {
+            const uint8_t* np_ = ix.vecs + (size_t)(uint32_t)s_keys[0][c + kFinWarps] * ix.row_bytes;
+            if (lane * 128u < ix.row_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + lane * 128u));
+        }
+        const uint8_t* rp = ix.vecs + (size_t)row * ix.row_bytes;
+        const float nb = ix.metric == VELES_COSINE ? *reinterpret_cast<const float*>(rp + ix.norm_off) : 0.0f;
+        const float v = ix.dtype == VELES_F32 ? warp_metric(ix.metric, true, qs, reinterpret_cast<const float*>(rp), ix.dim, na, nb, lane)
+                                              : warp_metric(ix.metric, true, qs, reinterpret_cast<const __half*>(rp), ix.dim, na, nb, lane);
+        const uint32_t ok = ord_key(v);
+        const uint64_t key = ((uint64_t)(desc ? ~ok : ok) << 32) | row;
+        if (len < k || key < mine[k - 1]) {
+            const uint32_t pos = lower_bound_warp(mine, len, key, lane);
+            if (len < k) {
+                insert_at(mine, pos, len + 1, key, lane);
+                ++len;
+            } else {
+                insert_at(mine, pos, len, key, lane);
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (lane == 0) s_len[warp] = len;
+    __syncthreads();
+    if (warp != 0) return;
+    for (uint32_t w = 1; w < kFinWarps; ++w) {
+        const uint64_t* other = lists + (size_t)w * k;
+        for (uint32_t j = 0; j < s_len[w]; ++j) {
+            const uint64_t key = other[j];
+            if (len == k && key >= mine[k - 1]) break;
+            const uint32_t pos = lower_bound_warp(mine, len, key, lane);
+            if (len < k) {
+                insert_at(mine, pos, len + 1, key, lane);
+                ++len;
+            } else {
+                insert_at(mine, pos, len, key, lane);
+            }
+            __syncwarp();
+        }
+    }
+    for (uint32_t j = lane; j < k; j += 32) {
+        uint32_t id = VELES_INVALID_ID;
+        float sc = __uint_as_float(0x7fc00000u);
+        if (j < len) {
+            id = (uint32_t)mine[j];
+            const uint32_t kb = (uint32_t)(mine[j] >> 32);
+            sc = ord_unkey(desc ? ~kb : kb);
+        }
+        out_ids[(size_t)q * k + j] = id;
+        out_score[(size_t)q * k + j] = sc;
+    }
+}
+
 // ---- host --------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -714,7 +856,15 @@ int32_t bruteforce_relaxed_d(const veles_index* ix, const float* q_d, uint32_t n
     const uint32_t n_mtiles = (uint32_t)((n + kTcBlockM - 1) / kTcBlockM);
     // sample: one row tile in 16 -- the expected candidates per query are kp * n / sample_rows ~ 16 * kp, spread over the
     // GEMM CTAs' segments of the query's list
-    const uint32_t s_tiles = std::min<uint32_t>(n_mtiles, std::max<uint32_t>(std::max<uint32_t>(kTcSampleTiles, n_mtiles / 16), kp / kTcBlockM + 2));
+    // VELES_TC_OLD_TAIL=1: round 2's first threshold / finish kernels (one warp per query; serial segment walk; every
+    // candidate re-ranked), for A/B.  The select finish (kp <= 128) re-ranks the kr best candidates by GEMM score, so
+    // its cost does not grow with the candidate lists and the sample shrinks to one row tile in 64.
+    const bool old_tail = std::getenv("VELES_TC_OLD_TAIL") != nullptr;
+    const bool select_fin = kp <= 128 && !old_tail && sms <= kFinMaxSeg && std::getenv("VELES_TC_RERANK_ALL") == nullptr;
+    uint32_t sample_div = select_fin ? 64u : 16u;
+    if (const char* e = std::getenv("VELES_TC_SAMPLE_DIV")) sample_div = std::max(1, std::atoi(e));
+    const uint32_t kr = std::min<uint32_t>(std::max<uint32_t>(2 * kp, 64), 128);
+    const uint32_t s_tiles = std::min<uint32_t>(n_mtiles, std::max<uint32_t>(std::max<uint32_t>(kTcSampleTiles, n_mtiles / sample_div), kp / kTcBlockM + 2));
     const uint32_t s_rows = s_tiles * kTcBlockM;
     const uint32_t n_seg = std::min<uint32_t>(n_mtiles, (uint32_t)sms);  // = the filter pass's grid: one segment per CTA
     const uint64_t expect = (uint64_t)kp * (n / s_rows + 1);  // per query, all segments
@@ -774,8 +924,6 @@ int32_t bruteforce_relaxed_d(const veles_index* ix, const float* q_d, uint32_t n
         p.ld_out = s_rows;
         if (gemm_ms) VELES_CUDA(cudaEventRecord(e0, st));
         VELES_TRY(launch_gemm(ta, tb, p, bn, st));
-        // VELES_TC_OLD_TAIL=1: round 2's first threshold / finish kernels (one warp per query; serial segment walk), for A/B
-        const bool old_tail = std::getenv("VELES_TC_OLD_TAIL") != nullptr;
         if (kp <= 128 && !old_tail) {
             if (kp <= 64)
                 tc_threshold_cta_kernel<2><<<nn, 256, 0, st>>>(sample.as<float>(), s_rows, s_rows, kp, thr.as<float>());
@@ -803,10 +951,17 @@ int32_t bruteforce_relaxed_d(const veles_index* ix, const float* q_d, uint32_t n
         }
         // 4. exact re-rank of the candidates, top-k
         const size_t fsm = ((ix->dim * 4 + 15) & ~15u) + (size_t)kFinWarps * k * 8;
-        auto fin = (sms <= kFinMaxSeg && !old_tail) ? relaxed_finish_flat_kernel : relaxed_finish_kernel;
-        VELES_CUDA(cudaFuncSetAttribute(fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-        fin<<<nn, kFinWarps * 32, fsm, st>>>(v, q_d + (size_t)q0 * ix->dim, nn, cand.as<uint64_t>(), cnt.as<uint32_t>(), cand_cap,
-                                          (uint32_t)sms, k, ids_d + (size_t)q0 * k, score_d + (size_t)q0 * k);
+        if (select_fin) {
+            VELES_CUDA(cudaFuncSetAttribute(relaxed_finish_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+            relaxed_finish_select_kernel<<<nn, kFinWarps * 32, fsm, st>>>(v, q_d + (size_t)q0 * ix->dim, nn, cand.as<uint64_t>(),
+                                                                       cnt.as<uint32_t>(), cand_cap, (uint32_t)sms, k, kr,
+                                                                       ids_d + (size_t)q0 * k, score_d + (size_t)q0 * k);
+        } else {
+            auto fin = (sms <= kFinMaxSeg && !old_tail) ? relaxed_finish_flat_kernel : relaxed_finish_kernel;
+            VELES_CUDA(cudaFuncSetAttribute(fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+            fin<<<nn, kFinWarps * 32, fsm, st>>>(v, q_d + (size_t)q0 * ix->dim, nn, cand.as<uint64_t>(), cnt.as<uint32_t>(), cand_cap,
+                                              (uint32_t)sms, k, ids_d + (size_t)q0 * k, score_d + (size_t)q0 * k);
+        }
         count_launch();
         VELES_CUDA(cudaGetLastError());
         if (gemm_ms) {
