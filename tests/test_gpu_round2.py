@@ -211,6 +211,12 @@ def test_tensor_core_relaxed_brute_force(metric, store, n, dim, nq, k, monkeypat
     assert np.array_equal(ai, oi) and bits_equal(as_, os_)
     rec_all = np.mean([len(set(ei[i].tolist()) & set(ai[i].tolist())) / k for i in range(nq)])
     assert rec_all >= rec - 1e-9, (rec_all, rec)
+    # the CTA-wide selection (bound from per-thread minima, collect, rank) against the register-list scans it replaces
+    # in the bound kernel and in the finish kernel: the same k-th key and the same kr keys -> identical output
+    monkeypatch.setenv("VELES_TC_REGTOPK", "1")
+    gi, gs = snap.bruteforce_batch_relaxed(q, k, oversample=4)
+    monkeypatch.delenv("VELES_TC_REGTOPK")
+    assert np.array_equal(ri, gi) and bits_equal(rs, gs)
 
 
 @pytest.mark.parametrize("metric,dim,nq,k", [(vo.COSINE, 64, 40, 10), (vo.EUCLIDEAN, 96, 9, 5), (vo.DOT, 128, 33, 20),

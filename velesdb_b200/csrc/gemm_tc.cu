@@ -401,17 +401,93 @@ __global__ void tc_threshold_kernel(const float* __restrict__ scores, uint32_t l
     if (lane == 0) thr[q] = len == kp ? ord_unkey(~(uint32_t)(res[kp - 1] >> 32)) : __int_as_float(0xff800000);
 }
 
-// The same bound with a CTA per query (kp <= 32 * R): the eight warps scan interleaved 256-score blocks with eight
-// independent coalesced loads in flight per lane, each keeping a register-resident sorted list (RegTopK); warp 0 merges
-// the lists.  The one-warp kernel above walks its row one dependent 128-byte load at a time: 1.1 ms for 1024 queries x
-// 62 K sampled scores -- as long as the filter GEMM itself.
+// ---- CTA-wide selection of the kr smallest of N unique u64 keys (256 threads, kr <= 256) ----------------------------
+// Pass 1: every thread takes the minimum of its strided share; the kr-th smallest of the 256 minima is an upper bound
+// of the kr-th smallest key (kr distinct keys lie at or below it).  Pass 2 collects the keys at or below the bound
+// (about -256 ln(1 - kr/256) of them when the keys are spread evenly: 96 for kr = 80), and each collected key's rank
+// among the collected is its position in the sorted output.  ~2 N / 256 key evaluations and a few hundred shared-memory
+// compares per thread, against one serial register-list insert (~100 warp instructions) per accepted key in the
+// RegTopK scan -- which made the bound kernel and the finish kernel issue-bound (0.16 and 0.39 ms per 1024 queries).
+// `key_at(i)` must return the same value in both passes, ~0 for "no key".  Returns false when more than `cap` keys
+// fall under the bound (keys laid out so that the best ones share a thread): the caller takes the RegTopK path.
+constexpr uint32_t kSelCap = 1024;
+struct SelScratch {
+    uint64_t mins[256];
+    uint64_t col[kSelCap];
+    uint64_t bound;
+    uint32_t count;
+};
+template <typename F>
+__device__ __forceinline__ bool cta_select_smallest(F&& key_at, uint32_t N, uint32_t kr, SelScratch& sc, uint64_t* out,
+                                                    uint32_t* out_cnt) {
+    const uint32_t tid = threadIdx.x;
+    uint64_t mn = ~0ull;
+#pragma unroll 4
+    for (uint32_t i = tid; i < N; i += 256) {
+        const uint64_t kk = key_at(i);
+        mn = kk < mn ? kk : mn;
+    }
+    sc.mins[tid] = mn;
+    if (tid == 0) sc.count = 0;
+    __syncthreads();
+    uint32_t r = 0;
+    for (uint32_t j = 0; j < 256; ++j) {
+        const uint64_t v = sc.mins[j];
+        r += (v < mn || (v == mn && j < tid)) ? 1u : 0u;  // only the ~0 sentinels can be equal
+    }
+    if (r == kr - 1) sc.bound = mn;
+    __syncthreads();
+    const uint64_t bound = sc.bound;
+#pragma unroll 4
+    for (uint32_t i = tid; i < N; i += 256) {
+        const uint64_t kk = key_at(i);
+        if (kk <= bound && kk != ~0ull) {
+            const uint32_t slot = atomicAdd(&sc.count, 1u);
+            if (slot < kSelCap) sc.col[slot] = kk;
+        }
+    }
+    __syncthreads();
+    const uint32_t m = sc.count;
+    if (m > kSelCap) return false;
+    for (uint32_t j = tid; j < m; j += 256) {
+        const uint64_t kj = sc.col[j];
+        uint32_t rank = 0;
+        for (uint32_t t = 0; t < m; ++t) rank += sc.col[t] < kj ? 1u : 0u;
+        if (rank < kr) out[rank] = kj;
+    }
+    if (tid == 0) *out_cnt = m < kr ? m : kr;
+    __syncthreads();
+    return true;
+}
+
+// The same bound with a CTA per query (kp <= 128): cta_select_smallest over the query's sampled scores; when that
+// overflows, the eight warps scan interleaved 256-score blocks with eight independent coalesced loads in flight per lane,
+// each keeping a register-resident sorted list (RegTopK), and warp 0 merges the lists.  The one-warp kernel above walks
+// its row one dependent 128-byte load at a time: 1.1 ms for 1024 queries x 62 K sampled scores -- as long as the filter
+// GEMM itself.
 template <int R>
 __global__ void __launch_bounds__(256) tc_threshold_cta_kernel(const float* __restrict__ scores, uint32_t ld, uint32_t m, uint32_t kp,
-                                                               float* __restrict__ thr) {
+                                                               float* __restrict__ thr, int use_select) {
     __shared__ uint64_t s_keys[8][32 * R];
+    __shared__ SelScratch s_sel;
+    __shared__ uint32_t s_cnt;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = blockIdx.x;
     const float* row = scores + (size_t)q * ld;
     const float ninf = __int_as_float(0xff800000);
+    if (use_select) {
+        uint64_t* out = &s_keys[0][0];  // kp <= 32 * R <= 8 * 32 * R entries
+        const bool ok = cta_select_smallest(
+            [&](uint32_t i) -> uint64_t {
+                const float v = row[i];
+                return v > ninf ? (((uint64_t)(~ord_key(v)) << 32) | i) : ~0ull;
+            },
+            m, kp, s_sel, out, &s_cnt);
+        if (ok) {
+            if (threadIdx.x == 0) thr[q] = s_cnt == kp ? ord_unkey(~(uint32_t)(out[kp - 1] >> 32)) : ninf;
+            return;
+        }
+        __syncthreads();
+    }
     RegTopK<R> top;
     top.init(kp, lane);
     constexpr uint32_t U = 8;
@@ -639,13 +715,14 @@ __global__ void __launch_bounds__(kFinWarps * 32) relaxed_finish_flat_kernel(Ind
 __global__ void __launch_bounds__(kFinWarps * 32) relaxed_finish_select_kernel(IndexView ix, const float* __restrict__ queries, uint32_t nq,
                                                                              const uint64_t* __restrict__ cand,
                                                                              const uint32_t* __restrict__ cand_cnt, uint32_t cand_cap,
-                                                                             uint32_t n_seg, uint32_t k, uint32_t kr,
+                                                                             uint32_t n_seg, uint32_t k, uint32_t kr, int use_select,
                                                                              uint32_t* __restrict__ out_ids, float* __restrict__ out_score) {
     constexpr int R = 4;
     extern __shared__ __align__(16) uint8_t fin_smem[];
     __shared__ uint32_t s_off[kFinMaxSeg + 1];
     __shared__ uint32_t s_len[kFinWarps];
     __shared__ uint64_t s_keys[kFinWarps][32 * R];
+    __shared__ SelScratch s_sel;
     __shared__ uint32_t s_pick;
     float* qs = reinterpret_cast<float*>(fin_smem);                                       // dim
     uint64_t* lists = reinterpret_cast<uint64_t*>(fin_smem + ((ix.dim * 4 + 15) & ~15u));  // kFinWarps x k
@@ -669,46 +746,52 @@ __global__ void __launch_bounds__(kFinWarps * 32) relaxed_finish_select_kernel(I
     }
     const uint32_t total = s_off[kFinWarps * 32];
     // ---- phase A: the kr best candidates by GEMM score (descending score = ascending key; ties by row id) ----
-    RegTopK<R> top;
-    top.init(kr, lane);
-    constexpr uint32_t U = 4;
-    for (uint32_t base = warp * 32 * U; base < total; base += kFinWarps * 32 * U) {
-        uint64_t key[U];
-#pragma unroll
-        for (uint32_t u = 0; u < U; ++u) {
-            const uint32_t f = base + u * 32 + lane;
-            key[u] = ~0ull;
-            if (f < total) {
-                uint32_t lo = 0, hi = kFinWarps * 32;  // s_off[lo] <= f < s_off[hi]
-                while (hi - lo > 1) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (s_off[mid] <= f)
-                        lo = mid;
-                    else
-                        hi = mid;
-                }
-                const uint64_t e = cand[((size_t)lo * nq + q) * cand_cap + (f - s_off[lo])];
-                key[u] = ((uint64_t)(~ord_key(__uint_as_float((uint32_t)(e >> 32)))) << 32) | (uint32_t)e;
-            }
+    // key of flattened candidate f: its segment is the last one whose offset is <= f
+    auto key_of = [&](uint32_t f) -> uint64_t {
+        uint32_t lo = 0, hi = kFinWarps * 32;  // s_off[lo] <= f < s_off[hi]
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_off[mid] <= f)
+                lo = mid;
+            else
+                hi = mid;
         }
+        const uint64_t e = cand[((size_t)lo * nq + q) * cand_cap + (f - s_off[lo])];
+        return ((uint64_t)(~ord_key(__uint_as_float((uint32_t)(e >> 32)))) << 32) | (uint32_t)e;
+    };
+    bool picked = false;
+    if (use_select) picked = cta_select_smallest(key_of, total, kr, s_sel, &s_keys[0][0], &s_pick);
+    if (!picked) {
+        __syncthreads();
+        RegTopK<R> top;
+        top.init(kr, lane);
+        constexpr uint32_t U = 4;
+        for (uint32_t base = warp * 32 * U; base < total; base += kFinWarps * 32 * U) {
+            uint64_t key[U];
 #pragma unroll
-        for (uint32_t u = 0; u < U; ++u) top.offer(key[u]);
-    }
-    top.store(s_keys[warp], 32 * R);
-    __syncthreads();
-    if (warp == 0) {
-        for (uint32_t w = 1; w < kFinWarps; ++w)
-            for (uint32_t j = 0; j < kr; j += 32) {
-                const uint64_t key = j + lane < kr ? s_keys[w][j + lane] : ~0ull;
-                if (__shfl_sync(FULL_MASK, key, 0) >= top.worst) break;  // ascending list: nothing further can enter
-                top.offer(key);
+            for (uint32_t u = 0; u < U; ++u) {
+                const uint32_t f = base + u * 32 + lane;
+                key[u] = f < total ? key_of(f) : ~0ull;
             }
-        const uint32_t cnt = top.size();
-        __syncwarp();
-        top.store(s_keys[0], 32 * R);
-        if (lane == 0) s_pick = cnt;
+#pragma unroll
+            for (uint32_t u = 0; u < U; ++u) top.offer(key[u]);
+        }
+        top.store(s_keys[warp], 32 * R);
+        __syncthreads();
+        if (warp == 0) {
+            for (uint32_t w = 1; w < kFinWarps; ++w)
+                for (uint32_t j = 0; j < kr; j += 32) {
+                    const uint64_t key = j + lane < kr ? s_keys[w][j + lane] : ~0ull;
+                    if (__shfl_sync(FULL_MASK, key, 0) >= top.worst) break;  // ascending list: nothing further can enter
+                    top.offer(key);
+                }
+            const uint32_t cnt = top.size();
+            __syncwarp();
+            top.store(s_keys[0], 32 * R);
+            if (lane == 0) s_pick = cnt;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     const uint32_t npick = s_pick;
     // ---- phase B: exact metric value of the picked rows, top-k in sort_results order ----
     const bool desc = ix.metric == VELES_COSINE || ix.metric == VELES_DOT || ix.metric == VELES_JACCARD;
@@ -864,6 +947,7 @@ int32_t bruteforce_relaxed_d(const veles_index* ix, const float* q_d, uint32_t n
     uint32_t sample_div = select_fin ? 64u : 16u;
     if (const char* e = std::getenv("VELES_TC_SAMPLE_DIV")) sample_div = std::max(1, std::atoi(e));
     const uint32_t kr = std::min<uint32_t>(std::max<uint32_t>(2 * kp, 64), 128);
+    const int use_select = std::getenv("VELES_TC_REGTOPK") == nullptr ? 1 : 0;  // 0: the RegTopK scans only (A/B, and their test)
     const uint32_t s_tiles = std::min<uint32_t>(n_mtiles, std::max<uint32_t>(std::max<uint32_t>(kTcSampleTiles, n_mtiles / sample_div), kp / kTcBlockM + 2));
     const uint32_t s_rows = s_tiles * kTcBlockM;
     const uint32_t n_seg = std::min<uint32_t>(n_mtiles, (uint32_t)sms);  // = the filter pass's grid: one segment per CTA
@@ -926,9 +1010,9 @@ int32_t bruteforce_relaxed_d(const veles_index* ix, const float* q_d, uint32_t n
         VELES_TRY(launch_gemm(ta, tb, p, bn, st));
         if (kp <= 128 && !old_tail) {
             if (kp <= 64)
-                tc_threshold_cta_kernel<2><<<nn, 256, 0, st>>>(sample.as<float>(), s_rows, s_rows, kp, thr.as<float>());
+                tc_threshold_cta_kernel<2><<<nn, 256, 0, st>>>(sample.as<float>(), s_rows, s_rows, kp, thr.as<float>(), use_select);
             else
-                tc_threshold_cta_kernel<4><<<nn, 256, 0, st>>>(sample.as<float>(), s_rows, s_rows, kp, thr.as<float>());
+                tc_threshold_cta_kernel<4><<<nn, 256, 0, st>>>(sample.as<float>(), s_rows, s_rows, kp, thr.as<float>(), use_select);
         } else {
             const uint32_t tw = kp <= 256 ? 8 : (kp <= 1024 ? 2 : 1);
             tc_threshold_kernel<<<(nn + tw - 1) / tw, tw * 32, (size_t)tw * kp * 8, st>>>(sample.as<float>(), s_rows, s_rows, nn, kp,
@@ -954,7 +1038,7 @@ int32_t bruteforce_relaxed_d(const veles_index* ix, const float* q_d, uint32_t n
         if (select_fin) {
             VELES_CUDA(cudaFuncSetAttribute(relaxed_finish_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
             relaxed_finish_select_kernel<<<nn, kFinWarps * 32, fsm, st>>>(v, q_d + (size_t)q0 * ix->dim, nn, cand.as<uint64_t>(),
-                                                                       cnt.as<uint32_t>(), cand_cap, (uint32_t)sms, k, kr,
+                                                                       cnt.as<uint32_t>(), cand_cap, (uint32_t)sms, k, kr, use_select,
                                                                        ids_d + (size_t)q0 * k, score_d + (size_t)q0 * k);
         } else {
             auto fin = (sms <= kFinMaxSeg && !old_tail) ? relaxed_finish_flat_kernel : relaxed_finish_kernel;
