@@ -532,7 +532,10 @@ def main():
 
     # ---------------- multi-GPU gather inside the step ----------------
     comm = None
-    if use_dist:
+    hybrid_one = kind == "hybrid" and not a.hybrid_three_calls
+    if use_dist and hybrid_one:
+        gather_note = "none: every rank answers its own batch through veles_hybrid_search_batch (host buffers in and out)"
+    elif use_dist:
         gather_note = None
         if a.gather == "p2p":
             from velesdb_b200.dist import PeerGather
@@ -541,7 +544,7 @@ def main():
                 comm = PeerGather(snap, rank, world, nq, k_vec, dev)
             except RuntimeError as e:  # raised on every rank together (see PeerGather): fall back together
                 gather_note = f"p2p gather unavailable ({e}); NCCL all-gather used"
-        if comm is None:
+        if comm is None and not hybrid_one:
             gath_ids = torch.empty((world * nq, k_vec), dtype=torch.int32, device=dev)
             gath_dist = torch.empty((world * nq, k_vec), dtype=torch.float32, device=dev)
 
@@ -556,7 +559,7 @@ def main():
             comm.search_gather(q_d, ef, stream)
         else:
             search_device()
-            if use_dist:
+            if use_dist and not hybrid_one:
                 dist.all_gather_into_tensor(gath_ids, ids_t)
                 dist.all_gather_into_tensor(gath_dist, dist_t)
         if kind == "hybrid":
@@ -566,7 +569,6 @@ def main():
 
     # hybrid: the product call is veles_hybrid_search_batch -- host buffers in, fused top-k out, both legs concurrent on
     # the device.  --hybrid-three-calls times round 2's first form (search, BM25 and RRF as three host-API calls).
-    hybrid_one = kind == "hybrid" and not a.hybrid_three_calls
     qn_host = q_h.numpy()
 
     def step_hybrid():
