@@ -1318,7 +1318,9 @@ static int32_t launch_scores(const veles_index* ixh, const IndexView& v, const f
                 // rows that do not fit the L2 and several query groups: dynamic chunk-major items (see the kernel), 64
                 // tiles (1024 rows) per item, or fewer when that would leave less than ~8 items per CTA
                 const uint64_t touched = v.n * (uint64_t)ix->dim * tb;
-                if (touched > ((uint64_t)64 << 20) && qgroups > 1 && qgroups <= 32768 && tiles * qgroups < 0xffffff00ull &&
+                uint64_t dyn_min = (uint64_t)64 << 20;
+                if (const char* e = std::getenv("VELES_BF_DYNAMIC_MIN_BYTES")) dyn_min = std::strtoull(e, nullptr, 10);  // probes
+                if (touched > dyn_min && qgroups > 1 && qgroups <= 32768 && tiles * qgroups < 0xffffff00ull &&
                     std::getenv("VELES_BF_STATIC_TILES") == nullptr) {
                     uint64_t chunk_tiles = 64;
                     while (chunk_tiles > 8 && (tiles / chunk_tiles) * qgroups < 8 * slots) chunk_tiles >>= 1;
