@@ -968,11 +968,15 @@ int32_t bruteforce_relaxed_d(const veles_index* ix, const float* q_d, uint32_t n
     VELES_TRY(cand.ensure((size_t)sms * chunk * cand_cap * 8));
     VELES_TRY(err.ensure(16));
     VELES_CUDA(cudaMemsetAsync(err.p, 0, 16, st));
-    {
+    if (ix->tc_tiles_key[0] != s_tiles || ix->tc_tiles_key[1] != n_mtiles) {
+        // the sample's row tiles, spread evenly over the collection: uploaded once per (snapshot, k * oversample) -- the
+        // copy from a local needs a stream synchronisation, which every later call is spared
         std::vector<uint32_t> tl(s_tiles);
         for (uint32_t i = 0; i < s_tiles; ++i) tl[i] = (uint32_t)((uint64_t)i * n_mtiles / s_tiles);
         VELES_CUDA(cudaMemcpyAsync(tiles_d.p, tl.data(), (size_t)s_tiles * 4, cudaMemcpyHostToDevice, st));
         VELES_CUDA(cudaStreamSynchronize(st));  // tl is a local
+        ix->tc_tiles_key[0] = s_tiles;
+        ix->tc_tiles_key[1] = n_mtiles;
     }
     CUtensorMap ta, tb;
     VELES_TRY(make_tensor_map(&ta, ix->x16.p, n, dpad, kTcBlockM));

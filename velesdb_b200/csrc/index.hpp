@@ -67,6 +67,7 @@ struct veles_index {
     mutable veles::DevBuf x16, x16_bias;
     mutable uint32_t x16_dpad = 0;
     mutable veles::DevBuf tc_q16, tc_tiles, tc_sample, tc_thr, tc_cnt, tc_cand, tc_err;  // work buffers of that path
+    mutable uint32_t tc_tiles_key[2] = {0, 0};  // (sample tiles, row tiles) the list in tc_tiles was written for
 
     // node index -> external id, live (not tombstoned) bitmap: ShardedMappings on the device (postfilter.cu)
     veles::DevBuf id_map_d, live_d;
