@@ -326,3 +326,30 @@ def test_hybrid_search_batch_one_call_equals_the_three_calls_and_the_oracle():
     vi, vd, vc = snap.search_batch(q, 10, 64)
     ri, rs, rc = rrf_hybrid_batch(vi, vc, np.full((4, 10), 0xFFFFFFFF, np.uint32), np.zeros(4, np.uint32), 5, 0.5)
     assert np.array_equal(cnt, rc) and np.array_equal(ids, ri) and bits_equal(sc, rs)
+
+
+def test_hybrid_search_reference_known_answers_on_gpu():
+    """collection/tests.rs:298-336, 394-446 (the reference's own answers for Collection::hybrid_search) through the host
+    mirror (HnswIndex + Bm25Index + hybrid_search) and through the one-call batch form on the same snapshots."""
+    from tests.test_oracle_known_answers import HYBRID_KNOWN_ANSWERS
+    from velesdb_b200 import HnswIndex, SearchQuality
+    from velesdb_b200 import _native as nv
+    from velesdb_b200.bm25 import tokenize
+
+    for points, query, text, k, w, first in HYBRID_KNOWN_ANSWERS:
+        hx, tx = HnswIndex(3, DistanceMetric.Cosine), Bm25Index()
+        for pid, vec, txt in points:
+            hx.insert(pid, np.asarray(vec, np.float32))
+            tx.add_document(pid, txt)
+        got = hybrid_search(hx, tx, np.asarray(query, np.float32), text, k, w)
+        assert got and got[0][0] == first, (got, first)
+        assert all(got[i][1] >= got[i + 1][1] for i in range(len(got) - 1))
+        # the batch form: node i and BM25 slot i both stand for points[i] (ids ascending), so ids map back by position
+        snap, bsnap = hx._ensure_snapshot(), tx._snapshot()
+        terms = [tx._term(t, False) for t in tokenize(text)]
+        q_terms = np.array([nv.INVALID_ID if t is None else t for t in terms], np.uint32)
+        ef = SearchQuality.Balanced.ef_search(2 * k)
+        ids, sc, cnt = hybrid_search_batch(snap, bsnap, np.asarray([query], np.float32), np.array([0, len(q_terms)], np.uint32),
+                                           q_terms, k, ef, w)
+        assert cnt[0] == len(got) and [points[int(i)][0] for i in ids[0, :cnt[0]]] == [g[0] for g in got]
+        assert bits_equal(sc[0, :cnt[0]], [g[1] for g in got])

@@ -387,6 +387,35 @@ def test_hybrid_rrf_formula():
     assert ids.tolist() == [1, 2] and sc[1] == 0.0
 
 
+# collection/tests.rs:298-336, 394-446: the reference's own answers for Collection::hybrid_search.  (points, query
+# vector, text query, k, vector_weight, id that must come first); a point's text is its payload strings joined by " "
+# (collection/types.rs:169-191)
+HYBRID_KNOWN_ANSWERS = [
+    ([(1, [1.0, 0.0, 0.0], "Rust Programming"), (2, [0.9, 0.1, 0.0], "Python Programming"), (3, [0.0, 1.0, 0.0], "Rust Performance")],
+     [1.0, 0.0, 0.0], "rust", 3, 0.5, 1),                                         # test_collection_hybrid_search
+    ([(1, [1.0, 0.0, 0.0], "Rust"), (2, [0.9, 0.1, 0.0], "Python")], [0.9, 0.1, 0.0], "rust", 2, 1.0, 2),   # ..._text_weight_zero
+    ([(1, [1.0, 0.0, 0.0], "Rust programming language"), (2, [0.99, 0.01, 0.0], "Python programming")],
+     [0.99, 0.01, 0.0], "rust", 2, 0.0, 1),                                       # ..._vector_weight_zero
+]
+
+
+@pytest.mark.parametrize("points,query,text,k,w,first", HYBRID_KNOWN_ANSWERS)
+def test_hybrid_search_reference_known_answers(points, query, text, k, w, first):
+    # Collection::hybrid_search (collection/search/text.rs:113-180) composed from the oracle's parts: index.search(q, 2k)
+    # with ef_search(Balanced, 2k), text_index.search(text, 2k), the RRF
+    g, bm = vo.Hnsw(vo.COSINE, 3, M=16, ef_construction=100), vo.Bm25()
+    for pid, vec, txt in points:
+        g.insert(np.asarray(vec, np.float32))
+        bm.add_document(pid, txt)
+    ef = vo.ef_search(vo.BALANCED, 2 * k)
+    nodes, _ = g.search(np.asarray(query, np.float32), 2 * k, ef)
+    vec_ids = [points[int(i)][0] for i in nodes]
+    txt_ids, _ = bm.search(text, 2 * k)
+    ids, sc = vo.rrf_hybrid(vec_ids, txt_ids, k, w)
+    assert len(ids) >= 1 and int(ids[0]) == first
+    assert all(sc[i] >= sc[i + 1] for i in range(len(sc) - 1))
+
+
 # ---- SQ8 dual precision (native/quantization_tests.rs, native/dual_precision_tests.rs) ----
 def test_sq8_quantizer_known_answers():
     # quantization_tests.rs:13-29 train min / scale
