@@ -196,3 +196,18 @@ def test_mappings_and_meta_files_follow_the_reference_bincode_layout():
         _parse_bincode_mappings(raw[:-3])
     with pytest.raises(OSError):
         _parse_bincode_mappings(struct.pack("<Q", 2 ** 60) + raw[8:])   # absurd length: rejected before allocating
+
+
+def test_distance_metric_semantics_known_answers():
+    # collection/search/distance_semantics_tests.rs:41-118 and core/distance.rs:76-103: which metrics are similarities,
+    # and the order DistanceMetric::sort_results puts scores in (most similar first)
+    from velesdb_b200.index import _sort_results
+
+    assert DistanceMetric.Cosine.higher_is_better() and DistanceMetric.DotProduct.higher_is_better()
+    assert DistanceMetric.Jaccard.higher_is_better()
+    assert not DistanceMetric.Euclidean.higher_is_better() and not DistanceMetric.Hamming.higher_is_better()
+    scores = [(0, 0.3), (1, 0.9), (2, 0.5), (3, 0.7)]
+    assert [s for _, s in _sort_results(DistanceMetric.Cosine, scores)] == [0.9, 0.7, 0.5, 0.3]
+    assert [s for _, s in _sort_results(DistanceMetric.Euclidean, scores)] == [0.3, 0.5, 0.7, 0.9]
+    # equal scores keep their input order (stable sort), negative zero sorts below zero (total order)
+    assert [i for i, _ in _sort_results(DistanceMetric.Euclidean, [(5, 1.0), (4, 1.0), (3, 0.0), (2, -0.0)])] == [2, 3, 5, 4]
