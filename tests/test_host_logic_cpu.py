@@ -211,3 +211,33 @@ def test_distance_metric_semantics_known_answers():
     assert [s for _, s in _sort_results(DistanceMetric.Euclidean, scores)] == [0.3, 0.5, 0.7, 0.9]
     # equal scores keep their input order (stable sort), negative zero sorts below zero (total order)
     assert [i for i, _ in _sort_results(DistanceMetric.Euclidean, [(5, 1.0), (4, 1.0), (3, 0.0), (2, -0.0)])] == [2, 3, 5, 4]
+
+
+def test_hnsw_params_presets_known_answers():
+    # index/hnsw/params_tests.rs:6-150, 198-246: every preset's M / ef_construction / capacity / storage mode
+    from velesdb_b200 import HnswParams as P
+
+    def t(p):
+        return (p.max_connections, p.ef_construction, p.max_elements, p.storage_mode)
+
+    assert t(P.default())[:2] == (32, 400) and P.default().storage_mode == "full"
+    assert t(P.auto(128))[:2] == (24, 300) and t(P.auto(1024))[:2] == (32, 400) and t(P.auto(256))[:2] == (24, 300)
+    assert t(P.fast()) == (16, 150, 100_000, "full") and t(P.turbo()) == (12, 100, 100_000, "full")
+    assert t(P.high_recall(768))[:2] == (40, 600) and t(P.fast_indexing(768))[:2] == (16, 200)
+    assert t(P.large_dataset(768))[:3] == (128, 2000, 750_000)
+    assert t(P.for_dataset_size(768, 5_000))[:3] == (32, 400, 20_000)
+    assert t(P.for_dataset_size(768, 50_000))[:3] == (128, 1600, 150_000)
+    assert t(P.for_dataset_size(768, 300_000))[:3] == (128, 2000, 750_000)
+    assert t(P.million_scale(768))[:3] == (128, 1600, 1_500_000)
+    assert t(P.for_dataset_size(768, 100_000))[:2] == (128, 1600) and t(P.for_dataset_size(768, 500_000))[:2] == (128, 2000)
+    assert t(P.for_dataset_size(128, 10_000))[:3] == (24, 200, 20_000) and t(P.for_dataset_size(128, 10_001))[:3] == (64, 800, 150_000)
+    assert t(P.for_dataset_size(128, 400_000))[:3] == (96, 1200, 750_000) and t(P.for_dataset_size(128, 2_000_000))[:3] == (64, 800, 1_500_000)
+    assert t(P.max_recall(128))[:2] == (32, 500) and t(P.max_recall(512))[:2] == (48, 800) and t(P.max_recall(1024))[:2] == (64, 1000)
+    assert t(P.custom(32, 400, 50_000)) == (32, 400, 50_000, "full")
+    assert t(P.with_sq8(768)) == (32, 400, 100_000, "sq8") and t(P.with_binary(768))[0] == 32 and P.with_binary(768).storage_mode == "binary"
+    assert P.custom(32, 400, 50_000) == P.custom(32, 400, 50_000) and P.fast() != P.turbo()
+    # params_tests.rs:153-196: quality -> ef_search
+    assert [SearchQuality.Fast.ef_search(10), SearchQuality.Balanced.ef_search(10), SearchQuality.Accurate.ef_search(10),
+            SearchQuality.Custom(50).ef_search(10)] == [64, 128, 512, 50]
+    assert [SearchQuality.Perfect.ef_search(k) for k in (10, 50, 100)] == [4096, 5000, 10000]
+    assert [SearchQuality.Fast.ef_search(100), SearchQuality.Balanced.ef_search(50), SearchQuality.Accurate.ef_search(40)] == [200, 200, 640]

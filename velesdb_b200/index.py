@@ -56,14 +56,87 @@ SearchQuality.Perfect = SearchQuality(nv.PERFECT)
 
 
 class HnswParams:
-    """index/hnsw/params.rs:14-57 (auto)"""
+    """``HnswParams`` (index/hnsw/params.rs:13-289): M, ef_construction, initial capacity and storage mode, with the
+    reference's presets.  ``storage_mode`` is one of "full", "sq8", "binary" (quantization.rs ``StorageMode``)."""
 
-    def __init__(self, max_connections=32, ef_construction=400, max_elements=100_000):
+    # (dimension <= 256, dimension > 256) -> (M, ef_construction) per expected dataset size (params.rs:71-141)
+    _BY_SIZE = ((10_000, 20_000, (24, 200), (32, 400)), (100_000, 150_000, (64, 800), (128, 1600)),
+                (500_000, 750_000, (96, 1200), (128, 2000)), (None, 1_500_000, (64, 800), (128, 1600)))
+
+    def __init__(self, max_connections=32, ef_construction=400, max_elements=100_000, storage_mode="full"):
         self.max_connections, self.ef_construction, self.max_elements = max_connections, ef_construction, max_elements
+        self.storage_mode = storage_mode
+
+    def __eq__(self, other):
+        return isinstance(other, HnswParams) and vars(self) == vars(other)
+
+    def __repr__(self):
+        return (f"HnswParams(max_connections={self.max_connections}, ef_construction={self.ef_construction}, "
+                f"max_elements={self.max_elements}, storage_mode={self.storage_mode!r})")
 
     @staticmethod
-    def auto(dimension: int) -> "HnswParams":
+    def default() -> "HnswParams":                                   # params.rs:29-33
+        return HnswParams.auto(768)
+
+    @staticmethod
+    def auto(dimension: int) -> "HnswParams":                        # params.rs:40-57
         return HnswParams(24, 300) if dimension <= 256 else HnswParams(32, 400)
+
+    @staticmethod
+    def for_dataset_size(dimension: int, expected_vectors: int) -> "HnswParams":   # params.rs:71-141
+        for limit, cap, small, large in HnswParams._BY_SIZE:
+            if limit is None or expected_vectors <= limit:
+                m, efc = small if dimension <= 256 else large
+                return HnswParams(m, efc, cap)
+        raise AssertionError("unreachable")
+
+    @staticmethod
+    def large_dataset(dimension: int) -> "HnswParams":               # params.rs:147-150
+        return HnswParams.for_dataset_size(dimension, 500_000)
+
+    @staticmethod
+    def million_scale(dimension: int) -> "HnswParams":               # params.rs:155-158
+        return HnswParams.for_dataset_size(dimension, 1_000_000)
+
+    @staticmethod
+    def fast() -> "HnswParams":                                      # params.rs:162-170
+        return HnswParams(16, 150)
+
+    @staticmethod
+    def turbo() -> "HnswParams":                                     # params.rs:189-197
+        return HnswParams(12, 100)
+
+    @staticmethod
+    def high_recall(dimension: int) -> "HnswParams":                 # params.rs:200-208
+        b = HnswParams.auto(dimension)
+        return HnswParams(b.max_connections + 8, b.ef_construction + 200, b.max_elements)
+
+    @staticmethod
+    def max_recall(dimension: int) -> "HnswParams":                  # params.rs:211-233
+        if dimension <= 256:
+            return HnswParams(32, 500)
+        return HnswParams(48, 800) if dimension <= 768 else HnswParams(64, 1000)
+
+    @staticmethod
+    def fast_indexing(dimension: int) -> "HnswParams":               # params.rs:236-244
+        b = HnswParams.auto(dimension)
+        return HnswParams(max(b.max_connections // 2, 8), b.ef_construction // 2, b.max_elements)
+
+    @staticmethod
+    def custom(max_connections: int, ef_construction: int, max_elements: int) -> "HnswParams":   # params.rs:247-259
+        return HnswParams(max_connections, ef_construction, max_elements)
+
+    @staticmethod
+    def with_sq8(dimension: int) -> "HnswParams":                    # params.rs:271-276
+        p = HnswParams.auto(dimension)
+        p.storage_mode = "sq8"
+        return p
+
+    @staticmethod
+    def with_binary(dimension: int) -> "HnswParams":                 # params.rs:280-285
+        p = HnswParams.auto(dimension)
+        p.storage_mode = "binary"
+        return p
 
 
 class VacuumError(RuntimeError):
