@@ -241,3 +241,34 @@ def test_hnsw_params_presets_known_answers():
             SearchQuality.Custom(50).ef_search(10)] == [64, 128, 512, 50]
     assert [SearchQuality.Perfect.ef_search(k) for k in (10, 50, 100)] == [4096, 5000, 10000]
     assert [SearchQuality.Fast.ef_search(100), SearchQuality.Balanced.ef_search(50), SearchQuality.Accurate.ef_search(40)] == [200, 200, 640]
+
+
+def test_constructor_variants_known_answers():
+    # index_tests.rs:118-134, 153-204 and constructors.rs:29-118: new / new_turbo / new_fast_insert / with_params
+    from velesdb_b200 import HnswParams, VacuumError
+
+    ix = HnswIndex.new(768, DistanceMetric.Cosine)
+    assert ix.is_empty() and ix.len() == 0 and ix.dimension() == 768 and ix.metric() == DistanceMetric.Cosine
+    assert ix._params == HnswParams.auto(768) and ix.enable_vector_storage
+    turbo = HnswIndex.new_turbo(64, DistanceMetric.Cosine)
+    assert (turbo._params.max_connections, turbo._params.ef_construction) == (24, 450) and turbo.enable_vector_storage
+    fast = HnswIndex.new_fast_insert(64, DistanceMetric.Cosine)
+    assert fast._params == HnswParams.auto(64) and not fast.enable_vector_storage
+    rows = np.array([[(i + j) * 0.01 for j in range(64)] for i in range(100)], np.float32)
+    for i in range(100):
+        fast.insert(i, rows[i])
+        turbo.insert(i, rows[i])
+    assert fast.len() == 100 and turbo.len() == 100
+    with pytest.raises(VacuumError):                       # VacuumError::VectorStorageDisabled
+        fast.vacuum()
+    assert HnswIndex.new(64, DistanceMetric.Cosine).vacuum() == 0
+    # searches: the fast-insert index has no stored vectors, so even a 100-vector index goes through the graph
+    for ix2 in (fast, turbo):
+        snap = OracleSnapshot(DistanceMetric.Cosine, rows)
+        ix2._snapshot, ix2._dirty = snap, False
+    q = np.array([j * 0.01 for j in range(64)], np.float32)
+    assert len(fast.search(q, 10)) == 10 and fast._snapshot.calls[-1][0] == "search"
+    assert len(turbo.search(q, 10)) == 10 and turbo._snapshot.calls[-1][0] == "brute"     # <= 100 vectors, stored
+    assert fast.search_brute_force(q, 5) == fast.search_with_quality(q, 5, SearchQuality.Accurate)   # search.rs:180-194
+    custom = HnswIndex.with_params(128, DistanceMetric.Euclidean, HnswParams.custom(48, 600, 1_000_000))
+    assert (custom._params.max_connections, custom._params.ef_construction) == (48, 600)

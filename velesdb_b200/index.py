@@ -509,6 +509,18 @@ class HnswIndex:
         return cls(dimension, metric)
 
     @classmethod
+    def new_fast_insert(cls, dimension, metric):
+        """constructors.rs:63-66: no ShardedVectors copy -- no brute force, no re-rank, ``vacuum`` is an error."""
+        return cls(dimension, metric, HnswParams.auto(int(dimension)), enable_vector_storage=False)
+
+    @classmethod
+    def new_turbo(cls, dimension, metric):
+        """constructors.rs:86-91: auto parameters with ef_construction raised by half."""
+        p = HnswParams.auto(int(dimension))
+        p.ef_construction = (p.ef_construction * 3) // 2
+        return cls(dimension, metric, p)
+
+    @classmethod
     def with_params(cls, dimension, metric, params):
         return cls(dimension, metric, params)
 
