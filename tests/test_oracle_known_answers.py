@@ -97,6 +97,57 @@ def test_hamming_and_jaccard_known():
     assert vo.metric_value(vo.JACCARD, zero, zero) == 1.0
 
 
+def test_more_distance_known_answers_from_the_simd_test_files():
+    # simd_tests.rs:24-127, 186-322; simd_explicit_tests.rs:19-57, 178-249; simd_native_tests.rs:28-66, 134-262 --
+    # exact-valued inputs, so the oracle must hit the expected numbers exactly (the reference tolerates 1e-5)
+    A = lambda *v: np.array(v, F)
+    v4 = A(1, 2, 3, 4)
+    assert abs(vo.metric_value(vo.COSINE, v4, v4) - 1.0) < 1e-6 and abs(vo.metric_value(vo.COSINE, v4, -v4) + 1.0) < 1e-6
+    assert vo.metric_value(vo.COSINE, A(1, 0, 0, 0), A(0, 1, 0, 0)) == 0.0
+    assert vo.metric_value(vo.COSINE, A(1, 2, 3), A(0, 0, 0)) == 0.0          # zero vector -> 0
+    assert vo.metric_value(vo.COSINE, A(1, 0), A(0, 1)) == 0.0
+    assert vo.metric_value(vo.EUCLIDEAN, v4, v4) == 0.0
+    assert vo.metric_value(vo.EUCLIDEAN, A(0, 0, 0), A(3, 4, 0)) == 5.0      # 3-4-5
+    assert vo.metric_value(vo.EUCLIDEAN, np.zeros(8, F), A(3, 4, 0, 0, 0, 0, 0, 0)) == 5.0
+    assert vo.metric_value(vo.EUCLIDEAN, A(3), A(4)) == 1.0
+    assert vo.l2sq(A(0, 0), A(3, 4)) == 25.0 and vo.l2sq(A(1, 2, 3), A(1, 2, 3)) == 0.0
+    assert vo.l2sq(v4, A(5, 6, 7, 8)) == 64.0
+    assert vo.dot(v4, A(5, 6, 7, 8)) == 70.0
+    assert vo.dot(A(1, 2, 3, 4, 5, 6, 7, 8), np.ones(8, F)) == 36.0
+    assert vo.dot(A(1, 2, 3, 4, 5), A(5, 4, 3, 2, 1)) == 35.0                # odd dimension
+    assert vo.dot(A(3), A(4)) == 12.0
+    assert vo.dot(np.zeros(16, F), np.ones(16, F)) == 0.0 and vo.dot(np.ones(16, F), np.ones(16, F)) == 16.0
+    assert vo.dot(np.ones(32, F), np.ones(32, F)) == 32.0
+    assert vo.dot(np.arange(19, dtype=F), np.ones(19, F)) == 171.0           # 16 + remainder 3
+    a = np.array([i * 0.001 for i in range(768)], F)
+    b = np.array([(768 - i) * 0.001 for i in range(768)], F)
+    assert abs(vo.dot(a, b) - float(np.dot(a.astype(np.float64), b.astype(np.float64)))) < 0.01
+    assert abs(vo.l2sq(a, b) - float(((a.astype(np.float64) - b) ** 2).sum())) < 0.01
+    x, y = sinvec(768, 0.0), sinvec(768, 1.0)
+    naive = float(np.sqrt(((x.astype(np.float64) - y) ** 2).sum()))
+    assert abs(vo.metric_value(vo.EUCLIDEAN, x, y) - naive) < 1e-5 * max(naive, 1.0)
+    # Hamming on f32 lanes (threshold 0.5), Jaccard
+    assert vo.metric_value(vo.HAMMING, A(1, 0, 1, 0), A(1, 0, 1, 0)) == 0.0
+    assert vo.metric_value(vo.HAMMING, A(1, 0, 1, 0), A(0, 1, 0, 1)) == 4.0
+    assert vo.metric_value(vo.HAMMING, A(1, 1, 0, 0), A(1, 0, 0, 1)) == 2.0
+    assert vo.metric_value(vo.HAMMING, A(1, 0, 1, 0, 1), A(0, 0, 1, 1, 1)) == 2.0
+    assert vo.metric_value(vo.HAMMING, A(1, 0, 1, 0, 1, 0, 1, 0), A(0, 1, 0, 1, 0, 1, 0, 1)) == 8.0
+    assert vo.metric_value(vo.HAMMING, A(1, 1, 0, 0, 1, 1, 0, 0), A(1, 0, 0, 1, 1, 0, 0, 1)) == 4.0
+    h3 = np.array([1.0 if i % 3 == 0 else 0.0 for i in range(768)], F)
+    h2 = np.array([1.0 if i % 2 == 0 else 0.0 for i in range(768)], F)
+    assert vo.metric_value(vo.HAMMING, h3, h2) == float(((h3 > 0.5) != (h2 > 0.5)).sum())
+    assert vo.metric_value(vo.JACCARD, A(1, 0, 1, 0), A(1, 0, 1, 0)) == 1.0
+    assert vo.metric_value(vo.JACCARD, A(1, 0, 0, 0), A(0, 1, 0, 0)) == 0.0
+    assert abs(vo.metric_value(vo.JACCARD, A(1, 1, 0, 0), A(1, 0, 1, 0)) - 1.0 / 3.0) < 1e-6
+    assert vo.metric_value(vo.JACCARD, np.zeros(4, F), np.zeros(4, F)) == 1.0
+    # packed u64 Hamming (simd_explicit_tests.rs:229-249)
+    ff = np.full(16, 0xFFFFFFFFFFFFFFFF, np.uint64)
+    assert vo.hamming_binary(ff, ff) == 0
+    assert vo.hamming_binary(np.zeros(1, np.uint64), ff[:1]) == 64
+    assert vo.hamming_binary(np.array([0b10101010], np.uint64), np.array([0b01010101], np.uint64)) == 8
+    assert vo.hamming_binary(np.zeros(16, np.uint64), ff) == 1024
+
+
 def test_packed_hamming_equals_f32_threshold_form():
     # simd_explicit.rs:308-360 vs :256-287 on {0,1} inputs
     rng = np.random.default_rng(3)
