@@ -225,6 +225,35 @@ def test_insert_and_search_ramp():
     assert 0 < len(ids) <= 10 and ids[0] == 0
 
 
+def test_native_hnsw_basic_and_alpha_known_answers():
+    # native/tests.rs:10-30: 100 x 128 sin vectors, M 16, ef_c 100; search(query of node 0, 10, 50)
+    g = vo.Hnsw(vo.COSINE, 128, M=16, ef_construction=100)
+    for i in range(100):
+        g.insert(np.array([math.sin((i + j) * 0.01) for j in range(128)], F))
+    assert len(g) == 100
+    ids, d = g.search(np.array([math.sin(j * 0.01) for j in range(128)], F), 10, 50)
+    assert len(ids) == 10 and d[0] < 0.1 and int(ids[0]) == 0
+    # native/tests.rs:136-178: alpha = 1.2 (VAMANA-style pruning), two clusters of 25, the search still answers
+    ga = vo.Hnsw(vo.COSINE, 32, M=16, ef_construction=100, alpha=1.2)
+    for hot in (0, 1):
+        for i in range(25):
+            ga.insert(np.array([1.0 if j == hot else (i + j) * 0.001 for j in range(32)], F))
+    assert len(ga) == 50
+    ids, d = ga.search(np.array([0.9 if j == 0 else 0.01 for j in range(32)], F), 5, 50)
+    assert len(ids) == 5 and all(int(i) < 25 for i in ids)          # the first cluster
+    # native/tests.rs:193-214: alpha changes the links, not the count; alpha = 1.0 is the default (:181-190)
+    g1, g2 = vo.Hnsw(vo.EUCLIDEAN, 32, M=16, ef_construction=100), vo.Hnsw(vo.EUCLIDEAN, 32, M=16, ef_construction=100, alpha=1.2)
+    for i in range(30):
+        v = np.array([(i + j) * 0.1 for j in range(32)], F)
+        g1.insert(v)
+        g2.insert(v)
+    assert len(g1) == len(g2) == 30
+    same = vo.Hnsw(vo.EUCLIDEAN, 32, M=16, ef_construction=100, alpha=1.0)
+    for i in range(30):
+        same.insert(np.array([(i + j) * 0.1 for j in range(32)], F))
+    assert all(np.array_equal(a[1], b[1]) for a, b in zip(g1.export_graph(), same.export_graph()))
+
+
 def test_empty_search():
     # native/graph_tests.rs:33-41
     g = vo.Hnsw(vo.COSINE, 3, M=16, ef_construction=100)
