@@ -272,3 +272,50 @@ def test_constructor_variants_known_answers():
     assert fast.search_brute_force(q, 5) == fast.search_with_quality(q, 5, SearchQuality.Accurate)   # search.rs:180-194
     custom = HnswIndex.with_params(128, DistanceMetric.Euclidean, HnswParams.custom(48, 600, 1_000_000))
     assert (custom._params.max_connections, custom._params.ef_construction) == (48, 600)
+
+
+def _attach(ix, rows):
+    snap = OracleSnapshot(ix.metric(), np.asarray(rows, np.float32))
+    ix._snapshot, ix._dirty = snap, False
+    return snap
+
+
+def test_batch_insert_rerank_and_batch_search_known_answers():
+    # index_tests.rs:441-494, 556-571, 633-650, 1018-1068 through the mirror (device snapshot = oracle stand-in)
+    pts = [(1, [1.0, 0.0, 0.0]), (2, [0.0, 1.0, 0.0]), (3, [0.0, 0.0, 1.0]), (4, [0.5, 0.5, 0.0]), (5, [0.5, 0.0, 0.5])]
+    ix = HnswIndex.new(3, DistanceMetric.Cosine)
+    assert ix.insert_batch_parallel(pts) == 5 and ix.len() == 5
+    _attach(ix, [v for _, v in pts])
+    ix.set_searching_mode()                                        # nothing left to build
+    res = ix.search([1.0, 0.0, 0.0], 3)
+    assert len(res) == 3 and res[0][0] == 1
+    rr = ix.search_with_rerank([1.0, 0.0, 0.0], 3, 100)            # rerank_k > index size
+    assert 0 < len(rr) <= 5 and rr[0][0] == 1
+    dup = HnswIndex.new(3, DistanceMetric.Cosine)
+    dup.insert(1, [1.0, 0.0, 0.0])
+    assert dup.insert_batch_parallel([(1, [0.0, 1.0, 0.0]), (2, [0.0, 0.0, 1.0])]) == 1 and dup.len() == 2
+    with pytest.raises(DimensionMismatch, match="Vector dimension mismatch"):
+        HnswIndex.new(3, DistanceMetric.Cosine).insert_batch_sequential([(1, [1.0, 0.0])])
+    assert HnswIndex.new(3, DistanceMetric.Cosine).insert_batch_sequential([]) == 0
+    # batch search = the individual searches, query by query (here even id for id: both paths end in the same graph
+    # search once the index holds more than 100 vectors)
+    big = HnswIndex.new(64, DistanceMetric.Cosine)
+    rows = np.array([[np.sin((i + j) * 0.01) for j in range(64)] for i in range(150)], np.float32)
+    for i in range(150):
+        big.insert(i, rows[i])
+    _attach(big, rows)
+    qs = np.array([[np.sin((200 + i + j) * 0.01) for j in range(64)] for i in range(10)], np.float32)
+    batch = big.search_batch_parallel(qs, 5, SearchQuality.Balanced)
+    single = [big.search_with_quality(q, 5, SearchQuality.Balanced) for q in qs]
+    assert len(batch) == 10 and all(len(b) == 5 for b in batch) and batch == single
+    one = HnswIndex.new(3, DistanceMetric.Cosine)
+    one.insert(1, [1.0, 0.0, 0.0])
+    assert one.search_batch_parallel([], 5, SearchQuality.Fast) == []
+    # tombstones (index_tests.rs:22-54)
+    t = HnswIndex.new(64, DistanceMetric.Cosine)
+    assert t.tombstone_count() == 0 and t.tombstone_ratio() == 0.0
+    for i in range(10):
+        t.insert(i, rows[i])
+    for i in range(3):
+        assert t.remove(i)
+    assert t.tombstone_count() == 3 and t.len() == 7 and abs(t.tombstone_ratio() - 0.3) < 1e-9
