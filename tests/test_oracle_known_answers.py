@@ -411,6 +411,39 @@ def test_bm25_known_answers():
     assert len(ix) == 1
 
 
+def test_bm25_bookkeeping_known_answers():
+    # bm25_tests.rs:8-62, 123-160, 316-345: sizes, removal, no-match / empty queries, the u32 id limit -- on the oracle
+    # and on the host mirror's CPU-side bookkeeping (no device call is made before the first non-empty search)
+    from velesdb_b200 import Bm25Index
+
+    for make in (vo.Bm25, Bm25Index):
+        ix = make()
+        assert len(ix) == 0 and ix.term_count() == 0
+        ix.add_document(1, "hello world")
+        assert len(ix) == 1 and ix.term_count() >= 2
+        ix.add_document(2, "goodbye world")
+        assert len(ix) == 2 and ix.remove_document(1) and len(ix) == 1 and not ix.remove_document(1)
+        ix = make()
+        for d, t in ((1, "rust programming language"), (2, "python programming language"), (3, "java programming")):
+            ix.add_document(d, t)
+        assert len(ix) == 3
+        ix = make()
+        ix.add_document(0xFFFFFFFF, "test document")                       # exactly u32::MAX is allowed
+        assert len(ix) == 1
+        with pytest.raises((AssertionError, ValueError), match="BM25 document ID"):   # the reference panics
+            make().add_document(0xFFFFFFFF + 1, "test document")
+    ix = vo.Bm25()
+    for d, t in ((1, "rust programming language fast"), (2, "python programming language"), (3, "rust systems programming")):
+        ix.add_document(d, t)
+    ids, _ = ix.search("rust programming", 10)
+    assert {1, 3} <= set(ids.tolist()) and len(ids) == 3
+    ix = vo.Bm25()
+    ix.add_document(1, "rust programming")
+    ix.add_document(2, "python programming")
+    assert len(ix.search("javascript", 10)[0]) == 0 and len(ix.search("", 10)[0]) == 0
+    assert Bm25Index().search("rust", 10) == [] and Bm25Index().search("", 10) == []
+
+
 def test_bm25_formula_by_hand():
     # bm25.rs:290-376 with k1=1.2, b=0.75
     ix = vo.Bm25()
